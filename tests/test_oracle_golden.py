@@ -1,0 +1,166 @@
+"""The oracle (oracle/oracle.py) against every golden vector the reference offers for the path.
+
+1. test_scripts/beta_vs_time.mat -- the reference's only numeric artefact (tests/golden/beta_vs_time.json).
+2. tests/golden/reference_vectors.npz -- produced by executing the reference's own cbf/obstacles.py,
+   cbf/cbf.py and the solver/plant/Stanley functions of test_scripts/*.py (gen_reference_vectors.py).
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as o
+
+AX = [0.0, 100.0, 100.0, 50.0, 60.0]
+AY = [0.0, 0.0, -30.0, -20.0, 0.0]
+
+
+@pytest.fixture(scope="module")
+def course():
+    return o.calc_spline_course(AX, AY, 0.1)
+
+
+def test_course_bit_exact_vs_reference_planner(course, refvec):
+    cx, cy, cyaw = course
+    assert len(cx) == 2034
+    assert np.array_equal(cx, refvec["course"][0])
+    assert np.array_equal(cy, refvec["course"][1])
+    assert np.array_equal(cyaw, refvec["course"][2])
+    assert cx[1524] == 75.63083239590846 and cy[1524] == -35.149858832676415
+
+
+def test_beta_vs_time_mat(course, golden_dir):
+    """277 samples, t_arr bit-exact, |dbeta| <= 1e-3 deg (IPM tolerance)."""
+    g = json.load(open(os.path.join(golden_dir, "beta_vs_time.json")))
+    cx, cy, cyaw = course
+    oi = int((len(cx) - 1) * 0.75)
+    a_cone = float(np.hypot(20, 10) / 2)
+    fields = [[cx[oi], cy[oi], 0.0, 0.0, a_cone + 1.5, 0.0, 0.0, 0.0]]
+    out = o.rollout([-0.0, 5.0, float(np.radians(20.0)), 10.0], [o.SLOT_CONE], fields, course, T=10 ** 6,
+                    params=dict(terminate=1, R=(0.5, 0.0, 0.0, 0.5)), record=True)
+    beta = np.degrees(np.array([0.0] + out["rec"]["beta"]))
+    t = np.array([0.0] + out["rec"]["t"])
+    assert len(beta) == 277 == len(g["beta_deg"])
+    assert np.array_equal(t, np.array(g["t_arr"]))          # fp64 time accumulation, bit-exact
+    assert t[-1] == 27.600000000000122
+    assert np.abs(beta - np.array(g["beta_deg"])).max() <= 1e-3
+    assert out["n_active"] == 59 and out["target_idx"] == 2033
+
+
+def test_cone_partials_bit_exact(refvec):
+    for row, ref in zip(refvec["cone_in"], refvec["cone_out"]):
+        x, y, th, v, cx, cy, tho, vo, a, beta = row
+        got = o.cone_partials(x, y, th, v, cx, cy, tho, vo, a + 1.5, beta)
+        assert tuple(float(g) for g in got) == tuple(ref), (row, got, ref)
+
+
+def test_ellipse_partials_bit_exact(refvec):
+    for row, ref in zip(refvec["ellipse_in"], refvec["ellipse_out"]):
+        x, y, cx, cy, a, b, th, buf, vx, vy = row
+        h, hx, hy, hth, hv, ht = o.ellipse_partials(x, y, cx, cy, a + buf, b + buf, th, vx, vy)
+        assert (float(h), float(hx), float(hy), float(ht)) == tuple(ref)
+        assert hth == 0.0 and hv == 0.0
+
+
+def test_lane_vs_reference_newton_cg(refvec):
+    """cx within the reference's own xtol (1e-8 .. scipy stops early); h, h_x, h_y follow."""
+    for row, ref in zip(refvec["lane_in"], refvec["lane_out"]):
+        x, y, c0, c1, c2, c3, buf, th, v = row
+        c = [c0, c1, c2, c3, 0.0, 0.0]
+        cx = o.lane_closest_x(c, x, y)
+        assert abs(cx - ref[0]) <= 2e-7 * (1 + abs(cx)), (row, cx, ref[0])
+        h, hx, hy, _, _, _ = o.lane_partials(x, y, c, buf)
+        assert abs(h - ref[1]) <= 1e-6 * (1 + abs(ref[1]))
+        assert abs(hx - ref[2]) <= 1e-6 * (1 + abs(ref[2]))
+        assert abs(hy - ref[3]) <= 1e-6 * (1 + abs(ref[3]))
+        # and the oracle's point is at least as good a minimiser as the reference's
+        def D(t):
+            g, _, _ = o._poly3(c, t)
+            return (t - x) ** 2 + (g - y) ** 2
+        assert D(cx) <= D(ref[0]) * (1 + 1e-12) + 1e-300
+
+
+def test_lane_linear_closed_form():
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        c0, c1 = rng.uniform(-20, 20), rng.uniform(-2, 2)
+        px, py = rng.uniform(-50, 50, 2)
+        cx = o.lane_closest_x([c0, c1, 0, 0, 0, 0], px, py)
+        exact = (px + c1 * (py - c0)) / (1 + c1 * c1)
+        assert abs(cx - exact) <= 1e-12 * (1 + abs(exact))
+
+
+def test_dbm_rows_and_output_vs_reference_class(refvec):
+    """Rows assembled by cbf/cbf.py:200-207 (captured inside solvers.cp) and the final [a, delta]."""
+    for i in range(refvec["dbm_in"].shape[0]):
+        s = list(refvec["dbm_in"][i, 0:4]); uref = list(refvec["dbm_in"][i, 4:6])
+        R = tuple(refvec["dbm_in"][i, 6:10]); alpha = refvec["dbm_in"][i, 10]; m = int(refvec["dbm_in"][i, 11])
+        types = [int(refvec["dbm_slot"][i, j, 0]) for j in range(m)]
+        fields = [list(refvec["dbm_slot"][i, j, 1:]) for j in range(m)]
+        A0, A1, b, _ = o.barrier_rows(o.MODEL_DBM, s, types, fields, alpha, 1.45)
+        ref = refvec["dbm_rows"][i, :m]
+        for j in range(m):
+            if types[j] == o.SLOT_LANE:      # lane rows inherit the Newton-CG stopping error
+                assert np.allclose([A0[j], A1[j], b[j]], ref[j], rtol=1e-6, atol=1e-6)
+            else:
+                assert (float(A0[j]), float(A1[j]), float(b[j])) == tuple(ref[j]), (i, j)
+        u0, d, mask, status, raw, _ = o.filter_step(o.MODEL_DBM, s, uref, types, fields, alpha, 1.45, 1.45, 2.9, R)
+        ru0, rd, rbeta, rmask, rstatus = refvec["dbm_out"][i]
+        assert o.delta_to_beta(uref[1], 1.45, 1.45) == rbeta
+        assert mask == int(rmask) and status == int(rstatus)
+        tol = 1e-6 if o.SLOT_LANE in types else 1e-13
+        assert abs(u0 - ru0) <= tol * (1 + abs(ru0)) and abs(d - rd) <= tol * (1 + abs(rd))
+
+
+@pytest.mark.parametrize("cbf_type", [0, 2, 4])
+def test_config1_closed_loop_vs_reference_functions(course, refvec, cbf_type):
+    """Closed loop of stanley_controller_ellipse.py main() for CBF_TYPE 0 (KBM, CBF()),
+    2 (DBM ellipse, CBF_A) and 4 (DBM cone, class API): step count, waypoint indices and active
+    sets identical; states/controls to 1e-9 (the twins CBF/CBF_A use algebraically equal but
+    differently rounded axis-aligned formulas, so bit equality is not expected for 0 and 2)."""
+    ref = refvec["cfg1_type%d" % cbf_type]
+    cx, cy, cyaw = course
+    oi = int((len(cx) - 1) * 0.75)
+    if cbf_type == 4:
+        types = [o.SLOT_CONE]
+        fields = [[cx[oi], cy[oi], 0.0, 0.0, float(np.hypot(20, 10) / 2) + 1.5, 0.0, 0, 0]]
+        prm = dict(terminate=1, R=(0.5, 0.0, 0.0, 0.5))
+    else:
+        types = [o.SLOT_ELLIPSE]
+        fields = [[cx[oi], cy[oi], 20.0, 10.0, 0.0, 0.0, 0.0, 0]]
+        prm = dict(terminate=1, model=o.MODEL_KBM if cbf_type == 0 else o.MODEL_DBM, kbm_driver_delta=1)
+    out = o.rollout([-0.0, 5.0, float(np.radians(20.0)), 10.0], types, fields, course, T=10 ** 6, params=prm, record=True)
+    assert out["steps"] == ref.shape[0]
+    rec = out["rec"]
+    assert np.array_equal(np.array(rec["idx"]), ref[:, 5].astype(int))
+    assert np.array_equal(np.array(rec["mask"]), ref[:, 9].astype(int))
+    assert np.array_equal(np.array(rec["t"]), ref[:, 11])
+    st = np.array(rec["state"]); u = np.array(rec["u"])
+    if cbf_type == 4:
+        # class path: rows are bit-exact (test_dbm_rows...); the trajectory is not quite, because
+        # the reference's np.dot([dx, dy], front_axle_vec) (sce.py:210) goes through BLAS ddot,
+        # whose FMA use is build-dependent (1 ulp in the cross-track error).
+        assert np.abs(st - ref[:, 0:4]).max() <= 1e-11
+        assert np.abs(u - ref[:, 6:8]).max() <= 1e-11
+        assert np.abs(np.array(rec["beta"]) - ref[:, 8]).max() <= 1e-11
+        # teacher-forced: rows from the reference's states are bit-exact
+        for i in range(0, ref.shape[0], 7):
+            A0, A1, b, _ = o.barrier_rows(o.MODEL_DBM, list(ref[i, 0:4]), types, fields, 1, 1.45)
+            assert (float(A0[0]), float(A1[0]), float(b[0])) == tuple(ref[i, 12:15])
+    else:
+        assert np.abs(st - ref[:, 0:4]).max() <= 1e-9
+        # type 0 runs with the driver's omega->delta conversion (sce.py:652), see filter_step
+        assert np.abs(u - ref[:, 6:8]).max() <= 1e-9
+
+
+def test_radial_rows_vs_reference_function(refvec):
+    for row, ref in zip(refvec["radial_in"], refvec["radial_out"]):
+        s = list(row[0:4]); uref = list(row[4:6]); c = row[6:8]; cd = row[8:10]; r, gamma, kv = row[10:13]
+        f = [[c[0], c[1], r, r, kv, cd[0], cd[1], 0.0]]
+        A0, A1, b, _ = o.barrier_rows(o.MODEL_DBM, s, [o.SLOT_RADIAL], f, gamma, 1.45)
+        assert np.allclose([A0[0], A1[0], b[0]], ref[2:5], rtol=1e-13, atol=1e-13)
+        u0, d, mask, status, _, _ = o.filter_step(o.MODEL_DBM, s, uref, [o.SLOT_RADIAL], f, gamma, 1.45, 1.45, 2.9, (1.0, 0.0, 0.0, 1.0))
+        assert mask == int(ref[5]) and status == int(ref[6])
+        assert abs(u0 - ref[0]) <= 1e-12 * (1 + abs(ref[0])) and abs(d - ref[1]) <= 1e-12 * (1 + abs(ref[1]))
