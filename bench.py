@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- closed-loop CBF-QP solves/sec (vehicles x obstacles x steps) on 1/2/4/8 B200.
+
+    python bench.py --gpus N --steps K --warmup W
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the CPU restatement of the reference loop, host cores
+
+A "step" is one pass of the hot path over one batch: ONE persistent closed-loop rollout
+(Stanley nominal -> barrier rows -> 2-variable QP -> bicycle plant, T = 1,000 timesteps) of
+BASELINE config #2 (65,536 vehicles x 8 static ellipses per GPU, synthetic, seed 0).  Scenarios are
+independent, so N GPUs = N shards of the scenario axis, no collective on the path (weak scaling:
+65,536 vehicles per GPU).
+
+One JSON line on stdout (rank 0):
+  value   whole-job solves/s with inputs resident in HBM (CUDA events around each rollout launch)
+  e2e     the same metric through ClosedLoopRollout.run_from_host(): pinned host inputs -> H2D ->
+          kernel -> D2H of the per-vehicle results, every step
+  roofline            the rollout kernel against the MEASURED fp64 FMA peak of this GPU
+                      (the path is fp64-pipe bound in persistent form, SURVEY 8d regime ii)
+  roofline_operator   the per-timestep fused filter kernel (K1+K2) against the measured HBM peak
+                      (regime i, 64.6 B/solve)
+  cpu_baseline        oracle/oracle.c ("port"; the reference itself cannot run here: no cvxopt)
+                      timed on the box's host cores on a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "closed-loop CBF-QP solves/sec (vehicles x obstacles x steps)"
+UNIT = "solves/s"
+P_COURSE = 2034
+
+
+def algorithmic_flops_per_solve(P: int, M: int) -> float:
+    """SURVEY 8(d) regime ii: F = 49 + (7 P + 25) / M fp64 flop per solve (rows + minimal QP per
+    solve; Stanley argmin 7 flop per way-point + integrator per vehicle-step, amortised over M)."""
+    return 49.0 + (7.0 * P + 25.0) / M
+
+
+def operator_bytes_per_solve(M: int, esize: int = 8) -> float:
+    """SURVEY 8(d) regime i: 7 obstacle fields per (vehicle, obstacle) + per vehicle state 4 +
+    u_ref 2 read, u 2 + mask (4 B) + status (1 B) written."""
+    return 7 * esize + ((4 + 2 + 2) * esize + 5) / M
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 8 and parts[0].isdigit() and int(parts[0]) == self.index:
+                self.rows.append((time.perf_counter(), parts))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        rows = [p for (t, p) in self.rows if t0 <= t <= t1] or [p for (_, p) in self.rows]
+        sm, mx, pw, reasons = [], [], [], set()
+        for p in rows:
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2])); pw.append(float(p[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def committed_traffic(kernel: str):
+    """dram bytes per launch of `kernel` from the committed ncu --set full capture, if any."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_rollout_rate(n_vehicles: int, M: int, T: int, threads: int, seed: int = 0):
+    """oracle/oracle.c closed loop on the first n_vehicles scenarios of config #2."""
+    from oracle import c_oracle as co
+    from sccav_cbf_b200 import scenarios as sc
+    b = sc.config2(n_total=65536, M=M, T=T, seed=seed, lo=0, hi=n_vehicles)
+    prm = co.default_params(**b.params)
+    t0 = time.perf_counter()
+    res = co.rollout(prm, b.slot_desc, b.state, b.obst, b.course, T, nthreads=threads)
+    dt = time.perf_counter() - t0
+    solves = float(res["steps"].sum()) * M
+    return solves / dt, dt, solves
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU loop cannot run here (cvxopt / euclid are not
+    installable: no network), so this arm times the oracle port of that loop (oracle/oracle.c,
+    all host threads) on the same config, metric and unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import c_oracle as co
+    threads = co.num_threads()
+    M, T = args.obstacles, args.T
+    rate, dt, _ = cpu_rollout_rate(max(threads, 8), M, T, threads)            # probe (also warms the page cache)
+    n = int(max(threads, min(65536, rate * args.ref_seconds / (M * T))))
+    for _ in range(args.warmup if args.warmup < 2 else 1):                     # CPU warm-up: one pass is enough
+        cpu_rollout_rate(n, M, T, threads)
+    t_tot, s_tot = 0.0, 0.0
+    for _ in range(args.steps):
+        r, d, s = cpu_rollout_rate(n, M, T, threads)
+        t_tot += d; s_tot += s
+    value = s_tot / t_tot
+    sample = "%d of 65536 vehicles x %d ellipses x %d steps per step (config #2 prefix), %d host threads" % (n, M, T, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "note": "reference loop itself not runnable: cvxopt/euclid absent and not installable (no network)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_name(args):
+    return ("config2: %d vehicles/GPU x %d static ellipses x %d-step closed-loop rollout "
+            "(DBM + Stanley + update_com, P=%d course points)" % (args.vehicles, args.obstacles, args.T, P_COURSE))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--vehicles", type=int, default=65536, help="vehicles per GPU")
+    ap.add_argument("--obstacles", type=int, default=8)
+    ap.add_argument("--T", type=int, default=1000, help="timesteps per rollout")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--ref-seconds", type=float, default=4.0, help="CPU seconds per reference step")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU seconds for the cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-operator", action="store_true", help="skip the regime-(i) operator roofline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = max(args.warmup, 1)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+
+    from sccav_cbf_b200 import ops, scenarios as sc
+    from sccav_cbf_b200.rollout import ClosedLoopRollout
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback on the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    dtype = torch.float64 if args.dtype == "f64" else torch.float32
+    esize = 8 if args.dtype == "f64" else 4
+    M, T, NV = args.obstacles, args.T, args.vehicles
+    n_total = NV * world
+    lo, hi = sc.shard_range(n_total, rank, world)
+    batch = sc.config2(n_total=n_total, M=M, T=T, seed=0, lo=lo, hi=hi)
+    cl = ClosedLoopRollout(batch, dtype=dtype, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    # ---- warm-up
+    for _ in range(max(args.warmup, 3)):
+        cl.run()
+    torch.cuda.synchronize()
+
+    # ---- timed region 1: inputs resident in HBM, one rollout launch per step
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    barrier()
+    l0 = ops.launch_count()
+    t_wall0 = time.perf_counter()
+    for e0, e1 in evs:
+        flush.fill_(1)                    # L2 flush between timed iterations (outside the event pair)
+        e0.record()
+        res = cl.run()
+        e1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = ops.launch_count() - l0
+    clocks = sampler.stop(t_wall0, t_wall1)
+    ms_steps = [e0.elapsed_time(e1) for e0, e1 in evs]
+    ms_total = max_over_ranks(sum(ms_steps))
+    solves_per_step_rank = float(res["steps"].sum().item()) * M
+    solves_per_step = sum_over_ranks(solves_per_step_rank)
+    value = solves_per_step * args.steps / (ms_total * 1e-3)
+    checksum = sum_over_ranks(float(res["n_active"].sum().item()))
+
+    # ---- timed region 2: end to end through the public API with HOST buffers
+    for _ in range(2):
+        cl.run_from_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cl.run_from_host()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = solves_per_step * args.steps / e2e_s
+
+    # ---- roofline of the dominant kernel (rollout): fp64 FMA peak measured on this GPU, now
+    peak_tf = ops.measure_fma_peak(dtype)
+    flops_per_launch = algorithmic_flops_per_solve(P_COURSE, M) * solves_per_step_rank
+    ms_launch = sum(ms_steps) / len(ms_steps)
+    ach_tf = flops_per_launch / (ms_launch * 1e-3) / 1e12
+    kname = "rollout_kernel<%s>" % ("double" if args.dtype == "f64" else "float")
+    roofline = {
+        "bound": "fp64" if args.dtype == "f64" else "fp32", "kernel": kname,
+        "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None,
+        "peak_source": "measured live: sccav_measure_fma_peak (unrolled FMA chains, FMA = 2 flop)",
+        "algorithmic_flops_per_solve": algorithmic_flops_per_solve(P_COURSE, M),
+        "traffic": committed_traffic("rollout"),
+        "hbm_gbs_achieved": (NV * (4 + M * 7) * esize + NV * (4 * esize + 16 + 4 * esize)) / (ms_launch * 1e-3) / 1e9,
+        "note": "not HBM- or tensor-bound: state lives in registers for 1000 steps (about 0.07 B/solve of DRAM traffic); "
+                "the non-FMA add/mul/compare mix caps the FMA-peak fraction at about 0.58",
+    }
+
+    # ---- regime (i): per-timestep fused operator against the HBM roofline (inputs >> L2)
+    roofline_op = None
+    if not args.no_operator:
+        hbm_peak, hbm_src = measured_peaks()
+        n_op = 2 * 1024 * 1024
+        gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
+        st = torch.empty((4, n_op), dtype=dtype, device=dev)
+        st[0].uniform_(-20, 120, generator=gen); st[1].uniform_(-45, 15, generator=gen)
+        st[2].uniform_(-3.2, 3.2, generator=gen); st[3].uniform_(2, 12, generator=gen)
+        ob = torch.zeros((M, 8, n_op), dtype=dtype, device=dev)
+        ob[:, 0].uniform_(-20, 120, generator=gen); ob[:, 1].uniform_(-45, 15, generator=gen)
+        ob[:, 2].uniform_(2.5, 6.5, generator=gen); ob[:, 3].uniform_(1.5, 3.5, generator=gen)
+        ob[:, 4].uniform_(-3.1, 3.1, generator=gen)
+        ur = torch.zeros((2, n_op), dtype=dtype, device=dev); ur[1].uniform_(-0.3, 0.3, generator=gen)
+        prm = ops.make_params()
+        for _ in range(3):
+            ops.filter_step(prm, batch.slot_desc, st, ob, ur)
+        oevs = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); ops.filter_step(prm, batch.slot_desc, st, ob, ur); e1.record()
+            oevs.append((e0, e1))
+        torch.cuda.synchronize()
+        oms = statistics.mean(e0.elapsed_time(e1) for e0, e1 in oevs)
+        obytes = operator_bytes_per_solve(M, esize) * n_op * M
+        roofline_op = {
+            "bound": "hbm", "kernel": "filter_step_kernel<%s>" % ("double" if args.dtype == "f64" else "float"),
+            "achieved": obytes / (oms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": obytes / (oms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+            "algorithmic_bytes_per_solve": operator_bytes_per_solve(M, esize), "solves_per_s": n_op * M / (oms * 1e-3),
+            "workload": "%d vehicles x %d ellipses, inputs %.0f MB (> L2)" % (n_op, M, obytes / 1e6),
+            "traffic": committed_traffic("filter_step"),
+        }
+        del st, ob, ur
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the box's host cores, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import c_oracle as co
+        threads = co.num_threads()
+        rate, _, _ = cpu_rollout_rate(max(threads, 8), M, T, threads)
+        n = int(max(threads, min(NV, rate * args.cpu_seconds / (M * T))))
+        rate, dt_cpu, _ = cpu_rollout_rate(n, M, T, threads)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "first %d of %d vehicles x %d ellipses x %d steps (%.1f s), oracle/oracle.c, gcc -O2, %d threads"
+                         % (n, NV, M, T, dt_cpu, threads),
+               "note": "reference loop not runnable here (cvxopt/euclid absent, no network); the port omits the IPM's python-callback cost"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": workload_name(args), "vehicles_total": n_total, "obstacles": M, "timesteps": T,
+                       "solves_per_step": solves_per_step, "parallelism": "scenario shards x%d, no collective" % world,
+                       "l2": "flushed (256 MB write) between timed iterations; inputs 36 MB/GPU",
+                       "seed": 0, "active_step_checksum": checksum},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cl.h2d_bytes(), "d2h_bytes_per_step": cl.d2h_bytes(),
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "roofline_operator": roofline_op,
+            "cpu_baseline": cpu,
+            "wall_s_timed_region": t_wall1 - t_wall0,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,212 @@
+/*
+ * sccav_cbf.h -- C-ABI of the B200-native batched CBF-QP safety filter (libsccav_cbf.so).
+ *
+ * This is the drop-in boundary for ONE hot path of Safety-Critical-Control-WIRIN/sccav_cbf:
+ *     barrier evaluation -> 2-variable CBF-QP -> closed-loop Stanley / bicycle rollout.
+ * The reference has no FFI of its own (pure Python); its boundary is the class API
+ *     DBM_CBF_2DS.solve_cbf            cbf/cbf.py:166-220
+ *     KBM_VC_CBF2D.solve_cbf           cbf/cbf.py:67-110
+ *     ObstacleList2D.f/dx/dy/dtheta/dv/dt   cbf/obstacles.py:879-925
+ *     the per-tick loop of             test_scripts/stanley_controller_ellipse.py:630-830
+ *                                      test_scripts/radial_dynamic_obstacles.py:427-507
+ * Each entry point below names the reference interface it replaces.  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++ / torch types; no exceptions cross the ABI.
+ *  - every function returns 0 on success, a negative SCCAV_E* code otherwise;
+ *    sccav_last_error() returns a thread-local message for the last failure.
+ *  - "dev" pointers are CUDA device pointers on the CURRENT device, BORROWED for the duration of
+ *    the call (stream-ordered: the call only enqueues work on `stream`, a cudaStream_t passed as
+ *    void*; NULL = the legacy default stream).  "host" pointers are ordinary host memory.
+ *  - no internal threads, no global mutable state besides a per-device attribute cache;
+ *    re-entrant per stream.
+ *  - batch layout is structure-of-arrays with the vehicle index n fastest:
+ *        state  [4][N]        x, y, theta(yaw), v
+ *        obst   [M][8][N]     slot m, field f, vehicle n  (field meaning depends on slot type)
+ *        u      [2][N]        DBM: (a, delta)   KBM: (v, delta)
+ *        A      [2][M][N], b [M][N]   constraint rows  A0*u0 + A1*u1 >= b  (u1 = beta / omega)
+ *  - `_f64` entry points take double arrays, `_f32` float arrays; integer outputs are the same.
+ */
+#ifndef SCCAV_CBF_H
+#define SCCAV_CBF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCCAV_VERSION 100          /* 0.1.0 */
+#define SCCAV_NFIELD 8             /* fields per obstacle slot */
+#define SCCAV_MAX_ROWS 32          /* M <= 32: the active set is a uint32 bit mask */
+#define SCCAV_TRAJ_FIELDS 7        /* x, y, yaw, v, u0, u1(delta), beta */
+
+/* ---- obstacle slot types (low 7 bits of slot_desc[m]) ------------------------------------ */
+/* ELLIPSE  Ellipse2D, cbf/obstacles.py:139-331.  fields: cx, cy, a, b, theta, vx, vy, -
+ *          (a, b already include the buffer, obstacles.py:159-160)                            */
+#define SCCAV_SLOT_ELLIPSE 0
+/* CONE     CollisionCone2D, cbf/obstacles.py:333-543.  fields: cx, cy, theta_o, v_o, a, beta, -, -
+ *          (a already includes the buffer, obstacles.py:357)                                  */
+#define SCCAV_SLOT_CONE 1
+/* LANE     PolyLane, cbf/obstacles.py:545-689.  fields: buffer, c0, c1, c2, c3, c4, c5, -     */
+#define SCCAV_SLOT_LANE 2
+/* RADIAL   single_obstacle_CBF1, test_scripts/radial_dynamic_obstacles.py:366-425.
+ *          fields: cx, cy, a, b, kv, vx, vy, -                                                */
+#define SCCAV_SLOT_RADIAL 3
+/* DISTANCE D_CBF, test_scripts/stanley_controller_ellipse.py:240-275.  fields: cx, cy, Ds     */
+#define SCCAV_SLOT_DISTANCE 4
+/* flag: the slot's 8 fields are shared by all vehicles (read from n = 0), e.g. global lanes   */
+#define SCCAV_SLOT_SHARED 0x80
+
+#define SCCAV_MODEL_DBM 0          /* DBM_CBF_2DS,  u = (a, beta),  cbf/cbf.py:112-220 */
+#define SCCAV_MODEL_KBM 1          /* KBM_VC_CBF2D, u = (v, omega), cbf/cbf.py:33-110  */
+#define SCCAV_MODEL_NONE 2         /* rollout only: USE_CBF = False, plant State.update (sce.py:86-101,828) */
+
+#define SCCAV_NOMINAL_STANLEY 0    /* Stanley + P speed, stanley_controller_ellipse.py:135-212 */
+#define SCCAV_NOMINAL_CONST 1      /* constant u_ref, radial_dynamic_obstacles.py:444          */
+
+#define SCCAV_STATUS_INACTIVE 0    /* u == u_ref                                               */
+#define SCCAV_STATUS_ACTIVE 1      /* KKT optimum with 1 or 2 active rows                      */
+#define SCCAV_STATUS_INFEASIBLE 2  /* no KKT point; least-violation candidate returned         */
+
+#define SCCAV_OK 0
+#define SCCAV_EINVAL (-1)          /* bad argument (M = 0 maps to the reference's ValueError, cbf.py:177) */
+#define SCCAV_ECUDA (-2)           /* a CUDA runtime call failed                               */
+#define SCCAV_ENOMEM (-3)
+
+/* Parameters of the filter and of the closed loop.  Doubles for both precisions (the _f32 entry
+ * points round them once).  Defaults = test_scripts/stanley_controller_ellipse.py:52-58,590.  */
+typedef struct sccav_params {
+    int32_t model;             /* SCCAV_MODEL_*                                                */
+    int32_t nominal;           /* SCCAV_NOMINAL_*                                              */
+    int32_t terminate;         /* 1: stop a vehicle when !(t_max >= time && last_idx > target_idx), sce.py:630 */
+    int32_t seeker;            /* 1: RADIAL slots chase the ego after every step, rdo.py:193-239 */
+    int32_t kbm_driver_delta;  /* KBM only. 0: delta = atan2(w L, v_ref) (cbf.py:109); 1: atan(w L / v) (sce.py:652) */
+    int32_t record_stride;     /* rollout: 0 = no trajectory, k = record every k-th step       */
+    int32_t reserved0;
+    int32_t reserved1;
+    double alpha;              /* class-K gain (gamma), cbf.py:128                             */
+    double lr, lf, L;          /* cbf.py:150-152, cbf.py:61                                    */
+    double max_steer;          /* sce.py:58                                                    */
+    double dt;                 /* sce.py:54                                                    */
+    double k_stanley;          /* sce.py:52                                                    */
+    double ks_stanley;         /* softening of LateralStanley, controllers.py:144 (0 = function form) */
+    double Kp;                 /* sce.py:53                                                    */
+    double target_speed;       /* sce.py:590                                                   */
+    double t_max;              /* sce.py:592                                                   */
+    double R[4];               /* QP weight, row-major 2x2 SPD, cbf.py:154                     */
+    double seeker_k, seeker_vmin;  /* rdo.py:193                                               */
+    double uref0, uref1;       /* NOMINAL_CONST reference                                      */
+} sccav_params;
+
+/* Optional per-vehicle overrides (Monte-Carlo sweeps); any pointer may be NULL.  dev pointers. */
+typedef struct sccav_pervehicle {
+    const void* alpha;         /* [N]    overrides params.alpha                                */
+    const void* R;             /* [4][N] overrides params.R                                    */
+    const void* target_speed;  /* [N]    overrides params.target_speed                         */
+} sccav_pervehicle;
+
+/* Outputs of a rollout; any pointer except `state` may be NULL.  dev pointers.                */
+typedef struct sccav_rollout_out {
+    void* state;               /* [4][N] final state (may alias the input state)               */
+    int32_t* steps;            /* [N] steps executed                                           */
+    int32_t* target_idx;       /* [N] last Stanley target index                                */
+    int32_t* n_active;         /* [N] steps with a non-empty active set                        */
+    int32_t* n_infeasible;     /* [N] steps with status INFEASIBLE                             */
+    void* h_min;               /* [N] min over steps and slots of h                            */
+    void* beta_min;            /* [N]                                                          */
+    void* beta_max;            /* [N]                                                          */
+    void* beta_int;            /* [N] sum beta*dt                                              */
+    void* traj;                /* [T_rec][7][N] pre-step x,y,yaw,v + u0,u1,beta of the step; T_rec = ceil(T/stride) */
+    int32_t* traj_idx;         /* [T_rec][N] target index used by the step                     */
+    uint32_t* traj_mask;       /* [T_rec][N] active set of the step                            */
+} sccav_rollout_out;
+
+int sccav_version(void);
+const char* sccav_last_error(void);
+/* 1 if a usable CUDA device is present (no compute is launched). */
+int sccav_device_ok(void);
+
+void sccav_default_params(sccav_params* p);
+
+/* K1 -- barrier evaluation + row assembly.
+ * Replaces ObstacleList2D.f/dx/dy/dtheta/dv/dt (obstacles.py:879-925) and the row assembly inside
+ * DBM_CBF_2DS.solve_cbf F() (cbf.py:194-207) / KBM_VC_CBF2D.solve_cbf F() (cbf.py:94-101).
+ * slot_desc: host, M bytes.  h_out (dev [M][N]) may be NULL. */
+int sccav_barrier_rows_f64(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N,
+                           const double* state, const double* obst, const sccav_pervehicle* pv,
+                           double* A_out, double* b_out, double* h_out, void* stream);
+int sccav_barrier_rows_f32(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N,
+                           const float* state, const float* obst, const sccav_pervehicle* pv,
+                           float* A_out, float* b_out, float* h_out, void* stream);
+
+/* K2 -- the 2-variable QP  min (u-r)^T R (u-r)  s.t.  A u >= b.
+ * Replaces cvxopt.solvers.cp(F) at cbf.py:107,213 (exact KKT optimum instead of an IPM iterate).
+ * r: dev [2][N] reference already in QP coordinates (beta / omega).
+ * warp_per_problem != 0 selects the warp-cooperative kernel (one problem per warp). */
+int sccav_qp2_solve_f64(const sccav_params* p, int32_t M, int64_t N, const double* A, const double* b,
+                        const double* r, const sccav_pervehicle* pv, double* u_out,
+                        uint32_t* active_out, uint8_t* status_out, int32_t warp_per_problem, void* stream);
+int sccav_qp2_solve_f32(const sccav_params* p, int32_t M, int64_t N, const float* A, const float* b,
+                        const float* r, const sccav_pervehicle* pv, float* u_out,
+                        uint32_t* active_out, uint8_t* status_out, int32_t warp_per_problem, void* stream);
+
+/* K1+K2 fused -- one batched solve_cbf(u_ref) call including delta<->beta (cbf.py:166-220) or
+ * the KBM conversions (cbf.py:75,109).  u_ref/u_out: dev [2][N] in (a|v, delta).
+ * h_min_out (dev [N]) may be NULL. */
+int sccav_filter_step_f64(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N,
+                          const double* state, const double* obst, const double* u_ref,
+                          const sccav_pervehicle* pv, double* u_out, uint32_t* active_out,
+                          uint8_t* status_out, double* h_min_out, void* stream);
+int sccav_filter_step_f32(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N,
+                          const float* state, const float* obst, const float* u_ref,
+                          const sccav_pervehicle* pv, float* u_out, uint32_t* active_out,
+                          uint8_t* status_out, float* h_min_out, void* stream);
+
+/* K3 -- persistent closed-loop rollout: T steps of
+ *   nominal (Stanley + P speed | const) -> filter -> plant (update_com | update_by_vel) [-> seekers]
+ * Replaces the while-loop of stanley_controller_ellipse.py:630-830 and animate() of
+ * radial_dynamic_obstacles.py:427-507.  state: dev [4][N] initial state (read).  obst: dev
+ * [M][8][N], READ-WRITE when params.seeker (moving centres are written back).  course_*: dev [P].
+ * M may be 0 (no filter: u = u_ref). */
+int sccav_rollout_f64(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N, int32_t T,
+                      const double* state, double* obst, const double* course_x, const double* course_y,
+                      const double* course_yaw, int32_t P, const sccav_pervehicle* pv,
+                      const sccav_rollout_out* out, void* stream);
+int sccav_rollout_f32(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N, int32_t T,
+                      const float* state, float* obst, const float* course_x, const float* course_y,
+                      const float* course_yaw, int32_t P, const sccav_pervehicle* pv,
+                      const sccav_rollout_out* out, void* stream);
+
+/* Host-buffer variants (what a host-language caller of the reference binds): all array pointers
+ * (including those inside pv / out) are HOST memory; the call copies inputs to the current
+ * device, runs the kernel, copies results back and synchronises `stream` before returning. */
+int sccav_filter_step_host_f64(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N,
+                               const double* state, const double* obst, const double* u_ref,
+                               const sccav_pervehicle* pv, double* u_out, uint32_t* active_out,
+                               uint8_t* status_out, double* h_min_out, void* stream);
+int sccav_filter_step_host_f32(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N,
+                               const float* state, const float* obst, const float* u_ref,
+                               const sccav_pervehicle* pv, float* u_out, uint32_t* active_out,
+                               uint8_t* status_out, float* h_min_out, void* stream);
+int sccav_rollout_host_f64(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N, int32_t T,
+                           const double* state, double* obst, const double* course_x, const double* course_y,
+                           const double* course_yaw, int32_t P, const sccav_pervehicle* pv,
+                           const sccav_rollout_out* out, void* stream);
+int sccav_rollout_host_f32(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N, int32_t T,
+                           const float* state, float* obst, const float* course_x, const float* course_y,
+                           const float* course_yaw, int32_t P, const sccav_pervehicle* pv,
+                           const sccav_rollout_out* out, void* stream);
+
+/* Measurement helpers used by bench.py (not part of the reference-facing path). */
+/* Launches an unrolled FMA chain kernel and returns the achieved TFLOP/s (FMA = 2 flop) on the
+ * current device; `dtype` 64 or 32.  Used as the measured FP64/FP32 CUDA-core peak. */
+int sccav_measure_fma_peak(int32_t dtype, double* tflops_out);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t sccav_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCCAV_CBF_H */

@@ -60,6 +60,7 @@ NFIELD = 8
 
 MODEL_DBM = 0      # DBM_CBF_2DS  (cbf/cbf.py:112-220)
 MODEL_KBM = 1      # KBM_VC_CBF2D (cbf/cbf.py:33-110)
+MODEL_NONE = 2     # rollout only: USE_CBF = False -> State.update (stanley_controller_ellipse.py:828)
 
 STATUS_INACTIVE = 0    # u == u_ref (no row active)
 STATUS_ACTIVE = 1      # optimum with 1 or 2 active rows
@@ -67,6 +68,7 @@ STATUS_INFEASIBLE = 2  # no KKT point: least-violation candidate returned
 
 QP_FEAS_EPS = 1e-12    # relative feasibility tolerance (fp64 spec)
 QP_PAR_EPS = 1e-12     # relative parallel-row tolerance (fp64 spec)
+QP_TIE_EPS = 1e-9      # infeasible fallback: a later candidate must beat the incumbent by this relative margin
 LANE_MAX_IT = 50
 LANE_LS_MAX = 30
 LANE_XTOL = 1e-12
@@ -304,7 +306,10 @@ def qp2_exact(A0, A1, b, r0, r1, R, feas_eps=QP_FEAS_EPS, par_eps=QP_PAR_EPS, co
     """min (u-r)^T R (u-r) s.t. A u >= b  (cbf/cbf.py:182-213), u in R^2.
 
     Deterministic enumeration order: {} , singles by index, pairs lexicographic; first KKT
-    point wins.  Returns (u0, u1, active_mask, status).  If ``collect`` is a list, *every*
+    point wins.  If no candidate is a KKT point (infeasible rows) the candidate with the least
+    worst-row violation is returned (ties within QP_TIE_EPS keep the earlier candidate: all
+    candidates on one boundary line often share their worst row exactly).
+    Returns (u0, u1, active_mask, status).  If ``collect`` is a list, *every*
     KKT-satisfying candidate is appended to it (used by the tests to assert uniqueness).
     """
     m = len(b)
@@ -366,7 +371,7 @@ def qp2_exact(A0, A1, b, r0, r1, R, feas_eps=QP_FEAS_EPS, par_eps=QP_PAR_EPS, co
                     return result
             if collect is not None:
                 collect.append(cand)
-        if worst < fb[0]:
+        if worst < fb[0] - QP_TIE_EPS * (abs(worst) + abs(fb[0])):
             fb = (worst, u0, u1, 1 << k)
 
     for j in range(m):
@@ -393,7 +398,7 @@ def qp2_exact(A0, A1, b, r0, r1, R, feas_eps=QP_FEAS_EPS, par_eps=QP_PAR_EPS, co
                         return result
                 if collect is not None:
                     collect.append(cand)
-            if worst < fb[0]:
+            if worst < fb[0] - QP_TIE_EPS * (abs(worst) + abs(fb[0])):
                 fb = (worst, u0, u1, (1 << j) | (1 << k))
 
     if result is not None:
@@ -465,7 +470,7 @@ def stanley_control(x, y, yaw, v, cx, cy, cyaw, last_idx, k, L, ks=0.0):
     if last_idx >= idx:
         idx = last_idx
     theta_e = normalize_angle(float(cyaw[idx]) - yaw)
-    theta_d = float(np.arctan2(k * e, v + ks)) if ks != 0.0 else float(np.arctan2(k * e, v))
+    theta_d = float(np.arctan2(k * e, v + ks))
     return theta_e + theta_d, idx
 
 
@@ -631,7 +636,7 @@ def rollout(s0, slot_types, fields, course, T, params=None, record=False, teache
     p = dict(DEFAULT_PARAMS)
     if params:
         p.update(params)
-    cx, cy, cyaw = course
+    cx, cy, cyaw = course if course is not None else ([], [], [])
     last_idx = len(cx) - 1
     s = [float(v) for v in s0]
     fields = [list(map(float, f)) for f in fields]
@@ -656,11 +661,11 @@ def rollout(s0, slot_types, fields, course, T, params=None, record=False, teache
             d_ref, target_idx = stanley_control(s[0], s[1], s[2], s[3], cx, cy, cyaw, target_idx, p['k'], p['L'])
         else:
             a_ref, d_ref = p['uref0'], p['uref1']
-        if p['model'] == MODEL_DBM:
-            uref = [a_ref, d_ref]
-        else:
+        if p['model'] == MODEL_KBM and p['nominal'] == NOMINAL_STANLEY:
             uref = [p['target_speed'], d_ref]                                  # :646-648
-        if len(slot_types) > 0:
+        else:
+            uref = [a_ref, d_ref]
+        if len(slot_types) > 0 and p['model'] != MODEL_NONE:
             u0, u1, mask, status, _raw, hm = filter_step(p['model'], s, uref, slot_types, fields,
                                                          p['alpha'], p['lr'], p['lf'], p['L'], p['R'],
                                                          p['kbm_driver_delta'])
@@ -671,8 +676,11 @@ def rollout(s0, slot_types, fields, course, T, params=None, record=False, teache
             rec['mask'].append(mask); rec['status'].append(status)
         if p['model'] == MODEL_DBM:
             s, beta = plant_update_com(s, u0, u1, p['dt'], p['lr'], p['lf'], p['max_steer'])
-        else:
+        elif p['model'] == MODEL_KBM:
             s = plant_update_by_vel(s, u0, u1, p['dt'], p['L'], p['max_steer'])
+            beta = 0.0
+        else:
+            s = plant_update(s, u0, u1, p['dt'], p['L'], p['max_steer'])
             beta = 0.0
         if p['seeker']:
             for m, st in enumerate(slot_types):

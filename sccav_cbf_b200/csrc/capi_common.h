@@ -1,0 +1,21 @@
+// capi_common.h -- host-side helpers shared by the per-precision C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/sccav_cbf.h"
+
+namespace sccav {
+void set_error(const char* fmt, ...);
+void count_launch();
+int sm_count();          // SMs of the current device (cached per device)
+int max_smem_optin();    // max opt-in dynamic shared memory per block of the current device
+}  // namespace sccav
+
+#define SCCAV_CUDA_CHECK(expr)                                                              \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            sccav::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return SCCAV_ECUDA;                                                             \
+        }                                                                                   \
+    } while (0)

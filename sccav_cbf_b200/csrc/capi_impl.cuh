@@ -1,0 +1,383 @@
+// capi_impl.cuh -- the extern "C" entry points for ONE precision.  Included by capi_f64.cu
+// (SCCAV_REAL = double, compiled with -fmad=false) and capi_f32.cu (SCCAV_REAL = float).
+#pragma once
+#include <cstring>
+#include <new>
+
+#include "capi_common.h"
+#include "kernels.cuh"
+
+#ifndef SCCAV_REAL
+#error "define SCCAV_REAL and SCCAV_SUFFIX before including capi_impl.cuh"
+#endif
+
+#define SCCAV_CAT_(a, b) a##b
+#define SCCAV_CAT(a, b) SCCAV_CAT_(a, b)
+#define SCCAV_FN(name) SCCAV_CAT(name, SCCAV_SUFFIX)
+
+namespace sccav {
+namespace {
+
+typedef SCCAV_REAL real;
+
+int check_common(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N, bool allow_m0) {
+    if (!p) { set_error("params is NULL"); return SCCAV_EINVAL; }
+    if (N < 0) { set_error("N < 0"); return SCCAV_EINVAL; }
+    if (M < 0 || M > SCCAV_MAX_ROWS) { set_error("M must be in [0, %d], got %d", SCCAV_MAX_ROWS, M); return SCCAV_EINVAL; }
+    if (M == 0 && !allow_m0) {
+        // DBM_CBF_2DS.solve_cbf raises ValueError on an empty obstacle list (cbf.py:177-180)
+        set_error("Cannot solve CBF for an empty obstacle list (M = 0)");
+        return SCCAV_EINVAL;
+    }
+    if (M > 0 && !slot_desc) { set_error("slot_desc is NULL"); return SCCAV_EINVAL; }
+    for (int m = 0; m < M; ++m) {
+        int t = slot_desc[m] & 0x7f;
+        if (t > SCCAV_SLOT_DISTANCE) { set_error("slot %d: unknown type %d", m, t); return SCCAV_EINVAL; }
+    }
+    if (p->model < 0 || p->model > SCCAV_MODEL_NONE) { set_error("unknown model %d", p->model); return SCCAV_EINVAL; }
+    double det = p->R[0] * p->R[3] - p->R[1] * p->R[2];
+    if (!(p->R[0] > 0.0) || !(det > 0.0)) {
+        // set_qp_cost_weight (cbf.py:154-157) expects a symmetric positive definite 2x2
+        set_error("R must be symmetric positive definite 2x2");
+        return SCCAV_EINVAL;
+    }
+    return SCCAV_OK;
+}
+
+Params<real> convert(const sccav_params* p) {
+    Params<real> q;
+    q.model = p->model; q.nominal = p->nominal; q.terminate = p->terminate; q.seeker = p->seeker;
+    q.kbm_driver_delta = p->kbm_driver_delta; q.record_stride = p->record_stride;
+    q.alpha = (real)p->alpha; q.lr = (real)p->lr; q.lf = (real)p->lf; q.L = (real)p->L;
+    q.max_steer = (real)p->max_steer; q.dt = (real)p->dt; q.k_stanley = (real)p->k_stanley;
+    q.ks_stanley = (real)p->ks_stanley; q.Kp = (real)p->Kp; q.target_speed = (real)p->target_speed;
+    q.t_max = (real)p->t_max;
+    for (int i = 0; i < 4; ++i) q.R[i] = (real)p->R[i];
+    q.seeker_k = (real)p->seeker_k; q.seeker_vmin = (real)p->seeker_vmin;
+    q.uref0 = (real)p->uref0; q.uref1 = (real)p->uref1;
+    return q;
+}
+
+SlotDesc make_desc(const uint8_t* slot_desc, int M) {
+    SlotDesc sd;
+    memset(&sd, 0, sizeof(sd));
+    for (int m = 0; m < M; ++m) sd.d[m] = slot_desc[m];
+    return sd;
+}
+
+PerVehicle<real> make_pv(const sccav_pervehicle* pv) {
+    PerVehicle<real> q{nullptr, nullptr, nullptr};
+    if (pv) {
+        q.alpha = (const real*)pv->alpha;
+        q.R = (const real*)pv->R;
+        q.target_speed = (const real*)pv->target_speed;
+    }
+    return q;
+}
+
+// grid for the HBM-bound grid-stride kernels: enough CTAs to fill every SM, in multiples of the SM count
+int stream_grid(int64_t N, int block) {
+    int64_t need = (N + block - 1) / block;
+    int64_t cap = (int64_t)sm_count() * 16;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+// block size for kernels that keep rows[3*M][block] in shared memory
+int rows_block(int M, size_t& smem) {
+    int block = 256;
+    while (block > 32 && (size_t)3 * M * block * sizeof(real) > 96 * 1024) block >>= 1;
+    smem = (size_t)3 * (M > 0 ? M : 1) * block * sizeof(real);
+    return block;
+}
+
+int do_barrier_rows(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N, const real* state,
+                    const real* obst, const sccav_pervehicle* pv, real* A, real* b, real* h, cudaStream_t st) {
+    int rc = check_common(p, slot_desc, M, N, false);
+    if (rc) return rc;
+    if (!state || !obst || !A || !b) { set_error("NULL array argument"); return SCCAV_EINVAL; }
+    if (N == 0) return SCCAV_OK;
+    RowsArgs<real> a;
+    a.P = convert(p); a.sd = make_desc(slot_desc, M); a.M = M; a.N = N;
+    a.state = state; a.obst = obst; a.pv = make_pv(pv); a.A = A; a.b = b; a.h = h;
+    const int block = 256;
+    barrier_rows_kernel<real><<<stream_grid(N, block), block, 0, st>>>(a);
+    count_launch();
+    SCCAV_CUDA_CHECK(cudaGetLastError());
+    return SCCAV_OK;
+}
+
+int do_qp2(const sccav_params* p, int32_t M, int64_t N, const real* A, const real* b, const real* r,
+           const sccav_pervehicle* pv, real* u, uint32_t* mask, uint8_t* status, int warp, cudaStream_t st) {
+    uint8_t dummy[SCCAV_MAX_ROWS] = {0};
+    int rc = check_common(p, dummy, M, N, false);
+    if (rc) return rc;
+    if (!A || !b || !r || !u) { set_error("NULL array argument"); return SCCAV_EINVAL; }
+    if (N == 0) return SCCAV_OK;
+    QpArgs<real> a;
+    a.P = convert(p); a.M = M; a.N = N; a.A = A; a.b = b; a.r = r; a.pv = make_pv(pv);
+    a.u = u; a.mask = mask; a.status = status;
+    if (warp) {
+        const int block = 256;
+        int64_t need = (N * 32 + block - 1) / block;
+        int64_t cap = (int64_t)sm_count() * 16;
+        qp2_warp_kernel<real><<<(int)(need < cap ? need : cap), block, 0, st>>>(a);
+    } else {
+        size_t smem;
+        const int block = rows_block(M, smem);
+        SCCAV_CUDA_CHECK(cudaFuncSetAttribute(qp2_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        qp2_kernel<real><<<stream_grid(N, block), block, smem, st>>>(a);
+    }
+    count_launch();
+    SCCAV_CUDA_CHECK(cudaGetLastError());
+    return SCCAV_OK;
+}
+
+int do_filter_step(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N, const real* state,
+                   const real* obst, const real* u_ref, const sccav_pervehicle* pv, real* u, uint32_t* mask,
+                   uint8_t* status, real* h_min, cudaStream_t st) {
+    int rc = check_common(p, slot_desc, M, N, false);
+    if (rc) return rc;
+    if (p->model == SCCAV_MODEL_NONE) { set_error("model NONE has no filter step"); return SCCAV_EINVAL; }
+    if (!state || !obst || !u_ref || !u) { set_error("NULL array argument"); return SCCAV_EINVAL; }
+    if (N == 0) return SCCAV_OK;
+    FilterArgs<real> a;
+    a.P = convert(p); a.sd = make_desc(slot_desc, M); a.M = M; a.N = N;
+    a.state = state; a.obst = obst; a.u_ref = u_ref; a.pv = make_pv(pv);
+    a.u = u; a.mask = mask; a.status = status; a.h_min = h_min;
+    size_t smem;
+    const int block = rows_block(M, smem);
+    SCCAV_CUDA_CHECK(cudaFuncSetAttribute(filter_step_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    filter_step_kernel<real><<<stream_grid(N, block), block, smem, st>>>(a);
+    count_launch();
+    SCCAV_CUDA_CHECK(cudaGetLastError());
+    return SCCAV_OK;
+}
+
+// Launch geometry of the persistent rollout: one vehicle per thread, ONE CTA per SM per wave.
+// For N <= 148*512 the block is sized so that a single balanced wave covers the batch
+// (e.g. N = 65,536 -> 147 CTAs of 448 threads); larger batches run 256-thread CTAs in many waves.
+void rollout_geometry(int64_t N, int& grid, int& block) {
+    const int sms = sm_count();
+    int64_t per_sm = (N + sms - 1) / sms;
+    if (per_sm <= SCCAV_ROLLOUT_MAXB) {
+        block = (int)((per_sm + 31) / 32 * 32);
+        if (block < 32) block = 32;
+    } else {
+        block = 256;
+    }
+    grid = (int)((N + block - 1) / block);
+}
+
+int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N, int32_t T, const real* state,
+               real* obst, const real* cx, const real* cy, const real* cyaw, int32_t P, const sccav_pervehicle* pv,
+               const sccav_rollout_out* out, cudaStream_t st) {
+    int rc = check_common(p, slot_desc, M, N, true);
+    if (rc) return rc;
+    if (T < 0) { set_error("T < 0"); return SCCAV_EINVAL; }
+    if (!state || !out || !out->state) { set_error("state / out->state is NULL"); return SCCAV_EINVAL; }
+    if (M > 0 && !obst) { set_error("obst is NULL"); return SCCAV_EINVAL; }
+    const bool stan = p->nominal == SCCAV_NOMINAL_STANLEY;
+    if (stan && (P < 1 || !cx || !cy || !cyaw)) { set_error("Stanley nominal control needs a course (P >= 1)"); return SCCAV_EINVAL; }
+    if (p->record_stride < 0) { set_error("record_stride < 0"); return SCCAV_EINVAL; }
+    if (N == 0) return SCCAV_OK;
+    RolloutArgs<real> a;
+    a.P = convert(p); a.sd = make_desc(slot_desc, M); a.M = M; a.N = N; a.T_steps = T; a.np = stan ? P : 0;
+    a.state = state; a.obst = obst; a.cx = cx; a.cy = cy; a.cyaw = cyaw; a.pv = make_pv(pv);
+    a.o_state = (real*)out->state; a.o_steps = out->steps; a.o_tidx = out->target_idx; a.o_nact = out->n_active;
+    a.o_ninf = out->n_infeasible; a.o_hmin = (real*)out->h_min; a.o_bmin = (real*)out->beta_min;
+    a.o_bmax = (real*)out->beta_max; a.o_bint = (real*)out->beta_int; a.o_traj = (real*)out->traj;
+    a.o_tridx = out->traj_idx; a.o_trmask = out->traj_mask;
+    int grid, block;
+    rollout_geometry(N, grid, block);
+    const int np_pad = (a.np + 1) & ~1;
+    size_t rows_b = (size_t)3 * (M > 0 ? M : 1) * block * sizeof(real);
+    size_t course_b = (size_t)3 * np_pad * sizeof(real);
+    const size_t cap = (size_t)max_smem_optin();
+    bool course_smem = stan && (course_b + rows_b <= cap);
+    size_t smem = rows_b + (course_smem ? course_b : 0);
+    while (smem > cap && block > 32) {            // huge M * block: shrink the CTA
+        block >>= 1;
+        grid = (int)((N + block - 1) / block);
+        rows_b = (size_t)3 * (M > 0 ? M : 1) * block * sizeof(real);
+        course_smem = stan && (course_b + rows_b <= cap);
+        smem = rows_b + (course_smem ? course_b : 0);
+    }
+    if (course_smem) {
+        SCCAV_CUDA_CHECK(cudaFuncSetAttribute(rollout_kernel<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rollout_kernel<real, true><<<grid, block, smem, st>>>(a);
+    } else {
+        SCCAV_CUDA_CHECK(cudaFuncSetAttribute(rollout_kernel<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rollout_kernel<real, false><<<grid, block, smem, st>>>(a);
+    }
+    count_launch();
+    SCCAV_CUDA_CHECK(cudaGetLastError());
+    return SCCAV_OK;
+}
+
+// ---- host-buffer variants: stream-ordered device allocations, H2D, kernel, D2H, sync
+struct DevBuf {
+    void* p = nullptr;
+    cudaStream_t st;
+    explicit DevBuf(cudaStream_t s) : st(s) {}
+    ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, st); }
+    cudaError_t upload(const void* src, size_t bytes) {
+        cudaError_t e = alloc(bytes);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, st);
+    }
+};
+
+}  // namespace
+}  // namespace sccav
+
+extern "C" {
+
+int SCCAV_FN(sccav_barrier_rows_)(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N,
+                                  const SCCAV_REAL* state, const SCCAV_REAL* obst, const sccav_pervehicle* pv,
+                                  SCCAV_REAL* A_out, SCCAV_REAL* b_out, SCCAV_REAL* h_out, void* stream) {
+    return sccav::do_barrier_rows(p, slot_desc, M, N, state, obst, pv, A_out, b_out, h_out, (cudaStream_t)stream);
+}
+
+int SCCAV_FN(sccav_qp2_solve_)(const sccav_params* p, int32_t M, int64_t N, const SCCAV_REAL* A, const SCCAV_REAL* b,
+                               const SCCAV_REAL* r, const sccav_pervehicle* pv, SCCAV_REAL* u_out, uint32_t* active_out,
+                               uint8_t* status_out, int32_t warp_per_problem, void* stream) {
+    return sccav::do_qp2(p, M, N, A, b, r, pv, u_out, active_out, status_out, warp_per_problem, (cudaStream_t)stream);
+}
+
+int SCCAV_FN(sccav_filter_step_)(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N,
+                                 const SCCAV_REAL* state, const SCCAV_REAL* obst, const SCCAV_REAL* u_ref,
+                                 const sccav_pervehicle* pv, SCCAV_REAL* u_out, uint32_t* active_out,
+                                 uint8_t* status_out, SCCAV_REAL* h_min_out, void* stream) {
+    return sccav::do_filter_step(p, slot_desc, M, N, state, obst, u_ref, pv, u_out, active_out, status_out, h_min_out,
+                                 (cudaStream_t)stream);
+}
+
+int SCCAV_FN(sccav_rollout_)(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N, int32_t T,
+                             const SCCAV_REAL* state, SCCAV_REAL* obst, const SCCAV_REAL* course_x,
+                             const SCCAV_REAL* course_y, const SCCAV_REAL* course_yaw, int32_t P,
+                             const sccav_pervehicle* pv, const sccav_rollout_out* out, void* stream) {
+    return sccav::do_rollout(p, slot_desc, M, N, T, state, obst, course_x, course_y, course_yaw, P, pv, out,
+                             (cudaStream_t)stream);
+}
+
+int SCCAV_FN(sccav_filter_step_host_)(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N,
+                                      const SCCAV_REAL* state, const SCCAV_REAL* obst, const SCCAV_REAL* u_ref,
+                                      const sccav_pervehicle* pv, SCCAV_REAL* u_out, uint32_t* active_out,
+                                      uint8_t* status_out, SCCAV_REAL* h_min_out, void* stream) {
+    using namespace sccav;
+    typedef SCCAV_REAL real;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_common(p, slot_desc, M, N, false);
+    if (rc) return rc;
+    if (!state || !obst || !u_ref || !u_out) { set_error("NULL array argument"); return SCCAV_EINVAL; }
+    if (N == 0) return SCCAV_OK;
+    const size_t n = (size_t)N;
+    DevBuf d_state(st), d_obst(st), d_uref(st), d_alpha(st), d_R(st), d_u(st), d_mask(st), d_status(st), d_hmin(st);
+    SCCAV_CUDA_CHECK(d_state.upload(state, 4 * n * sizeof(real)));
+    SCCAV_CUDA_CHECK(d_obst.upload(obst, (size_t)M * SCCAV_NFIELD * n * sizeof(real)));
+    SCCAV_CUDA_CHECK(d_uref.upload(u_ref, 2 * n * sizeof(real)));
+    sccav_pervehicle dpv = {nullptr, nullptr, nullptr};
+    if (pv && pv->alpha) { SCCAV_CUDA_CHECK(d_alpha.upload(pv->alpha, n * sizeof(real))); dpv.alpha = d_alpha.p; }
+    if (pv && pv->R) { SCCAV_CUDA_CHECK(d_R.upload(pv->R, 4 * n * sizeof(real))); dpv.R = d_R.p; }
+    SCCAV_CUDA_CHECK(d_u.alloc(2 * n * sizeof(real)));
+    if (active_out) SCCAV_CUDA_CHECK(d_mask.alloc(n * sizeof(uint32_t)));
+    if (status_out) SCCAV_CUDA_CHECK(d_status.alloc(n));
+    if (h_min_out) SCCAV_CUDA_CHECK(d_hmin.alloc(n * sizeof(real)));
+    rc = do_filter_step(p, slot_desc, M, N, (const real*)d_state.p, (const real*)d_obst.p, (const real*)d_uref.p, &dpv,
+                        (real*)d_u.p, (uint32_t*)d_mask.p, (uint8_t*)d_status.p, (real*)d_hmin.p, st);
+    if (rc) return rc;
+    SCCAV_CUDA_CHECK(cudaMemcpyAsync(u_out, d_u.p, 2 * n * sizeof(real), cudaMemcpyDeviceToHost, st));
+    if (active_out) SCCAV_CUDA_CHECK(cudaMemcpyAsync(active_out, d_mask.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (status_out) SCCAV_CUDA_CHECK(cudaMemcpyAsync(status_out, d_status.p, n, cudaMemcpyDeviceToHost, st));
+    if (h_min_out) SCCAV_CUDA_CHECK(cudaMemcpyAsync(h_min_out, d_hmin.p, n * sizeof(real), cudaMemcpyDeviceToHost, st));
+    SCCAV_CUDA_CHECK(cudaStreamSynchronize(st));
+    return SCCAV_OK;
+}
+
+int SCCAV_FN(sccav_rollout_host_)(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N, int32_t T,
+                                  const SCCAV_REAL* state, SCCAV_REAL* obst, const SCCAV_REAL* course_x,
+                                  const SCCAV_REAL* course_y, const SCCAV_REAL* course_yaw, int32_t P,
+                                  const sccav_pervehicle* pv, const sccav_rollout_out* out, void* stream) {
+    using namespace sccav;
+    typedef SCCAV_REAL real;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_common(p, slot_desc, M, N, true);
+    if (rc) return rc;
+    if (!state || !out || !out->state) { set_error("state / out->state is NULL"); return SCCAV_EINVAL; }
+    if (M > 0 && !obst) { set_error("obst is NULL"); return SCCAV_EINVAL; }
+    if (T < 0 || p->record_stride < 0) { set_error("T < 0 or record_stride < 0"); return SCCAV_EINVAL; }
+    if (N == 0) return SCCAV_OK;
+    const size_t n = (size_t)N;
+    const bool stan = p->nominal == SCCAV_NOMINAL_STANLEY;
+    if (stan && (P < 1 || !course_x || !course_y || !course_yaw)) { set_error("Stanley nominal control needs a course"); return SCCAV_EINVAL; }
+    const size_t trec = p->record_stride > 0 ? ((size_t)T + p->record_stride - 1) / p->record_stride : 0;
+    DevBuf d_state(st), d_obst(st), d_cx(st), d_cy(st), d_cyaw(st), d_alpha(st), d_R(st), d_ts(st);
+    DevBuf o_state(st), o_steps(st), o_tidx(st), o_nact(st), o_ninf(st), o_hmin(st), o_bmin(st), o_bmax(st), o_bint(st),
+        o_traj(st), o_tridx(st), o_trmask(st);
+    SCCAV_CUDA_CHECK(d_state.upload(state, 4 * n * sizeof(real)));
+    const size_t obst_b = (size_t)M * SCCAV_NFIELD * n * sizeof(real);
+    if (M > 0) SCCAV_CUDA_CHECK(d_obst.upload(obst, obst_b));
+    if (stan) {
+        SCCAV_CUDA_CHECK(d_cx.upload(course_x, (size_t)P * sizeof(real)));
+        SCCAV_CUDA_CHECK(d_cy.upload(course_y, (size_t)P * sizeof(real)));
+        SCCAV_CUDA_CHECK(d_cyaw.upload(course_yaw, (size_t)P * sizeof(real)));
+    }
+    sccav_pervehicle dpv = {nullptr, nullptr, nullptr};
+    if (pv && pv->alpha) { SCCAV_CUDA_CHECK(d_alpha.upload(pv->alpha, n * sizeof(real))); dpv.alpha = d_alpha.p; }
+    if (pv && pv->R) { SCCAV_CUDA_CHECK(d_R.upload(pv->R, 4 * n * sizeof(real))); dpv.R = d_R.p; }
+    if (pv && pv->target_speed) { SCCAV_CUDA_CHECK(d_ts.upload(pv->target_speed, n * sizeof(real))); dpv.target_speed = d_ts.p; }
+    sccav_rollout_out dout;
+    memset(&dout, 0, sizeof(dout));
+    SCCAV_CUDA_CHECK(o_state.alloc(4 * n * sizeof(real)));
+    dout.state = o_state.p;
+#define SCCAV_OUT(field, buf, bytes)                         \
+    if (out->field) {                                        \
+        SCCAV_CUDA_CHECK(buf.alloc(bytes));                  \
+        dout.field = (decltype(dout.field))buf.p;            \
+    }
+    SCCAV_OUT(steps, o_steps, n * 4)
+    SCCAV_OUT(target_idx, o_tidx, n * 4)
+    SCCAV_OUT(n_active, o_nact, n * 4)
+    SCCAV_OUT(n_infeasible, o_ninf, n * 4)
+    SCCAV_OUT(h_min, o_hmin, n * sizeof(real))
+    SCCAV_OUT(beta_min, o_bmin, n * sizeof(real))
+    SCCAV_OUT(beta_max, o_bmax, n * sizeof(real))
+    SCCAV_OUT(beta_int, o_bint, n * sizeof(real))
+    if (trec) {
+        SCCAV_OUT(traj, o_traj, trec * SCCAV_TRAJ_FIELDS * n * sizeof(real))
+        SCCAV_OUT(traj_idx, o_tridx, trec * n * 4)
+        SCCAV_OUT(traj_mask, o_trmask, trec * n * 4)
+        // rows past a vehicle's last step keep the caller's initial contents
+        if (out->traj) SCCAV_CUDA_CHECK(cudaMemcpyAsync(o_traj.p, out->traj, trec * SCCAV_TRAJ_FIELDS * n * sizeof(real), cudaMemcpyHostToDevice, st));
+        if (out->traj_idx) SCCAV_CUDA_CHECK(cudaMemcpyAsync(o_tridx.p, out->traj_idx, trec * n * 4, cudaMemcpyHostToDevice, st));
+        if (out->traj_mask) SCCAV_CUDA_CHECK(cudaMemcpyAsync(o_trmask.p, out->traj_mask, trec * n * 4, cudaMemcpyHostToDevice, st));
+    }
+#undef SCCAV_OUT
+    rc = do_rollout(p, slot_desc, M, N, T, (const real*)d_state.p, (real*)d_obst.p, (const real*)d_cx.p, (const real*)d_cy.p,
+                    (const real*)d_cyaw.p, P, &dpv, &dout, st);
+    if (rc) return rc;
+#define SCCAV_BACK(field, buf, bytes) \
+    if (out->field) SCCAV_CUDA_CHECK(cudaMemcpyAsync(out->field, buf.p, bytes, cudaMemcpyDeviceToHost, st));
+    SCCAV_BACK(state, o_state, 4 * n * sizeof(real))
+    SCCAV_BACK(steps, o_steps, n * 4)
+    SCCAV_BACK(target_idx, o_tidx, n * 4)
+    SCCAV_BACK(n_active, o_nact, n * 4)
+    SCCAV_BACK(n_infeasible, o_ninf, n * 4)
+    SCCAV_BACK(h_min, o_hmin, n * sizeof(real))
+    SCCAV_BACK(beta_min, o_bmin, n * sizeof(real))
+    SCCAV_BACK(beta_max, o_bmax, n * sizeof(real))
+    SCCAV_BACK(beta_int, o_bint, n * sizeof(real))
+    if (trec) {
+        SCCAV_BACK(traj, o_traj, trec * SCCAV_TRAJ_FIELDS * n * sizeof(real))
+        SCCAV_BACK(traj_idx, o_tridx, trec * n * 4)
+        SCCAV_BACK(traj_mask, o_trmask, trec * n * 4)
+    }
+#undef SCCAV_BACK
+    if (M > 0 && p->seeker) SCCAV_CUDA_CHECK(cudaMemcpyAsync(obst, d_obst.p, obst_b, cudaMemcpyDeviceToHost, st));
+    SCCAV_CUDA_CHECK(cudaStreamSynchronize(st));
+    return SCCAV_OK;
+}
+
+}  // extern "C"

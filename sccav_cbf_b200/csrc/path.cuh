@@ -1,0 +1,449 @@
+// path.cuh -- device functions of the CBF-QP hot path (barriers, rows, QP, nominal, plant).
+//
+// Written for sm_100a.  Every function restates the reference arithmetic in the SAME operation
+// order as oracle/oracle.py (compiled with -fmad=false for the fp64 build so that a*b+c is not
+// contracted: the waypoint index and the active set are compared bit-for-bit with the oracle).
+// Citations are file:line under the reference root.
+//
+// No tensor cores here on purpose: n = 2 unknowns, tens of rows -- nothing is a dense contraction.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/sccav_cbf.h"
+
+namespace sccav {
+
+// ------------------------------------------------------------------------------------------
+// scalar traits
+// ------------------------------------------------------------------------------------------
+template <typename T> struct Real;
+
+template <> struct Real<double> {
+    typedef double2 T2;
+    static __device__ __forceinline__ double pi() { return 3.141592653589793; }       // np.pi
+    static __device__ __forceinline__ double zero_tol() { return 1e-3; }              // cbf/utils.py:27
+    static __device__ __forceinline__ double feas_eps() { return 1e-12; }
+    static __device__ __forceinline__ double par_eps() { return 1e-12; }
+    static __device__ __forceinline__ double tie_eps() { return 1e-9; }
+    static __device__ __forceinline__ double lane_xtol() { return 1e-12; }
+    static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+    static __device__ __forceinline__ void sincos_(double x, double* s, double* c) { ::sincos(x, s, c); }
+    static __device__ __forceinline__ double tan_(double x) { return ::tan(x); }
+    static __device__ __forceinline__ double atan_(double x) { return ::atan(x); }
+    static __device__ __forceinline__ double atan2_(double y, double x) { return ::atan2(y, x); }
+    static __device__ __forceinline__ double sqrt_(double x) { return ::sqrt(x); }
+    static __device__ __forceinline__ double hypot_(double x, double y) { return ::hypot(x, y); }
+    static __device__ __forceinline__ double abs_(double x) { return ::fabs(x); }
+    static __device__ __forceinline__ T2 make2(double a, double b) { return make_double2(a, b); }
+};
+
+template <> struct Real<float> {
+    typedef float2 T2;
+    static __device__ __forceinline__ float pi() { return 3.14159274f; }
+    static __device__ __forceinline__ float zero_tol() { return 1e-3f; }
+    static __device__ __forceinline__ float feas_eps() { return 1e-5f; }
+    static __device__ __forceinline__ float par_eps() { return 1e-5f; }
+    static __device__ __forceinline__ float tie_eps() { return 1e-4f; }
+    static __device__ __forceinline__ float lane_xtol() { return 1e-6f; }
+    static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+    static __device__ __forceinline__ void sincos_(float x, float* s, float* c) { ::sincosf(x, s, c); }
+    static __device__ __forceinline__ float tan_(float x) { return ::tanf(x); }
+    static __device__ __forceinline__ float atan_(float x) { return ::atanf(x); }
+    static __device__ __forceinline__ float atan2_(float y, float x) { return ::atan2f(y, x); }
+    static __device__ __forceinline__ float sqrt_(float x) { return ::sqrtf(x); }
+    static __device__ __forceinline__ float hypot_(float x, float y) { return ::hypotf(x, y); }
+    static __device__ __forceinline__ float abs_(float x) { return ::fabsf(x); }
+    static __device__ __forceinline__ T2 make2(float a, float b) { return make_float2(a, b); }
+};
+
+// parameters in the kernel's precision
+template <typename T> struct Params {
+    int model, nominal, terminate, seeker, kbm_driver_delta, record_stride;
+    T alpha, lr, lf, L, max_steer, dt, k_stanley, ks_stanley, Kp, target_speed, t_max;
+    T R[4];
+    T seeker_k, seeker_vmin, uref0, uref1;
+};
+
+struct SlotDesc {
+    uint8_t d[SCCAV_MAX_ROWS];
+};
+
+template <typename T> struct Partials {
+    T h, hx, hy, hth, hv, ht;
+};
+
+// cbf/utils.py:93-106 == stanley_controller_ellipse.py:172-185
+template <typename T> __device__ __forceinline__ T normalize_angle(T a) {
+    const T pi = Real<T>::pi();
+    while (a > pi) a -= T(2.0) * pi;
+    while (a < -pi) a += T(2.0) * pi;
+    return a;
+}
+
+// ------------------------------------------------------------------------------------------
+// barriers
+// ------------------------------------------------------------------------------------------
+// Ellipse2D.evaluate/dx/dy/dt -- cbf/obstacles.py:183-230,310-317 (h_t ignores theta, as there)
+template <typename T>
+__device__ __forceinline__ Partials<T> ellipse_partials(T x, T y, T cx, T cy, T a, T b, T th, T vx, T vy) {
+    typedef Real<T> R;
+    Partials<T> o;
+    T dx = x - cx, dy = y - cy, st, ct;
+    R::sincos_(th, &st, &ct);
+    T p = dx * ct + dy * st;
+    T q = (-dx) * st + dy * ct;
+    T pa = p / a, qb = q / b;
+    o.h = (pa * pa + qb * qb) - T(1);
+    T aa = a * a, bb = b * b;
+    o.hx = ((T(2) * ct) / aa) * p + ((T(-2) * st) / bb) * q;
+    o.hy = ((T(2) * st) / aa) * p + ((T(2) * ct) / bb) * q;
+    o.hth = T(0);
+    o.hv = T(0);
+    o.ht = T(-2) * ((dx / aa) * vx + (dy / bb) * vy);
+    return o;
+}
+
+// single_obstacle_CBF1 -- test_scripts/radial_dynamic_obstacles.py:391-405
+template <typename T>
+__device__ __forceinline__ Partials<T> radial_partials(T x, T y, T v, T cx, T cy, T a, T b, T kv, T vx, T vy) {
+    Partials<T> o;
+    T dx = x - cx, dy = y - cy;
+    T da = dx / a, db = dy / b;
+    o.h = ((da * da + db * db) - T(1)) - ((kv * v) / (T(1) + v));
+    T aa = a * a, bb = b * b;
+    o.hx = (T(2) * dx) / aa;
+    o.hy = (T(2) * dy) / bb;
+    o.hth = T(0);
+    T opv = T(1) + v;
+    o.hv = (-kv) / (opv * opv);
+    o.ht = T(-2) * ((dx / aa) * vx + (dy / bb) * vy);
+    return o;
+}
+
+// D_CBF -- test_scripts/stanley_controller_ellipse.py:251-255
+template <typename T>
+__device__ __forceinline__ Partials<T> distance_partials(T x, T y, T cx, T cy, T Ds) {
+    Partials<T> o;
+    T dx = x - cx, dy = y - cy;
+    o.h = Real<T>::sqrt_(dx * dx + dy * dy) - Ds;
+    o.hx = (T(2) * dx) / (o.h + Ds);
+    o.hy = (T(2) * dy) / (o.h + Ds);
+    o.hth = o.hv = o.ht = T(0);
+    return o;
+}
+
+// CollisionCone2D.update/evaluate/dx/dy/dv/dtheta/dt -- cbf/obstacles.py:468-502,401-458
+// (sv, cv) = sin/cos of the ego yaw, computed once by the caller.
+template <typename T>
+__device__ __forceinline__ Partials<T> cone_partials(T x, T y, T th, T v, T sth, T cth, T cx, T cy, T tho, T vo, T a, T beta) {
+    typedef Real<T> R;
+    const T ZT = R::zero_tol();
+    Partials<T> o;
+    T s_vx = v * cth, s_vy = v * sth;
+    T so, co;
+    R::sincos_(tho + beta, &so, &co);
+    T o_vx = vo * co, o_vy = vo * so;
+    T prx = x - cx, pry = y - cy;
+    T vrx = s_vx - o_vx, vry = s_vy - o_vy;
+    T dist = R::sqrt_(prx * prx + pry * pry);
+    T vrn = R::sqrt_(vrx * vrx + vry * vry);
+    T cb = ZT;
+    if (R::abs_(dist) > R::abs_(a)) cb = R::sqrt_(dist * dist - a * a) + ZT;
+    T cos_phi = T(0);
+    if (dist > ZT) cos_phi = cb / dist;
+    o.h = (prx * vrx + pry * vry) + ((dist * vrn) * cos_phi);
+    o.hx = vrx + (vrn * prx) / (cb + ZT);
+    o.hy = vry + (vrn * pry) / (cb + ZT);
+    T sb, cbt;
+    if (beta == T(0)) { sb = sth; cbt = cth; }          // th + 0 == th exactly
+    else R::sincos_(th + beta, &sb, &cbt);
+    o.hv = (prx * cbt + pry * sb) + ((vrx * cbt + vry * sb) * cb) / (vrn + ZT);
+    o.hth = ((-prx) * s_vy + pry * s_vx) + (((-vrx) * s_vy + vry * s_vx) * cb) / (vrn + ZT);
+    o.ht = ((-vrx) * o_vx - vry * o_vy) + (((-vrn) * (prx * o_vx + pry * o_vy)) / (cb + ZT));
+    return o;
+}
+
+// Horner value / first / second derivative of sum c_i x^i (cbf/obstacles.py:589-592)
+template <typename T>
+__device__ __forceinline__ void poly3(const T (&c)[6], T x, T& g, T& dg, T& ddg) {
+    g = T(0);
+#pragma unroll
+    for (int i = 5; i >= 0; --i) g = c[i] + g * x;
+    dg = T(0);
+#pragma unroll
+    for (int i = 5; i >= 1; --i) dg = (T(i) * c[i]) + dg * x;
+    ddg = T(0);
+#pragma unroll
+    for (int i = 5; i >= 2; --i) ddg = (T(i - 1) * (T(i) * c[i])) + ddg * x;
+}
+
+template <typename T> __device__ __forceinline__ T poly0(const T (&c)[6], T x) {
+    T g = T(0);
+#pragma unroll
+    for (int i = 5; i >= 0; --i) g = c[i] + g * x;
+    return g;
+}
+
+// PolyLane.get_shortest_distance_x (cbf/obstacles.py:641-679): safeguarded Newton from x0 = px,
+// same iteration / stopping rule as oracle.lane_closest_x.
+template <typename T> __device__ T lane_closest_x(const T (&c)[6], T px, T py) {
+    typedef Real<T> R;
+    T x = px;
+    for (int it = 0; it < 50; ++it) {
+        T g, dg, ddg;
+        poly3(c, x, g, dg, ddg);
+        T ex = x - px, ey = g - py;
+        T grad = ex + ey * dg;
+        T hess = (T(1) + dg * dg) + ey * ddg;
+        T step = (hess > T(0)) ? (-grad) / hess : -grad;
+        T D0 = ex * ex + ey * ey;
+        T t = T(1), xn = x;
+        bool ok = false;
+        for (int ls = 0; ls < 30; ++ls) {
+            xn = x + t * step;
+            T gn = poly0(c, xn);
+            T Dn = (xn - px) * (xn - px) + (gn - py) * (gn - py);
+            if (Dn <= D0) { ok = true; break; }
+            t = t * T(0.5);
+        }
+        if (!ok) break;
+        T dxn = R::abs_(xn - x);
+        T lim = R::lane_xtol() * (T(1) + R::abs_(x));
+        x = xn;
+        if (dxn <= lim) break;
+    }
+    return x;
+}
+
+// PolyLane.update/evaluate/dx/dy -- cbf/obstacles.py:620-636,607-612,681-689
+template <typename T>
+__device__ __forceinline__ Partials<T> lane_partials(T x, T y, const T (&c)[6], T buffer) {
+    typedef Real<T> R;
+    Partials<T> o;
+    T cx = lane_closest_x(c, x, y);
+    T g, dg, ddg;
+    poly3(c, cx, g, dg, ddg);
+    T eta = ((T(1) + dg * ddg) + dg * dg) - y * ddg;
+    if (R::abs_(eta) < R::zero_tol()) eta = R::zero_tol();
+    T ex = cx - x, ey = g - y;
+    o.h = (ex * ex + ey * ey) - buffer;
+    T te = T(2) / eta;
+    o.hx = te * ((x - cx) * (eta - T(1)) - (y - g) * dg);
+    o.hy = te * ((-(x - cx)) * dg + (y - g) * (eta - dg * dg));
+    o.hth = o.hv = o.ht = T(0);
+    return o;
+}
+
+// dispatch on slot type; fields are read from the SoA obstacle buffer obst[(m*8+f)*N + n]
+template <typename T>
+__device__ __forceinline__ Partials<T> slot_partials(int type, const T* __restrict__ f, int64_t fs,
+                                                     T x, T y, T th, T v, T sth, T cth) {
+    // f points at field 0 of this slot for this vehicle; fs = stride between fields (N)
+    switch (type) {
+        case SCCAV_SLOT_ELLIPSE: {
+            T cx = f[0], cy = f[fs], a = f[2 * fs], b = f[3 * fs], t = f[4 * fs], vx = f[5 * fs], vy = f[6 * fs];
+            return ellipse_partials<T>(x, y, cx, cy, a, b, t, vx, vy);
+        }
+        case SCCAV_SLOT_CONE: {
+            T cx = f[0], cy = f[fs], to = f[2 * fs], vo = f[3 * fs], a = f[4 * fs], be = f[5 * fs];
+            return cone_partials<T>(x, y, th, v, sth, cth, cx, cy, to, vo, a, be);
+        }
+        case SCCAV_SLOT_LANE: {
+            T buf = f[0];
+            T c[6] = {f[fs], f[2 * fs], f[3 * fs], f[4 * fs], f[5 * fs], f[6 * fs]};
+            return lane_partials<T>(x, y, c, buf);
+        }
+        case SCCAV_SLOT_RADIAL: {
+            T cx = f[0], cy = f[fs], a = f[2 * fs], b = f[3 * fs], kv = f[4 * fs], vx = f[5 * fs], vy = f[6 * fs];
+            return radial_partials<T>(x, y, v, cx, cy, a, b, kv, vx, vy);
+        }
+        default: {
+            T cx = f[0], cy = f[fs], Ds = f[2 * fs];
+            return distance_partials<T>(x, y, cx, cy, Ds);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// row assembly: A0*u0 + A1*u1 >= b
+// ------------------------------------------------------------------------------------------
+// DBM_CBF_2DS gc/fc + F -- cbf/cbf.py:159-164,200-207
+template <typename T>
+__device__ __forceinline__ void dbm_row(const Partials<T>& p, T sth, T cth, T v, T alpha, T lr, T& A0, T& A1, T& b) {
+    A0 = p.hv;
+    A1 = (p.hx * ((-v) * sth) + p.hy * (v * cth)) + p.hth * (v / lr);
+    T Lf = p.hx * (v * cth) + p.hy * (v * sth);
+    b = -((Lf + alpha * p.h) + p.ht);
+}
+
+// KBM_VC_CBF2D F -- cbf/cbf.py:94-101
+template <typename T>
+__device__ __forceinline__ void kbm_row(const Partials<T>& p, T sth, T cth, T alpha, T& A0, T& A1, T& b) {
+    A0 = p.hx * cth + p.hy * sth;
+    A1 = p.hth;
+    b = -(alpha * p.h);
+}
+
+// ------------------------------------------------------------------------------------------
+// 2-variable QP on rows held in shared memory: row k at rows[(3k + {0,1,2}) * stride]
+// Same enumeration order / tolerances as oracle.qp2_exact: {} , singles, pairs; first KKT point.
+// ------------------------------------------------------------------------------------------
+template <typename T> struct RowView {
+    const T* rows;
+    int stride;
+    __device__ __forceinline__ T A0(int k) const { return rows[(3 * k + 0) * stride]; }
+    __device__ __forceinline__ T A1(int k) const { return rows[(3 * k + 1) * stride]; }
+    __device__ __forceinline__ T b(int k) const { return rows[(3 * k + 2) * stride]; }
+};
+
+template <typename T>
+__device__ __forceinline__ bool qp_check(const RowView<T>& rv, int m, T u0, T u1, int skip_a, int skip_b, T& worst) {
+    typedef Real<T> R;
+    bool feas = true;
+    worst = -R::inf();
+    for (int k = 0; k < m; ++k) {
+        T a0 = rv.A0(k), a1 = rv.A1(k), bk = rv.b(k);
+        T t0 = a0 * u0, t1 = a1 * u1;
+        T rk = (t0 + t1) - bk;
+        if (-rk > worst) worst = -rk;
+        if (k == skip_a || k == skip_b) continue;
+        T tol = R::feas_eps() * ((R::abs_(t0) + R::abs_(t1)) + R::abs_(bk));
+        if (!(rk >= -tol)) feas = false;
+    }
+    return feas;
+}
+
+template <typename T>
+__device__ int qp2_solve(const RowView<T>& rv, int m, T r0, T r1, T R00, T R01, T R10, T R11,
+                         T& u0o, T& u1o, uint32_t& masko) {
+    typedef Real<T> R;
+    T worst;
+    if (qp_check(rv, m, r0, r1, -1, -1, worst)) {
+        u0o = r0; u1o = r1; masko = 0u;
+        return SCCAV_STATUS_INACTIVE;
+    }
+    T fbw = worst, fb0 = r0, fb1 = r1;
+    uint32_t fbm = 0u;
+    const T det = R00 * R11 - R01 * R10;
+    const T Ri00 = R11 / det, Ri01 = (-R01) / det, Ri10 = (-R10) / det, Ri11 = R00 / det;
+    for (int k = 0; k < m; ++k) {
+        T a0 = rv.A0(k), a1 = rv.A1(k), bk = rv.b(k);
+        T rk = (a0 * r0 + a1 * r1) - bk;
+        if (!(rk < T(0))) continue;
+        T g0 = Ri00 * a0 + Ri01 * a1;
+        T g1 = Ri10 * a0 + Ri11 * a1;
+        T den = a0 * g0 + a1 * g1;
+        if (!(den > T(0))) continue;
+        T t = (-rk) / den;
+        T u0 = r0 + g0 * t, u1 = r1 + g1 * t;
+        if (qp_check(rv, m, u0, u1, k, -1, worst)) {
+            u0o = u0; u1o = u1; masko = 1u << k;
+            return SCCAV_STATUS_ACTIVE;
+        }
+        if (worst < fbw - R::tie_eps() * (R::abs_(worst) + R::abs_(fbw))) { fbw = worst; fb0 = u0; fb1 = u1; fbm = 1u << k; }
+    }
+    for (int j = 0; j < m; ++j) {
+        T aj0 = rv.A0(j), aj1 = rv.A1(j), bj = rv.b(j);
+        for (int k = j + 1; k < m; ++k) {
+            T ak0 = rv.A0(k), ak1 = rv.A1(k), bk = rv.b(k);
+            T t1 = aj0 * ak1, t2 = aj1 * ak0;
+            T det2 = t1 - t2;
+            if (!(R::abs_(det2) > R::par_eps() * (R::abs_(t1) + R::abs_(t2)))) continue;
+            T u0 = (bj * ak1 - aj1 * bk) / det2;
+            T u1 = (aj0 * bk - bj * ak0) / det2;
+            T e0 = u0 - r0, e1 = u1 - r1;
+            T w0 = T(2) * (R00 * e0 + R01 * e1);
+            T w1 = T(2) * (R10 * e0 + R11 * e1);
+            T lj = (w0 * ak1 - ak0 * w1) / det2;
+            T lk = (aj0 * w1 - w0 * aj1) / det2;
+            bool feas = qp_check(rv, m, u0, u1, j, k, worst);
+            if (feas && lj >= T(0) && lk >= T(0)) {
+                u0o = u0; u1o = u1; masko = (1u << j) | (1u << k);
+                return SCCAV_STATUS_ACTIVE;
+            }
+            if (worst < fbw - R::tie_eps() * (R::abs_(worst) + R::abs_(fbw))) { fbw = worst; fb0 = u0; fb1 = u1; fbm = (1u << j) | (1u << k); }
+        }
+    }
+    u0o = fb0; u1o = fb1; masko = fbm;
+    return SCCAV_STATUS_INFEASIBLE;
+}
+
+// ------------------------------------------------------------------------------------------
+// one solve_cbf for one vehicle: rows of all slots -> smem -> QP -> converted output
+// (cbf/cbf.py:166-220 for DBM, :67-110 for KBM).  u_ref = (a|v, delta); returns (a|v, delta).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc& sd, int M, int64_t N, int64_t n,
+                                              const T* __restrict__ obst, T x, T y, T th, T v, T sth, T cth,
+                                              T alpha, T R00, T R01, T R10, T R11, T uref0, T uref1,
+                                              T* rows, int stride, T& u0, T& u1, T& u1raw, uint32_t& mask, T& hmin) {
+    typedef Real<T> R;
+    hmin = R::inf();
+    for (int m = 0; m < M; ++m) {
+        const int desc = sd.d[m];
+        const int64_t nn = (desc & SCCAV_SLOT_SHARED) ? 0 : n;
+        const T* f = obst + (int64_t)m * SCCAV_NFIELD * N + nn;
+        Partials<T> p = slot_partials<T>(desc & 0x7f, f, N, x, y, th, v, sth, cth);
+        T A0, A1, b;
+        if (P.model == SCCAV_MODEL_KBM) kbm_row<T>(p, sth, cth, alpha, A0, A1, b);
+        else dbm_row<T>(p, sth, cth, v, alpha, P.lr, A0, A1, b);
+        rows[(3 * m + 0) * stride] = A0;
+        rows[(3 * m + 1) * stride] = A1;
+        rows[(3 * m + 2) * stride] = b;
+        if (p.h < hmin) hmin = p.h;
+    }
+    T r0 = uref0, r1;
+    if (P.model == SCCAV_MODEL_KBM) r1 = (uref0 * R::tan_(uref1)) / P.L;                // cbf.py:75
+    else r1 = R::atan2_(P.lr * R::tan_(uref1), P.lf + P.lr);                             // cbf.py:175
+    RowView<T> rv{rows, stride};
+    T q0, q1;
+    int status = qp2_solve<T>(rv, M, r0, r1, R00, R01, R10, R11, q0, q1, mask);
+    u0 = q0;
+    u1raw = q1;
+    if (P.model == SCCAV_MODEL_KBM) {
+        if (P.kbm_driver_delta) u1 = R::atan_((q1 * P.L) / q0);                          // sce.py:652
+        else u1 = R::atan2_(q1 * P.L, r0);                                               // cbf.py:109
+    } else {
+        u1 = R::atan2_((P.lf + P.lr) * R::tan_(q1), P.lr);                               // cbf.py:216
+    }
+    return status;
+}
+
+// ------------------------------------------------------------------------------------------
+// nominal controller: Stanley (function form) -- stanley_controller_ellipse.py:146-212
+// The global argmin compares squared distances dx*dx + dy*dy (monotone in np.hypot; first
+// minimum wins, strict <), over ALL P points, like calc_target_index (:202-205).
+// ------------------------------------------------------------------------------------------
+template <typename T, typename CXY>
+__device__ __forceinline__ int nearest_index(const CXY* __restrict__ cxy, int P, T fx, T fy) {
+    T best = Real<T>::inf();
+    int ib = 0;
+#pragma unroll 8
+    for (int i = 0; i < P; ++i) {
+        CXY c = cxy[i];
+        T dx = fx - c.x, dy = fy - c.y;
+        T d2 = dx * dx + dy * dy;
+        if (d2 < best) { best = d2; ib = i; }
+    }
+    return ib;
+}
+
+template <typename T, typename CXY>
+__device__ __forceinline__ T stanley(const Params<T>& P, const CXY* __restrict__ cxy, const T* __restrict__ cyaw, int np,
+                                     T x, T y, T yaw, T v, T syaw, T cyw, int& target_idx) {
+    typedef Real<T> R;
+    T fx = x + P.L * cyw;
+    T fy = y + P.L * syaw;
+    int idx = nearest_index<T, CXY>(cxy, np, fx, fy);
+    CXY c = cxy[idx];
+    T s2, c2;
+    R::sincos_(yaw + R::pi() / T(2), &s2, &c2);                                          // sce.py:208-209
+    T e = (fx - c.x) * (-c2) + (fy - c.y) * (-s2);
+    if (target_idx >= idx) idx = target_idx;                                             // sce.py:159-160
+    T theta_e = normalize_angle<T>(cyaw[idx] - yaw);
+    T theta_d = R::atan2_(P.k_stanley * e, v + P.ks_stanley);
+    target_idx = idx;
+    return theta_e + theta_d;
+}
+
+}  // namespace sccav

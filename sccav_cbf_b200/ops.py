@@ -1,0 +1,245 @@
+"""Tensor-level operators over the C-ABI (libsccav_cbf.so): thin, no arithmetic in Python.
+
+All arrays are structure-of-arrays torch tensors with the vehicle index last (fastest):
+
+    state [4, N]   obst [M, 8, N]   u_ref / u [2, N]   A [2, M, N]   b [M, N]
+
+CUDA tensors go through the device-pointer entry points on the current torch stream; CPU tensors
+go through the ``*_host_*`` entry points (H2D + kernel + D2H inside the call).  dtype float64
+(default, parity-checked) or float32 (reported variant).  There is no CPU compute path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _native as nv
+from ._native import Params
+
+_SFX = {torch.float64: "f64", torch.float32: "f32"}
+
+
+def make_params(**kw) -> Params:
+    """sccav_params with the reference defaults (stanley_controller_ellipse.py:52-58,590),
+    overridden by keyword.  ``R`` may be a 2x2 nested sequence / tensor or 4 numbers row-major."""
+    p = nv.default_params()
+    for k, v in kw.items():
+        if k == "R":
+            flat = torch.as_tensor(v, dtype=torch.float64).reshape(-1).tolist()
+            if len(flat) != 4:
+                raise ValueError("Expected a symmetrix matrix of size 2 as input.")     # cbf.py:156-157
+            for i in range(4):
+                p.R[i] = flat[i]
+        elif hasattr(p, k):
+            setattr(p, k, v)
+        else:
+            raise TypeError("unknown parameter %r" % k)
+    return p
+
+
+def slot_bytes(slot_desc: Sequence[int]) -> bytes:
+    b = bytes(int(d) & 0xFF for d in slot_desc)
+    if len(b) > nv.MAX_ROWS:
+        raise ValueError("at most %d obstacle slots are supported" % nv.MAX_ROWS)
+    return b
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _chk(t: torch.Tensor, shape, dtype, device, name: str) -> torch.Tensor:
+    if t.dtype != dtype:
+        raise TypeError("%s: expected dtype %s, got %s" % (name, dtype, t.dtype))
+    if t.device != device:
+        raise ValueError("%s: expected device %s, got %s" % (name, device, t.device))
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError("%s: expected shape %s, got %s" % (name, tuple(shape), tuple(t.shape)))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _stream(device: torch.device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _pv(N, dtype, device, alpha=None, R=None, target_speed=None):
+    pv = nv.PerVehicle()
+    keep = []
+    if alpha is not None:
+        alpha = _chk(alpha, (N,), dtype, device, "alpha"); keep.append(alpha); pv.alpha = alpha.data_ptr()
+    if R is not None:
+        R = _chk(R, (4, N), dtype, device, "R"); keep.append(R); pv.R = R.data_ptr()
+    if target_speed is not None:
+        target_speed = _chk(target_speed, (N,), dtype, device, "target_speed"); keep.append(target_speed)
+        pv.target_speed = target_speed.data_ptr()
+    return pv, keep
+
+
+def _need_cuda_lib():
+    nv.require_cuda()
+    return nv.lib()
+
+
+def barrier_rows(params: Params, slot_desc, state: torch.Tensor, obst: torch.Tensor, alpha=None):
+    """K1: rows (A [2,M,N], b [M,N]) and barrier values h [M,N] -- ObstacleList2D.f/dx/.. +
+    the assembly of cbf/cbf.py:194-207."""
+    L = _need_cuda_lib()
+    sd = slot_bytes(slot_desc)
+    M, N = len(sd), state.shape[-1]
+    dt, dev = state.dtype, state.device
+    if not state.is_cuda:
+        raise ValueError("barrier_rows takes CUDA tensors")
+    state = _chk(state, (4, N), dt, dev, "state")
+    obst = _chk(obst, (M, nv.NFIELD, N), dt, dev, "obst")
+    pv, keep = _pv(N, dt, dev, alpha=alpha)
+    A = torch.empty((2, M, N), dtype=dt, device=dev)
+    b = torch.empty((M, N), dtype=dt, device=dev)
+    h = torch.empty((M, N), dtype=dt, device=dev)
+    with torch.cuda.device(dev):
+        nv.check(getattr(L, "sccav_barrier_rows_" + _SFX[dt])(
+            C.byref(params), sd, M, N, _ptr(state), _ptr(obst), C.byref(pv), _ptr(A), _ptr(b), _ptr(h), _stream(dev)))
+    return A, b, h
+
+
+def qp2_solve(params: Params, A: torch.Tensor, b: torch.Tensor, r: torch.Tensor, R=None, warp_per_problem=False):
+    """K2: exact optimum of min (u-r)^T R (u-r) s.t. A u >= b (what cvxopt.solvers.cp approximates
+    at cbf/cbf.py:213).  Returns u [2,N], active mask int32 [N] (bit k = row k), status uint8 [N]."""
+    L = _need_cuda_lib()
+    M, N = b.shape
+    dt, dev = b.dtype, b.device
+    if not b.is_cuda:
+        raise ValueError("qp2_solve takes CUDA tensors")
+    A = _chk(A, (2, M, N), dt, dev, "A")
+    b = _chk(b, (M, N), dt, dev, "b")
+    r = _chk(r, (2, N), dt, dev, "r")
+    pv, keep = _pv(N, dt, dev, R=R)
+    u = torch.empty((2, N), dtype=dt, device=dev)
+    mask = torch.empty((N,), dtype=torch.int32, device=dev)
+    status = torch.empty((N,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        nv.check(getattr(L, "sccav_qp2_solve_" + _SFX[dt])(
+            C.byref(params), M, N, _ptr(A), _ptr(b), _ptr(r), C.byref(pv), _ptr(u), _ptr(mask), _ptr(status),
+            1 if warp_per_problem else 0, _stream(dev)))
+    return u, mask, status
+
+
+def filter_step(params: Params, slot_desc, state: torch.Tensor, obst: torch.Tensor, u_ref: torch.Tensor,
+                alpha=None, R=None):
+    """K1+K2 fused: one batched ``solve_cbf(u_ref)`` (cbf/cbf.py:166-220 / :67-110).
+    CUDA tensors -> device entry point on the current stream; CPU tensors -> host entry point.
+    Returns u [2,N] = (a|v, delta), active mask int32 [N], status uint8 [N], h_min [N]."""
+    L = nv.lib()
+    nv.require_cuda()
+    sd = slot_bytes(slot_desc)
+    M, N = len(sd), state.shape[-1]
+    dt, dev = state.dtype, state.device
+    state = _chk(state, (4, N), dt, dev, "state")
+    obst = _chk(obst, (M, nv.NFIELD, N), dt, dev, "obst")
+    u_ref = _chk(u_ref, (2, N), dt, dev, "u_ref")
+    pv, keep = _pv(N, dt, dev, alpha=alpha, R=R)
+    u = torch.empty((2, N), dtype=dt, device=dev)
+    mask = torch.empty((N,), dtype=torch.int32, device=dev)
+    status = torch.empty((N,), dtype=torch.uint8, device=dev)
+    hmin = torch.empty((N,), dtype=dt, device=dev)
+    if state.is_cuda:
+        with torch.cuda.device(dev):
+            nv.check(getattr(L, "sccav_filter_step_" + _SFX[dt])(
+                C.byref(params), sd, M, N, _ptr(state), _ptr(obst), _ptr(u_ref), C.byref(pv), _ptr(u), _ptr(mask),
+                _ptr(status), _ptr(hmin), _stream(dev)))
+    else:
+        cur = torch.device("cuda", torch.cuda.current_device())
+        nv.check(getattr(L, "sccav_filter_step_host_" + _SFX[dt])(
+            C.byref(params), sd, M, N, _ptr(state), _ptr(obst), _ptr(u_ref), C.byref(pv), _ptr(u), _ptr(mask),
+            _ptr(status), _ptr(hmin), _stream(cur)))
+    return u, mask, status, hmin
+
+
+ROLLOUT_SUMMARY = ("steps", "target_idx", "n_active", "n_infeasible", "h_min", "beta_min", "beta_max", "beta_int")
+
+
+def rollout(params: Params, slot_desc, state: torch.Tensor, obst: Optional[torch.Tensor], course, T: int,
+            alpha=None, R=None, target_speed=None, record_stride: int = 0, summary: bool = True,
+            out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+    """K3: persistent closed-loop rollout of T steps (stanley_controller_ellipse.py:630-830 /
+    radial_dynamic_obstacles.py:427-507).
+
+    ``course`` = (cx, cy, cyaw) tensors [P] (ignored for NOMINAL_CONST; may be None then).
+    ``obst`` is updated in place when ``params.seeker``.  Returns a dict: ``state`` [4,N] final,
+    the summary arrays of ROLLOUT_SUMMARY, and with ``record_stride`` > 0 ``traj`` [T_rec,7,N]
+    (NaN-initialised), ``traj_idx`` / ``traj_mask`` [T_rec,N] (-1 / 0 initialised).
+    ``out`` may carry preallocated tensors to reuse (keys as returned).
+    """
+    L = nv.lib()
+    nv.require_cuda()
+    sd = slot_bytes(slot_desc)
+    M, N = len(sd), state.shape[-1]
+    dt, dev = state.dtype, state.device
+    state = _chk(state, (4, N), dt, dev, "state")
+    if M > 0:
+        if obst is None:
+            raise ValueError("obst is required when there are obstacle slots")
+        if not obst.is_contiguous():
+            raise ValueError("obst must be contiguous (it is updated in place for moving obstacles)")
+        obst = _chk(obst, (M, nv.NFIELD, N), dt, dev, "obst")
+    if course is not None:
+        cx, cy, cyaw = course
+        P = cx.shape[0]
+        cx = _chk(cx, (P,), dt, dev, "course_x"); cy = _chk(cy, (P,), dt, dev, "course_y")
+        cyaw = _chk(cyaw, (P,), dt, dev, "course_yaw")
+    else:
+        cx = cy = cyaw = None
+        P = 0
+    pv, keep = _pv(N, dt, dev, alpha=alpha, R=R, target_speed=target_speed)
+    import copy
+    prm = copy.copy(params)
+    prm.record_stride = int(record_stride)
+    res: Dict[str, torch.Tensor] = {} if out is None else out
+
+    def buf(name, shape, dtype, fill=None):
+        t = res.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != dev:
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            res[name] = t
+        if fill is not None:
+            t.fill_(fill)
+        return t
+
+    ro = nv.RolloutOut()
+    ro.state = buf("state", (4, N), dt).data_ptr()
+    if summary:
+        ro.steps = buf("steps", (N,), torch.int32).data_ptr()
+        ro.target_idx = buf("target_idx", (N,), torch.int32).data_ptr()
+        ro.n_active = buf("n_active", (N,), torch.int32).data_ptr()
+        ro.n_infeasible = buf("n_infeasible", (N,), torch.int32).data_ptr()
+        ro.h_min = buf("h_min", (N,), dt).data_ptr()
+        ro.beta_min = buf("beta_min", (N,), dt).data_ptr()
+        ro.beta_max = buf("beta_max", (N,), dt).data_ptr()
+        ro.beta_int = buf("beta_int", (N,), dt).data_ptr()
+    if record_stride > 0:
+        trec = (T + record_stride - 1) // record_stride
+        ro.traj = buf("traj", (trec, nv.TRAJ_FIELDS, N), dt, float("nan")).data_ptr()
+        ro.traj_idx = buf("traj_idx", (trec, N), torch.int32, -1).data_ptr()
+        ro.traj_mask = buf("traj_mask", (trec, N), torch.int32, 0).data_ptr()
+    args = (C.byref(prm), sd, M, N, int(T), _ptr(state), _ptr(obst), _ptr(cx), _ptr(cy), _ptr(cyaw), P,
+            C.byref(pv), C.byref(ro))
+    if state.is_cuda:
+        with torch.cuda.device(dev):
+            nv.check(getattr(L, "sccav_rollout_" + _SFX[dt])(*args, _stream(dev)))
+    else:
+        cur = torch.device("cuda", torch.cuda.current_device())
+        nv.check(getattr(L, "sccav_rollout_host_" + _SFX[dt])(*args, _stream(cur)))
+    return res
+
+
+def measure_fma_peak(dtype=torch.float64) -> float:
+    """Achieved TFLOP/s of an unrolled FMA-chain kernel (the CUDA-core roofline denominator)."""
+    L = _need_cuda_lib()
+    v = C.c_double(0.0)
+    nv.check(L.sccav_measure_fma_peak(64 if dtype == torch.float64 else 32, C.byref(v)))
+    return v.value
+
+
+def launch_count() -> int:
+    return int(nv.lib().sccav_launch_count())

@@ -1,0 +1,111 @@
+"""Closed-loop rollout front end: the batched counterpart of the reference's per-tick loops
+(test_scripts/stanley_controller_ellipse.py:630-830, radial_dynamic_obstacles.py:427-507).
+
+``ClosedLoopRollout`` owns the device buffers of one scenario shard (one process per GPU; shards
+are independent, there is no collective on the path) and exposes
+
+* ``run()``          -- inputs already resident in HBM (what ``bench.py`` reports as ``value``);
+* ``run_from_host()``-- the end-to-end call: pinned host inputs -> H2D -> kernel -> D2H of the
+                        per-vehicle results (what ``bench.py`` reports as ``e2e``).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from .scenarios import ScenarioBatch
+
+
+class ClosedLoopRollout:
+    def __init__(self, batch: ScenarioBatch, dtype: torch.dtype = torch.float64, device: Optional[torch.device] = None,
+                 pin: bool = True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("ClosedLoopRollout needs a CUDA device (no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.dtype = dtype
+        self.batch = batch
+        self.params = ops.make_params(**batch.params)
+        self.slot_desc = list(batch.slot_desc)
+        self.T = batch.T
+
+        def host(a):
+            if a is None:
+                return None
+            t = torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
+            return t.pin_memory() if pin else t
+
+        # host copies (pinned): the source of the e2e path
+        self.h_state = host(batch.state)
+        self.h_obst = host(batch.obst)
+        self.h_alpha = host(batch.alpha)
+        self.h_R = host(batch.R)
+        self.h_tspeed = host(batch.target_speed)
+        self.course = None
+        if batch.course is not None:
+            self.course = tuple(torch.from_numpy(np.ascontiguousarray(c)).to(dtype).to(self.device) for c in batch.course)
+        # device-resident inputs
+        self.d_state = self.h_state.to(self.device)
+        self.d_obst0 = None if self.h_obst is None else self.h_obst.to(self.device)
+        self.d_obst = None if self.d_obst0 is None else self.d_obst0.clone()
+        self.d_alpha = None if self.h_alpha is None else self.h_alpha.to(self.device)
+        self.d_R = None if self.h_R is None else self.h_R.to(self.device)
+        self.d_tspeed = None if self.h_tspeed is None else self.h_tspeed.to(self.device)
+        self.out: Dict[str, torch.Tensor] = {}
+        self._host_out: Dict[str, torch.Tensor] = {}
+
+    @property
+    def N(self) -> int:
+        return self.h_state.shape[1]
+
+    @property
+    def M(self) -> int:
+        return len(self.slot_desc)
+
+    def h2d_bytes(self) -> int:
+        n = self.h_state.numel() * self.h_state.element_size()
+        for t in (self.h_obst, self.h_alpha, self.h_R, self.h_tspeed):
+            if t is not None:
+                n += t.numel() * t.element_size()
+        return n
+
+    def d2h_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self._host_out.values())
+
+    def reset(self) -> None:
+        """Restore the moving-obstacle buffer (rollouts with seekers update it in place)."""
+        if self.d_obst is not None and self.params.seeker:
+            self.d_obst.copy_(self.d_obst0)
+
+    def run(self, T: Optional[int] = None, record_stride: int = 0) -> Dict[str, torch.Tensor]:
+        self.reset()
+        return ops.rollout(self.params, self.slot_desc, self.d_state, self.d_obst, self.course,
+                           self.T if T is None else T, alpha=self.d_alpha, R=self.d_R, target_speed=self.d_tspeed,
+                           record_stride=record_stride, out=self.out)
+
+    def run_from_host(self, T: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """H2D of this step's inputs from pinned memory, the rollout kernel, and D2H of the
+        per-vehicle results; returns host tensors.  Synchronises the current stream."""
+        dev = self.device
+        self.d_state.copy_(self.h_state, non_blocking=True)
+        if self.h_obst is not None:
+            self.d_obst.copy_(self.h_obst, non_blocking=True)
+        if self.h_alpha is not None:
+            self.d_alpha.copy_(self.h_alpha, non_blocking=True)
+        if self.h_R is not None:
+            self.d_R.copy_(self.h_R, non_blocking=True)
+        if self.h_tspeed is not None:
+            self.d_tspeed.copy_(self.h_tspeed, non_blocking=True)
+        res = ops.rollout(self.params, self.slot_desc, self.d_state, self.d_obst, self.course,
+                          self.T if T is None else T, alpha=self.d_alpha, R=self.d_R, target_speed=self.d_tspeed,
+                          record_stride=0, out=self.out)
+        for k, t in res.items():
+            h = self._host_out.get(k)
+            if h is None or h.shape != t.shape or h.dtype != t.dtype:
+                h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                self._host_out[k] = h
+            h.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return self._host_out

@@ -1,0 +1,351 @@
+"""Parity of the CUDA path (through the C-ABI, libsccav_cbf.so) with the CPU oracle.  -m gpu.
+
+Bars (BASELINE.json north_star): controls within 1e-6 relative in fp64 (measured ~1e-13),
+identical active-constraint sets and statuses, bit-exact integer bookkeeping (waypoint indices,
+step counts).  CUDA's sin/cos/tan/atan2 differ from glibc's by <= 1-2 ulp, so floating-point
+outputs are compared to 1e-9 (three orders tighter than the bar), integers with ==.
+"""
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle as co
+from oracle import oracle as o
+from tests import helpers as H
+
+gpu = pytest.mark.gpu
+pytestmark = gpu
+
+RTOL = 1e-9
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def T(a, dtype=torch.float64):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dtype).to(dev())
+
+
+def close(got, ref, rtol=RTOL, atol=1e-12):
+    got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else got
+    err = np.abs(got - ref) / (atol / rtol + np.abs(ref))
+    return float(err.max())
+
+
+SLOTSETS = {
+    "ellipse8": [o.SLOT_ELLIPSE] * 8,
+    "cone5": [o.SLOT_CONE] * 5,
+    "lane2_cone3": [o.SLOT_LANE, o.SLOT_LANE, o.SLOT_CONE, o.SLOT_CONE, o.SLOT_CONE],
+    "radial16": [o.SLOT_RADIAL] * 16,
+    "mixed": [o.SLOT_ELLIPSE, o.SLOT_CONE, o.SLOT_LANE, o.SLOT_RADIAL, o.SLOT_DISTANCE, o.SLOT_ELLIPSE],
+    "single": [o.SLOT_ELLIPSE],
+    "max32": [o.SLOT_ELLIPSE, o.SLOT_CONE] * 16,
+}
+
+
+@pytest.mark.parametrize("name", list(SLOTSETS))
+@pytest.mark.parametrize("model", [o.MODEL_DBM, o.MODEL_KBM])
+def test_filter_step_vs_oracle(name, model):
+    from sccav_cbf_b200 import ops
+    slots = SLOTSETS[name]
+    N = 4096 if len(slots) <= 16 else 1024
+    rng = np.random.default_rng(zlib.crc32(name.encode()) + model)
+    s = H.random_states(rng, N)
+    ob = H.random_slots(rng, N, slots, s)
+    ur = H.random_uref(rng, N, kbm=(model == o.MODEL_KBM))
+    R = [1.0, 0.0, 0.0, 1.0] if name != "mixed" else [1.0, 0.3, 0.3, 2.5]
+    ref = co.filter_step(co.default_params(model=model, R=R, alpha=1.3), slots, s, ob, ur, rows=True)
+    prm = ops.make_params(model=model, R=R, alpha=1.3)
+    u, mask, status, hmin = ops.filter_step(prm, slots, T(s), T(ob), T(ur))
+    A, b, h = ops.barrier_rows(prm, slots, T(s), T(ob))
+    assert close(A, ref["A"]) < 1.0 and close(b, ref["b"]) < 1.0
+    m_ = mask.cpu().numpy().view(np.uint32)
+    same = (m_ == ref["mask"]) & (status.cpu().numpy() == ref["status"])
+    # a flipped decision needs a residual within rounding of zero: allow none at these sizes
+    assert same.all(), "active set / status mismatch on %d of %d" % ((~same).sum(), N)
+    assert close(u, ref["u"]) < 1.0, close(u, ref["u"])
+    assert close(hmin, ref["h_min"]) < 1.0
+    frac_active = float((ref["mask"] != 0).mean())
+    assert frac_active > 0.02, "generator produced too few active problems (%g)" % frac_active
+
+
+def test_k1_k2_equal_fused_and_warp_variant():
+    from sccav_cbf_b200 import ops
+    slots = SLOTSETS["max32"]
+    N = 2048
+    rng = np.random.default_rng(11)
+    s = H.random_states(rng, N); ob = H.random_slots(rng, N, slots, s); ur = H.random_uref(rng, N)
+    prm = ops.make_params(R=[2.0, 0.1, 0.1, 0.7])
+    u, mask, status, _ = ops.filter_step(prm, slots, T(s), T(ob), T(ur))
+    A, b, _ = ops.barrier_rows(prm, slots, T(s), T(ob))
+    r = T(np.stack([ur[0], np.arctan2(1.45 * np.tan(ur[1]), 2.9)]))
+    u2, mask2, status2 = ops.qp2_solve(prm, A, b, r)
+    u3, mask3, status3 = ops.qp2_solve(prm, A, b, r, warp_per_problem=True)
+    assert torch.equal(mask, mask2) and torch.equal(status, status2)
+    assert torch.equal(mask2, mask3) and torch.equal(status2, status3)
+    assert torch.equal(u2, u3)                       # same enumeration, same arithmetic: bit-identical
+    assert torch.equal(u[0], u2[0])
+    # u[1] of the fused kernel is delta = atan2((lf+lr) tan(beta), lr)
+    d2 = torch.atan2(2.9 * torch.tan(u2[1]), torch.full_like(u2[1], 1.45))
+    assert close(u[1], d2.cpu().numpy()) < 1.0
+    assert int((status == 2).sum()) > 0, "want some infeasible problems in this set"
+
+
+def test_qp_kkt_property_full_size():
+    """Size-independent property at BASELINE size (65,536 x 8): every returned point is primal
+    feasible, stationary on its active set, with non-negative multipliers."""
+    from sccav_cbf_b200 import ops
+    slots = SLOTSETS["ellipse8"][:4] + [o.SLOT_CONE] * 4
+    N = 65536
+    rng = np.random.default_rng(5)
+    s = H.random_states(rng, N); ob = H.random_slots(rng, N, slots, s); ur = H.random_uref(rng, N)
+    R = [1.0, 0.2, 0.2, 3.0]
+    prm = ops.make_params(R=R)
+    A, b, _ = ops.barrier_rows(prm, slots, T(s), T(ob))
+    r = np.stack([ur[0], np.arctan2(1.45 * np.tan(ur[1]), 2.9)])
+    u, mask, status = ops.qp2_solve(prm, A, b, T(r))
+    A_, b_, u_ = A.cpu().numpy(), b.cpu().numpy(), u.cpu().numpy()
+    m_ = mask.cpu().numpy().view(np.uint32); st = status.cpu().numpy()
+    ok = st != 2
+    sub = np.nonzero(ok)[0][:: max(1, ok.sum() // 6000)]          # a spread sample for the python check
+    prim, stat, lmin = H.kkt_residuals(A_[:, :, sub], b_[:, sub], u_[:, sub], r[:, sub], R, m_[sub])
+    assert prim.max() <= 1e-9 and stat.max() <= 1e-9 and lmin.min() >= -1e-9
+    # inactive <=> u == r exactly
+    ina = st == 0
+    assert np.array_equal(u_[:, ina], r[:, ina]) and (m_[ina] == 0).all()
+    # vectorised primal feasibility for ALL optimal problems
+    res = A_[0] * u_[0] + A_[1] * u_[1] - b_
+    scale = np.abs(A_[0] * u_[0]) + np.abs(A_[1] * u_[1]) + np.abs(b_)
+    assert ((res >= -1e-9 * scale) | ~ok[None, :]).all()
+
+
+def test_empty_and_error_behaviour():
+    from sccav_cbf_b200 import ops
+    prm = ops.make_params()
+    s = T(np.zeros((4, 0))); ob = T(np.zeros((1, 8, 0))); ur = T(np.zeros((2, 0)))
+    u, mask, status, hmin = ops.filter_step(prm, [0], s, ob, ur)           # N = 0: no-op
+    assert u.shape == (2, 0)
+    with pytest.raises(ValueError):                                         # cbf.py:177 ValueError
+        ops.filter_step(prm, [], T(np.zeros((4, 3))), T(np.zeros((0, 8, 3))), T(np.zeros((2, 3))))
+    with pytest.raises(ValueError):
+        ops.make_params(R=[1.0, 0.0, 0.0])
+    with pytest.raises(ValueError):                                         # not SPD
+        ops.filter_step(ops.make_params(R=[1.0, 2.0, 2.0, 1.0]), [0], T(np.zeros((4, 3))), T(np.ones((1, 8, 3))), T(np.zeros((2, 3))))
+    with pytest.raises(ValueError):
+        ops.filter_step(prm, [0] * 33, T(np.zeros((4, 3))), T(np.ones((33, 8, 3))), T(np.zeros((2, 3))))
+
+
+def test_host_entry_point_equals_device_path():
+    from sccav_cbf_b200 import ops
+    slots = SLOTSETS["mixed"]
+    N = 3000
+    rng = np.random.default_rng(8)
+    s = H.random_states(rng, N); ob = H.random_slots(rng, N, slots, s); ur = H.random_uref(rng, N)
+    prm = ops.make_params()
+    u, mask, status, hmin = ops.filter_step(prm, slots, T(s), T(ob), T(ur))
+    hu, hmask, hstatus, hhmin = ops.filter_step(prm, slots, torch.from_numpy(s), torch.from_numpy(ob), torch.from_numpy(ur))
+    assert not hu.is_cuda
+    assert torch.equal(u.cpu(), hu) and torch.equal(mask.cpu(), hmask) and torch.equal(status.cpu(), hstatus)
+    assert torch.equal(hmin.cpu(), hhmin)
+
+
+# ------------------------------------------------------------------------------------------ rollouts
+def _run(batch, dtype=torch.float64, record_stride=0, T=None):
+    from sccav_cbf_b200 import ops
+    prm = ops.make_params(**batch.params)
+    course = None if batch.course is None else tuple(T_(c, dtype) for c in batch.course)
+    kw = {}
+    for k in ("alpha", "R", "target_speed"):
+        v = getattr(batch, k)
+        if v is not None:
+            kw[k] = T_(v, dtype)
+    obst = None if batch.obst is None else T_(batch.obst, dtype)
+    out = ops.rollout(prm, batch.slot_desc, T_(batch.state, dtype), obst, course, batch.T if T is None else T,
+                      record_stride=record_stride, **kw)
+    torch.cuda.synchronize()
+    res = {k: v.cpu().numpy() for k, v in out.items()}
+    res["obst"] = None if obst is None else obst.cpu().numpy()
+    return res
+
+
+def T_(a, dtype):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dtype).to(dev())
+
+
+def _oracle(batch, record_stride=0, T=None):
+    kw = {k: getattr(batch, k) for k in ("alpha", "R", "target_speed") if getattr(batch, k) is not None}
+    return co.rollout(co.default_params(**batch.params), batch.slot_desc, batch.state, batch.obst, batch.course,
+                      batch.T if T is None else T, record_stride=record_stride, **kw)
+
+
+@pytest.mark.parametrize("kind,steps,nact,tidx", [("cone", 276, 59, 2033), ("ellipse_dbm", 280, 72, 2033), ("ellipse_kbm", 300, 139, 1385)])
+def test_rollout_config1_reference_run(kind, steps, nact, tidx, golden_dir):
+    """BASELINE config #1: the reference's own single-vehicle run, free-running on the GPU."""
+    from sccav_cbf_b200 import scenarios as sc
+    b = sc.config1(kind)
+    g = _run(b, record_stride=1, T=400)
+    r = _oracle(b, record_stride=1, T=400)
+    assert int(g["steps"][0]) == steps == int(r["steps"][0])
+    assert int(g["n_active"][0]) == nact and int(g["target_idx"][0]) == tidx
+    assert np.array_equal(g["traj_idx"], r["traj_idx"])                      # waypoint indices: bit-exact
+    assert np.array_equal(g["traj_mask"].view(np.uint32), r["traj_mask"])    # active sets: identical
+    assert close(g["traj"][:steps], r["traj"][:steps]) < 1.0
+    assert np.isnan(g["traj"][steps:]).all()
+    if kind == "cone":
+        gold = json.load(open(os.path.join(golden_dir, "beta_vs_time.json")))
+        beta = np.degrees(np.concatenate([[0.0], g["traj"][:steps, 6, 0]]))
+        assert len(beta) == 277 and np.abs(beta - np.array(gold["beta_deg"])).max() <= 1e-3
+
+
+def _compare_rollout(g, r, N, T, min_exact=0.999, state_tol=1e-6):
+    """Free-running comparison: integer bookkeeping must agree on (almost) every vehicle -- a flip
+    needs a quantity within ~1e-13 of a decision boundary -- and states to 1e-6."""
+    exact = (g["steps"] == r["steps"]) & (g["target_idx"] == r["target_idx"]) & (g["n_active"] == r["n_active"]) \
+        & (g["n_infeasible"] == r["n_infeasible"])
+    frac = float(exact.mean())
+    assert frac >= min_exact, "bookkeeping identical on only %.5f of vehicles" % frac
+    err = np.abs(g["state"] - r["state"])[:, exact] / (1.0 + np.abs(r["state"][:, exact]))
+    assert err.max() <= state_tol, err.max()
+    for k in ("h_min", "beta_min", "beta_max", "beta_int"):
+        e = np.abs(g[k] - r[k])[exact] / (1.0 + np.abs(r[k][exact]))
+        assert e.max() <= state_tol, (k, e.max())
+    return frac
+
+
+def test_rollout_config2_vs_oracle():
+    """BASELINE config #2 at oracle-sized N: 2,048 vehicles x 8 ellipses x 1,000 steps."""
+    from sccav_cbf_b200 import scenarios as sc
+    b = sc.config2(n_total=65536, M=8, T=1000, lo=0, hi=2048)
+    g = _run(b, record_stride=50)
+    r = _oracle(b, record_stride=50)
+    frac = _compare_rollout(g, r, b.N, b.T)
+    same_tr = (g["traj_idx"] == r["traj_idx"]).all(axis=0) & (g["traj_mask"].view(np.uint32) == r["traj_mask"]).all(axis=0)
+    assert same_tr.mean() >= 0.999
+    assert (g["steps"] == 1000).all() and g["n_active"].sum() > 0
+    print("config2 identical bookkeeping fraction", frac, "active steps/vehicle", g["n_active"].mean())
+
+
+def test_rollout_teacher_forced_per_step_parity():
+    """Strict per-step parity: the oracle's recorded states are fed to the fused filter kernel
+    (K1+K2) step by step; controls to 1e-9, active sets identical at EVERY sampled step."""
+    from sccav_cbf_b200 import ops, scenarios as sc
+    b = sc.config2(n_total=65536, M=8, T=400, lo=4096, hi=4096 + 512)
+    r = _oracle(b, record_stride=1)
+    prm = ops.make_params(**b.params)
+    ob = T(b.obst)
+    bad = 0
+    tot = 0
+    for t in range(0, 400, 7):
+        st = r["traj"][t, 0:4]                                         # pre-step state of step t
+        # nominal control of the oracle at this step is not recorded; use the recorded output u
+        # as u_ref for inactive rows is exact: instead re-solve with the oracle on the same input
+        ur = np.stack([r["traj"][t, 4], r["traj"][t, 5]])
+        ref = co.filter_step(co.default_params(**b.params), b.slot_desc, st, b.obst, ur)
+        u, mask, status, _ = ops.filter_step(prm, b.slot_desc, T(st), ob, T(ur))
+        bad += int((mask.cpu().numpy().view(np.uint32) != ref["mask"]).sum())
+        tot += st.shape[1]
+        assert close(u, ref["u"]) < 1.0
+    assert bad == 0, "%d of %d teacher-forced active sets differ" % (bad, tot)
+
+
+def test_rollout_config3_seekers_vs_oracle():
+    """BASELINE config #3 (radial_dynamic_obstacles.py): moving seekers, time-varying barriers."""
+    from sccav_cbf_b200 import scenarios as sc
+    b = sc.config3(n_total=262144, M=16, T=600, lo=0, hi=1024)
+    g = _run(b, record_stride=60)
+    r = _oracle(b, record_stride=60)
+    _compare_rollout(g, r, b.N, b.T, min_exact=0.995, state_tol=1e-5)
+    exact = (g["n_active"] == r["n_active"]) & (g["n_infeasible"] == r["n_infeasible"])
+    e = np.abs(g["obst"] - r["obst"])[:, :, exact] / (1.0 + np.abs(r["obst"][:, :, exact]))
+    assert e.max() <= 1e-5                                              # seeker centres / velocities written back
+
+
+def test_rollout_config3_stanley_variant():
+    from sccav_cbf_b200 import scenarios as sc
+    b = sc.config3(n_total=262144, M=16, T=300, lo=0, hi=512, stanley=True)
+    _compare_rollout(_run(b), _oracle(b), b.N, b.T, min_exact=0.99, state_tol=1e-5)
+
+
+def test_rollout_config4_lanes_vs_oracle():
+    """BASELINE config #4: 8 ellipses + 2 shared lane barriers (Newton closest point on device)."""
+    from sccav_cbf_b200 import scenarios as sc
+    b = sc.config4(n_total=1048576, M=8, T=500, lo=65536, hi=65536 + 1024)
+    g = _run(b)
+    r = _oracle(b)
+    _compare_rollout(g, r, b.N, b.T, min_exact=0.995)
+
+
+def test_rollout_config5_sweep_vs_oracle():
+    """BASELINE config #5: per-scenario alpha / R / y0 sweep of the beta_vs_time experiment."""
+    from sccav_cbf_b200 import scenarios as sc
+    lo = 5 * 65536 + 17
+    b = sc.config5(n_total=16777216, T=320, lo=lo, hi=lo + 768)
+    g = _run(b)
+    r = _oracle(b)
+    _compare_rollout(g, r, b.N, b.T, min_exact=0.995)
+    assert len(np.unique(g["steps"])) > 1                               # per-vehicle termination differs
+
+
+def test_rollout_no_filter_and_m0():
+    from sccav_cbf_b200 import scenarios as sc
+    b = sc.config2(n_total=65536, M=8, T=300, lo=0, hi=256)
+    b.params = dict(model=o.MODEL_NONE, terminate=1)
+    b.slot_desc = []
+    b.obst = None
+    g = _run(b)
+    r = _oracle(b)
+    _compare_rollout(g, r, b.N, b.T)
+    assert (g["n_active"] == 0).all()
+
+
+def test_rollout_host_path_and_shards_are_independent_of_world_size():
+    """Scenario sharding: shard [lo, hi) of a batch gives the same per-vehicle results as the
+    same vehicles inside a bigger shard (no cross-vehicle coupling, no collective needed)."""
+    from sccav_cbf_b200 import scenarios as sc
+    from sccav_cbf_b200.rollout import ClosedLoopRollout
+    whole = sc.config2(n_total=4096, M=8, T=200, lo=0, hi=1024)
+    part = sc.config2(n_total=4096, M=8, T=200, lo=512, hi=768)
+    gw = _run(whole)
+    gp = _run(part)
+    for k in ("state", "steps", "target_idx", "n_active", "h_min"):
+        assert np.array_equal(gw[k][..., 512:768], gp[k]), k
+    cl = ClosedLoopRollout(part)
+    a = {k: v.cpu().numpy() for k, v in cl.run().items()}
+    h = {k: v.numpy().copy() for k, v in cl.run_from_host().items()}
+    for k in a:
+        assert np.array_equal(a[k], h[k], equal_nan=True), k
+    assert cl.h2d_bytes() == (4 + 8 * 8) * 256 * 8 and cl.d2h_bytes() > 0
+
+
+def test_fp32_variant_error_vs_fp64():
+    """The fp32 variant is REPORTED, not parity-checked: h near 0 is a cancellation.
+    Here: filter step error distribution against the fp64 kernel."""
+    from sccav_cbf_b200 import ops
+    slots = SLOTSETS["ellipse8"]
+    N = 8192
+    rng = np.random.default_rng(21)
+    s = H.random_states(rng, N); ob = H.random_slots(rng, N, slots, s); ur = H.random_uref(rng, N)
+    prm = ops.make_params()
+    u64, m64, s64, _ = ops.filter_step(prm, slots, T(s), T(ob), T(ur))
+    u32, m32, s32, _ = ops.filter_step(prm, slots, T(s, torch.float32), T(ob, torch.float32), T(ur, torch.float32))
+    same = (m64 == m32).cpu().numpy()
+    rel = (u32.double() - u64).abs() / (1 + u64.abs())
+    rel = rel.cpu().numpy()[:, same]
+    assert same.mean() > 0.98
+    assert np.quantile(rel, 0.999) < 5e-3
+    print("fp32 vs fp64: active-set mismatch %.4f, max rel err %.3g, p99.9 %.3g" % (1 - same.mean(), rel.max(), np.quantile(rel, 0.999)))
+
+
+def test_fp32_rollout_runs_and_tracks_fp64():
+    from sccav_cbf_b200 import scenarios as sc
+    b = sc.config2(n_total=65536, M=8, T=300, lo=0, hi=1024)
+    g64 = _run(b)
+    g32 = _run(b, dtype=torch.float32)
+    assert (g32["steps"] == 300).all()
+    close_idx = np.abs(g32["target_idx"].astype(int) - g64["target_idx"].astype(int)) <= 30
+    assert close_idx.mean() > 0.9

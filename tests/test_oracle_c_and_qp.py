@@ -1,0 +1,145 @@
+"""CPU tests (no GPU): the C oracle against the pinned Python oracle, and properties of the exact
+2-variable QP that replaces cvxopt.solvers.cp (KKT residuals, uniqueness of the
+KKT working set, m = 1 closed form vs enumeration)."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co
+from oracle import oracle as o
+from tests import helpers as H
+
+
+def test_c_oracle_filter_step_equals_python_oracle():
+    rng = np.random.default_rng(42)
+    slots = [o.SLOT_ELLIPSE, o.SLOT_CONE, o.SLOT_LANE, o.SLOT_RADIAL, o.SLOT_DISTANCE, o.SLOT_CONE]
+    N = 300
+    s = H.random_states(rng, N); ob = H.random_slots(rng, N, slots, s); ur = H.random_uref(rng, N)
+    R = (1.0, 0.3, 0.3, 2.5)
+    for model in (o.MODEL_DBM, o.MODEL_KBM):
+        c = co.filter_step(co.default_params(model=model, R=R, alpha=0.7), slots, s, ob, ur, rows=True)
+        for n in range(N):
+            fields = [list(ob[m, :, n]) for m in range(len(slots))]
+            A0, A1, b, hs = o.barrier_rows(model, list(s[:, n]), slots, fields, 0.7, 1.45)
+            # numpy's scalar sin/cos and glibc's may differ by an ulp: rows to 1e-12, decisions equal
+            assert np.allclose(c["A"][0, :, n], A0, rtol=1e-12, atol=1e-12)
+            assert np.allclose(c["A"][1, :, n], A1, rtol=1e-12, atol=1e-12)
+            assert np.allclose(c["b"][:, n], b, rtol=1e-12, atol=1e-12)
+            u0, u1, mask, status, _, hm = o.filter_step(model, list(s[:, n]), list(ur[:, n]), slots, fields, 0.7, 1.45, 1.45, 2.9, R)
+            assert mask == int(c["mask"][n]) and status == int(c["status"][n]), n
+            assert abs(u0 - c["u"][0, n]) <= 1e-10 * (1 + abs(u0)) and abs(u1 - c["u"][1, n]) <= 1e-10 * (1 + abs(u1))
+            assert abs(hm - c["h_min"][n]) <= 1e-12 * (1 + abs(hm))
+
+
+def test_c_oracle_rollout_equals_python_oracle():
+    from sccav_cbf_b200 import scenarios as sc
+    b = sc.config2(n_total=65536, M=8, T=150, lo=100, hi=108)
+    c = co.rollout(co.default_params(), b.slot_desc, b.state, b.obst, b.course, b.T, record_stride=1)
+    for n in range(b.N):
+        p = o.rollout(b.state[:, n], b.slot_desc, [b.obst[m, :, n] for m in range(b.M)], b.course, b.T, record=True)
+        assert p["steps"] == c["steps"][n] and p["target_idx"] == c["target_idx"][n]
+        assert p["n_active"] == c["n_active"][n] and p["n_infeasible"] == c["n_infeasible"][n]
+        assert np.array_equal(np.array(p["rec"]["idx"]), c["traj_idx"][:, n])
+        assert np.array_equal(np.array(p["rec"]["mask"], dtype=np.uint32), c["traj_mask"][:, n])
+        assert np.abs(np.array(p["rec"]["state"]) - c["traj"][:, 0:4, n]).max() <= 1e-9
+        assert np.abs(np.array(p["state"]) - c["state"][:, n]).max() <= 1e-9
+
+
+def test_c_oracle_seeker_rollout_equals_python_oracle():
+    from sccav_cbf_b200 import scenarios as sc
+    b = sc.config3(n_total=262144, M=4, T=90, lo=0, hi=6)
+    prm = dict(b.params)
+    c = co.rollout(co.default_params(**prm), b.slot_desc, b.state, b.obst, b.course, b.T)
+    for n in range(b.N):
+        p = o.rollout(b.state[:, n], b.slot_desc, [b.obst[m, :, n] for m in range(b.M)], None, b.T,
+                      params=dict(seeker=1, dt=1.0 / 30.0, nominal=o.NOMINAL_CONST))
+        assert p["n_active"] == c["n_active"][n] and p["n_infeasible"] == c["n_infeasible"][n]
+        assert np.abs(np.array(p["state"]) - c["state"][:, n]).max() <= 1e-8
+        assert np.abs(np.array(p["fields"]) - c["obst"][:, :, n]).max() <= 1e-8
+
+
+def _random_qp(rng, m):
+    A0 = rng.normal(size=m) * rng.choice([0.0, 1.0, 30.0], size=m)
+    A1 = rng.normal(size=m) * rng.choice([1.0, 50.0], size=m)
+    b = rng.normal(size=m) * 10 - 5
+    r = rng.normal(size=2) * np.array([2.0, 0.3])
+    Rm = np.array([[1.0, 0.0], [0.0, 1.0]]) if rng.uniform() < 0.5 else np.array([[1.5, 0.4], [0.4, 2.0]])
+    return A0, A1, b, r, Rm
+
+
+def test_qp2_unique_kkt_point_and_residuals():
+    rng = np.random.default_rng(7)
+    n_act = 0
+    for it in range(1500):
+        m = int(rng.integers(1, 9))
+        A0, A1, b, r, Rm = _random_qp(rng, m)
+        cands = []
+        u0, u1, mask, status = o.qp2_exact(list(A0), list(A1), list(b), r[0], r[1], tuple(Rm.ravel()), collect=cands)
+        if status == o.STATUS_INFEASIBLE:
+            assert not cands
+            continue
+        # strict convexity: every KKT working set gives the same point
+        for c in cands:
+            assert abs(c[0] - u0) <= 1e-8 * (1 + abs(u0)) and abs(c[1] - u1) <= 1e-8 * (1 + abs(u1))
+        A = np.stack([A0, A1])[:, :, None]
+        prim, stat, lmin = H.kkt_residuals(A, b[:, None], np.array([[u0], [u1]]), r[:, None], Rm.ravel(), np.array([mask]))
+        assert prim[0] <= 1e-9 and stat[0] <= 1e-9 and lmin[0] >= -1e-9
+        n_act += status == o.STATUS_ACTIVE
+        # cost is minimal among a cloud of feasible points
+        cost = (np.array([u0, u1]) - r) @ Rm @ (np.array([u0, u1]) - r)
+        pts = np.array([u0, u1]) + rng.normal(size=(64, 2)) * 0.5
+        feas = ((pts[:, 0:1] * A0 + pts[:, 1:2] * A1) >= b - 1e-12).all(axis=1)
+        for q in pts[feas]:
+            assert (q - r) @ Rm @ (q - r) >= cost - 1e-9 * (1 + cost)
+    assert n_act > 200
+
+
+def test_qp2_single_row_closed_form():
+    """m = 1: u = r + R^-1 A^T (b - A r)/(A R^-1 A^T) when violated (the closed form the survey
+    probe used against beta_vs_time.mat; also members_scripts' psi-projection)."""
+    rng = np.random.default_rng(9)
+    for _ in range(500):
+        A0, A1, b, r, Rm = _random_qp(rng, 1)
+        u0, u1, mask, status = o.qp2_exact(list(A0), list(A1), list(b), r[0], r[1], tuple(Rm.ravel()))
+        a = np.array([A0[0], A1[0]])
+        if a @ r >= b[0] or not np.any(a):
+            assert (u0, u1, mask) == (r[0], r[1], 0) or not np.any(a)
+        else:
+            Ri = np.linalg.inv(Rm)
+            ex = r + Ri @ a * (b[0] - a @ r) / (a @ Ri @ a)
+            assert np.allclose([u0, u1], ex, rtol=1e-12, atol=1e-12) and mask == 1
+
+
+def test_qp2_degenerate_cases():
+    R = (1.0, 0.0, 0.0, 1.0)
+    # v = 0: every row is 0*u >= b: vacuous if b <= 0, infeasible otherwise
+    assert o.qp2_exact([0.0, 0.0], [0.0, 0.0], [-1.0, -2.0], 0.3, 0.1, R) == (0.3, 0.1, 0, o.STATUS_INACTIVE)
+    assert o.qp2_exact([0.0], [0.0], [1.0], 0.3, 0.1, R) == (0.3, 0.1, 0, o.STATUS_INFEASIBLE)
+    # ellipse rows constrain beta only: interval clipping, tightest bound wins, a untouched
+    u0, u1, mask, st = o.qp2_exact([0.0, 0.0, 0.0], [1.0, 2.0, -1.0], [0.2, 0.9, -1.0], 0.5, 0.0, R)
+    assert (u0, u1, mask, st) == (0.5, 0.45, 0b010, o.STATUS_ACTIVE)
+    # duplicate rows: lowest index reported
+    u0, u1, mask, st = o.qp2_exact([0.0, 0.0], [1.0, 1.0], [0.2, 0.2], 0.5, 0.0, R)
+    assert (u1, mask, st) == (0.2, 0b01, o.STATUS_ACTIVE)
+    # conflicting parallel rows: infeasible, least-violation candidate, flagged
+    u0, u1, mask, st = o.qp2_exact([0.0, 0.0], [1.0, -1.0], [0.3, -0.1], 0.5, 0.0, R)
+    assert st == o.STATUS_INFEASIBLE and mask in (0b01, 0b10)
+    # vertex solution
+    u0, u1, mask, st = o.qp2_exact([1.0, 0.0], [0.0, 1.0], [1.0, 1.0], 0.0, 0.0, R)
+    assert (u0, u1, mask, st) == (1.0, 1.0, 0b11, o.STATUS_ACTIVE)
+
+
+def test_c_oracle_qp_degenerate_cases_match_python():
+    """Same degenerate inputs through the C oracle's filter (distance slots give hand-set rows is
+    not possible; instead compare on many random problems incl. infeasible ones)."""
+    rng = np.random.default_rng(13)
+    slots = [o.SLOT_LANE, o.SLOT_LANE, o.SLOT_ELLIPSE, o.SLOT_ELLIPSE]
+    N = 400
+    s = H.random_states(rng, N); ob = H.random_slots(rng, N, slots, s); ur = H.random_uref(rng, N)
+    c = co.filter_step(co.default_params(), slots, s, ob, ur)
+    n_inf = 0
+    for n in range(N):
+        fields = [list(ob[m, :, n]) for m in range(len(slots))]
+        u0, u1, mask, status, _, _ = o.filter_step(o.MODEL_DBM, list(s[:, n]), list(ur[:, n]), slots, fields, 1.0, 1.45, 1.45, 2.9, (1.0, 0.0, 0.0, 1.0))
+        assert mask == int(c["mask"][n]) and status == int(c["status"][n]), n
+        n_inf += status == o.STATUS_INFEASIBLE
+    assert n_inf > 5          # all rows here constrain beta only: conflicts are common
