@@ -121,6 +121,8 @@ typedef struct sccav_rollout_out {
     void* traj;                /* [T_rec][7][N] pre-step x,y,yaw,v + u0,u1,beta of the step; T_rec = ceil(T/stride) */
     int32_t* traj_idx;         /* [T_rec][N] target index used by the step                     */
     uint32_t* traj_mask;       /* [T_rec][N] active set of the step                            */
+    int32_t* n_evals;          /* [N] way-point distance evaluations + bounding-circle tests of the
+                                  Stanley nearest-index search (roofline accounting)            */
 } sccav_rollout_out;
 
 int sccav_version(void);
@@ -205,6 +207,21 @@ int sccav_rollout_host_f32(const sccav_params* p, const uint8_t* slot_desc, int3
 int sccav_measure_fma_peak(int32_t dtype, double* tflops_out);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t sccav_launch_count(void);
+
+/* Launch shape the rollout entry point would use for (M, N, P) on the current device:
+ * info[8] = grid, block, dynamic smem bytes, registers/thread, max threads/block of the kernel,
+ * resident CTAs/SM at that shape, course-in-shared-memory flag, SM count.  Launches nothing. */
+int sccav_rollout_launch_info_f64(int32_t M, int64_t N, int32_t P, int32_t* info);
+int sccav_rollout_launch_info_f32(int32_t M, int64_t N, int32_t P, int32_t* info);
+
+/* TEST HOOK, host-only, launches nothing: runs the rollout kernel's pruned nearest-way-point search
+ * (csrc/course_index.cuh, the same __host__ __device__ code) on the CPU for nq query points, next to
+ * the exhaustive scan of calc_target_index (stanley_controller_ellipse.py:188-212), so that the
+ * CPU test-suite can prove index equality (ties, far points, NaN) without a GPU.  All pointers are
+ * HOST memory; hint / idx_full_out / evals_out may be NULL; dtype 64 or 32. */
+int sccav_debug_course_index_host(const double* cx, const double* cy, int32_t P, const double* fx, const double* fy,
+                                  const int32_t* hint, int64_t nq, int32_t dtype, int32_t* idx_out,
+                                  int32_t* idx_full_out, int64_t* evals_out);
 
 #ifdef __cplusplus
 }

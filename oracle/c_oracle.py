@@ -33,7 +33,7 @@ class PerVehicle(C.Structure):
 
 class RolloutOut(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("state", "steps", "target_idx", "n_active", "n_infeasible", "h_min",
-                                          "beta_min", "beta_max", "beta_int", "traj", "traj_idx", "traj_mask")]
+                                          "beta_min", "beta_max", "beta_int", "traj", "traj_idx", "traj_mask", "n_evals")]
 
 
 def build(force: bool = False) -> str:

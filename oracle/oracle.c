@@ -40,6 +40,9 @@ typedef struct { double h, hx, hy, hth, hv, ht; } part_t;
 
 /* cbf/utils.py:93-106 */
 static double normalize_angle(double a) {
+    /* cbf/utils.py:93-106.  The reference's two while-loops never terminate for |a| >~ 1e16 (a -= 2 pi
+     * no longer changes a) or inf; beyond 1e4 (a diverged scenario) whole turns are removed first. */
+    if (!(fabs(a) <= 1e4)) a = a - (2.0 * PI_) * rint(a / (2.0 * PI_));
     while (a > PI_) a -= 2.0 * PI_;
     while (a < -PI_) a += 2.0 * PI_;
     return a;

@@ -75,7 +75,11 @@ LANE_XTOL = 1e-12
 
 
 def normalize_angle(angle):
-    """cbf/utils.py:93-106 == stanley_controller_ellipse.py:172-185 (strict inequalities)."""
+    """cbf/utils.py:93-106 == stanley_controller_ellipse.py:172-185 (strict inequalities).
+    The reference's loops never terminate for |angle| >~ 1e16 or inf; beyond 1e4 (a diverged
+    scenario) whole turns are removed first (same rule in oracle.c and the CUDA path)."""
+    if not (abs(angle) <= 1e4):
+        angle = angle - (2.0 * PI) * float(np.rint(angle / (2.0 * PI)))
     while angle > PI:
         angle -= 2.0 * PI
     while angle < -PI:

@@ -45,6 +45,7 @@ class RolloutOut(C.Structure):
         ("state", C.c_void_p), ("steps", C.c_void_p), ("target_idx", C.c_void_p), ("n_active", C.c_void_p),
         ("n_infeasible", C.c_void_p), ("h_min", C.c_void_p), ("beta_min", C.c_void_p), ("beta_max", C.c_void_p),
         ("beta_int", C.c_void_p), ("traj", C.c_void_p), ("traj_idx", C.c_void_p), ("traj_mask", C.c_void_p),
+        ("n_evals", C.c_void_p),
     ]
 
 
@@ -60,7 +61,8 @@ SYMBOLS = [
     "sccav_barrier_rows_f64", "sccav_barrier_rows_f32", "sccav_qp2_solve_f64", "sccav_qp2_solve_f32",
     "sccav_filter_step_f64", "sccav_filter_step_f32", "sccav_rollout_f64", "sccav_rollout_f32",
     "sccav_filter_step_host_f64", "sccav_filter_step_host_f32", "sccav_rollout_host_f64", "sccav_rollout_host_f32",
-    "sccav_measure_fma_peak", "sccav_launch_count",
+    "sccav_measure_fma_peak", "sccav_launch_count", "sccav_debug_course_index_host",
+    "sccav_rollout_launch_info_f64", "sccav_rollout_launch_info_f32",
 ]
 
 
@@ -83,9 +85,12 @@ def lib() -> C.CDLL:
     L.sccav_default_params.restype = None
     L.sccav_measure_fma_peak.argtypes = [i32, C.POINTER(C.c_double)]
     L.sccav_launch_count.restype = i64
+    L.sccav_debug_course_index_host.argtypes = [vp, vp, i32, vp, vp, vp, i64, i32, vp, vp, vp]
     for sfx in ("f64", "f32"):
         f = getattr(L, "sccav_barrier_rows_" + sfx)
         f.argtypes = [PP, C.c_char_p, i32, i64, vp, vp, PV, vp, vp, vp, vp]
+        f = getattr(L, "sccav_rollout_launch_info_" + sfx)
+        f.argtypes = [i32, i64, i32, vp]
         f = getattr(L, "sccav_qp2_solve_" + sfx)
         f.argtypes = [PP, i32, i64, vp, vp, vp, PV, vp, vp, vp, i32, vp]
         for host in ("", "host_"):

@@ -6,7 +6,10 @@
 #include <cstdio>
 #include <cstring>
 
+#include <vector>
+
 #include "capi_common.h"
+#include "course_index.cuh"
 
 namespace sccav {
 
@@ -136,5 +139,48 @@ int sccav_measure_fma_peak(int32_t dtype, double* tflops_out) {
 }
 
 int64_t sccav_launch_count(void) { return sccav::g_launches.load(); }
+
+}  // extern "C"
+
+namespace sccav {
+template <typename T, typename T2>
+static void debug_course_index(const double* cx, const double* cy, int P, const double* fx, const double* fy,
+                               const int32_t* hint, int64_t nq, int32_t* idx, int32_t* idx_full, int64_t* evals) {
+    std::vector<T2> xy(P);
+    for (int i = 0; i < P; ++i) { xy[i].x = (T)cx[i]; xy[i].y = (T)cy[i]; }
+    const int nleaf = course_nleaf(P), nsup = course_nsup(P);
+    std::vector<T2> lc(nleaf), sc(nsup);
+    std::vector<T> lr(nleaf), sr(nsup);
+    for (int l = 0; l < nleaf; ++l) {
+        int lo = l * SCCAV_LEAF, hi = lo + SCCAV_LEAF < P ? lo + SCCAV_LEAF : P;
+        bounding_circle<T, T2>(xy.data(), lo, hi, lc[l], lr[l]);
+    }
+    for (int q = 0; q < nsup; ++q) {
+        int lo = q * SCCAV_LEAF * SCCAV_SUPER_LEAVES, hi = lo + SCCAV_LEAF * SCCAV_SUPER_LEAVES < P ? lo + SCCAV_LEAF * SCCAV_SUPER_LEAVES : P;
+        bounding_circle<T, T2>(xy.data(), lo, hi, sc[q], sr[q]);
+    }
+    CourseIndex<T, T2> ci;
+    ci.xy = xy.data(); ci.leaf_c = lc.data(); ci.leaf_r = lr.data(); ci.sup_c = sc.data(); ci.sup_r = sr.data();
+    ci.np = P; ci.nleaf = nleaf; ci.nsup = nsup;
+    for (int64_t k = 0; k < nq; ++k) {
+        int ne = 0;
+        idx[k] = course_nearest<T, T2>(ci, (T)fx[k], (T)fy[k], hint ? hint[k] : 0, &ne);
+        if (idx_full) idx_full[k] = course_nearest_full<T, T2>(xy.data(), P, (T)fx[k], (T)fy[k]);
+        if (evals) evals[k] = ne;
+    }
+}
+}  // namespace sccav
+
+extern "C" {
+
+int sccav_debug_course_index_host(const double* cx, const double* cy, int32_t P, const double* fx, const double* fy,
+                                  const int32_t* hint, int64_t nq, int32_t dtype, int32_t* idx_out,
+                                  int32_t* idx_full_out, int64_t* evals_out) {
+    if (!cx || !cy || P < 1 || !fx || !fy || nq < 0 || !idx_out) { sccav::set_error("bad argument"); return SCCAV_EINVAL; }
+    if (dtype == 64) sccav::debug_course_index<double, double2>(cx, cy, P, fx, fy, hint, nq, idx_out, idx_full_out, evals_out);
+    else if (dtype == 32) sccav::debug_course_index<float, float2>(cx, cy, P, fx, fy, hint, nq, idx_out, idx_full_out, evals_out);
+    else { sccav::set_error("dtype must be 32 or 64"); return SCCAV_EINVAL; }
+    return SCCAV_OK;
+}
 
 }  // extern "C"

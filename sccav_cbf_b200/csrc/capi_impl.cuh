@@ -95,8 +95,8 @@ int do_barrier_rows(const sccav_params* p, const uint8_t* slot_desc, int32_t M, 
                     const real* obst, const sccav_pervehicle* pv, real* A, real* b, real* h, cudaStream_t st) {
     int rc = check_common(p, slot_desc, M, N, false);
     if (rc) return rc;
-    if (!state || !obst || !A || !b) { set_error("NULL array argument"); return SCCAV_EINVAL; }
     if (N == 0) return SCCAV_OK;
+    if (!state || !obst || !A || !b) { set_error("NULL array argument"); return SCCAV_EINVAL; }
     RowsArgs<real> a;
     a.P = convert(p); a.sd = make_desc(slot_desc, M); a.M = M; a.N = N;
     a.state = state; a.obst = obst; a.pv = make_pv(pv); a.A = A; a.b = b; a.h = h;
@@ -112,8 +112,8 @@ int do_qp2(const sccav_params* p, int32_t M, int64_t N, const real* A, const rea
     uint8_t dummy[SCCAV_MAX_ROWS] = {0};
     int rc = check_common(p, dummy, M, N, false);
     if (rc) return rc;
-    if (!A || !b || !r || !u) { set_error("NULL array argument"); return SCCAV_EINVAL; }
     if (N == 0) return SCCAV_OK;
+    if (!A || !b || !r || !u) { set_error("NULL array argument"); return SCCAV_EINVAL; }
     QpArgs<real> a;
     a.P = convert(p); a.M = M; a.N = N; a.A = A; a.b = b; a.r = r; a.pv = make_pv(pv);
     a.u = u; a.mask = mask; a.status = status;
@@ -139,8 +139,8 @@ int do_filter_step(const sccav_params* p, const uint8_t* slot_desc, int32_t M, i
     int rc = check_common(p, slot_desc, M, N, false);
     if (rc) return rc;
     if (p->model == SCCAV_MODEL_NONE) { set_error("model NONE has no filter step"); return SCCAV_EINVAL; }
-    if (!state || !obst || !u_ref || !u) { set_error("NULL array argument"); return SCCAV_EINVAL; }
     if (N == 0) return SCCAV_OK;
+    if (!state || !obst || !u_ref || !u) { set_error("NULL array argument"); return SCCAV_EINVAL; }
     FilterArgs<real> a;
     a.P = convert(p); a.sd = make_desc(slot_desc, M); a.M = M; a.N = N;
     a.state = state; a.obst = obst; a.u_ref = u_ref; a.pv = make_pv(pv);
@@ -155,8 +155,8 @@ int do_filter_step(const sccav_params* p, const uint8_t* slot_desc, int32_t M, i
 }
 
 // Launch geometry of the persistent rollout: one vehicle per thread, ONE CTA per SM per wave.
-// For N <= 148*512 the block is sized so that a single balanced wave covers the batch
-// (e.g. N = 65,536 -> 147 CTAs of 448 threads); larger batches run 256-thread CTAs in many waves.
+// For N <= 148*448 the block is sized so that a single balanced wave covers the batch
+// (e.g. N = 65,536 -> 147 CTAs of 448 threads); larger batches run 448-thread CTAs in many waves.
 void rollout_geometry(int64_t N, int& grid, int& block) {
     const int sms = sm_count();
     int64_t per_sm = (N + sms - 1) / sms;
@@ -164,9 +164,32 @@ void rollout_geometry(int64_t N, int& grid, int& block) {
         block = (int)((per_sm + 31) / 32 * 32);
         if (block < 32) block = 32;
     } else {
-        block = 256;
+        block = SCCAV_ROLLOUT_MAXB;               // many waves of full CTAs (144 registers/thread: one CTA per SM)
     }
     grid = (int)((N + block - 1) / block);
+}
+
+// grid / block / dynamic shared memory of a rollout launch; the block is capped by what the
+// kernel's register count allows (cudaFuncGetAttributes), the course goes to shared memory if it fits
+int rollout_launch_shape(int M, int64_t N, int np, bool stan, int& grid, int& block, size_t& smem, bool& course_smem) {
+    rollout_geometry(N, grid, block);
+    cudaFuncAttributes fa;
+    SCCAV_CUDA_CHECK(cudaFuncGetAttributes(&fa, rollout_kernel<real, true>));
+    const int max_block = fa.maxThreadsPerBlock / 32 * 32;
+    if (block > max_block) { block = max_block; grid = (int)((N + block - 1) / block); }
+    const size_t cap = (size_t)max_smem_optin();
+    const RolloutSmem<real> lay(np, true);
+    size_t rows_b = (size_t)3 * (M > 0 ? M : 1) * block * sizeof(real);
+    course_smem = stan && (lay.course_bytes + rows_b <= cap);
+    smem = rows_b + (course_smem ? lay.course_bytes : 0);
+    while (smem > cap && block > 32) {            // huge M * block: shrink the CTA
+        block >>= 1;
+        grid = (int)((N + block - 1) / block);
+        rows_b = (size_t)3 * (M > 0 ? M : 1) * block * sizeof(real);
+        course_smem = stan && (lay.course_bytes + rows_b <= cap);
+        smem = rows_b + (course_smem ? lay.course_bytes : 0);
+    }
+    return SCCAV_OK;
 }
 
 int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N, int32_t T, const real* state,
@@ -175,12 +198,12 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
     int rc = check_common(p, slot_desc, M, N, true);
     if (rc) return rc;
     if (T < 0) { set_error("T < 0"); return SCCAV_EINVAL; }
+    if (p->record_stride < 0) { set_error("record_stride < 0"); return SCCAV_EINVAL; }
+    if (N == 0) return SCCAV_OK;
     if (!state || !out || !out->state) { set_error("state / out->state is NULL"); return SCCAV_EINVAL; }
     if (M > 0 && !obst) { set_error("obst is NULL"); return SCCAV_EINVAL; }
     const bool stan = p->nominal == SCCAV_NOMINAL_STANLEY;
     if (stan && (P < 1 || !cx || !cy || !cyaw)) { set_error("Stanley nominal control needs a course (P >= 1)"); return SCCAV_EINVAL; }
-    if (p->record_stride < 0) { set_error("record_stride < 0"); return SCCAV_EINVAL; }
-    if (N == 0) return SCCAV_OK;
     RolloutArgs<real> a;
     a.P = convert(p); a.sd = make_desc(slot_desc, M); a.M = M; a.N = N; a.T_steps = T; a.np = stan ? P : 0;
     a.state = state; a.obst = obst; a.cx = cx; a.cy = cy; a.cyaw = cyaw; a.pv = make_pv(pv);
@@ -188,30 +211,32 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
     a.o_ninf = out->n_infeasible; a.o_hmin = (real*)out->h_min; a.o_bmin = (real*)out->beta_min;
     a.o_bmax = (real*)out->beta_max; a.o_bint = (real*)out->beta_int; a.o_traj = (real*)out->traj;
     a.o_tridx = out->traj_idx; a.o_trmask = out->traj_mask;
+    a.o_evals = out->n_evals;
     int grid, block;
-    rollout_geometry(N, grid, block);
-    const int np_pad = (a.np + 1) & ~1;
-    size_t rows_b = (size_t)3 * (M > 0 ? M : 1) * block * sizeof(real);
-    size_t course_b = (size_t)3 * np_pad * sizeof(real);
-    const size_t cap = (size_t)max_smem_optin();
-    bool course_smem = stan && (course_b + rows_b <= cap);
-    size_t smem = rows_b + (course_smem ? course_b : 0);
-    while (smem > cap && block > 32) {            // huge M * block: shrink the CTA
-        block >>= 1;
-        grid = (int)((N + block - 1) / block);
-        rows_b = (size_t)3 * (M > 0 ? M : 1) * block * sizeof(real);
-        course_smem = stan && (course_b + rows_b <= cap);
-        smem = rows_b + (course_smem ? course_b : 0);
+    size_t smem;
+    bool course_smem;
+    rc = rollout_launch_shape(M, N, a.np, stan, grid, block, smem, course_smem);
+    if (rc) return rc;
+    // scratch for the loop-invariant terms of static ellipses: stream-ordered, lives for this launch
+    a.pre = nullptr;
+    bool any_ellipse = false;
+    for (int m = 0; m < M; ++m) any_ellipse |= (slot_desc[m] & 0x7f) == SCCAV_SLOT_ELLIPSE;
+    if (any_ellipse && T >= 2 && p->model != SCCAV_MODEL_NONE) {
+        void* scratch = nullptr;
+        SCCAV_CUDA_CHECK(cudaMallocAsync(&scratch, (size_t)M * SCCAV_NPRE * (size_t)N * sizeof(real), st));
+        a.pre = (real*)scratch;
     }
+    cudaError_t le;
     if (course_smem) {
-        SCCAV_CUDA_CHECK(cudaFuncSetAttribute(rollout_kernel<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rollout_kernel<real, true><<<grid, block, smem, st>>>(a);
+        le = cudaFuncSetAttribute(rollout_kernel<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (le == cudaSuccess) { rollout_kernel<real, true><<<grid, block, smem, st>>>(a); le = cudaGetLastError(); }
     } else {
-        SCCAV_CUDA_CHECK(cudaFuncSetAttribute(rollout_kernel<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rollout_kernel<real, false><<<grid, block, smem, st>>>(a);
+        le = cudaFuncSetAttribute(rollout_kernel<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (le == cudaSuccess) { rollout_kernel<real, false><<<grid, block, smem, st>>>(a); le = cudaGetLastError(); }
     }
     count_launch();
-    SCCAV_CUDA_CHECK(cudaGetLastError());
+    if (a.pre) cudaFreeAsync(a.pre, st);
+    SCCAV_CUDA_CHECK(le);
     return SCCAV_OK;
 }
 
@@ -262,6 +287,24 @@ int SCCAV_FN(sccav_rollout_)(const sccav_params* p, const uint8_t* slot_desc, in
                              (cudaStream_t)stream);
 }
 
+int SCCAV_FN(sccav_rollout_launch_info_)(int32_t M, int64_t N, int32_t P, int32_t* info) {
+    using namespace sccav;
+    if (!info || N < 1) { set_error("bad argument"); return SCCAV_EINVAL; }
+    int grid, block;
+    size_t smem;
+    bool course_smem;
+    int rc = rollout_launch_shape(M, N, P, P > 0, grid, block, smem, course_smem);
+    if (rc) return rc;
+    cudaFuncAttributes fa;
+    SCCAV_CUDA_CHECK(cudaFuncGetAttributes(&fa, rollout_kernel<SCCAV_REAL, true>));
+    int occ = 0;
+    SCCAV_CUDA_CHECK(cudaFuncSetAttribute(rollout_kernel<SCCAV_REAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SCCAV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rollout_kernel<SCCAV_REAL, true>, block, smem));
+    info[0] = grid; info[1] = block; info[2] = (int32_t)smem; info[3] = fa.numRegs; info[4] = fa.maxThreadsPerBlock;
+    info[5] = occ; info[6] = course_smem ? 1 : 0; info[7] = sm_count();
+    return SCCAV_OK;
+}
+
 int SCCAV_FN(sccav_filter_step_host_)(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N,
                                       const SCCAV_REAL* state, const SCCAV_REAL* obst, const SCCAV_REAL* u_ref,
                                       const sccav_pervehicle* pv, SCCAV_REAL* u_out, uint32_t* active_out,
@@ -271,8 +314,8 @@ int SCCAV_FN(sccav_filter_step_host_)(const sccav_params* p, const uint8_t* slot
     cudaStream_t st = (cudaStream_t)stream;
     int rc = check_common(p, slot_desc, M, N, false);
     if (rc) return rc;
-    if (!state || !obst || !u_ref || !u_out) { set_error("NULL array argument"); return SCCAV_EINVAL; }
     if (N == 0) return SCCAV_OK;
+    if (!state || !obst || !u_ref || !u_out) { set_error("NULL array argument"); return SCCAV_EINVAL; }
     const size_t n = (size_t)N;
     DevBuf d_state(st), d_obst(st), d_uref(st), d_alpha(st), d_R(st), d_u(st), d_mask(st), d_status(st), d_hmin(st);
     SCCAV_CUDA_CHECK(d_state.upload(state, 4 * n * sizeof(real)));
@@ -305,17 +348,17 @@ int SCCAV_FN(sccav_rollout_host_)(const sccav_params* p, const uint8_t* slot_des
     cudaStream_t st = (cudaStream_t)stream;
     int rc = check_common(p, slot_desc, M, N, true);
     if (rc) return rc;
-    if (!state || !out || !out->state) { set_error("state / out->state is NULL"); return SCCAV_EINVAL; }
-    if (M > 0 && !obst) { set_error("obst is NULL"); return SCCAV_EINVAL; }
     if (T < 0 || p->record_stride < 0) { set_error("T < 0 or record_stride < 0"); return SCCAV_EINVAL; }
     if (N == 0) return SCCAV_OK;
+    if (!state || !out || !out->state) { set_error("state / out->state is NULL"); return SCCAV_EINVAL; }
+    if (M > 0 && !obst) { set_error("obst is NULL"); return SCCAV_EINVAL; }
     const size_t n = (size_t)N;
     const bool stan = p->nominal == SCCAV_NOMINAL_STANLEY;
     if (stan && (P < 1 || !course_x || !course_y || !course_yaw)) { set_error("Stanley nominal control needs a course"); return SCCAV_EINVAL; }
     const size_t trec = p->record_stride > 0 ? ((size_t)T + p->record_stride - 1) / p->record_stride : 0;
     DevBuf d_state(st), d_obst(st), d_cx(st), d_cy(st), d_cyaw(st), d_alpha(st), d_R(st), d_ts(st);
     DevBuf o_state(st), o_steps(st), o_tidx(st), o_nact(st), o_ninf(st), o_hmin(st), o_bmin(st), o_bmax(st), o_bint(st),
-        o_traj(st), o_tridx(st), o_trmask(st);
+        o_traj(st), o_tridx(st), o_trmask(st), o_evals(st);
     SCCAV_CUDA_CHECK(d_state.upload(state, 4 * n * sizeof(real)));
     const size_t obst_b = (size_t)M * SCCAV_NFIELD * n * sizeof(real);
     if (M > 0) SCCAV_CUDA_CHECK(d_obst.upload(obst, obst_b));
@@ -345,6 +388,7 @@ int SCCAV_FN(sccav_rollout_host_)(const sccav_params* p, const uint8_t* slot_des
     SCCAV_OUT(beta_min, o_bmin, n * sizeof(real))
     SCCAV_OUT(beta_max, o_bmax, n * sizeof(real))
     SCCAV_OUT(beta_int, o_bint, n * sizeof(real))
+    SCCAV_OUT(n_evals, o_evals, n * 4)
     if (trec) {
         SCCAV_OUT(traj, o_traj, trec * SCCAV_TRAJ_FIELDS * n * sizeof(real))
         SCCAV_OUT(traj_idx, o_tridx, trec * n * 4)
@@ -369,6 +413,7 @@ int SCCAV_FN(sccav_rollout_host_)(const sccav_params* p, const uint8_t* slot_des
     SCCAV_BACK(beta_min, o_bmin, n * sizeof(real))
     SCCAV_BACK(beta_max, o_bmax, n * sizeof(real))
     SCCAV_BACK(beta_int, o_bint, n * sizeof(real))
+    SCCAV_BACK(n_evals, o_evals, n * 4)
     if (trec) {
         SCCAV_BACK(traj, o_traj, trec * SCCAV_TRAJ_FIELDS * n * sizeof(real))
         SCCAV_BACK(traj_idx, o_tridx, trec * n * 4)

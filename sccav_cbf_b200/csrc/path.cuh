@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/sccav_cbf.h"
+#include "course_index.cuh"
 
 namespace sccav {
 
@@ -34,6 +35,7 @@ template <> struct Real<double> {
     static __device__ __forceinline__ double sqrt_(double x) { return ::sqrt(x); }
     static __device__ __forceinline__ double hypot_(double x, double y) { return ::hypot(x, y); }
     static __device__ __forceinline__ double abs_(double x) { return ::fabs(x); }
+    static __device__ __forceinline__ double rint_(double x) { return ::rint(x); }
     static __device__ __forceinline__ T2 make2(double a, double b) { return make_double2(a, b); }
 };
 
@@ -53,6 +55,7 @@ template <> struct Real<float> {
     static __device__ __forceinline__ float sqrt_(float x) { return ::sqrtf(x); }
     static __device__ __forceinline__ float hypot_(float x, float y) { return ::hypotf(x, y); }
     static __device__ __forceinline__ float abs_(float x) { return ::fabsf(x); }
+    static __device__ __forceinline__ float rint_(float x) { return ::rintf(x); }
     static __device__ __forceinline__ T2 make2(float a, float b) { return make_float2(a, b); }
 };
 
@@ -73,8 +76,11 @@ template <typename T> struct Partials {
 };
 
 // cbf/utils.py:93-106 == stanley_controller_ellipse.py:172-185
+// The reference's loops never terminate for |a| >~ 1e16 or inf; beyond 1e4 (a diverged scenario)
+// whole turns are removed first -- same rule as oracle.normalize_angle.
 template <typename T> __device__ __forceinline__ T normalize_angle(T a) {
     const T pi = Real<T>::pi();
+    if (!(Real<T>::abs_(a) <= T(1e4))) a = a - (T(2.0) * pi) * Real<T>::rint_(a / (T(2.0) * pi));
     while (a > pi) a -= T(2.0) * pi;
     while (a < -pi) a += T(2.0) * pi;
     return a;
@@ -100,6 +106,45 @@ __device__ __forceinline__ Partials<T> ellipse_partials(T x, T y, T cx, T cy, T 
     o.hth = T(0);
     o.hv = T(0);
     o.ht = T(-2) * ((dx / aa) * vx + (dy / bb) * vy);
+    return o;
+}
+
+// Loop-invariant part of ellipse_partials for an obstacle whose fields do not change during a
+// rollout: cos/sin(theta) and the four gradient coefficients (obstacles.py:218,229), computed ONCE
+// with the same operations, so the per-step values below are bit-identical to ellipse_partials.
+#define SCCAV_NPRE 6   // ct, st, 2ct/a^2, -2st/b^2, 2st/a^2, 2ct/b^2
+template <typename T>
+__device__ __forceinline__ void ellipse_precompute(T a, T b, T th, T* pre, int64_t ps) {
+    T st, ct;
+    Real<T>::sincos_(th, &st, &ct);
+    T aa = a * a, bb = b * b;
+    pre[0] = ct;
+    pre[ps] = st;
+    pre[2 * ps] = (T(2) * ct) / aa;
+    pre[3 * ps] = (T(-2) * st) / bb;
+    pre[4 * ps] = (T(2) * st) / aa;
+    pre[5 * ps] = (T(2) * ct) / bb;
+}
+
+template <typename T>
+__device__ __forceinline__ Partials<T> ellipse_partials_pre(T x, T y, T cx, T cy, T a, T b, T vx, T vy,
+                                                            const T* __restrict__ pre, int64_t ps) {
+    Partials<T> o;
+    const T ct = pre[0], st = pre[ps];
+    T dx = x - cx, dy = y - cy;
+    T p = dx * ct + dy * st;
+    T q = (-dx) * st + dy * ct;
+    T pa = p / a, qb = q / b;
+    o.h = (pa * pa + qb * qb) - T(1);
+    o.hx = pre[2 * ps] * p + pre[3 * ps] * q;
+    o.hy = pre[4 * ps] * p + pre[5 * ps] * q;
+    o.hth = T(0);
+    o.hv = T(0);
+    o.ht = T(0);
+    if (vx != T(0) || vy != T(0)) {                       // static obstacle: h_t = -2 (x 0 + y 0) = 0
+        T aa = a * a, bb = b * b;
+        o.ht = T(-2) * ((dx / aa) * vx + (dy / bb) * vy);
+    }
     return o;
 }
 
@@ -237,10 +282,16 @@ __device__ __forceinline__ Partials<T> lane_partials(T x, T y, const T (&c)[6], 
 // dispatch on slot type; fields are read from the SoA obstacle buffer obst[(m*8+f)*N + n]
 template <typename T>
 __device__ __forceinline__ Partials<T> slot_partials(int type, const T* __restrict__ f, int64_t fs,
-                                                     T x, T y, T th, T v, T sth, T cth) {
+                                                     T x, T y, T th, T v, T sth, T cth,
+                                                     const T* __restrict__ pre = nullptr, int64_t ps = 0) {
     // f points at field 0 of this slot for this vehicle; fs = stride between fields (N)
+    // pre (optional): this slot's loop-invariant values for this vehicle, stride ps
     switch (type) {
         case SCCAV_SLOT_ELLIPSE: {
+            if (pre) {
+                T cx = f[0], cy = f[fs], a = f[2 * fs], b = f[3 * fs], vx = f[5 * fs], vy = f[6 * fs];
+                return ellipse_partials_pre<T>(x, y, cx, cy, a, b, vx, vy, pre, ps);
+            }
             T cx = f[0], cy = f[fs], a = f[2 * fs], b = f[3 * fs], t = f[4 * fs], vx = f[5 * fs], vy = f[6 * fs];
             return ellipse_partials<T>(x, y, cx, cy, a, b, t, vx, vy);
         }
@@ -313,16 +364,13 @@ __device__ __forceinline__ bool qp_check(const RowView<T>& rv, int m, T u0, T u1
     return feas;
 }
 
+// the reference point r violates at least one row (worst0 = its largest violation): singles, pairs
 template <typename T>
-__device__ int qp2_solve(const RowView<T>& rv, int m, T r0, T r1, T R00, T R01, T R10, T R11,
-                         T& u0o, T& u1o, uint32_t& masko) {
+__device__ int qp2_solve_active(const RowView<T>& rv, int m, T r0, T r1, T R00, T R01, T R10, T R11, T worst0,
+                                T& u0o, T& u1o, uint32_t& masko) {
     typedef Real<T> R;
     T worst;
-    if (qp_check(rv, m, r0, r1, -1, -1, worst)) {
-        u0o = r0; u1o = r1; masko = 0u;
-        return SCCAV_STATUS_INACTIVE;
-    }
-    T fbw = worst, fb0 = r0, fb1 = r1;
+    T fbw = worst0, fb0 = r0, fb1 = r1;
     uint32_t fbm = 0u;
     const T det = R00 * R11 - R01 * R10;
     const T Ri00 = R11 / det, Ri01 = (-R01) / det, Ri10 = (-R10) / det, Ri11 = R00 / det;
@@ -368,6 +416,17 @@ __device__ int qp2_solve(const RowView<T>& rv, int m, T r0, T r1, T R00, T R01, 
     return SCCAV_STATUS_INFEASIBLE;
 }
 
+template <typename T>
+__device__ __forceinline__ int qp2_solve(const RowView<T>& rv, int m, T r0, T r1, T R00, T R01, T R10, T R11,
+                                         T& u0o, T& u1o, uint32_t& masko) {
+    T worst;
+    if (qp_check(rv, m, r0, r1, -1, -1, worst)) {
+        u0o = r0; u1o = r1; masko = 0u;
+        return SCCAV_STATUS_INACTIVE;
+    }
+    return qp2_solve_active<T>(rv, m, r0, r1, R00, R01, R10, R11, worst, u0o, u1o, masko);
+}
+
 // ------------------------------------------------------------------------------------------
 // one solve_cbf for one vehicle: rows of all slots -> smem -> QP -> converted output
 // (cbf/cbf.py:166-220 for DBM, :67-110 for KBM).  u_ref = (a|v, delta); returns (a|v, delta).
@@ -376,14 +435,23 @@ template <typename T>
 __device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc& sd, int M, int64_t N, int64_t n,
                                               const T* __restrict__ obst, T x, T y, T th, T v, T sth, T cth,
                                               T alpha, T R00, T R01, T R10, T R11, T uref0, T uref1,
-                                              T* rows, int stride, T& u0, T& u1, T& u1raw, uint32_t& mask, T& hmin) {
+                                              T* rows, int stride, T& u0, T& u1, T& u1raw, uint32_t& mask, T& hmin,
+                                              const T* __restrict__ pre = nullptr) {
     typedef Real<T> R;
     hmin = R::inf();
+    T r0 = uref0, r1;
+    if (P.model == SCCAV_MODEL_KBM) r1 = (uref0 * R::tan_(uref1)) / P.L;                // cbf.py:75
+    else r1 = R::atan2_(P.lr * R::tan_(uref1), P.lf + P.lr);                             // cbf.py:175
+    // rows -> shared memory; the feasibility of the reference point (qp_check(r) of qp2_solve) is
+    // evaluated on the fly with the same operations, so an inactive step never re-reads the rows
+    bool feas = true;
+    T worst = -R::inf();
     for (int m = 0; m < M; ++m) {
         const int desc = sd.d[m];
         const int64_t nn = (desc & SCCAV_SLOT_SHARED) ? 0 : n;
         const T* f = obst + (int64_t)m * SCCAV_NFIELD * N + nn;
-        Partials<T> p = slot_partials<T>(desc & 0x7f, f, N, x, y, th, v, sth, cth);
+        const T* pr = pre ? pre + (int64_t)m * SCCAV_NPRE * N + n : nullptr;
+        Partials<T> p = slot_partials<T>(desc & 0x7f, f, N, x, y, th, v, sth, cth, pr, N);
         T A0, A1, b;
         if (P.model == SCCAV_MODEL_KBM) kbm_row<T>(p, sth, cth, alpha, A0, A1, b);
         else dbm_row<T>(p, sth, cth, v, alpha, P.lr, A0, A1, b);
@@ -391,13 +459,19 @@ __device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc
         rows[(3 * m + 1) * stride] = A1;
         rows[(3 * m + 2) * stride] = b;
         if (p.h < hmin) hmin = p.h;
+        T t0 = A0 * r0, t1 = A1 * r1;
+        T rk = (t0 + t1) - b;
+        if (-rk > worst) worst = -rk;
+        T tol = R::feas_eps() * ((R::abs_(t0) + R::abs_(t1)) + R::abs_(b));
+        if (!(rk >= -tol)) feas = false;
     }
-    T r0 = uref0, r1;
-    if (P.model == SCCAV_MODEL_KBM) r1 = (uref0 * R::tan_(uref1)) / P.L;                // cbf.py:75
-    else r1 = R::atan2_(P.lr * R::tan_(uref1), P.lf + P.lr);                             // cbf.py:175
-    RowView<T> rv{rows, stride};
-    T q0, q1;
-    int status = qp2_solve<T>(rv, M, r0, r1, R00, R01, R10, R11, q0, q1, mask);
+    T q0 = r0, q1 = r1;
+    int status = SCCAV_STATUS_INACTIVE;
+    mask = 0u;
+    if (!feas) {
+        RowView<T> rv{rows, stride};
+        status = qp2_solve_active<T>(rv, M, r0, r1, R00, R01, R10, R11, worst, q0, q1, mask);
+    }
     u0 = q0;
     u1raw = q1;
     if (P.model == SCCAV_MODEL_KBM) {
@@ -414,28 +488,11 @@ __device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc
 // The global argmin compares squared distances dx*dx + dy*dy (monotone in np.hypot; first
 // minimum wins, strict <), over ALL P points, like calc_target_index (:202-205).
 // ------------------------------------------------------------------------------------------
+// cross-track error + steering law once the nearest index is known (sce.py:208-212,159-167)
 template <typename T, typename CXY>
-__device__ __forceinline__ int nearest_index(const CXY* __restrict__ cxy, int P, T fx, T fy) {
-    T best = Real<T>::inf();
-    int ib = 0;
-#pragma unroll 8
-    for (int i = 0; i < P; ++i) {
-        CXY c = cxy[i];
-        T dx = fx - c.x, dy = fy - c.y;
-        T d2 = dx * dx + dy * dy;
-        if (d2 < best) { best = d2; ib = i; }
-    }
-    return ib;
-}
-
-template <typename T, typename CXY>
-__device__ __forceinline__ T stanley(const Params<T>& P, const CXY* __restrict__ cxy, const T* __restrict__ cyaw, int np,
-                                     T x, T y, T yaw, T v, T syaw, T cyw, int& target_idx) {
+__device__ __forceinline__ T stanley_law(const Params<T>& P, CXY c, const T* __restrict__ cyaw, int idx,
+                                         T fx, T fy, T yaw, T v, int& target_idx) {
     typedef Real<T> R;
-    T fx = x + P.L * cyw;
-    T fy = y + P.L * syaw;
-    int idx = nearest_index<T, CXY>(cxy, np, fx, fy);
-    CXY c = cxy[idx];
     T s2, c2;
     R::sincos_(yaw + R::pi() / T(2), &s2, &c2);                                          // sce.py:208-209
     T e = (fx - c.x) * (-c2) + (fy - c.y) * (-s2);
@@ -444,6 +501,17 @@ __device__ __forceinline__ T stanley(const Params<T>& P, const CXY* __restrict__
     T theta_d = R::atan2_(P.k_stanley * e, v + P.ks_stanley);
     target_idx = idx;
     return theta_e + theta_d;
+}
+
+// course staged in shared memory with its bounding-circle index: exact pruned nearest search
+template <typename T, typename T2>
+__device__ __forceinline__ T stanley(const Params<T>& P, const CourseIndex<T, T2>& ci, const T* __restrict__ cyaw,
+                                     T x, T y, T yaw, T v, T syaw, T cyw, int& target_idx, int& near_idx, int* evals) {
+    T fx = x + P.L * cyw;
+    T fy = y + P.L * syaw;
+    int idx = course_nearest<T, T2>(ci, fx, fy, near_idx, evals);
+    near_idx = idx;
+    return stanley_law<T, T2>(P, ci.xy[idx], cyaw, idx, fx, fy, yaw, v, target_idx);
 }
 
 }  // namespace sccav

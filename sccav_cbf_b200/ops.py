@@ -156,7 +156,8 @@ def filter_step(params: Params, slot_desc, state: torch.Tensor, obst: torch.Tens
     return u, mask, status, hmin
 
 
-ROLLOUT_SUMMARY = ("steps", "target_idx", "n_active", "n_infeasible", "h_min", "beta_min", "beta_max", "beta_int")
+ROLLOUT_SUMMARY = ("steps", "target_idx", "n_active", "n_infeasible", "h_min", "beta_min", "beta_max", "beta_int",
+                   "n_evals")
 
 
 def rollout(params: Params, slot_desc, state: torch.Tensor, obst: Optional[torch.Tensor], course, T: int,
@@ -217,6 +218,7 @@ def rollout(params: Params, slot_desc, state: torch.Tensor, obst: Optional[torch
         ro.beta_min = buf("beta_min", (N,), dt).data_ptr()
         ro.beta_max = buf("beta_max", (N,), dt).data_ptr()
         ro.beta_int = buf("beta_int", (N,), dt).data_ptr()
+        ro.n_evals = buf("n_evals", (N,), torch.int32).data_ptr()
     if record_stride > 0:
         trec = (T + record_stride - 1) // record_stride
         ro.traj = buf("traj", (trec, nv.TRAJ_FIELDS, N), dt, float("nan")).data_ptr()
@@ -243,3 +245,12 @@ def measure_fma_peak(dtype=torch.float64) -> float:
 
 def launch_count() -> int:
     return int(nv.lib().sccav_launch_count())
+
+
+def rollout_launch_info(M: int, N: int, P: int, dtype=torch.float64) -> Dict[str, int]:
+    """Launch shape of the rollout kernel for (M, N, P) on the current device (no launch)."""
+    L = _need_cuda_lib()
+    info = (C.c_int32 * 8)()
+    nv.check(getattr(L, "sccav_rollout_launch_info_" + _SFX[dtype])(int(M), int(N), int(P), info))
+    keys = ("grid", "block", "smem_bytes", "registers", "max_threads_per_block", "ctas_per_sm", "course_in_smem", "sms")
+    return dict(zip(keys, [int(v) for v in info]))

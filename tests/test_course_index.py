@@ -1,0 +1,108 @@
+"""The rollout kernel's pruned nearest-way-point search (csrc/course_index.cuh) must return exactly
+the index of the reference's exhaustive scan (calc_target_index,
+test_scripts/stanley_controller_ellipse.py:188-212: first minimum over ALL course points).
+
+The search code is __host__ __device__; libsccav_cbf.so exposes it on the CPU through the test hook
+sccav_debug_course_index_host, so this runs without a GPU.  The checker is numpy's argmin of the
+squared distance computed with the same operations (dx*dx + dy*dy, no FMA)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from sccav_cbf_b200 import _native as nv
+from sccav_cbf_b200.course import config1_course, spline_course
+
+
+def run(cx, cy, fx, fy, hint=None, dtype=64):
+    L = nv.lib()
+    cx = np.ascontiguousarray(cx, np.float64); cy = np.ascontiguousarray(cy, np.float64)
+    fx = np.ascontiguousarray(fx, np.float64); fy = np.ascontiguousarray(fy, np.float64)
+    nq = fx.size
+    idx = np.empty(nq, np.int32); full = np.empty(nq, np.int32); ev = np.empty(nq, np.int64)
+    hp = None
+    if hint is not None:
+        hint = np.ascontiguousarray(hint, np.int32)
+        hp = hint.ctypes.data
+    rc = L.sccav_debug_course_index_host(cx.ctypes.data, cy.ctypes.data, len(cx), fx.ctypes.data, fy.ctypes.data, hp, nq,
+                                         dtype, idx.ctypes.data, full.ctypes.data, ev.ctypes.data)
+    assert rc == 0
+    return idx, full, ev
+
+
+def numpy_argmin(cx, cy, fx, fy, dt=np.float64):
+    cx = cx.astype(dt); cy = cy.astype(dt)
+    out = np.empty(fx.size, np.int32)
+    for k in range(fx.size):
+        dx = dt(fx[k]) - cx; dy = dt(fy[k]) - cy
+        out[k] = int(np.argmin(dx * dx + dy * dy))
+    return out
+
+
+def test_pruned_search_equals_exhaustive_scan_on_config1_course():
+    cx, cy, _ = config1_course()
+    rng = np.random.default_rng(5)
+    n = 4000
+    # queries near the course (what a rollout sees), with good, stale and absurd hints
+    base = rng.integers(0, len(cx), n)
+    fx = cx[base] + rng.normal(0, 2.0, n); fy = cy[base] + rng.normal(0, 2.0, n)
+    for hint in (base, np.clip(base - 10, 0, None), rng.integers(0, len(cx), n), np.zeros(n, np.int32),
+                 np.full(n, 10 ** 6, np.int32), np.full(n, -5, np.int32)):
+        idx, full, ev = run(cx, cy, fx, fy, hint)
+        assert np.array_equal(idx, full)
+        assert np.array_equal(idx, numpy_argmin(cx, cy, fx, fy))
+    # with the previous index as hint the search touches a small fraction of the 2034 points
+    idx, full, ev = run(cx, cy, fx, fy, np.clip(idx - 10, 0, None))
+    assert ev.mean() < 150, ev.mean()
+    # far-away and degenerate queries
+    fx = rng.uniform(-500, 500, n); fy = rng.uniform(-500, 500, n)
+    idx, full, _ = run(cx, cy, fx, fy, rng.integers(0, len(cx), n))
+    assert np.array_equal(idx, full) and np.array_equal(idx, numpy_argmin(cx, cy, fx, fy))
+
+
+def test_ties_pick_the_first_minimum():
+    # a course that revisits the same points (figure-of-eight style duplicates) and a circle whose
+    # centre is equidistant from every point: the FIRST minimum must win whatever the hint
+    t = np.linspace(0, 2 * np.pi, 400, endpoint=False)
+    cx = np.concatenate([np.cos(t), np.cos(t), np.cos(t)]) * 8.0
+    cy = np.concatenate([np.sin(t), np.sin(t), np.sin(t)]) * 8.0
+    rng = np.random.default_rng(1)
+    n = 600
+    k = rng.integers(0, len(cx), n)
+    fx = cx[k] * rng.uniform(0.5, 1.5, n); fy = cy[k] * rng.uniform(0.5, 1.5, n)
+    fx[:50] = cx[k[:50]]; fy[:50] = cy[k[:50]]            # exactly on a (triplicated) point
+    fx[50:60] = 0.0; fy[50:60] = 0.0                      # the centre
+    for hint in (k, rng.integers(0, len(cx), n), np.full(n, len(cx) - 1, np.int32)):
+        idx, full, _ = run(cx, cy, fx, fy, hint)
+        assert np.array_equal(idx, full)
+        assert np.array_equal(idx, numpy_argmin(cx, cy, fx, fy))
+    assert (idx[:50] < 400).all()
+
+
+@pytest.mark.parametrize("P", [1, 2, 15, 16, 17, 127, 128, 129, 1000, 5000])
+def test_course_lengths_and_tails(P):
+    rng = np.random.default_rng(P)
+    s = np.linspace(0, 40, P)
+    cx = s * 3.0; cy = 5.0 * np.sin(s / 3.0)
+    n = 500
+    fx = rng.uniform(-10, 130, n); fy = rng.uniform(-12, 12, n)
+    idx, full, _ = run(cx, cy, fx, fy, rng.integers(0, P, n))
+    assert np.array_equal(idx, full) and np.array_equal(idx, numpy_argmin(cx, cy, fx, fy))
+
+
+def test_nan_and_inf_queries_behave_like_argmin():
+    cx, cy, _ = config1_course()
+    fx = np.array([np.nan, 1.0, np.inf, -np.inf, 1e308]); fy = np.array([0.0, np.nan, 0.0, 1.0, 1e308])
+    idx, full, _ = run(cx, cy, fx, fy, np.array([5, 100, 2000, 7, 9], np.int32))
+    assert np.array_equal(idx, full)
+    assert (idx == 0).all()
+
+
+def test_fp32_variant_matches_its_own_exhaustive_scan():
+    cx, cy, _ = spline_course([0.0, 30.0, 60.0, 40.0], [0.0, 10.0, -5.0, -30.0], ds=0.05)
+    rng = np.random.default_rng(11)
+    n = 3000
+    base = rng.integers(0, len(cx), n)
+    fx = cx[base] + rng.normal(0, 1.5, n); fy = cy[base] + rng.normal(0, 1.5, n)
+    idx, full, _ = run(cx, cy, fx, fy, np.clip(base - 8, 0, None), dtype=32)
+    assert np.array_equal(idx, full)
