@@ -143,6 +143,28 @@ int sccav_barrier_rows_f32(const sccav_params* p, const uint8_t* slot_desc, int3
                            const float* state, const float* obst, const sccav_pervehicle* pv,
                            float* A_out, float* b_out, float* h_out, void* stream);
 
+/* K0 -- barrier values and partials only: out dev [M][6][N] = h, h_x, h_y, h_theta, h_v, h_t.
+ * Replaces the per-obstacle getters f/evaluate, dx, dy, dtheta, dv, dt (obstacles.py:183-236,304-317,
+ * 401-458,607-612,681-689) and their stacked ObstacleList2D forms (obstacles.py:879-925). */
+int sccav_barrier_partials_f64(const uint8_t* slot_desc, int32_t M, int64_t N, const double* state,
+                               const double* obst, double* out, void* stream);
+int sccav_barrier_partials_f32(const uint8_t* slot_desc, int32_t M, int64_t N, const float* state,
+                               const float* obst, float* out, void* stream);
+
+/* KS -- one Stanley steering call for N vehicles.  Replaces LateralStanley.control
+ * (controllers.py:104-151) / stanley_control (stanley_controller_ellipse.py:146-169): exact global
+ * nearest way-point (first minimum over all P points), front-axle error, monotone index clamp,
+ * delta = normalize(cyaw[idx] - yaw) + atan2(k e, v + ks).  Uses params L (front-axle offset: L in the
+ * function form, lf in the class form), k_stanley, ks_stanley.  front: dev [2][N] externally supplied
+ * front-axle coordinates (controllers.py:105-110) or NULL.  target_idx: dev [N], in = last target
+ * index, out = new one.  err_out (dev [N]) may be NULL. */
+int sccav_stanley_control_f64(const sccav_params* p, int64_t N, const double* state, const double* front,
+                              const double* course_x, const double* course_y, const double* course_yaw, int32_t P,
+                              int32_t* target_idx, double* delta_out, double* err_out, void* stream);
+int sccav_stanley_control_f32(const sccav_params* p, int64_t N, const float* state, const float* front,
+                              const float* course_x, const float* course_y, const float* course_yaw, int32_t P,
+                              int32_t* target_idx, float* delta_out, float* err_out, void* stream);
+
 /* K2 -- the 2-variable QP  min (u-r)^T R (u-r)  s.t.  A u >= b.
  * Replaces cvxopt.solvers.cp(F) at cbf.py:107,213 (exact KKT optimum instead of an IPM iterate).
  * r: dev [2][N] reference already in QP coordinates (beta / omega).

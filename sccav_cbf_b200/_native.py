@@ -63,6 +63,7 @@ SYMBOLS = [
     "sccav_filter_step_host_f64", "sccav_filter_step_host_f32", "sccav_rollout_host_f64", "sccav_rollout_host_f32",
     "sccav_measure_fma_peak", "sccav_launch_count", "sccav_debug_course_index_host",
     "sccav_rollout_launch_info_f64", "sccav_rollout_launch_info_f32",
+    "sccav_barrier_partials_f64", "sccav_barrier_partials_f32", "sccav_stanley_control_f64", "sccav_stanley_control_f32",
 ]
 
 
@@ -89,6 +90,10 @@ def lib() -> C.CDLL:
     for sfx in ("f64", "f32"):
         f = getattr(L, "sccav_barrier_rows_" + sfx)
         f.argtypes = [PP, C.c_char_p, i32, i64, vp, vp, PV, vp, vp, vp, vp]
+        f = getattr(L, "sccav_barrier_partials_" + sfx)
+        f.argtypes = [C.c_char_p, i32, i64, vp, vp, vp, vp]
+        f = getattr(L, "sccav_stanley_control_" + sfx)
+        f.argtypes = [PP, i64, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]
         f = getattr(L, "sccav_rollout_launch_info_" + sfx)
         f.argtypes = [i32, i64, i32, vp]
         f = getattr(L, "sccav_qp2_solve_" + sfx)

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 
+#include <algorithm>
 #include <vector>
 
 #include "capi_common.h"
@@ -146,22 +147,27 @@ namespace sccav {
 template <typename T, typename T2>
 static void debug_course_index(const double* cx, const double* cy, int P, const double* fx, const double* fy,
                                const int32_t* hint, int64_t nq, int32_t* idx, int32_t* idx_full, int64_t* evals) {
-    std::vector<T2> xy(P);
-    for (int i = 0; i < P; ++i) { xy[i].x = (T)cx[i]; xy[i].y = (T)cy[i]; }
+    std::vector<T2> xy(course_nslot(P));
+    T ext = T(0);
+    for (int i = 0; i < P; ++i) {
+        xy[course_slot(i)].x = (T)cx[i]; xy[course_slot(i)].y = (T)cy[i];
+        ext = std::max(ext, std::max((T)fabs((T)cx[i]), (T)fabs((T)cy[i])));
+    }
     const int nleaf = course_nleaf(P), nsup = course_nsup(P);
-    std::vector<T2> lc(nleaf), sc(nsup);
-    std::vector<T> lr(nleaf), sr(nsup);
+    std::vector<T2> lc(3 * nleaf), sc(3 * nsup);
+    CourseIndex<T, T2> ci;
+    ci.xy = xy.data();
+    ci.np = P; ci.nleaf = nleaf; ci.nsup = nsup;
+    ci.leaf.a = lc.data(); ci.leaf.ab = lc.data() + nleaf; ci.leaf.ir = lc.data() + 2 * nleaf;
+    ci.sup.a = sc.data(); ci.sup.ab = sc.data() + nsup; ci.sup.ir = sc.data() + 2 * nsup;
     for (int l = 0; l < nleaf; ++l) {
         int lo = l * SCCAV_LEAF, hi = lo + SCCAV_LEAF < P ? lo + SCCAV_LEAF : P;
-        bounding_circle<T, T2>(xy.data(), lo, hi, lc[l], lr[l]);
+        capsule_build<T, T2>(xy.data(), lo, hi, ext, ci.leaf.a[l], ci.leaf.ab[l], ci.leaf.ir[l]);
     }
     for (int q = 0; q < nsup; ++q) {
         int lo = q * SCCAV_LEAF * SCCAV_SUPER_LEAVES, hi = lo + SCCAV_LEAF * SCCAV_SUPER_LEAVES < P ? lo + SCCAV_LEAF * SCCAV_SUPER_LEAVES : P;
-        bounding_circle<T, T2>(xy.data(), lo, hi, sc[q], sr[q]);
+        capsule_build<T, T2>(xy.data(), lo, hi, ext, ci.sup.a[q], ci.sup.ab[q], ci.sup.ir[q]);
     }
-    CourseIndex<T, T2> ci;
-    ci.xy = xy.data(); ci.leaf_c = lc.data(); ci.leaf_r = lr.data(); ci.sup_c = sc.data(); ci.sup_r = sr.data();
-    ci.np = P; ci.nleaf = nleaf; ci.nsup = nsup;
     for (int64_t k = 0; k < nq; ++k) {
         int ne = 0;
         idx[k] = course_nearest<T, T2>(ci, (T)fx[k], (T)fy[k], hint ? hint[k] : 0, &ne);

@@ -107,6 +107,46 @@ int do_barrier_rows(const sccav_params* p, const uint8_t* slot_desc, int32_t M, 
     return SCCAV_OK;
 }
 
+int do_barrier_partials(const uint8_t* slot_desc, int32_t M, int64_t N, const real* state, const real* obst, real* out,
+                        cudaStream_t st) {
+    sccav_params dp;
+    sccav_default_params(&dp);
+    int rc = check_common(&dp, slot_desc, M, N, false);
+    if (rc) return rc;
+    if (N == 0) return SCCAV_OK;
+    if (!state || !obst || !out) { set_error("NULL array argument"); return SCCAV_EINVAL; }
+    PartialsArgs<real> a;
+    a.sd = make_desc(slot_desc, M); a.M = M; a.N = N; a.state = state; a.obst = obst; a.out = out;
+    const int block = 256;
+    barrier_partials_kernel<real><<<stream_grid(N, block), block, 0, st>>>(a);
+    count_launch();
+    SCCAV_CUDA_CHECK(cudaGetLastError());
+    return SCCAV_OK;
+}
+
+int do_stanley(const sccav_params* p, int64_t N, const real* state, const real* front, const real* cx, const real* cy,
+               const real* cyaw, int32_t P, int32_t* target_idx, real* delta, real* err, cudaStream_t st) {
+    if (!p) { set_error("params is NULL"); return SCCAV_EINVAL; }
+    if (N < 0) { set_error("N < 0"); return SCCAV_EINVAL; }
+    if (P < 1 || !cx || !cy || !cyaw) { set_error("Stanley control needs a trajectory (P >= 1)"); return SCCAV_EINVAL; }
+    if (N == 0) return SCCAV_OK;
+    if (!state || !target_idx || !delta) { set_error("NULL array argument"); return SCCAV_EINVAL; }
+    const RolloutSmem<real> lay(P, true);
+    const int block = 256;
+    size_t smem = lay.off_cyaw + (size_t)block * sizeof(real);
+    if (smem > (size_t)max_smem_optin()) { set_error("trajectory of %d points does not fit in shared memory", P); return SCCAV_EINVAL; }
+    StanleyArgs<real> a;
+    a.P = convert(p); a.N = N; a.np = P; a.state = state; a.front = front; a.cx = cx; a.cy = cy; a.cyaw = cyaw;
+    a.target_idx = target_idx; a.delta = delta; a.err = err;
+    int64_t need = (N + block - 1) / block;
+    int64_t cap = (int64_t)sm_count() * 4;
+    SCCAV_CUDA_CHECK(cudaFuncSetAttribute(stanley_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stanley_kernel<real><<<(int)(need < cap ? need : cap), block, smem, st>>>(a);
+    count_launch();
+    SCCAV_CUDA_CHECK(cudaGetLastError());
+    return SCCAV_OK;
+}
+
 int do_qp2(const sccav_params* p, int32_t M, int64_t N, const real* A, const real* b, const real* r,
            const sccav_pervehicle* pv, real* u, uint32_t* mask, uint8_t* status, int warp, cudaStream_t st) {
     uint8_t dummy[SCCAV_MAX_ROWS] = {0};
@@ -263,6 +303,18 @@ int SCCAV_FN(sccav_barrier_rows_)(const sccav_params* p, const uint8_t* slot_des
                                   const SCCAV_REAL* state, const SCCAV_REAL* obst, const sccav_pervehicle* pv,
                                   SCCAV_REAL* A_out, SCCAV_REAL* b_out, SCCAV_REAL* h_out, void* stream) {
     return sccav::do_barrier_rows(p, slot_desc, M, N, state, obst, pv, A_out, b_out, h_out, (cudaStream_t)stream);
+}
+
+int SCCAV_FN(sccav_barrier_partials_)(const uint8_t* slot_desc, int32_t M, int64_t N, const SCCAV_REAL* state,
+                                      const SCCAV_REAL* obst, SCCAV_REAL* out, void* stream) {
+    return sccav::do_barrier_partials(slot_desc, M, N, state, obst, out, (cudaStream_t)stream);
+}
+
+int SCCAV_FN(sccav_stanley_control_)(const sccav_params* p, int64_t N, const SCCAV_REAL* state, const SCCAV_REAL* front,
+                                     const SCCAV_REAL* course_x, const SCCAV_REAL* course_y, const SCCAV_REAL* course_yaw,
+                                     int32_t P, int32_t* target_idx, SCCAV_REAL* delta_out, SCCAV_REAL* err_out, void* stream) {
+    return sccav::do_stanley(p, N, state, front, course_x, course_y, course_yaw, P, target_idx, delta_out, err_out,
+                             (cudaStream_t)stream);
 }
 
 int SCCAV_FN(sccav_qp2_solve_)(const sccav_params* p, int32_t M, int64_t N, const SCCAV_REAL* A, const SCCAV_REAL* b,

@@ -68,6 +68,37 @@ __global__ void __launch_bounds__(256) barrier_rows_kernel(const __grid_constant
     }
 }
 
+// ------------------------------------------------------------------------------------------ K0
+// Barrier values and partials only (what the obstacle objects of the class API return):
+// out[m][6][N] = h, h_x, h_y, h_theta, h_v, h_t   -- ObstacleList2D.f/dx/dy/dtheta/dv/dt
+template <typename T> struct PartialsArgs {
+    SlotDesc sd;
+    int M;
+    int64_t N;
+    const T* state;
+    const T* obst;
+    T* out;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) barrier_partials_kernel(const __grid_constant__ PartialsArgs<T> a) {
+    typedef Real<T> R;
+    const int64_t N = a.N;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        T x = a.state[n], y = a.state[N + n], th = a.state[2 * N + n], v = a.state[3 * N + n];
+        T sth, cth;
+        R::sincos_(th, &sth, &cth);
+        for (int m = 0; m < a.M; ++m) {
+            const int desc = a.sd.d[m];
+            const int64_t nn = (desc & SCCAV_SLOT_SHARED) ? 0 : n;
+            const T* f = a.obst + (int64_t)m * SCCAV_NFIELD * N + nn;
+            Partials<T> p = slot_partials<T>(desc & 0x7f, f, N, x, y, th, v, sth, cth);
+            T* o = a.out + (int64_t)m * 6 * N + n;
+            o[0] = p.h; o[N] = p.hx; o[2 * N] = p.hy; o[3 * N] = p.hth; o[4 * N] = p.hv; o[5 * N] = p.ht;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ K2
 template <typename T> struct QpArgs {
     Params<T> P;
@@ -302,21 +333,20 @@ __device__ __forceinline__ void seeker_update(T* f, int64_t fs, T ex, T ey, T dt
 #define SCCAV_ROLLOUT_MAXB 448
 
 // Shared-memory layout of the rollout kernel (bytes), shared by the launcher and the kernel:
-//   [ course xy : T2 x np_pad ][ cyaw : T x np_pad ][ leaf_c : T2 x nleaf_pad ][ sup_c : T2 x nsup_pad ]
-//   [ leaf_r : T x nleaf_pad ][ sup_r : T x nsup_pad ][ rows : T x 3 M block ]
+//   [ course xy : T2 x nslot (leaf-padded) ][ leaf capsules : 3 x T2 x nleaf ][ super capsules : 3 x T2 x nsup ]
+//   [ cyaw : T x np_pad ][ rows : T x 3 M block ]
 template <typename T> struct RolloutSmem {
-    int np_pad, nleaf_pad, nsup_pad;
-    size_t off_cyaw, off_leafc, off_supc, off_leafr, off_supr, off_rows, course_bytes;
+    int nslot, nleaf, nsup, np_pad;
+    size_t off_leaf, off_sup, off_cyaw, off_rows, course_bytes;
     __host__ __device__ RolloutSmem(int np, bool course_smem) {
+        nslot = course_smem ? course_nslot(np) : 0;
+        nleaf = course_smem ? course_nleaf(np) : 0;
+        nsup = course_smem ? course_nsup(np) : 0;
         np_pad = course_smem ? ((np + 1) & ~1) : 0;
-        nleaf_pad = course_smem ? ((course_nleaf(np) + 1) & ~1) : 0;
-        nsup_pad = course_smem ? ((course_nsup(np) + 1) & ~1) : 0;
-        size_t o = (size_t)np_pad * 2 * sizeof(T);
-        off_cyaw = o;  o += (size_t)np_pad * sizeof(T);
-        off_leafc = o; o += (size_t)nleaf_pad * 2 * sizeof(T);
-        off_supc = o;  o += (size_t)nsup_pad * 2 * sizeof(T);
-        off_leafr = o; o += (size_t)nleaf_pad * sizeof(T);
-        off_supr = o;  o += (size_t)nsup_pad * sizeof(T);
+        size_t o = (size_t)nslot * 2 * sizeof(T);
+        off_leaf = o; o += (size_t)nleaf * 6 * sizeof(T);
+        off_sup = o;  o += (size_t)nsup * 6 * sizeof(T);
+        off_cyaw = o; o += (size_t)np_pad * sizeof(T);
         off_rows = o;
         course_bytes = o;
     }
@@ -330,31 +360,40 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
     const int np = a.np;
     const RolloutSmem<T> lay(np, COURSE_SMEM);
     T2* s_cxy = reinterpret_cast<T2*>(smem_raw);
+    T2* s_leaf = reinterpret_cast<T2*>(smem_raw + lay.off_leaf);
+    T2* s_sup = reinterpret_cast<T2*>(smem_raw + lay.off_sup);
     T* s_cyaw = reinterpret_cast<T*>(smem_raw + lay.off_cyaw);
-    T2* s_leafc = reinterpret_cast<T2*>(smem_raw + lay.off_leafc);
-    T2* s_supc = reinterpret_cast<T2*>(smem_raw + lay.off_supc);
-    T* s_leafr = reinterpret_cast<T*>(smem_raw + lay.off_leafr);
-    T* s_supr = reinterpret_cast<T*>(smem_raw + lay.off_supr);
     T* rows = reinterpret_cast<T*>(smem_raw + lay.off_rows) + threadIdx.x;
     const int stride = blockDim.x;
     const bool stan = a.P.nominal == SCCAV_NOMINAL_STANLEY;
     CourseIndex<T, T2> ci;
-    ci.xy = s_cxy; ci.leaf_c = s_leafc; ci.leaf_r = s_leafr; ci.sup_c = s_supc; ci.sup_r = s_supr;
-    ci.np = np; ci.nleaf = course_nleaf(np); ci.nsup = course_nsup(np);
+    ci.xy = s_cxy;
+    ci.np = np; ci.nleaf = lay.nleaf; ci.nsup = lay.nsup;
+    ci.leaf.a = s_leaf; ci.leaf.ab = s_leaf + lay.nleaf; ci.leaf.ir = s_leaf + 2 * lay.nleaf;
+    ci.sup.a = s_sup; ci.sup.ab = s_sup + lay.nsup; ci.sup.ir = s_sup + 2 * lay.nsup;
     if (COURSE_SMEM && stan) {
-        // stage the course once per CTA, then build the bounding circles of its leaves / supers
+        // stage the course once per CTA (leaf-padded), then build the capsules of its leaves / supers
+        T ext = T(0);
         for (int i = threadIdx.x; i < np; i += blockDim.x) {
-            s_cxy[i] = R::make2(a.cx[i], a.cy[i]);
+            T px = a.cx[i], py = a.cy[i];
+            s_cxy[course_slot(i)] = R::make2(px, py);
             s_cyaw[i] = a.cyaw[i];
+            ext = fmax(ext, fmax(R::abs_(px), R::abs_(py)));
         }
+        // course extent (absolute slack of the capsule radii): CTA-wide max through shared memory
+        T* s_ext = reinterpret_cast<T*>(smem_raw + lay.off_rows);
+        s_ext[threadIdx.x] = ext;
         __syncthreads();
-        for (int l = threadIdx.x; l < ci.nleaf; l += blockDim.x) {
+        ext = T(0);
+        for (int i = 0; i < (int)blockDim.x; ++i) ext = fmax(ext, s_ext[i]);
+        __syncthreads();
+        for (int l = threadIdx.x; l < lay.nleaf; l += blockDim.x) {
             const int lo = l * SCCAV_LEAF, hi = min(np, lo + SCCAV_LEAF);
-            bounding_circle<T, T2>(s_cxy, lo, hi, s_leafc[l], s_leafr[l]);
+            capsule_build<T, T2>(s_cxy, lo, hi, ext, ci.leaf.a[l], ci.leaf.ab[l], ci.leaf.ir[l]);
         }
-        for (int q = threadIdx.x; q < ci.nsup; q += blockDim.x) {
+        for (int q = threadIdx.x; q < lay.nsup; q += blockDim.x) {
             const int lo = q * SCCAV_LEAF * SCCAV_SUPER_LEAVES, hi = min(np, lo + SCCAV_LEAF * SCCAV_SUPER_LEAVES);
-            bounding_circle<T, T2>(s_cxy, lo, hi, s_supc[q], s_supr[q]);
+            capsule_build<T, T2>(s_cxy, lo, hi, ext, ci.sup.a[q], ci.sup.ab[q], ci.sup.ir[q]);
         }
         __syncthreads();
     }
@@ -499,6 +538,87 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
     if (a.o_bmax) a.o_bmax[n] = bmax;
     if (a.o_bint) a.o_bint[n] = bint;
     if (a.o_evals) a.o_evals[n] = evals;
+}
+
+// ------------------------------------------------------------------------------------------ KS
+// One Stanley control call for N vehicles (LateralStanley.control, cbf/controllers.py:104-151 ==
+// stanley_control, stanley_controller_ellipse.py:146-169): nearest way-point (exact pruned search
+// from the previous target index), front-axle error, monotone index clamp, steering law.
+template <typename T> struct StanleyArgs {
+    Params<T> P;          // L (front-axle offset), k_stanley, ks_stanley
+    int64_t N;
+    int np;
+    const T* state;       // [4][N]
+    const T* front;       // [2][N] externally supplied front-axle coordinates, or NULL
+    const T* cx;
+    const T* cy;
+    const T* cyaw;
+    int32_t* target_idx;  // [N] in: last target index, out: new one
+    T* delta;             // [N]
+    T* err;               // [N] front-axle cross-track error (may be NULL)
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) stanley_kernel(const __grid_constant__ StanleyArgs<T> a) {
+    typedef Real<T> R;
+    typedef typename R::T2 T2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int np = a.np;
+    const RolloutSmem<T> lay(np, true);
+    T2* s_cxy = reinterpret_cast<T2*>(smem_raw);
+    T2* s_leaf = reinterpret_cast<T2*>(smem_raw + lay.off_leaf);
+    T2* s_sup = reinterpret_cast<T2*>(smem_raw + lay.off_sup);
+    T* s_ext = reinterpret_cast<T*>(smem_raw + lay.off_cyaw);      // scratch during the build only
+    CourseIndex<T, T2> ci;
+    ci.xy = s_cxy;
+    ci.np = np; ci.nleaf = lay.nleaf; ci.nsup = lay.nsup;
+    ci.leaf.a = s_leaf; ci.leaf.ab = s_leaf + lay.nleaf; ci.leaf.ir = s_leaf + 2 * lay.nleaf;
+    ci.sup.a = s_sup; ci.sup.ab = s_sup + lay.nsup; ci.sup.ir = s_sup + 2 * lay.nsup;
+    T ext = T(0);
+    for (int i = threadIdx.x; i < np; i += blockDim.x) {
+        T px = a.cx[i], py = a.cy[i];
+        s_cxy[course_slot(i)] = R::make2(px, py);
+        ext = fmax(ext, fmax(R::abs_(px), R::abs_(py)));
+    }
+    s_ext[threadIdx.x] = ext;
+    __syncthreads();
+    ext = T(0);
+    for (int i = 0; i < (int)blockDim.x; ++i) ext = fmax(ext, s_ext[i]);
+    __syncthreads();
+    for (int l = threadIdx.x; l < lay.nleaf; l += blockDim.x) {
+        const int lo = l * SCCAV_LEAF, hi = min(np, lo + SCCAV_LEAF);
+        capsule_build<T, T2>(s_cxy, lo, hi, ext, ci.leaf.a[l], ci.leaf.ab[l], ci.leaf.ir[l]);
+    }
+    for (int q = threadIdx.x; q < lay.nsup; q += blockDim.x) {
+        const int lo = q * SCCAV_LEAF * SCCAV_SUPER_LEAVES, hi = min(np, lo + SCCAV_LEAF * SCCAV_SUPER_LEAVES);
+        capsule_build<T, T2>(s_cxy, lo, hi, ext, ci.sup.a[q], ci.sup.ab[q], ci.sup.ir[q]);
+    }
+    __syncthreads();
+    const int64_t N = a.N;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        T x = a.state[n], y = a.state[N + n], yaw = a.state[2 * N + n], v = a.state[3 * N + n];
+        T fx, fy;
+        if (a.front) { fx = a.front[n]; fy = a.front[N + n]; }           // controllers.py:105-110
+        else {
+            T syaw, cyw;
+            R::sincos_(yaw, &syaw, &cyw);
+            fx = x + a.P.L * cyw;
+            fy = y + a.P.L * syaw;
+        }
+        int tidx = a.target_idx[n];
+        const int idx = course_nearest<T, T2>(ci, fx, fy, tidx, nullptr);
+        T2 c = ci.pt(idx);
+        T s2, c2;
+        R::sincos_(yaw + R::pi() / T(2), &s2, &c2);
+        T e = (fx - c.x) * (-c2) + (fy - c.y) * (-s2);
+        int use = idx;
+        if (tidx >= idx) use = tidx;
+        T theta_e = normalize_angle<T>(a.cyaw[use] - yaw);
+        T theta_d = R::atan2_(a.P.k_stanley * e, v + a.P.ks_stanley);
+        a.delta[n] = theta_e + theta_d;
+        a.target_idx[n] = use;
+        if (a.err) a.err[n] = e;
+    }
 }
 
 }  // namespace sccav

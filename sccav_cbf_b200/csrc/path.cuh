@@ -128,7 +128,7 @@ __device__ __forceinline__ void ellipse_precompute(T a, T b, T th, T* pre, int64
 
 template <typename T>
 __device__ __forceinline__ Partials<T> ellipse_partials_pre(T x, T y, T cx, T cy, T a, T b, T vx, T vy,
-                                                            const T* __restrict__ pre, int64_t ps) {
+                                                            const T* pre, int64_t ps) {
     Partials<T> o;
     const T ct = pre[0], st = pre[ps];
     T dx = x - cx, dy = y - cy;
@@ -283,7 +283,7 @@ __device__ __forceinline__ Partials<T> lane_partials(T x, T y, const T (&c)[6], 
 template <typename T>
 __device__ __forceinline__ Partials<T> slot_partials(int type, const T* __restrict__ f, int64_t fs,
                                                      T x, T y, T th, T v, T sth, T cth,
-                                                     const T* __restrict__ pre = nullptr, int64_t ps = 0) {
+                                                     const T* pre = nullptr, int64_t ps = 0) {
     // f points at field 0 of this slot for this vehicle; fs = stride between fields (N)
     // pre (optional): this slot's loop-invariant values for this vehicle, stride ps
     switch (type) {
@@ -436,7 +436,7 @@ __device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc
                                               const T* __restrict__ obst, T x, T y, T th, T v, T sth, T cth,
                                               T alpha, T R00, T R01, T R10, T R11, T uref0, T uref1,
                                               T* rows, int stride, T& u0, T& u1, T& u1raw, uint32_t& mask, T& hmin,
-                                              const T* __restrict__ pre = nullptr) {
+                                              const T* pre = nullptr) {
     typedef Real<T> R;
     hmin = R::inf();
     T r0 = uref0, r1;
@@ -511,7 +511,7 @@ __device__ __forceinline__ T stanley(const Params<T>& P, const CourseIndex<T, T2
     T fy = y + P.L * syaw;
     int idx = course_nearest<T, T2>(ci, fx, fy, near_idx, evals);
     near_idx = idx;
-    return stanley_law<T, T2>(P, ci.xy[idx], cyaw, idx, fx, fy, yaw, v, target_idx);
+    return stanley_law<T, T2>(P, ci.pt(idx), cyaw, idx, fx, fy, yaw, v, target_idx);
 }
 
 }  // namespace sccav

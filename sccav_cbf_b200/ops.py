@@ -103,6 +103,50 @@ def barrier_rows(params: Params, slot_desc, state: torch.Tensor, obst: torch.Ten
     return A, b, h
 
 
+def barrier_partials(slot_desc, state: torch.Tensor, obst: torch.Tensor) -> torch.Tensor:
+    """K0: barrier values and partials [M, 6, N] = (h, h_x, h_y, h_theta, h_v, h_t) per slot --
+    the obstacle getters f/dx/dy/dtheta/dv/dt of cbf/obstacles.py."""
+    L = _need_cuda_lib()
+    sd = slot_bytes(slot_desc)
+    M, N = len(sd), state.shape[-1]
+    dt, dev = state.dtype, state.device
+    if not state.is_cuda:
+        raise ValueError("barrier_partials takes CUDA tensors")
+    state = _chk(state, (4, N), dt, dev, "state")
+    obst = _chk(obst, (M, nv.NFIELD, N), dt, dev, "obst")
+    out = torch.empty((M, 6, N), dtype=dt, device=dev)
+    with torch.cuda.device(dev):
+        nv.check(getattr(L, "sccav_barrier_partials_" + _SFX[dt])(sd, M, N, _ptr(state), _ptr(obst), _ptr(out), _stream(dev)))
+    return out
+
+
+def stanley_control(params: Params, state: torch.Tensor, course, target_idx: torch.Tensor,
+                    front: Optional[torch.Tensor] = None, want_error: bool = False):
+    """KS: one Stanley steering call (LateralStanley.control / stanley_control).  ``target_idx``
+    (int32 [N]) is updated IN PLACE to the new target index.  Returns delta [N] (and the
+    front-axle error [N] with ``want_error``)."""
+    L = _need_cuda_lib()
+    N = state.shape[-1]
+    dt, dev = state.dtype, state.device
+    if not state.is_cuda:
+        raise ValueError("stanley_control takes CUDA tensors")
+    state = _chk(state, (4, N), dt, dev, "state")
+    cx, cy, cyaw = course
+    P = cx.shape[0]
+    cx = _chk(cx, (P,), dt, dev, "course_x"); cy = _chk(cy, (P,), dt, dev, "course_y"); cyaw = _chk(cyaw, (P,), dt, dev, "course_yaw")
+    if target_idx.dtype != torch.int32 or tuple(target_idx.shape) != (N,) or target_idx.device != dev or not target_idx.is_contiguous():
+        raise ValueError("target_idx must be a contiguous int32 [N] tensor on the state's device")
+    if front is not None:
+        front = _chk(front, (2, N), dt, dev, "front")
+    delta = torch.empty((N,), dtype=dt, device=dev)
+    err = torch.empty((N,), dtype=dt, device=dev) if want_error else None
+    with torch.cuda.device(dev):
+        nv.check(getattr(L, "sccav_stanley_control_" + _SFX[dt])(
+            C.byref(params), N, _ptr(state), _ptr(front), _ptr(cx), _ptr(cy), _ptr(cyaw), P, _ptr(target_idx), _ptr(delta),
+            _ptr(err), _stream(dev)))
+    return (delta, err) if want_error else delta
+
+
 def qp2_solve(params: Params, A: torch.Tensor, b: torch.Tensor, r: torch.Tensor, R=None, warp_per_problem=False):
     """K2: exact optimum of min (u-r)^T R (u-r) s.t. A u >= b (what cvxopt.solvers.cp approximates
     at cbf/cbf.py:213).  Returns u [2,N], active mask int32 [N] (bit k = row k), status uint8 [N]."""

@@ -88,5 +88,48 @@ def report(path):
                     print("%-86s %-12s %s" % (h, u, v))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and sys.argv[1] in ("launches", "report"):
     {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
+
+
+def source(path, top=45):
+    """Hot source lines (needs -lineinfo): samples, executed warp instructions, thread efficiency."""
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "cuda,sass"],
+                         capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    cur = None
+    recs = []
+    hdr = None
+    for r in rows:
+        if not r:
+            continue
+        if r[0] == "File Path":
+            cur = r[1].split("/")[-1]
+            continue
+        if r[0] == "Line No":
+            hdr = r
+            continue
+        if hdr is None or cur is None or r[0] in ("Function Name", "Kernel Name") or not r[0].isdigit():
+            continue
+        d = dict(zip(hdr, r))
+        recs.append((cur, int(r[0]), r[1].strip()[:90], int(d["# Samples"] or 0), int(d["Instructions Executed"] or 0),
+                     int(d["Thread Instructions Executed"] or 0), int(d["L1 Wavefronts Shared"] or 0),
+                     int(d["stall_no_inst"] or 0), int(d["stall_wait"] or 0), int(d["stall_short_sb"] or 0), int(d["stall_long_sb"] or 0)))
+    ts = sum(x[3] for x in recs) or 1
+    ti = sum(x[4] for x in recs) or 1
+    print("# ncu source page, hottest CUDA source lines of %s" % path)
+    print("# total samples %d, executed warp instructions %d" % (ts, ti))
+    byfile = defaultdict(lambda: [0, 0])
+    for x in recs:
+        byfile[x[0]][0] += x[3]
+        byfile[x[0]][1] += x[4]
+    for f, v in sorted(byfile.items(), key=lambda kv: -kv[1][0]):
+        print("  file %-28s samples %5.1f%%  warp-inst %5.1f%%" % (f, 100 * v[0] / ts, 100 * v[1] / ti))
+    print("%-22s %6s %6s %5s %9s %6s %6s %6s %6s  %s" % ("file:line", "samp%", "inst%", "thr/w", "smem_wf", "noinst", "wait", "shortsb", "longsb", "source"))
+    for x in sorted(recs, key=lambda x: -x[3])[:top]:
+        eff = x[5] / x[4] if x[4] else 0
+        print("%-22s %6.2f %6.2f %5.1f %9d %6d %6d %6d %6d  %s" % ("%s:%d" % (x[0], x[1]), 100 * x[3] / ts, 100 * x[4] / ti, eff, x[6], x[7], x[8], x[9], x[10], x[2]))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "source":
+    source(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 45)
