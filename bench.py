@@ -15,8 +15,12 @@ One JSON line on stdout (rank 0):
   value   whole-job solves/s with inputs resident in HBM (CUDA events around each rollout launch)
   e2e     the same metric through ClosedLoopRollout.run_from_host(): pinned host inputs -> H2D ->
           kernel -> D2H of the per-vehicle results, every step
-  roofline            the rollout kernel against the MEASURED fp64 FMA peak of this GPU
-                      (the path is fp64-pipe bound in persistent form, SURVEY 8d regime ii)
+  roofline            the rollout kernel against the MEASURED fp64 FMA peak of this GPU (persistent
+                      form: state in registers, ~0.07 B/solve of DRAM traffic -- neither HBM- nor
+                      tensor-bound, SURVEY 8d regime ii).  Algorithmic flops are those of the algorithm
+                      as implemented: 7 per way-point distance evaluation /
+                      capsule test actually made (counted by the kernel, n_evals) + 34 M + 27 per
+                      vehicle-step; the 9 transcendental calls per vehicle-step are listed, not counted
   roofline_operator   the per-timestep fused filter kernel (K1+K2) against the measured HBM peak
                       (regime i, 64.6 B/solve)
   cpu_baseline        oracle/oracle.c ("port"; the reference itself cannot run here: no cvxopt)
@@ -42,10 +46,21 @@ UNIT = "solves/s"
 P_COURSE = 2034
 
 
-def algorithmic_flops_per_solve(P: int, M: int) -> float:
-    """SURVEY 8(d) regime ii: F = 49 + (7 P + 25) / M fp64 flop per solve (rows + minimal QP per
-    solve; Stanley argmin 7 flop per way-point + integrator per vehicle-step, amortised over M)."""
+def exhaustive_flops_per_solve(P: int, M: int) -> float:
+    """SURVEY 8(d) regime ii for the REFERENCE's algorithm (exhaustive argmin over all P way-points):
+    F = 49 + (7 P + 25) / M fp64 flop per solve.  Reported for continuity only."""
     return 49.0 + (7.0 * P + 25.0) / M
+
+
+FLOP_PER_EVAL = 7.0            # dx, dy, dx*dx, dy*dy, +, compare (+1); capsule tests are counted at the same rate
+FLOP_PER_ROW = 34.0            # static ellipse row with hoisted coefficients (29) + reference-point feasibility test (5)
+FLOP_PER_VEHICLE_STEP = 27.0   # P speed loop 2 + Stanley law 8 + update_com plant 17
+TRANSCENDENTALS_PER_VEHICLE_STEP = 9   # sincos(yaw), sincos(yaw+pi/2), 4 atan2, 3 tan
+
+
+def rollout_flops(evals: float, vehicle_steps: float, M: int) -> float:
+    """Algorithmic fp64 flops of one rollout launch for the algorithm AS IMPLEMENTED."""
+    return FLOP_PER_EVAL * evals + vehicle_steps * (FLOP_PER_ROW * M + FLOP_PER_VEHICLE_STEP)
 
 
 def operator_bytes_per_solve(M: int, esize: int = 8) -> float:
@@ -116,9 +131,10 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def committed_traffic(kernel: str):
-    """dram bytes per launch of `kernel` from the committed ncu --set full capture, if any."""
-    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+def committed_ncu(kernel: str):
+    """Numbers of `kernel` from the committed ncu --set full capture (profiles/ncu_metrics.json):
+    dram bytes per launch ("traffic"), fp64-pipe / issue utilisation.  None if absent."""
+    path = os.path.join(ROOT, "profiles", "ncu_metrics.json")
     if os.path.exists(path):
         try:
             return json.load(open(path)).get(kernel)
@@ -196,47 +212,24 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-operator", action="store_true", help="skip the regime-(i) operator roofline leg")
     args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "ours":
-        args.warmup = max(args.warmup, 1)
     if args.impl == "reference":
         return run_reference(args)
+    args.warmup = max(args.warmup, 3)
 
     import numpy as np
     import torch
 
     from sccav_cbf_b200 import ops, scenarios as sc
+    from sccav_cbf_b200.dist import Shards
     from sccav_cbf_b200.rollout import ClosedLoopRollout
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback on the product path)")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    sh = Shards(backend="nccl", device=dev)
+    rank, world = sh.rank, sh.world
 
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
     esize = 8 if args.dtype == "f64" else 4
@@ -248,7 +241,7 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
     # ---- warm-up
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(args.warmup):
         cl.run()
     torch.cuda.synchronize()
 
@@ -257,7 +250,7 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.25)
-    barrier()
+    sh.barrier()
     l0 = ops.launch_count()
     t_wall0 = time.perf_counter()
     for e0, e1 in evs:
@@ -265,44 +258,61 @@ def main():
         e0.record()
         res = cl.run()
         e1.record()
-    barrier()
+    sh.barrier()
     t_wall1 = time.perf_counter()
     launches = ops.launch_count() - l0
     clocks = sampler.stop(t_wall0, t_wall1)
     ms_steps = [e0.elapsed_time(e1) for e0, e1 in evs]
-    ms_total = max_over_ranks(sum(ms_steps))
-    solves_per_step_rank = float(res["steps"].sum().item()) * M
-    solves_per_step = sum_over_ranks(solves_per_step_rank)
+    ms_total = sh.max(sum(ms_steps))
+    vehicle_steps_rank = float(res["steps"].sum().item())
+    evals_rank = float(res["n_evals"].to(torch.float64).sum().item())
+    solves_per_step_rank = vehicle_steps_rank * M
+    solves_per_step = sh.sum(solves_per_step_rank)
     value = solves_per_step * args.steps / (ms_total * 1e-3)
-    checksum = sum_over_ranks(float(res["n_active"].sum().item()))
+    checksum = sh.sum(float(res["n_active"].sum().item()))
 
-    # ---- timed region 2: end to end through the public API with HOST buffers
+    # ---- timed region 2: end to end through the C-ABI host entry point (sccav_rollout_host_*):
+    #      pinned HOST buffers in, H2D + kernel + D2H inside the call, HOST results out -- every step
     for _ in range(2):
         cl.run_from_host()
-    barrier()
+    sh.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cl.run_from_host()
+        hres = cl.run_from_host()
     torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
+    e2e_s = sh.max(time.perf_counter() - t0)
+    sh.barrier()
     e2e_value = solves_per_step * args.steps / e2e_s
+    assert int(hres["steps"].sum().item()) == int(vehicle_steps_rank)
 
     # ---- roofline of the dominant kernel (rollout): fp64 FMA peak measured on this GPU, now
     peak_tf = ops.measure_fma_peak(dtype)
-    flops_per_launch = algorithmic_flops_per_solve(P_COURSE, M) * solves_per_step_rank
+    flops_per_launch = rollout_flops(evals_rank, vehicle_steps_rank, M)
     ms_launch = sum(ms_steps) / len(ms_steps)
     ach_tf = flops_per_launch / (ms_launch * 1e-3) / 1e12
-    kname = "rollout_kernel<%s>" % ("double" if args.dtype == "f64" else "float")
+    tname = "double" if args.dtype == "f64" else "float"
+    ncu_roll = committed_ncu("rollout_kernel<%s>" % tname) or {}
+    info = ops.rollout_launch_info(M, batch.N, P_COURSE, dtype)
+    hbm_bytes = batch.N * ((4 + M * 7) * esize + M * 6 * esize * 2 + 4 * esize + 5 * 4 + 4 * esize)
     roofline = {
-        "bound": "fp64" if args.dtype == "f64" else "fp32", "kernel": kname,
+        "bound": "fp64" if args.dtype == "f64" else "fp32", "kernel": "rollout_kernel<%s>" % tname,
         "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None,
-        "peak_source": "measured live: sccav_measure_fma_peak (unrolled FMA chains, FMA = 2 flop)",
-        "algorithmic_flops_per_solve": algorithmic_flops_per_solve(P_COURSE, M),
-        "traffic": committed_traffic("rollout"),
-        "hbm_gbs_achieved": (NV * (4 + M * 7) * esize + NV * (4 * esize + 16 + 4 * esize)) / (ms_launch * 1e-3) / 1e9,
-        "note": "not HBM- or tensor-bound: state lives in registers for 1000 steps (about 0.07 B/solve of DRAM traffic); "
-                "the non-FMA add/mul/compare mix caps the FMA-peak fraction at about 0.58",
+        "peak_source": "measured live: sccav_measure_fma_peak (unrolled FMA chains, FMA = 2 flop; the fp64 path is "
+                       "compiled without FMA contraction for parity, so 0.5 is its ceiling)",
+        "algorithmic_flops_per_launch": flops_per_launch,
+        "algorithmic_flops_per_solve": flops_per_launch / solves_per_step_rank,
+        "flops_model": "7 x n_evals (counted by the kernel) + vehicle_steps x (34 M + 27); %d transcendental calls per "
+                       "vehicle-step not counted" % TRANSCENDENTALS_PER_VEHICLE_STEP,
+        "nearest_search_evals_per_vehicle_step": evals_rank / max(vehicle_steps_rank, 1.0),
+        "exhaustive_scan_flops_per_solve": exhaustive_flops_per_solve(P_COURSE, M),
+        "traffic": ncu_roll.get("dram_bytes"),
+        "fp64_pipe_active_pct_ncu": ncu_roll.get("fp64_pipe_active_pct"),
+        "issue_active_pct_ncu": ncu_roll.get("issue_active_pct"),
+        "tensor_pipe_active_pct_ncu": ncu_roll.get("tensor_pipe_active_pct"),
+        "hbm_gbs_achieved": hbm_bytes / (ms_launch * 1e-3) / 1e9,
+        "launch": info,
+        "note": "not HBM- or tensor-bound: state lives in registers for the whole rollout; DRAM traffic is the one-off "
+                "read of the inputs (about 0.07 B/solve); the limiter is instruction issue / fp64 latency at 14 warps per SM",
     }
 
     # ---- regime (i): per-timestep fused operator against the HBM roofline (inputs >> L2)
@@ -330,13 +340,14 @@ def main():
         torch.cuda.synchronize()
         oms = statistics.mean(e0.elapsed_time(e1) for e0, e1 in oevs)
         obytes = operator_bytes_per_solve(M, esize) * n_op * M
+        ncu_op = committed_ncu("filter_step_kernel<%s>" % tname) or {}
         roofline_op = {
-            "bound": "hbm", "kernel": "filter_step_kernel<%s>" % ("double" if args.dtype == "f64" else "float"),
+            "bound": "hbm", "kernel": "filter_step_kernel<%s>" % tname,
             "achieved": obytes / (oms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": obytes / (oms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
             "algorithmic_bytes_per_solve": operator_bytes_per_solve(M, esize), "solves_per_s": n_op * M / (oms * 1e-3),
             "workload": "%d vehicles x %d ellipses, inputs %.0f MB (> L2)" % (n_op, M, obytes / 1e6),
-            "traffic": committed_traffic("filter_step"),
+            "traffic": ncu_op.get("dram_bytes"),
         }
         del st, ob, ur
 
@@ -351,11 +362,12 @@ def main():
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "first %d of %d vehicles x %d ellipses x %d steps (%.1f s), oracle/oracle.c, gcc -O2, %d threads"
                          % (n, NV, M, T, dt_cpu, threads),
-               "note": "reference loop not runnable here (cvxopt/euclid absent, no network); the port omits the IPM's python-callback cost"}
+               "note": "reference loop not runnable here (cvxopt/euclid absent, no network); the port solves each QP exactly "
+                       "instead of paying cvxopt's python-callback interior-point iterations, so it flatters the reference"}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload_name(args), "vehicles_total": n_total, "obstacles": M, "timesteps": T,
@@ -363,7 +375,8 @@ def main():
                        "l2": "flushed (256 MB write) between timed iterations; inputs 36 MB/GPU",
                        "seed": 0, "active_step_checksum": checksum},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cl.h2d_bytes(), "d2h_bytes_per_step": cl.d2h_bytes(),
-                    "ms_per_step": 1e3 * e2e_s / args.steps},
+                    "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "path": "sccav_rollout_host_%s (C-ABI, host pointers): H2D + rollout kernel + D2H inside the call" % args.dtype},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
@@ -372,8 +385,7 @@ def main():
             "wall_s_timed_region": t_wall1 - t_wall0,
         }
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    sh.close()
     return 0
 
 

@@ -245,7 +245,8 @@ def rollout(params: Params, slot_desc, state: torch.Tensor, obst: Optional[torch
     def buf(name, shape, dtype, fill=None):
         t = res.get(name)
         if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != dev:
-            t = torch.empty(shape, dtype=dtype, device=dev)
+            # host path: results land in pinned memory (plain D2H DMA, no staging copy)
+            t = torch.empty(shape, dtype=dtype, pin_memory=True) if dev.type == "cpu" else torch.empty(shape, dtype=dtype, device=dev)
             res[name] = t
         if fill is not None:
             t.fill_(fill)

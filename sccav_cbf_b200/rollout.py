@@ -44,8 +44,10 @@ class ClosedLoopRollout:
         self.h_R = host(batch.R)
         self.h_tspeed = host(batch.target_speed)
         self.course = None
+        self.h_course = None
         if batch.course is not None:
-            self.course = tuple(torch.from_numpy(np.ascontiguousarray(c)).to(dtype).to(self.device) for c in batch.course)
+            self.h_course = tuple(host(c) for c in batch.course)
+            self.course = tuple(c.to(self.device) for c in self.h_course)
         # device-resident inputs
         self.d_state = self.h_state.to(self.device)
         self.d_obst0 = None if self.h_obst is None else self.h_obst.to(self.device)
@@ -64,13 +66,6 @@ class ClosedLoopRollout:
     def M(self) -> int:
         return len(self.slot_desc)
 
-    def h2d_bytes(self) -> int:
-        n = self.h_state.numel() * self.h_state.element_size()
-        for t in (self.h_obst, self.h_alpha, self.h_R, self.h_tspeed):
-            if t is not None:
-                n += t.numel() * t.element_size()
-        return n
-
     def d2h_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self._host_out.values())
 
@@ -86,26 +81,19 @@ class ClosedLoopRollout:
                            record_stride=record_stride, out=self.out)
 
     def run_from_host(self, T: Optional[int] = None) -> Dict[str, torch.Tensor]:
-        """H2D of this step's inputs from pinned memory, the rollout kernel, and D2H of the
-        per-vehicle results; returns host tensors.  Synchronises the current stream."""
-        dev = self.device
-        self.d_state.copy_(self.h_state, non_blocking=True)
-        if self.h_obst is not None:
-            self.d_obst.copy_(self.h_obst, non_blocking=True)
-        if self.h_alpha is not None:
-            self.d_alpha.copy_(self.h_alpha, non_blocking=True)
-        if self.h_R is not None:
-            self.d_R.copy_(self.h_R, non_blocking=True)
-        if self.h_tspeed is not None:
-            self.d_tspeed.copy_(self.h_tspeed, non_blocking=True)
-        res = ops.rollout(self.params, self.slot_desc, self.d_state, self.d_obst, self.course,
-                          self.T if T is None else T, alpha=self.d_alpha, R=self.d_R, target_speed=self.d_tspeed,
-                          record_stride=0, out=self.out)
-        for k, t in res.items():
-            h = self._host_out.get(k)
-            if h is None or h.shape != t.shape or h.dtype != t.dtype:
-                h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-                self._host_out[k] = h
-            h.copy_(t, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        return self._host_out
+        """The end-to-end call: ONE C-ABI call with HOST pointers (sccav_rollout_host_*): the inputs are
+        copied from pinned host memory, the rollout kernel runs, the per-vehicle results are copied
+        back, and the stream is synchronised inside the call.  Returns pinned host tensors."""
+        with torch.cuda.device(self.device):
+            res = ops.rollout(self.params, self.slot_desc, self.h_state, self.h_obst, self.h_course,
+                              self.T if T is None else T, alpha=self.h_alpha, R=self.h_R, target_speed=self.h_tspeed,
+                              record_stride=0, out=self._host_out)
+        self._host_out = res
+        return res
+
+    def h2d_bytes(self) -> int:
+        n = self.h_state.numel() * self.h_state.element_size()
+        for t in (self.h_obst, self.h_alpha, self.h_R, self.h_tspeed) + (self.h_course or ()):
+            if t is not None:
+                n += t.numel() * t.element_size()
+        return n

@@ -133,3 +133,42 @@ def source(path, top=45):
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "source":
     source(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 45)
+
+
+def metrics(paths, out_json):
+    """profiles/ncu_metrics.json: per kernel, the few numbers bench.py quotes next to its live timings."""
+    import json
+    import os
+    import re
+    res = {}
+    if os.path.exists(out_json):
+        res = json.load(open(out_json))
+    for path in paths:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = [r for r in csv.reader(out.splitlines()) if r]
+        hdr, units = rows[0], rows[1]
+        for vals in rows[2:]:
+            d = dict(zip(hdr, zip(units, vals)))
+            name = d["Kernel Name"][1]
+            m = re.match(r"(?:void )?(?:sccav::)?(\w+)<(double|float)", name)
+            key = "%s<%s>" % (m.group(1), m.group(2)) if m else name
+
+            def val(k, scale={"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}):
+                u, v = d[k]
+                return float(v.replace(",", "")) * scale.get(u, 1.0)
+            res[key] = {
+                "source": path, "duration_ms": val("gpu__time_duration.sum"),
+                "dram_bytes": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
+                "fp64_pipe_active_pct": val("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                "issue_active_pct": val("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "tensor_pipe_active_pct": val("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                "dram_throughput_pct": val("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                "registers_per_thread": val("launch__registers_per_thread"),
+                "grid": d["Grid Size"][1], "block": d["Block Size"][1],
+            }
+    json.dump(res, open(out_json, "w"), indent=1, sort_keys=True)
+    print(json.dumps(res, indent=1, sort_keys=True))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "metrics":
+    metrics(sys.argv[3:], sys.argv[2])

@@ -367,7 +367,7 @@ def test_rollout_host_path_and_shards_are_independent_of_world_size():
     h = {k: v.numpy().copy() for k, v in cl.run_from_host().items()}
     for k in a:
         assert np.array_equal(a[k], h[k], equal_nan=True), k
-    assert cl.h2d_bytes() == (4 + 8 * 8) * 256 * 8 and cl.d2h_bytes() > 0
+    assert cl.h2d_bytes() == ((4 + 8 * 8) * 256 + 3 * 2034) * 8 and cl.d2h_bytes() > 0      # state + obstacles + course
 
 
 def test_fp32_variant_error_vs_fp64():
