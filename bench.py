@@ -292,7 +292,7 @@ def main():
     ach_tf = flops_per_launch / (ms_launch * 1e-3) / 1e12
     tname = "double" if args.dtype == "f64" else "float"
     ncu_roll = committed_ncu("rollout_kernel<%s>" % tname) or {}
-    info = ops.rollout_launch_info(M, batch.N, P_COURSE, dtype)
+    info = ops.rollout_launch_info(batch.slot_desc, batch.N, P_COURSE, dtype)
     hbm_bytes = batch.N * ((4 + M * 7) * esize + M * 6 * esize * 2 + 4 * esize + 5 * 4 + 4 * esize)
     roofline = {
         "bound": "fp64" if args.dtype == "f64" else "fp32", "kernel": "rollout_kernel<%s>" % tname,

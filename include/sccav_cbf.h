@@ -230,11 +230,11 @@ int sccav_measure_fma_peak(int32_t dtype, double* tflops_out);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t sccav_launch_count(void);
 
-/* Launch shape the rollout entry point would use for (M, N, P) on the current device:
+/* Launch shape the rollout entry point would use for (slot_desc[M], N, P) on the current device:
  * info[8] = grid, block, dynamic smem bytes, registers/thread, max threads/block of the kernel,
  * resident CTAs/SM at that shape, course-in-shared-memory flag, SM count.  Launches nothing. */
-int sccav_rollout_launch_info_f64(int32_t M, int64_t N, int32_t P, int32_t* info);
-int sccav_rollout_launch_info_f32(int32_t M, int64_t N, int32_t P, int32_t* info);
+int sccav_rollout_launch_info_f64(const uint8_t* slot_desc, int32_t M, int64_t N, int32_t P, int32_t* info);
+int sccav_rollout_launch_info_f32(const uint8_t* slot_desc, int32_t M, int64_t N, int32_t P, int32_t* info);
 
 /* TEST HOOK, host-only, launches nothing: runs the rollout kernel's pruned nearest-way-point search
  * (csrc/course_index.cuh, the same __host__ __device__ code) on the CPU for nq query points, next to

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsccav_cbf.so")
+# SCCAV_CBF_LIB: developer override (scripts/exp_variants.py times alternative builds of the same ABI)
+LIB_PATH = os.environ.get("SCCAV_CBF_LIB") or os.path.join(HERE, "libsccav_cbf.so")
 
 NFIELD = 8
 MAX_ROWS = 32
@@ -95,7 +96,7 @@ def lib() -> C.CDLL:
         f = getattr(L, "sccav_stanley_control_" + sfx)
         f.argtypes = [PP, i64, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]
         f = getattr(L, "sccav_rollout_launch_info_" + sfx)
-        f.argtypes = [i32, i64, i32, vp]
+        f.argtypes = [C.c_char_p, i32, i64, i32, vp]
         f = getattr(L, "sccav_qp2_solve_" + sfx)
         f.argtypes = [PP, i32, i64, vp, vp, vp, PV, vp, vp, vp, i32, vp]
         for host in ("", "host_"):

@@ -187,8 +187,13 @@ int do_filter_step(const sccav_params* p, const uint8_t* slot_desc, int32_t M, i
     a.u = u; a.mask = mask; a.status = status; a.h_min = h_min;
     size_t smem;
     const int block = rows_block(M, smem);
-    SCCAV_CUDA_CHECK(cudaFuncSetAttribute(filter_step_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    filter_step_kernel<real><<<stream_grid(N, block), block, smem, st>>>(a);
+    if (all_private_ellipses(slot_desc, M)) {
+        SCCAV_CUDA_CHECK(cudaFuncSetAttribute(filter_step_kernel<real, SCCAV_SPEC_ELLIPSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        filter_step_kernel<real, SCCAV_SPEC_ELLIPSE><<<stream_grid(N, block), block, smem, st>>>(a);
+    } else {
+        SCCAV_CUDA_CHECK(cudaFuncSetAttribute(filter_step_kernel<real, SCCAV_SPEC_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        filter_step_kernel<real, SCCAV_SPEC_GENERIC><<<stream_grid(N, block), block, smem, st>>>(a);
+    }
     count_launch();
     SCCAV_CUDA_CHECK(cudaGetLastError());
     return SCCAV_OK;
@@ -209,12 +214,20 @@ void rollout_geometry(int64_t N, int& grid, int& block) {
     grid = (int)((N + block - 1) / block);
 }
 
+// the four instances of the persistent kernel: course in shared memory or not x slot specialisation
+typedef void (*rollout_fn)(RolloutArgs<real>);
+rollout_fn rollout_instance(bool course_smem, int spec) {
+    if (spec == SCCAV_SPEC_ELLIPSE)
+        return course_smem ? rollout_kernel<real, true, SCCAV_SPEC_ELLIPSE> : rollout_kernel<real, false, SCCAV_SPEC_ELLIPSE>;
+    return course_smem ? rollout_kernel<real, true, SCCAV_SPEC_GENERIC> : rollout_kernel<real, false, SCCAV_SPEC_GENERIC>;
+}
+
 // grid / block / dynamic shared memory of a rollout launch; the block is capped by what the
 // kernel's register count allows (cudaFuncGetAttributes), the course goes to shared memory if it fits
-int rollout_launch_shape(int M, int64_t N, int np, bool stan, int& grid, int& block, size_t& smem, bool& course_smem) {
+int rollout_launch_shape(int M, int64_t N, int np, bool stan, int spec, int& grid, int& block, size_t& smem, bool& course_smem) {
     rollout_geometry(N, grid, block);
     cudaFuncAttributes fa;
-    SCCAV_CUDA_CHECK(cudaFuncGetAttributes(&fa, rollout_kernel<real, true>));
+    SCCAV_CUDA_CHECK(cudaFuncGetAttributes(&fa, (const void*)rollout_instance(true, spec)));
     const int max_block = fa.maxThreadsPerBlock / 32 * 32;
     if (block > max_block) { block = max_block; grid = (int)((N + block - 1) / block); }
     const size_t cap = (size_t)max_smem_optin();
@@ -255,7 +268,8 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
     int grid, block;
     size_t smem;
     bool course_smem;
-    rc = rollout_launch_shape(M, N, a.np, stan, grid, block, smem, course_smem);
+    const int spec = (all_private_ellipses(slot_desc, M) && p->model != SCCAV_MODEL_NONE) ? SCCAV_SPEC_ELLIPSE : SCCAV_SPEC_GENERIC;
+    rc = rollout_launch_shape(M, N, a.np, stan, spec, grid, block, smem, course_smem);
     if (rc) return rc;
     // scratch for the loop-invariant terms of static ellipses: stream-ordered, lives for this launch
     a.pre = nullptr;
@@ -266,14 +280,9 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
         SCCAV_CUDA_CHECK(cudaMallocAsync(&scratch, (size_t)M * SCCAV_NPRE * (size_t)N * sizeof(real), st));
         a.pre = (real*)scratch;
     }
-    cudaError_t le;
-    if (course_smem) {
-        le = cudaFuncSetAttribute(rollout_kernel<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (le == cudaSuccess) { rollout_kernel<real, true><<<grid, block, smem, st>>>(a); le = cudaGetLastError(); }
-    } else {
-        le = cudaFuncSetAttribute(rollout_kernel<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (le == cudaSuccess) { rollout_kernel<real, false><<<grid, block, smem, st>>>(a); le = cudaGetLastError(); }
-    }
+    const rollout_fn kern = rollout_instance(course_smem, spec);
+    cudaError_t le = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (le == cudaSuccess) { kern<<<grid, block, smem, st>>>(a); le = cudaGetLastError(); }
     count_launch();
     if (a.pre) cudaFreeAsync(a.pre, st);
     SCCAV_CUDA_CHECK(le);
@@ -339,19 +348,21 @@ int SCCAV_FN(sccav_rollout_)(const sccav_params* p, const uint8_t* slot_desc, in
                              (cudaStream_t)stream);
 }
 
-int SCCAV_FN(sccav_rollout_launch_info_)(int32_t M, int64_t N, int32_t P, int32_t* info) {
+int SCCAV_FN(sccav_rollout_launch_info_)(const uint8_t* slot_desc, int32_t M, int64_t N, int32_t P, int32_t* info) {
     using namespace sccav;
-    if (!info || N < 1) { set_error("bad argument"); return SCCAV_EINVAL; }
+    if (!info || N < 1 || M < 0 || M > SCCAV_MAX_ROWS || (M > 0 && !slot_desc)) { set_error("bad argument"); return SCCAV_EINVAL; }
     int grid, block;
     size_t smem;
     bool course_smem;
-    int rc = rollout_launch_shape(M, N, P, P > 0, grid, block, smem, course_smem);
+    const int spec = all_private_ellipses(slot_desc, M) ? SCCAV_SPEC_ELLIPSE : SCCAV_SPEC_GENERIC;
+    int rc = rollout_launch_shape(M, N, P, P > 0, spec, grid, block, smem, course_smem);
     if (rc) return rc;
+    const void* kern = (const void*)rollout_instance(course_smem, spec);
     cudaFuncAttributes fa;
-    SCCAV_CUDA_CHECK(cudaFuncGetAttributes(&fa, rollout_kernel<SCCAV_REAL, true>));
+    SCCAV_CUDA_CHECK(cudaFuncGetAttributes(&fa, kern));
     int occ = 0;
-    SCCAV_CUDA_CHECK(cudaFuncSetAttribute(rollout_kernel<SCCAV_REAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SCCAV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rollout_kernel<SCCAV_REAL, true>, block, smem));
+    SCCAV_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SCCAV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));
     info[0] = grid; info[1] = block; info[2] = (int32_t)smem; info[3] = fa.numRegs; info[4] = fa.maxThreadsPerBlock;
     info[5] = occ; info[6] = course_smem ? 1 : 0; info[7] = sm_count();
     return SCCAV_OK;

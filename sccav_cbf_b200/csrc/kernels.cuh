@@ -253,7 +253,7 @@ template <typename T> struct FilterArgs {
     T* h_min;
 };
 
-template <typename T>
+template <typename T, int SPEC>
 __global__ void __launch_bounds__(256) filter_step_kernel(const __grid_constant__ FilterArgs<T> a) {
     typedef Real<T> R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -269,8 +269,8 @@ __global__ void __launch_bounds__(256) filter_step_kernel(const __grid_constant_
         R::sincos_(th, &sth, &cth);
         T u0, u1, u1raw, hmin;
         uint32_t mask;
-        int st = filter_vehicle<T>(a.P, a.sd, a.M, N, n, a.obst, x, y, th, v, sth, cth, alpha, R00, R01, R10, R11,
-                                   ur0, ur1, rows, stride, u0, u1, u1raw, mask, hmin);
+        int st = filter_vehicle<T, SPEC>(a.P, a.sd, a.M, N, n, a.obst, x, y, th, v, sth, cth, alpha, R00, R01, R10, R11,
+                                         ur0, ur1, rows, stride, u0, u1, u1raw, mask, hmin);
         a.u[n] = u0;
         a.u[N + n] = u1;
         if (a.mask) a.mask[n] = mask;
@@ -352,7 +352,7 @@ template <typename T> struct RolloutSmem {
     }
 };
 
-template <typename T, bool COURSE_SMEM>
+template <typename T, bool COURSE_SMEM, int SPEC>
 __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
     typedef Real<T> R;
     typedef typename R::T2 T2;
@@ -409,7 +409,9 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
     const int last_idx = np - 1;
     const bool filt = a.M > 0 && P.model != SCCAV_MODEL_NONE;
 
-    // loop-invariant obstacle terms (static ellipses): once per (vehicle, slot) into the scratch
+    // loop-invariant obstacle terms (ellipses): once per (vehicle, slot) into the scratch; `moving`
+    // = slots whose ellipse has a velocity (their h_t needs vx, vy, a^2, b^2 every step)
+    uint32_t moving = 0u;
     if (a.pre && filt) {
         for (int m = 0; m < a.M; ++m) {
             const int desc = a.sd.d[m];
@@ -417,6 +419,7 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
             const int64_t nn = (desc & SCCAV_SLOT_SHARED) ? 0 : n;
             const T* f = a.obst + (int64_t)m * SCCAV_NFIELD * N + nn;
             ellipse_precompute<T>(f[2 * N], f[3 * N], f[4 * N], a.pre + (int64_t)m * SCCAV_NPRE * N + n, N);
+            if (f[5 * N] != T(0) || f[6 * N] != T(0)) moving |= 1u << m;
         }
     }
 
@@ -475,8 +478,8 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
         uint32_t mask = 0u;
         int status = SCCAV_STATUS_INACTIVE;
         if (filt)
-            status = filter_vehicle<T>(P, a.sd, a.M, N, n, a.obst, x, y, yaw, v, syaw, cyw, alpha, R00, R01, R10, R11,
-                                       ur0, ur1, rows, stride, u0, u1, u1raw, mask, hmin, a.pre);
+            status = filter_vehicle<T, SPEC>(P, a.sd, a.M, N, n, a.obst, x, y, yaw, v, syaw, cyw, alpha, R00, R01, R10, R11,
+                                             ur0, ur1, rows, stride, u0, u1, u1raw, mask, hmin, a.pre, moving);
         // ---- plant
         T px = x, py = y, pyaw = yaw, pv_ = v;
         T delta = u1;

@@ -357,17 +357,32 @@ __device__ __forceinline__ bool qp_check(const RowView<T>& rv, int m, T u0, T u1
         T t0 = a0 * u0, t1 = a1 * u1;
         T rk = (t0 + t1) - bk;
         if (-rk > worst) worst = -rk;
-        if (k == skip_a || k == skip_b) continue;
         T tol = R::feas_eps() * ((R::abs_(t0) + R::abs_(t1)) + R::abs_(bk));
-        if (!(rk >= -tol)) feas = false;
+        if (!(rk >= -tol) && k != skip_a && k != skip_b) feas = false;
     }
     return feas;
 }
 
-// the reference point r violates at least one row (worst0 = its largest violation): singles, pairs
+// Which pairs (j, k) can have a non-zero determinant?  det2 = A0_j A1_k - A1_j A0_k is exactly 0 (or NaN)
+// -- and oracle.qp2_exact skips the pair at its parallel-rows test -- whenever A0_j = A0_k = 0 or
+// A1_j = A1_k = 0.  nz0 / nz1 = bit masks of the rows whose A0 / A1 is not exactly zero (NaN counts as
+// non-zero).  Ellipse, lane, radial and distance rows under DBM have A0 = h_v = 0 (cbf/obstacles.py:232-236):
+// for an all-ellipse problem the whole pair phase vanishes.
+struct RowNz {
+    uint32_t nz0, nz1;
+    __device__ __forceinline__ bool any_pair() const { return nz0 != 0u && nz1 != 0u; }
+    __device__ __forceinline__ bool pair(int j, int k) const {
+        return (((nz0 >> j) | (nz0 >> k)) & ((nz1 >> j) | (nz1 >> k)) & 1u) != 0u;
+    }
+};
+
+// Enumeration with the least-violation bookkeeping of oracle.qp2_exact (every candidate checked against
+// every row), minus the pairs that RowNz proves degenerate.
+// (Measured on B200: a cheaper first pass with early exits does not pay -- a warp runs as long as its
+// slowest lane, and nearly every warp of the benchmark batches holds an infeasible problem.)
 template <typename T>
-__device__ int qp2_solve_active(const RowView<T>& rv, int m, T r0, T r1, T R00, T R01, T R10, T R11, T worst0,
-                                T& u0o, T& u1o, uint32_t& masko) {
+__device__ __forceinline__ int qp2_solve_active_full(const RowView<T>& rv, int m, RowNz nz, T r0, T r1, T R00, T R01, T R10, T R11,
+                                                  T worst0, T& u0o, T& u1o, uint32_t& masko) {
     typedef Real<T> R;
     T worst;
     T fbw = worst0, fb0 = r0, fb1 = r1;
@@ -390,88 +405,171 @@ __device__ int qp2_solve_active(const RowView<T>& rv, int m, T r0, T r1, T R00, 
         }
         if (worst < fbw - R::tie_eps() * (R::abs_(worst) + R::abs_(fbw))) { fbw = worst; fb0 = u0; fb1 = u1; fbm = 1u << k; }
     }
-    for (int j = 0; j < m; ++j) {
-        T aj0 = rv.A0(j), aj1 = rv.A1(j), bj = rv.b(j);
-        for (int k = j + 1; k < m; ++k) {
-            T ak0 = rv.A0(k), ak1 = rv.A1(k), bk = rv.b(k);
-            T t1 = aj0 * ak1, t2 = aj1 * ak0;
-            T det2 = t1 - t2;
-            if (!(R::abs_(det2) > R::par_eps() * (R::abs_(t1) + R::abs_(t2)))) continue;
-            T u0 = (bj * ak1 - aj1 * bk) / det2;
-            T u1 = (aj0 * bk - bj * ak0) / det2;
-            T e0 = u0 - r0, e1 = u1 - r1;
-            T w0 = T(2) * (R00 * e0 + R01 * e1);
-            T w1 = T(2) * (R10 * e0 + R11 * e1);
-            T lj = (w0 * ak1 - ak0 * w1) / det2;
-            T lk = (aj0 * w1 - w0 * aj1) / det2;
-            bool feas = qp_check(rv, m, u0, u1, j, k, worst);
-            if (feas && lj >= T(0) && lk >= T(0)) {
-                u0o = u0; u1o = u1; masko = (1u << j) | (1u << k);
-                return SCCAV_STATUS_ACTIVE;
+    if (nz.any_pair()) {
+        for (int j = 0; j < m; ++j) {
+            T aj0 = rv.A0(j), aj1 = rv.A1(j), bj = rv.b(j);
+            for (int k = j + 1; k < m; ++k) {
+                if (!nz.pair(j, k)) continue;
+                T ak0 = rv.A0(k), ak1 = rv.A1(k), bk = rv.b(k);
+                T t1 = aj0 * ak1, t2 = aj1 * ak0;
+                T det2 = t1 - t2;
+                if (!(R::abs_(det2) > R::par_eps() * (R::abs_(t1) + R::abs_(t2)))) continue;
+                T u0 = (bj * ak1 - aj1 * bk) / det2;
+                T u1 = (aj0 * bk - bj * ak0) / det2;
+                T e0 = u0 - r0, e1 = u1 - r1;
+                T w0 = T(2) * (R00 * e0 + R01 * e1);
+                T w1 = T(2) * (R10 * e0 + R11 * e1);
+                T lj = (w0 * ak1 - ak0 * w1) / det2;
+                T lk = (aj0 * w1 - w0 * aj1) / det2;
+                bool feas = qp_check(rv, m, u0, u1, j, k, worst);
+                if (feas && lj >= T(0) && lk >= T(0)) {
+                    u0o = u0; u1o = u1; masko = (1u << j) | (1u << k);
+                    return SCCAV_STATUS_ACTIVE;
+                }
+                if (worst < fbw - R::tie_eps() * (R::abs_(worst) + R::abs_(fbw))) { fbw = worst; fb0 = u0; fb1 = u1; fbm = (1u << j) | (1u << k); }
             }
-            if (worst < fbw - R::tie_eps() * (R::abs_(worst) + R::abs_(fbw))) { fbw = worst; fb0 = u0; fb1 = u1; fbm = (1u << j) | (1u << k); }
         }
     }
     u0o = fb0; u1o = fb1; masko = fbm;
     return SCCAV_STATUS_INFEASIBLE;
 }
 
+// The reference point r violates at least one row (worst0 = its largest violation): singles, pairs.
+template <typename T>
+__device__ __forceinline__ int qp2_solve_active(const RowView<T>& rv, int m, RowNz nz, T r0, T r1,
+                                                T R00, T R01, T R10, T R11, T worst0, T& u0o, T& u1o, uint32_t& masko) {
+    return qp2_solve_active_full<T>(rv, m, nz, r0, r1, R00, R01, R10, R11, worst0, u0o, u1o, masko);
+}
+
+// rows already in shared memory (K2): reference-point check, masks, then the active solve
 template <typename T>
 __device__ __forceinline__ int qp2_solve(const RowView<T>& rv, int m, T r0, T r1, T R00, T R01, T R10, T R11,
                                          T& u0o, T& u1o, uint32_t& masko) {
-    T worst;
-    if (qp_check(rv, m, r0, r1, -1, -1, worst)) {
+    typedef Real<T> R;
+    bool feas = true;
+    T worst = -R::inf();
+    RowNz nz{0u, 0u};
+    for (int k = 0; k < m; ++k) {
+        T a0 = rv.A0(k), a1 = rv.A1(k), bk = rv.b(k);
+        if (a0 != T(0)) nz.nz0 |= 1u << k;
+        if (a1 != T(0)) nz.nz1 |= 1u << k;
+        T t0 = a0 * r0, t1 = a1 * r1;
+        T rk = (t0 + t1) - bk;
+        if (-rk > worst) worst = -rk;
+        T tol = R::feas_eps() * ((R::abs_(t0) + R::abs_(t1)) + R::abs_(bk));
+        if (!(rk >= -tol)) feas = false;
+    }
+    if (feas) {
         u0o = r0; u1o = r1; masko = 0u;
         return SCCAV_STATUS_INACTIVE;
     }
-    return qp2_solve_active<T>(rv, m, r0, r1, R00, R01, R10, R11, worst, u0o, u1o, masko);
+    return qp2_solve_active<T>(rv, m, nz, r0, r1, R00, R01, R10, R11, worst, u0o, u1o, masko);
 }
 
 // ------------------------------------------------------------------------------------------
 // one solve_cbf for one vehicle: rows of all slots -> smem -> QP -> converted output
 // (cbf/cbf.py:166-220 for DBM, :67-110 for KBM).  u_ref = (a|v, delta); returns (a|v, delta).
+//
+// SPEC selects a compile-time specialisation of the slot loop (identical arithmetic):
+//   SPEC_GENERIC  any slot mix, dispatch on the slot descriptor
+//   SPEC_ELLIPSE  every slot is a per-vehicle (not SHARED) ELLIPSE -- the BASELINE configs 2 and 5;
+//                 no dispatch, and the fields of slot m+1 are in flight while slot m is evaluated
 // ------------------------------------------------------------------------------------------
+#define SCCAV_SPEC_GENERIC 0
+#define SCCAV_SPEC_ELLIPSE 1
+
+// row of one slot into shared memory + running feasibility test of the reference point
+// (qp_check(r) of qp2_solve, evaluated on the fly with the same operations)
 template <typename T>
+__device__ __forceinline__ void put_row(const Params<T>& P, const Partials<T>& p, T sth, T cth, T v, T alpha, T r0, T r1,
+                                        T* rows, int stride, int m, T& hmin, T& worst, bool& feas, RowNz& nz) {
+    typedef Real<T> R;
+    T A0, A1, b;
+    if (P.model == SCCAV_MODEL_KBM) kbm_row<T>(p, sth, cth, alpha, A0, A1, b);
+    else dbm_row<T>(p, sth, cth, v, alpha, P.lr, A0, A1, b);
+    rows[(3 * m + 0) * stride] = A0;
+    rows[(3 * m + 1) * stride] = A1;
+    rows[(3 * m + 2) * stride] = b;
+    if (p.h < hmin) hmin = p.h;
+    if (A0 != T(0)) nz.nz0 |= 1u << m;
+    if (A1 != T(0)) nz.nz1 |= 1u << m;
+    T t0 = A0 * r0, t1 = A1 * r1;
+    T rk = (t0 + t1) - b;
+    if (-rk > worst) worst = -rk;
+    T tol = R::feas_eps() * ((R::abs_(t0) + R::abs_(t1)) + R::abs_(b));
+    if (!(rk >= -tol)) feas = false;
+}
+
+template <typename T, int SPEC>
 __device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc& sd, int M, int64_t N, int64_t n,
                                               const T* __restrict__ obst, T x, T y, T th, T v, T sth, T cth,
                                               T alpha, T R00, T R01, T R10, T R11, T uref0, T uref1,
                                               T* rows, int stride, T& u0, T& u1, T& u1raw, uint32_t& mask, T& hmin,
-                                              const T* pre = nullptr) {
+                                              const T* __restrict__ pre = nullptr, uint32_t moving = 0xffffffffu) {
     typedef Real<T> R;
     hmin = R::inf();
     T r0 = uref0, r1;
     if (P.model == SCCAV_MODEL_KBM) r1 = (uref0 * R::tan_(uref1)) / P.L;                // cbf.py:75
     else r1 = R::atan2_(P.lr * R::tan_(uref1), P.lf + P.lr);                             // cbf.py:175
-    // rows -> shared memory; the feasibility of the reference point (qp_check(r) of qp2_solve) is
-    // evaluated on the fly with the same operations, so an inactive step never re-reads the rows
+    // rows -> shared memory; an inactive step never re-reads them
     bool feas = true;
     T worst = -R::inf();
-    for (int m = 0; m < M; ++m) {
-        const int desc = sd.d[m];
-        const int64_t nn = (desc & SCCAV_SLOT_SHARED) ? 0 : n;
-        const T* f = obst + (int64_t)m * SCCAV_NFIELD * N + nn;
-        const T* pr = pre ? pre + (int64_t)m * SCCAV_NPRE * N + n : nullptr;
-        Partials<T> p = slot_partials<T>(desc & 0x7f, f, N, x, y, th, v, sth, cth, pr, N);
-        T A0, A1, b;
-        if (P.model == SCCAV_MODEL_KBM) kbm_row<T>(p, sth, cth, alpha, A0, A1, b);
-        else dbm_row<T>(p, sth, cth, v, alpha, P.lr, A0, A1, b);
-        rows[(3 * m + 0) * stride] = A0;
-        rows[(3 * m + 1) * stride] = A1;
-        rows[(3 * m + 2) * stride] = b;
-        if (p.h < hmin) hmin = p.h;
-        T t0 = A0 * r0, t1 = A1 * r1;
-        T rk = (t0 + t1) - b;
-        if (-rk > worst) worst = -rk;
-        T tol = R::feas_eps() * ((R::abs_(t0) + R::abs_(t1)) + R::abs_(b));
-        if (!(rk >= -tol)) feas = false;
+    RowNz nz{0u, 0u};
+    if (SPEC == SCCAV_SPEC_ELLIPSE) {
+        const int64_t ss = (int64_t)SCCAV_NFIELD * N;          // slot stride
+        const T* f = obst + n;
+        if (pre) {
+            // rollout: loop-invariant terms hoisted into `pre`; a static obstacle (moving bit clear)
+            // needs neither its velocity nor a^2, b^2 (h_t = -2 (. * 0 + . * 0) = 0)
+            const int64_t ps = (int64_t)SCCAV_NPRE * N;
+            const T* q = pre + n;
+            for (int m = 0; m < M; ++m, f += ss, q += ps) {
+                T cx = f[0], cy = f[N], a = f[2 * N], b = f[3 * N];
+                T vx = T(0), vy = T(0);
+                if ((moving >> m) & 1u) { vx = f[5 * N]; vy = f[6 * N]; }
+                Partials<T> p = ellipse_partials_pre<T>(x, y, cx, cy, a, b, vx, vy, q, N);
+                put_row<T>(P, p, sth, cth, v, alpha, r0, r1, rows, stride, m, hmin, worst, feas, nz);
+            }
+        } else {
+#ifdef SCCAV_EXP_NO_PIPE
+            for (int m = 0; m < M; ++m, f += ss) {
+                T cx = f[0], cy = f[N], a = f[2 * N], b = f[3 * N], t = f[4 * N], vx = f[5 * N], vy = f[6 * N];
+                Partials<T> p = ellipse_partials<T>(x, y, cx, cy, a, b, t, vx, vy);
+                put_row<T>(P, p, sth, cth, v, alpha, r0, r1, rows, stride, m, hmin, worst, feas, nz);
+            }
+#else
+            T cx = f[0], cy = f[N], a = f[2 * N], b = f[3 * N], t = f[4 * N], vx = f[5 * N], vy = f[6 * N];
+            for (int m = 0; m < M; ++m) {
+                f += ss;
+                T ncx = cx, ncy = cy, na = a, nb = b, nt = t, nvx = vx, nvy = vy;
+                if (m + 1 < M) { ncx = f[0]; ncy = f[N]; na = f[2 * N]; nb = f[3 * N]; nt = f[4 * N]; nvx = f[5 * N]; nvy = f[6 * N]; }
+                Partials<T> p = ellipse_partials<T>(x, y, cx, cy, a, b, t, vx, vy);
+                put_row<T>(P, p, sth, cth, v, alpha, r0, r1, rows, stride, m, hmin, worst, feas, nz);
+                cx = ncx; cy = ncy; a = na; b = nb; t = nt; vx = nvx; vy = nvy;
+            }
+#endif
+        }
+    } else {
+        for (int m = 0; m < M; ++m) {
+            const int desc = sd.d[m];
+            const int64_t nn = (desc & SCCAV_SLOT_SHARED) ? 0 : n;
+            const T* f = obst + (int64_t)m * SCCAV_NFIELD * N + nn;
+            const T* pr = pre ? pre + (int64_t)m * SCCAV_NPRE * N + n : nullptr;
+            Partials<T> p = slot_partials<T>(desc & 0x7f, f, N, x, y, th, v, sth, cth, pr, N);
+            put_row<T>(P, p, sth, cth, v, alpha, r0, r1, rows, stride, m, hmin, worst, feas, nz);
+        }
     }
     T q0 = r0, q1 = r1;
     int status = SCCAV_STATUS_INACTIVE;
     mask = 0u;
+#ifndef SCCAV_EXP_NO_QP
     if (!feas) {
         RowView<T> rv{rows, stride};
-        status = qp2_solve_active<T>(rv, M, r0, r1, R00, R01, R10, R11, worst, q0, q1, mask);
+        status = qp2_solve_active<T>(rv, M, nz, r0, r1, R00, R01, R10, R11, worst, q0, q1, mask);
     }
+#else
+    if (!feas) { status = SCCAV_STATUS_ACTIVE; mask = 1u; }
+#endif
     u0 = q0;
     u1raw = q1;
     if (P.model == SCCAV_MODEL_KBM) {
@@ -481,6 +579,17 @@ __device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc
         u1 = R::atan2_((P.lf + P.lr) * R::tan_(q1), P.lr);                               // cbf.py:216
     }
     return status;
+}
+
+// true when every slot is a per-vehicle ELLIPSE (host-side choice of SCCAV_SPEC_ELLIPSE)
+__host__ __device__ inline bool all_private_ellipses(const uint8_t* d, int M) {
+    if (M < 1) return false;
+#ifdef SCCAV_EXP_NO_SPEC
+    return false;
+#endif
+    for (int m = 0; m < M; ++m)
+        if (d[m] != SCCAV_SLOT_ELLIPSE) return false;
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -292,10 +292,14 @@ def launch_count() -> int:
     return int(nv.lib().sccav_launch_count())
 
 
-def rollout_launch_info(M: int, N: int, P: int, dtype=torch.float64) -> Dict[str, int]:
-    """Launch shape of the rollout kernel for (M, N, P) on the current device (no launch)."""
+def rollout_launch_info(slot_desc, N: int, P: int, dtype=torch.float64) -> Dict[str, int]:
+    """Launch shape of the rollout kernel for (slot_desc, N, P) on the current device (no launch).
+    `slot_desc`: the slot descriptors of the batch, or an int M meaning M per-vehicle ellipses."""
     L = _need_cuda_lib()
     info = (C.c_int32 * 8)()
-    nv.check(getattr(L, "sccav_rollout_launch_info_" + _SFX[dtype])(int(M), int(N), int(P), info))
+    if isinstance(slot_desc, int):
+        slot_desc = [0] * slot_desc
+    sd = bytes(bytearray(int(d) for d in slot_desc))
+    nv.check(getattr(L, "sccav_rollout_launch_info_" + _SFX[dtype])(sd, len(sd), int(N), int(P), info))
     keys = ("grid", "block", "smem_bytes", "registers", "max_threads_per_block", "ctas_per_sm", "course_in_smem", "sms")
     return dict(zip(keys, [int(v) for v in info]))

@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""Developer tool: kernel-only timings of the rollout (config 2) and of the fused operator (2 M x 8),
+CUDA events, median of a few launches.  Not a bench line -- bench.py is the contract."""
+import argparse
+import os
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from sccav_cbf_b200 import ops, scenarios as sc  # noqa: E402
+from sccav_cbf_b200.rollout import ClosedLoopRollout  # noqa: E402
+
+
+def timed(fn, reps):
+    ms = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    return statistics.median(ms)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--vehicles", type=int, default=65536)
+    ap.add_argument("--T", type=int, default=1000)
+    ap.add_argument("--M", type=int, default=8)
+    ap.add_argument("--dtype", default="f64")
+    ap.add_argument("--no-rollout", action="store_true")
+    ap.add_argument("--no-operator", action="store_true")
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    dtype = torch.float64 if a.dtype == "f64" else torch.float32
+    out = []
+    M = a.M
+    if not a.no_rollout:
+        batch = sc.config2(n_total=a.vehicles, M=M, T=a.T, seed=0, lo=0, hi=a.vehicles)
+        cl = ClosedLoopRollout(batch, dtype=dtype, device=dev)
+        for _ in range(2):
+            res = cl.run()
+        ms = timed(cl.run, 5)
+        solves = float(res["steps"].sum().item()) * M
+        out.append("rollout %.3f ms  %.4g solves/s  (nact %d, ninf %d, evals/step %.1f, %s)" % (
+            ms, solves / ms * 1e3, int(res["n_active"].sum().item()), int(res["n_infeasible"].sum().item()),
+            float(res["n_evals"].double().sum().item()) / float(res["steps"].sum().item()),
+            ops.rollout_launch_info(batch.slot_desc, batch.N, 2034, dtype)))
+    if not a.no_operator:
+        n_op = 2 * 1024 * 1024
+        gen = torch.Generator(device=dev); gen.manual_seed(1234)
+        st = torch.empty((4, n_op), dtype=dtype, device=dev)
+        st[0].uniform_(-20, 120, generator=gen); st[1].uniform_(-45, 15, generator=gen)
+        st[2].uniform_(-3.2, 3.2, generator=gen); st[3].uniform_(2, 12, generator=gen)
+        ob = torch.zeros((M, 8, n_op), dtype=dtype, device=dev)
+        ob[:, 0].uniform_(-20, 120, generator=gen); ob[:, 1].uniform_(-45, 15, generator=gen)
+        ob[:, 2].uniform_(2.5, 6.5, generator=gen); ob[:, 3].uniform_(1.5, 3.5, generator=gen)
+        ob[:, 4].uniform_(-3.1, 3.1, generator=gen)
+        ur = torch.zeros((2, n_op), dtype=dtype, device=dev); ur[1].uniform_(-0.3, 0.3, generator=gen)
+        prm = ops.make_params()
+        sd = [0] * M
+        for _ in range(3):
+            u, mask, status, hmin = ops.filter_step(prm, sd, st, ob, ur)
+        ms = timed(lambda: ops.filter_step(prm, sd, st, ob, ur), 7)
+        es = 8 if a.dtype == "f64" else 4
+        bps = 7 * es + (4 * es + 2 * es + 2 * es + 4 + 1) / M
+        out.append("operator %.4f ms  %.1f GB/s algorithmic  %.4g solves/s  (active %.3f%%, infeasible %.4f%%)" % (
+            ms, bps * n_op * M / ms / 1e6, n_op * M / ms * 1e3,
+            100.0 * float((status == 1).sum().item()) / n_op, 100.0 * float((status == 2).sum().item()) / n_op))
+    print("\n".join(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()
