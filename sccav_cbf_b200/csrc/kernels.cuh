@@ -253,8 +253,11 @@ template <typename T> struct FilterArgs {
     T* h_min;
 };
 
+#ifndef SCCAV_K12_MINB
+#define SCCAV_K12_MINB 2
+#endif
 template <typename T, int SPEC>
-__global__ void __launch_bounds__(256) filter_step_kernel(const __grid_constant__ FilterArgs<T> a) {
+__global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_kernel(const __grid_constant__ FilterArgs<T> a) {
     typedef Real<T> R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* rows = reinterpret_cast<T*>(smem_raw) + threadIdx.x;

@@ -105,7 +105,10 @@ __device__ __forceinline__ Partials<T> ellipse_partials(T x, T y, T cx, T cy, T 
     o.hy = ((T(2) * st) / aa) * p + ((T(2) * ct) / bb) * q;
     o.hth = T(0);
     o.hv = T(0);
-    o.ht = T(-2) * ((dx / aa) * vx + (dy / bb) * vy);
+    // a static obstacle has h_t = -2 (. * 0 + . * 0) = 0: skip the two divisions (the sign of that zero
+    // cannot reach u or the active set)
+    o.ht = T(0);
+    if (vx != T(0) || vy != T(0)) o.ht = T(-2) * ((dx / aa) * vx + (dy / bb) * vy);
     return o;
 }
 
