@@ -42,7 +42,7 @@ extern "C" {
 #define SCCAV_MAX_ROWS 32          /* M <= 32: the active set is a uint32 bit mask */
 #define SCCAV_TRAJ_FIELDS 7        /* x, y, yaw, v, u0, u1(delta), beta */
 
-/* ---- obstacle slot types (low 7 bits of slot_desc[m]) ------------------------------------ */
+/* ---- obstacle slot types (low 6 bits of slot_desc[m]) ------------------------------------ */
 /* ELLIPSE  Ellipse2D, cbf/obstacles.py:139-331.  fields: cx, cy, a, b, theta, vx, vy, -
  *          (a, b already include the buffer, obstacles.py:159-160)                            */
 #define SCCAV_SLOT_ELLIPSE 0
@@ -56,6 +56,16 @@ extern "C" {
 #define SCCAV_SLOT_RADIAL 3
 /* DISTANCE D_CBF, test_scripts/stanley_controller_ellipse.py:240-275.  fields: cx, cy, Ds     */
 #define SCCAV_SLOT_DISTANCE 4
+/* ELLIPSE_PREP  an ELLIPSE slot after sccav_prepare_obstacles_*: the terms that do not depend on
+ *          the vehicle are evaluated once at ingest instead of at every solve --
+ *          fields: cx, cy, m00 = cos(theta)/a, m01 = sin(theta)/a, m10 = -sin(theta)/b, m11 = cos(theta)/b,
+ *          wx = vx/a^2, wy = vy/b^2.   With d = (x - cx, y - cy), (pa, qb) = M d:
+ *          h = pa^2 + qb^2 - 1, grad h = 2 M^T (pa, qb), h_t = -2 (dx wx + dy wy)
+ *          (the same functions as cbf/obstacles.py:193,218,229,316, a few ulp apart)              */
+#define SCCAV_SLOT_ELLIPSE_PREP 5
+#define SCCAV_SLOT_TYPE_MASK 0x3f
+/* flag: the obstacle does not move -- its velocity fields are not read and h_t = 0            */
+#define SCCAV_SLOT_STATIC 0x40
 /* flag: the slot's 8 fields are shared by all vehicles (read from n = 0), e.g. global lanes   */
 #define SCCAV_SLOT_SHARED 0x80
 
@@ -65,6 +75,11 @@ extern "C" {
 
 #define SCCAV_NOMINAL_STANLEY 0    /* Stanley + P speed, stanley_controller_ellipse.py:135-212 */
 #define SCCAV_NOMINAL_CONST 1      /* constant u_ref, radial_dynamic_obstacles.py:444          */
+
+/* sccav_params.flags */
+/* rollout: ELLIPSE slots are ingested once per launch (sccav_prepare_obstacles_*) and evaluated in
+ * their prepared form at every step -- same results to a few ulp, no division or sincos per row   */
+#define SCCAV_FLAG_PREPARED_ROWS 1
 
 #define SCCAV_STATUS_INACTIVE 0    /* u == u_ref                                               */
 #define SCCAV_STATUS_ACTIVE 1      /* KKT optimum with 1 or 2 active rows                      */
@@ -84,7 +99,7 @@ typedef struct sccav_params {
     int32_t seeker;            /* 1: RADIAL slots chase the ego after every step, rdo.py:193-239 */
     int32_t kbm_driver_delta;  /* KBM only. 0: delta = atan2(w L, v_ref) (cbf.py:109); 1: atan(w L / v) (sce.py:652) */
     int32_t record_stride;     /* rollout: 0 = no trajectory, k = record every k-th step       */
-    int32_t reserved0;
+    int32_t flags;             /* SCCAV_FLAG_* (0 = none)                                     */
     int32_t reserved1;
     double alpha;              /* class-K gain (gamma), cbf.py:128                             */
     double lr, lf, L;          /* cbf.py:150-152, cbf.py:61                                    */
@@ -222,6 +237,16 @@ int sccav_rollout_host_f32(const sccav_params* p, const uint8_t* slot_desc, int3
                            const float* state, float* obst, const float* course_x, const float* course_y,
                            const float* course_yaw, int32_t P, const sccav_pervehicle* pv,
                            const sccav_rollout_out* out, void* stream);
+
+/* Obstacle ingest for repeated solves (the batched counterpart of constructing Ellipse2D objects,
+ * cbf/obstacles.py:146-165, once and then calling solve_cbf every tick): every ELLIPSE slot of
+ * obst_in [M][8][N] is rewritten as an ELLIPSE_PREP slot into obst_out [M][8][N] (may alias obst_in),
+ * all other slots are copied; slot_desc_out[M] receives the new descriptors (flags preserved).
+ * DEVICE pointers, asynchronous on `stream`. */
+int sccav_prepare_obstacles_f64(const uint8_t* slot_desc, int32_t M, int64_t N, const double* obst_in, double* obst_out,
+                                uint8_t* slot_desc_out, void* stream);
+int sccav_prepare_obstacles_f32(const uint8_t* slot_desc, int32_t M, int64_t N, const float* obst_in, float* obst_out,
+                                uint8_t* slot_desc_out, void* stream);
 
 /* Measurement helpers used by bench.py (not part of the reference-facing path). */
 /* Launches an unrolled FMA chain kernel and returns the achieved TFLOP/s (FMA = 2 flop) on the

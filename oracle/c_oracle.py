@@ -18,7 +18,7 @@ LIB = os.path.join(HERE, "_build", "liboracle.so")
 class Params(C.Structure):
     _fields_ = [
         ("model", C.c_int32), ("nominal", C.c_int32), ("terminate", C.c_int32), ("seeker", C.c_int32),
-        ("kbm_driver_delta", C.c_int32), ("record_stride", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_int32),
+        ("kbm_driver_delta", C.c_int32), ("record_stride", C.c_int32), ("flags", C.c_int32), ("reserved1", C.c_int32),
         ("alpha", C.c_double), ("lr", C.c_double), ("lf", C.c_double), ("L", C.c_double),
         ("max_steer", C.c_double), ("dt", C.c_double), ("k_stanley", C.c_double), ("ks_stanley", C.c_double),
         ("Kp", C.c_double), ("target_speed", C.c_double), ("t_max", C.c_double),

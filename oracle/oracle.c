@@ -165,9 +165,31 @@ static part_t lane_partials(double x, double y, const double* c, double buffer) 
     return o;
 }
 
-static part_t slot_partials(int type, const double* f, int64_t fs, double x, double y, double th, double v) {
+/* ELLIPSE_PREP (include/sccav_cbf.h): an Ellipse2D whose vehicle-independent terms were evaluated at
+ * ingest (prepare_obstacles below) -- same h, grad h, h_t as ellipse_partials up to a few ulp */
+static part_t ellipse_prep_partials(double x, double y, double cx, double cy, double m00, double m01, double m10,
+                                    double m11, double wx, double wy) {
+    part_t o;
+    double dx = x - cx, dy = y - cy;
+    double pa = m00 * dx + m01 * dy;
+    double qb = m10 * dx + m11 * dy;
+    o.h = (pa * pa + qb * qb) - 1;
+    o.hx = 2 * (m00 * pa + m10 * qb);
+    o.hy = 2 * (m01 * pa + m11 * qb);
+    o.hth = 0.0;
+    o.hv = 0.0;
+    o.ht = -2 * (dx * wx + dy * wy);
+    return o;
+}
+
+static part_t slot_partials(int desc, const double* f, int64_t fs, double x, double y, double th, double v) {
+    const int type = desc & SCCAV_SLOT_TYPE_MASK;
+    const int is_static = (desc & SCCAV_SLOT_STATIC) != 0;      /* velocity fields are not read */
     switch (type) {
-        case SCCAV_SLOT_ELLIPSE: return ellipse_partials(x, y, f[0], f[fs], f[2 * fs], f[3 * fs], f[4 * fs], f[5 * fs], f[6 * fs]);
+        case SCCAV_SLOT_ELLIPSE: return ellipse_partials(x, y, f[0], f[fs], f[2 * fs], f[3 * fs], f[4 * fs],
+                                                         is_static ? 0.0 : f[5 * fs], is_static ? 0.0 : f[6 * fs]);
+        case SCCAV_SLOT_ELLIPSE_PREP: return ellipse_prep_partials(x, y, f[0], f[fs], f[2 * fs], f[3 * fs], f[4 * fs], f[5 * fs],
+                                                                   is_static ? 0.0 : f[6 * fs], is_static ? 0.0 : f[7 * fs]);
         case SCCAV_SLOT_CONE: return cone_partials(x, y, th, v, f[0], f[fs], f[2 * fs], f[3 * fs], f[4 * fs], f[5 * fs]);
         case SCCAV_SLOT_LANE: {
             double c[6] = {f[fs], f[2 * fs], f[3 * fs], f[4 * fs], f[5 * fs], f[6 * fs]};
@@ -258,7 +280,7 @@ static int filter_vehicle(const sccav_params* p, const uint8_t* sd, int M, int64
     *hmin = INFINITY;
     for (int m = 0; m < M; ++m) {
         int64_t nn = (sd[m] & SCCAV_SLOT_SHARED) ? 0 : n;
-        part_t pt = slot_partials(sd[m] & 0x7f, obst + (int64_t)m * SCCAV_NFIELD * N + nn, N, x, y, th, v);
+        part_t pt = slot_partials(sd[m], obst + (int64_t)m * SCCAV_NFIELD * N + nn, N, x, y, th, v);
         make_row(p->model, &pt, th, v, alpha, p->lr, &A0[m], &A1[m], &b[m]);
         if (pt.h < *hmin) *hmin = pt.h;
     }
@@ -442,7 +464,7 @@ static void rollout_body(void* vctx, int64_t n) {
             }
             if (p->seeker)
                 for (int m = 0; m < M; ++m)
-                    if ((sd[m] & 0x7f) == SCCAV_SLOT_RADIAL && !(sd[m] & SCCAV_SLOT_SHARED))
+                    if ((sd[m] & SCCAV_SLOT_TYPE_MASK) == SCCAV_SLOT_RADIAL && !(sd[m] & SCCAV_SLOT_SHARED))
                         seeker_update(obst + (int64_t)m * SCCAV_NFIELD * N + n, N, x, y, p->dt, p->seeker_k, p->seeker_vmin);
             if (p->record_stride > 0 && (steps % p->record_stride) == 0) {
                 int64_t rec = steps / p->record_stride;

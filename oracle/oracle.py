@@ -56,6 +56,10 @@ SLOT_CONE = 1      # f: cx, cy, theta_o, v_o, a, beta, -, -
 SLOT_LANE = 2      # f: buffer, c0, c1, c2, c3, c4, c5, -
 SLOT_RADIAL = 3    # f: cx, cy, a, b, kv, vx, vy, -
 SLOT_DISTANCE = 4  # f: cx, cy, Ds, -, -, -, -, -
+SLOT_ELLIPSE_PREP = 5  # f: cx, cy, m00, m01, m10, m11, wx, wy   (prepare_ellipse below)
+SLOT_TYPE_MASK = 0x3F
+SLOT_STATIC = 0x40  # flag: velocity fields are not read, h_t = 0
+FLAG_PREPARED_ROWS = 1  # sccav_params.flags (GPU rollout only; the oracle's arithmetic is always canonical)
 NFIELD = 8
 
 MODEL_DBM = 0      # DBM_CBF_2DS  (cbf/cbf.py:112-220)
@@ -248,11 +252,39 @@ def lane_partials(x, y, c, buffer):
     return h, h_x, h_y, 0.0, 0.0, 0.0
 
 
-def slot_partials(slot_type, f, s):
+def prepare_ellipse(f):
+    """Ingest-time half of Ellipse2D (include/sccav_cbf.h, ELLIPSE_PREP): canonical fields
+    (cx, cy, a, b, theta, vx, vy, -) -> (cx, cy, cos/a, sin/a, -sin/b, cos/b, vx/a^2, vy/b^2)."""
+    cx, cy, a, b, th, vx, vy = (float(v) for v in f[:7])
+    ct = float(np.cos(th))
+    st = float(np.sin(th))
+    return [cx, cy, ct / a, st / a, -st / b, ct / b, vx / (a * a), vy / (b * b)]
+
+
+def ellipse_prep_partials(x, y, cx, cy, m00, m01, m10, m11, wx, wy):
+    """Per-solve half: with d = (x - cx, y - cy) and (pa, qb) = M d,  h = pa^2 + qb^2 - 1,
+    grad h = 2 M^T (pa, qb), h_t = -2 (dx wx + dy wy) -- the functions of cbf/obstacles.py:193,218,229,316
+    regrouped (equal to ellipse_partials up to a few ulp)."""
+    dx = x - cx
+    dy = y - cy
+    pa = m00 * dx + m01 * dy
+    qb = m10 * dx + m11 * dy
+    h = (pa * pa + qb * qb) - 1.0
+    h_x = 2.0 * (m00 * pa + m10 * qb)
+    h_y = 2.0 * (m01 * pa + m11 * qb)
+    h_t = -2.0 * (dx * wx + dy * wy)
+    return h, h_x, h_y, 0.0, 0.0, h_t
+
+
+def slot_partials(slot_desc, f, s):
     """Dispatch on the slot type; ``f`` = the 8 slot fields, ``s`` = (x, y, theta, v)."""
     x, y, th, v = s
+    slot_type = int(slot_desc) & SLOT_TYPE_MASK
+    static = bool(int(slot_desc) & SLOT_STATIC)
     if slot_type == SLOT_ELLIPSE:
-        return ellipse_partials(x, y, f[0], f[1], f[2], f[3], f[4], f[5], f[6])
+        return ellipse_partials(x, y, f[0], f[1], f[2], f[3], f[4], 0.0 if static else f[5], 0.0 if static else f[6])
+    if slot_type == SLOT_ELLIPSE_PREP:
+        return ellipse_prep_partials(x, y, f[0], f[1], f[2], f[3], f[4], f[5], 0.0 if static else f[6], 0.0 if static else f[7])
     if slot_type == SLOT_CONE:
         return cone_partials(x, y, th, v, f[0], f[1], f[2], f[3], f[4], f[5])
     if slot_type == SLOT_LANE:

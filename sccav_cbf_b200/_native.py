@@ -16,8 +16,11 @@ NFIELD = 8
 MAX_ROWS = 32
 TRAJ_FIELDS = 7
 
-SLOT_ELLIPSE, SLOT_CONE, SLOT_LANE, SLOT_RADIAL, SLOT_DISTANCE = 0, 1, 2, 3, 4
+SLOT_ELLIPSE, SLOT_CONE, SLOT_LANE, SLOT_RADIAL, SLOT_DISTANCE, SLOT_ELLIPSE_PREP = 0, 1, 2, 3, 4, 5
+SLOT_TYPE_MASK = 0x3F
+SLOT_STATIC = 0x40
 SLOT_SHARED = 0x80
+FLAG_PREPARED_ROWS = 1
 MODEL_DBM, MODEL_KBM, MODEL_NONE = 0, 1, 2
 NOMINAL_STANLEY, NOMINAL_CONST = 0, 1
 STATUS_INACTIVE, STATUS_ACTIVE, STATUS_INFEASIBLE = 0, 1, 2
@@ -28,7 +31,7 @@ class Params(C.Structure):
     """struct sccav_params (include/sccav_cbf.h)."""
     _fields_ = [
         ("model", C.c_int32), ("nominal", C.c_int32), ("terminate", C.c_int32), ("seeker", C.c_int32),
-        ("kbm_driver_delta", C.c_int32), ("record_stride", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_int32),
+        ("kbm_driver_delta", C.c_int32), ("record_stride", C.c_int32), ("flags", C.c_int32), ("reserved1", C.c_int32),
         ("alpha", C.c_double), ("lr", C.c_double), ("lf", C.c_double), ("L", C.c_double),
         ("max_steer", C.c_double), ("dt", C.c_double), ("k_stanley", C.c_double), ("ks_stanley", C.c_double),
         ("Kp", C.c_double), ("target_speed", C.c_double), ("t_max", C.c_double),
@@ -65,6 +68,7 @@ SYMBOLS = [
     "sccav_measure_fma_peak", "sccav_launch_count", "sccav_debug_course_index_host",
     "sccav_rollout_launch_info_f64", "sccav_rollout_launch_info_f32",
     "sccav_barrier_partials_f64", "sccav_barrier_partials_f32", "sccav_stanley_control_f64", "sccav_stanley_control_f32",
+    "sccav_prepare_obstacles_f64", "sccav_prepare_obstacles_f32",
 ]
 
 
@@ -92,6 +96,8 @@ def lib() -> C.CDLL:
         f = getattr(L, "sccav_barrier_rows_" + sfx)
         f.argtypes = [PP, C.c_char_p, i32, i64, vp, vp, PV, vp, vp, vp, vp]
         f = getattr(L, "sccav_barrier_partials_" + sfx)
+        f.argtypes = [C.c_char_p, i32, i64, vp, vp, vp, vp]
+        f = getattr(L, "sccav_prepare_obstacles_" + sfx)
         f.argtypes = [C.c_char_p, i32, i64, vp, vp, vp, vp]
         f = getattr(L, "sccav_stanley_control_" + sfx)
         f.argtypes = [PP, i64, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]

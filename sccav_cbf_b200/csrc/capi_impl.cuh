@@ -31,8 +31,8 @@ int check_common(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int
     }
     if (M > 0 && !slot_desc) { set_error("slot_desc is NULL"); return SCCAV_EINVAL; }
     for (int m = 0; m < M; ++m) {
-        int t = slot_desc[m] & 0x7f;
-        if (t > SCCAV_SLOT_DISTANCE) { set_error("slot %d: unknown type %d", m, t); return SCCAV_EINVAL; }
+        int t = slot_desc[m] & SCCAV_SLOT_TYPE_MASK;
+        if (t > SCCAV_SLOT_ELLIPSE_PREP) { set_error("slot %d: unknown type %d", m, t); return SCCAV_EINVAL; }
     }
     if (p->model < 0 || p->model > SCCAV_MODEL_NONE) { set_error("unknown model %d", p->model); return SCCAV_EINVAL; }
     double det = p->R[0] * p->R[3] - p->R[1] * p->R[2];
@@ -47,7 +47,7 @@ int check_common(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int
 Params<real> convert(const sccav_params* p) {
     Params<real> q;
     q.model = p->model; q.nominal = p->nominal; q.terminate = p->terminate; q.seeker = p->seeker;
-    q.kbm_driver_delta = p->kbm_driver_delta; q.record_stride = p->record_stride;
+    q.kbm_driver_delta = p->kbm_driver_delta; q.record_stride = p->record_stride; q.flags = p->flags;
     q.alpha = (real)p->alpha; q.lr = (real)p->lr; q.lf = (real)p->lf; q.L = (real)p->L;
     q.max_steer = (real)p->max_steer; q.dt = (real)p->dt; q.k_stanley = (real)p->k_stanley;
     q.ks_stanley = (real)p->ks_stanley; q.Kp = (real)p->Kp; q.target_speed = (real)p->target_speed;
@@ -89,6 +89,27 @@ int rows_block(int M, size_t& smem) {
     while (block > 32 && (size_t)3 * M * block * sizeof(real) > 96 * 1024) block >>= 1;
     smem = (size_t)3 * (M > 0 ? M : 1) * block * sizeof(real);
     return block;
+}
+
+int do_prepare(const uint8_t* slot_desc, int32_t M, int64_t N, const real* in, real* out, uint8_t* desc_out, cudaStream_t st) {
+    sccav_params dp;
+    sccav_default_params(&dp);
+    int rc = check_common(&dp, slot_desc, M, N, true);
+    if (rc) return rc;
+    if (M > 0 && !desc_out) { set_error("slot_desc_out is NULL"); return SCCAV_EINVAL; }
+    for (int m = 0; m < M; ++m) {
+        const int t = slot_desc[m] & SCCAV_SLOT_TYPE_MASK;
+        desc_out[m] = t == SCCAV_SLOT_ELLIPSE ? (uint8_t)((slot_desc[m] & ~SCCAV_SLOT_TYPE_MASK) | SCCAV_SLOT_ELLIPSE_PREP) : slot_desc[m];
+    }
+    if (N == 0 || M == 0) return SCCAV_OK;
+    if (!in || !out) { set_error("NULL array argument"); return SCCAV_EINVAL; }
+    PrepareArgs<real> a;
+    a.sd = make_desc(slot_desc, M); a.M = M; a.N = N; a.in = in; a.out = out;
+    const int block = 256;
+    prepare_obstacles_kernel<real><<<stream_grid((int64_t)M * N, block), block, 0, st>>>(a);
+    count_launch();
+    SCCAV_CUDA_CHECK(cudaGetLastError());
+    return SCCAV_OK;
 }
 
 int do_barrier_rows(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N, const real* state,
@@ -187,13 +208,13 @@ int do_filter_step(const sccav_params* p, const uint8_t* slot_desc, int32_t M, i
     a.u = u; a.mask = mask; a.status = status; a.h_min = h_min;
     size_t smem;
     const int block = rows_block(M, smem);
-    if (all_private_ellipses(slot_desc, M)) {
-        SCCAV_CUDA_CHECK(cudaFuncSetAttribute(filter_step_kernel<real, SCCAV_SPEC_ELLIPSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        filter_step_kernel<real, SCCAV_SPEC_ELLIPSE><<<stream_grid(N, block), block, smem, st>>>(a);
-    } else {
-        SCCAV_CUDA_CHECK(cudaFuncSetAttribute(filter_step_kernel<real, SCCAV_SPEC_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        filter_step_kernel<real, SCCAV_SPEC_GENERIC><<<stream_grid(N, block), block, smem, st>>>(a);
-    }
+    typedef void (*filter_fn)(FilterArgs<real>);
+    const int spec = choose_spec(slot_desc, M);
+    const filter_fn kern = spec == SCCAV_SPEC_ELLIPSE ? filter_step_kernel<real, SCCAV_SPEC_ELLIPSE>
+                         : spec == SCCAV_SPEC_ELLIPSE_PREP ? filter_step_kernel<real, SCCAV_SPEC_ELLIPSE_PREP>
+                                                           : filter_step_kernel<real, SCCAV_SPEC_GENERIC>;
+    SCCAV_CUDA_CHECK(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<stream_grid(N, block), block, smem, st>>>(a);
     count_launch();
     SCCAV_CUDA_CHECK(cudaGetLastError());
     return SCCAV_OK;
@@ -214,11 +235,13 @@ void rollout_geometry(int64_t N, int& grid, int& block) {
     grid = (int)((N + block - 1) / block);
 }
 
-// the four instances of the persistent kernel: course in shared memory or not x slot specialisation
+// the six instances of the persistent kernel: course in shared memory or not x slot specialisation
 typedef void (*rollout_fn)(RolloutArgs<real>);
 rollout_fn rollout_instance(bool course_smem, int spec) {
     if (spec == SCCAV_SPEC_ELLIPSE)
         return course_smem ? rollout_kernel<real, true, SCCAV_SPEC_ELLIPSE> : rollout_kernel<real, false, SCCAV_SPEC_ELLIPSE>;
+    if (spec == SCCAV_SPEC_ELLIPSE_PREP)
+        return course_smem ? rollout_kernel<real, true, SCCAV_SPEC_ELLIPSE_PREP> : rollout_kernel<real, false, SCCAV_SPEC_ELLIPSE_PREP>;
     return course_smem ? rollout_kernel<real, true, SCCAV_SPEC_GENERIC> : rollout_kernel<real, false, SCCAV_SPEC_GENERIC>;
 }
 
@@ -268,16 +291,31 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
     int grid, block;
     size_t smem;
     bool course_smem;
-    const int spec = (all_private_ellipses(slot_desc, M) && p->model != SCCAV_MODEL_NONE) ? SCCAV_SPEC_ELLIPSE : SCCAV_SPEC_GENERIC;
-    rc = rollout_launch_shape(M, N, a.np, stan, spec, grid, block, smem, course_smem);
-    if (rc) return rc;
-    // scratch for the loop-invariant terms of static ellipses: stream-ordered, lives for this launch
-    a.pre = nullptr;
+    // SCCAV_FLAG_PREPARED_ROWS: ingest the ELLIPSE slots once (KP) into a stream-ordered scratch and
+    // run the closed loop on their prepared form
+    const bool filt = M > 0 && p->model != SCCAV_MODEL_NONE;
+    uint8_t desc2[SCCAV_MAX_ROWS];
+    for (int m = 0; m < M; ++m) desc2[m] = slot_desc[m];
+    void* prep = nullptr;
     bool any_ellipse = false;
-    for (int m = 0; m < M; ++m) any_ellipse |= (slot_desc[m] & 0x7f) == SCCAV_SLOT_ELLIPSE;
-    if (any_ellipse && T >= 2 && p->model != SCCAV_MODEL_NONE) {
+    for (int m = 0; m < M; ++m) any_ellipse |= (slot_desc[m] & SCCAV_SLOT_TYPE_MASK) == SCCAV_SLOT_ELLIPSE;
+    if (filt && any_ellipse && (p->flags & SCCAV_FLAG_PREPARED_ROWS) && !p->seeker) {
+        SCCAV_CUDA_CHECK(cudaMallocAsync(&prep, (size_t)M * SCCAV_NFIELD * (size_t)N * sizeof(real), st));
+        rc = do_prepare(slot_desc, M, N, obst, (real*)prep, desc2, st);
+        if (rc) { cudaFreeAsync(prep, st); return rc; }
+        a.obst = (real*)prep;
+        a.sd = make_desc(desc2, M);
+        any_ellipse = false;
+    }
+    const int spec = filt ? choose_spec(desc2, M) : SCCAV_SPEC_GENERIC;
+    rc = rollout_launch_shape(M, N, a.np, stan, spec, grid, block, smem, course_smem);
+    if (rc) { if (prep) cudaFreeAsync(prep, st); return rc; }
+    // scratch for the loop-invariant terms of canonical ellipses: stream-ordered, lives for this launch
+    a.pre = nullptr;
+    if (any_ellipse && T >= 2 && filt) {
         void* scratch = nullptr;
-        SCCAV_CUDA_CHECK(cudaMallocAsync(&scratch, (size_t)M * SCCAV_NPRE * (size_t)N * sizeof(real), st));
+        cudaError_t me = cudaMallocAsync(&scratch, (size_t)M * SCCAV_NPRE * (size_t)N * sizeof(real), st);
+        if (me != cudaSuccess) { if (prep) cudaFreeAsync(prep, st); SCCAV_CUDA_CHECK(me); }
         a.pre = (real*)scratch;
     }
     const rollout_fn kern = rollout_instance(course_smem, spec);
@@ -285,6 +323,7 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
     if (le == cudaSuccess) { kern<<<grid, block, smem, st>>>(a); le = cudaGetLastError(); }
     count_launch();
     if (a.pre) cudaFreeAsync(a.pre, st);
+    if (prep) cudaFreeAsync(prep, st);
     SCCAV_CUDA_CHECK(le);
     return SCCAV_OK;
 }
@@ -312,6 +351,11 @@ int SCCAV_FN(sccav_barrier_rows_)(const sccav_params* p, const uint8_t* slot_des
                                   const SCCAV_REAL* state, const SCCAV_REAL* obst, const sccav_pervehicle* pv,
                                   SCCAV_REAL* A_out, SCCAV_REAL* b_out, SCCAV_REAL* h_out, void* stream) {
     return sccav::do_barrier_rows(p, slot_desc, M, N, state, obst, pv, A_out, b_out, h_out, (cudaStream_t)stream);
+}
+
+int SCCAV_FN(sccav_prepare_obstacles_)(const uint8_t* slot_desc, int32_t M, int64_t N, const SCCAV_REAL* obst_in,
+                                        SCCAV_REAL* obst_out, uint8_t* slot_desc_out, void* stream) {
+    return sccav::do_prepare(slot_desc, M, N, obst_in, obst_out, slot_desc_out, (cudaStream_t)stream);
 }
 
 int SCCAV_FN(sccav_barrier_partials_)(const uint8_t* slot_desc, int32_t M, int64_t N, const SCCAV_REAL* state,
@@ -354,7 +398,7 @@ int SCCAV_FN(sccav_rollout_launch_info_)(const uint8_t* slot_desc, int32_t M, in
     int grid, block;
     size_t smem;
     bool course_smem;
-    const int spec = all_private_ellipses(slot_desc, M) ? SCCAV_SPEC_ELLIPSE : SCCAV_SPEC_GENERIC;
+    const int spec = choose_spec(slot_desc, M);
     int rc = rollout_launch_shape(M, N, P, P > 0, spec, grid, block, smem, course_smem);
     if (rc) return rc;
     const void* kern = (const void*)rollout_instance(course_smem, spec);

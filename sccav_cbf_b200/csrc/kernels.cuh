@@ -29,6 +29,40 @@ __device__ __forceinline__ void load_weights(const Params<T>& P, const PerVehicl
     else { R00 = P.R[0]; R01 = P.R[1]; R10 = P.R[2]; R11 = P.R[3]; }
 }
 
+// ------------------------------------------------------------------------------------------ KP
+// Obstacle ingest: ELLIPSE slots -> ELLIPSE_PREP (include/sccav_cbf.h), other slots copied.
+// HBM-bound: 64 B read + 64 B written per (vehicle, slot).  in == out is allowed (every thread
+// reads its 8 fields before it writes them).
+template <typename T> struct PrepareArgs {
+    SlotDesc sd;
+    int M;
+    int64_t N;
+    const T* in;
+    T* out;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) prepare_obstacles_kernel(const __grid_constant__ PrepareArgs<T> a) {
+    const int64_t N = a.N;
+    const int64_t total = (int64_t)a.M * N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int m = (int)(i / N);
+        const int64_t n = i - (int64_t)m * N;
+        const T* f = a.in + (int64_t)m * SCCAV_NFIELD * N + n;
+        T* o = a.out + (int64_t)m * SCCAV_NFIELD * N + n;
+        T v[SCCAV_NFIELD];
+#pragma unroll
+        for (int k = 0; k < SCCAV_NFIELD; ++k) v[k] = f[k * N];
+        if ((a.sd.d[m] & SCCAV_SLOT_TYPE_MASK) == SCCAV_SLOT_ELLIPSE) {
+            T m00, m01, m10, m11, wx, wy;
+            ellipse_prepare<T>(v[2], v[3], v[4], v[5], v[6], m00, m01, m10, m11, wx, wy);
+            v[2] = m00; v[3] = m01; v[4] = m10; v[5] = m11; v[6] = wx; v[7] = wy;
+        }
+#pragma unroll
+        for (int k = 0; k < SCCAV_NFIELD; ++k) o[k * N] = v[k];
+    }
+}
+
 // ------------------------------------------------------------------------------------------ K1
 template <typename T> struct RowsArgs {
     Params<T> P;
@@ -56,7 +90,7 @@ __global__ void __launch_bounds__(256) barrier_rows_kernel(const __grid_constant
             const int desc = a.sd.d[m];
             const int64_t nn = (desc & SCCAV_SLOT_SHARED) ? 0 : n;
             const T* f = a.obst + (int64_t)m * SCCAV_NFIELD * N + nn;
-            Partials<T> p = slot_partials<T>(desc & 0x7f, f, N, x, y, th, v, sth, cth);
+            Partials<T> p = slot_partials<T>(desc, f, N, x, y, th, v, sth, cth);
             T A0, A1, b;
             if (a.P.model == SCCAV_MODEL_KBM) kbm_row<T>(p, sth, cth, alpha, A0, A1, b);
             else dbm_row<T>(p, sth, cth, v, alpha, a.P.lr, A0, A1, b);
@@ -92,7 +126,7 @@ __global__ void __launch_bounds__(256) barrier_partials_kernel(const __grid_cons
             const int desc = a.sd.d[m];
             const int64_t nn = (desc & SCCAV_SLOT_SHARED) ? 0 : n;
             const T* f = a.obst + (int64_t)m * SCCAV_NFIELD * N + nn;
-            Partials<T> p = slot_partials<T>(desc & 0x7f, f, N, x, y, th, v, sth, cth);
+            Partials<T> p = slot_partials<T>(desc, f, N, x, y, th, v, sth, cth);
             T* o = a.out + (int64_t)m * 6 * N + n;
             o[0] = p.h; o[N] = p.hx; o[2 * N] = p.hy; o[3 * N] = p.hth; o[4 * N] = p.hv; o[5 * N] = p.ht;
         }
@@ -418,11 +452,11 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
     if (a.pre && filt) {
         for (int m = 0; m < a.M; ++m) {
             const int desc = a.sd.d[m];
-            if ((desc & 0x7f) != SCCAV_SLOT_ELLIPSE) continue;
+            if ((desc & SCCAV_SLOT_TYPE_MASK) != SCCAV_SLOT_ELLIPSE) continue;
             const int64_t nn = (desc & SCCAV_SLOT_SHARED) ? 0 : n;
             const T* f = a.obst + (int64_t)m * SCCAV_NFIELD * N + nn;
             ellipse_precompute<T>(f[2 * N], f[3 * N], f[4 * N], a.pre + (int64_t)m * SCCAV_NPRE * N + n, N);
-            if (f[5 * N] != T(0) || f[6 * N] != T(0)) moving |= 1u << m;
+            if (!(desc & SCCAV_SLOT_STATIC) && (f[5 * N] != T(0) || f[6 * N] != T(0))) moving |= 1u << m;
         }
     }
 
@@ -510,7 +544,7 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
         if (P.seeker) {
             for (int m = 0; m < a.M; ++m) {
                 const int desc = a.sd.d[m];
-                if ((desc & 0x7f) == SCCAV_SLOT_RADIAL && !(desc & SCCAV_SLOT_SHARED))
+                if ((desc & SCCAV_SLOT_TYPE_MASK) == SCCAV_SLOT_RADIAL && !(desc & SCCAV_SLOT_SHARED))
                     seeker_update<T>(a.obst + (int64_t)m * SCCAV_NFIELD * N + n, N, x, y, P.dt, P.seeker_k, P.seeker_vmin);
             }
         }

@@ -61,7 +61,7 @@ template <> struct Real<float> {
 
 // parameters in the kernel's precision
 template <typename T> struct Params {
-    int model, nominal, terminate, seeker, kbm_driver_delta, record_stride;
+    int model, nominal, terminate, seeker, kbm_driver_delta, record_stride, flags;
     T alpha, lr, lf, L, max_steer, dt, k_stanley, ks_stanley, Kp, target_speed, t_max;
     T R[4];
     T seeker_k, seeker_vmin, uref0, uref1;
@@ -148,6 +148,34 @@ __device__ __forceinline__ Partials<T> ellipse_partials_pre(T x, T y, T cx, T cy
         T aa = a * a, bb = b * b;
         o.ht = T(-2) * ((dx / aa) * vx + (dy / bb) * vy);
     }
+    return o;
+}
+
+// ELLIPSE_PREP (include/sccav_cbf.h): the ingest-time half of Ellipse2D -- everything that does not
+// depend on the vehicle -- and the per-solve half.  Same functions as ellipse_partials
+// (cbf/obstacles.py:193,218,229,316), a few ulp apart; written with explicit fma (this is not
+// reference operation order, so contraction is welcome).
+template <typename T>
+__device__ __forceinline__ void ellipse_prepare(T a, T b, T th, T vx, T vy, T& m00, T& m01, T& m10, T& m11, T& wx, T& wy) {
+    T st, ct;
+    Real<T>::sincos_(th, &st, &ct);
+    m00 = ct / a; m01 = st / a;
+    m10 = (-st) / b; m11 = ct / b;
+    wx = vx / (a * a); wy = vy / (b * b);
+}
+
+template <typename T>
+__device__ __forceinline__ Partials<T> ellipse_prep_partials(T x, T y, T cx, T cy, T m00, T m01, T m10, T m11, T wx, T wy) {
+    Partials<T> o;
+    T dx = x - cx, dy = y - cy;
+    T pa = fma(m00, dx, m01 * dy);
+    T qb = fma(m10, dx, m11 * dy);
+    o.h = fma(pa, pa, fma(qb, qb, T(-1)));
+    o.hx = T(2) * fma(m00, pa, m10 * qb);
+    o.hy = T(2) * fma(m01, pa, m11 * qb);
+    o.hth = T(0);
+    o.hv = T(0);
+    o.ht = T(-2) * fma(dx, wx, dy * wy);
     return o;
 }
 
@@ -284,18 +312,22 @@ __device__ __forceinline__ Partials<T> lane_partials(T x, T y, const T (&c)[6], 
 
 // dispatch on slot type; fields are read from the SoA obstacle buffer obst[(m*8+f)*N + n]
 template <typename T>
-__device__ __forceinline__ Partials<T> slot_partials(int type, const T* __restrict__ f, int64_t fs,
+__device__ __forceinline__ Partials<T> slot_partials(int desc, const T* __restrict__ f, int64_t fs,
                                                      T x, T y, T th, T v, T sth, T cth,
                                                      const T* pre = nullptr, int64_t ps = 0) {
+    const int type = desc & SCCAV_SLOT_TYPE_MASK;
+    const bool is_static = (desc & SCCAV_SLOT_STATIC) != 0;
     // f points at field 0 of this slot for this vehicle; fs = stride between fields (N)
     // pre (optional): this slot's loop-invariant values for this vehicle, stride ps
     switch (type) {
         case SCCAV_SLOT_ELLIPSE: {
+            T vx = T(0), vy = T(0);
+            if (!is_static) { vx = f[5 * fs]; vy = f[6 * fs]; }
             if (pre) {
-                T cx = f[0], cy = f[fs], a = f[2 * fs], b = f[3 * fs], vx = f[5 * fs], vy = f[6 * fs];
+                T cx = f[0], cy = f[fs], a = f[2 * fs], b = f[3 * fs];
                 return ellipse_partials_pre<T>(x, y, cx, cy, a, b, vx, vy, pre, ps);
             }
-            T cx = f[0], cy = f[fs], a = f[2 * fs], b = f[3 * fs], t = f[4 * fs], vx = f[5 * fs], vy = f[6 * fs];
+            T cx = f[0], cy = f[fs], a = f[2 * fs], b = f[3 * fs], t = f[4 * fs];
             return ellipse_partials<T>(x, y, cx, cy, a, b, t, vx, vy);
         }
         case SCCAV_SLOT_CONE: {
@@ -310,6 +342,11 @@ __device__ __forceinline__ Partials<T> slot_partials(int type, const T* __restri
         case SCCAV_SLOT_RADIAL: {
             T cx = f[0], cy = f[fs], a = f[2 * fs], b = f[3 * fs], kv = f[4 * fs], vx = f[5 * fs], vy = f[6 * fs];
             return radial_partials<T>(x, y, v, cx, cy, a, b, kv, vx, vy);
+        }
+        case SCCAV_SLOT_ELLIPSE_PREP: {
+            T wx = T(0), wy = T(0);
+            if (!is_static) { wx = f[6 * fs]; wy = f[7 * fs]; }
+            return ellipse_prep_partials<T>(x, y, f[0], f[fs], f[2 * fs], f[3 * fs], f[4 * fs], f[5 * fs], wx, wy);
         }
         default: {
             T cx = f[0], cy = f[fs], Ds = f[2 * fs];
@@ -477,9 +514,12 @@ __device__ __forceinline__ int qp2_solve(const RowView<T>& rv, int m, T r0, T r1
 //   SPEC_GENERIC  any slot mix, dispatch on the slot descriptor
 //   SPEC_ELLIPSE  every slot is a per-vehicle (not SHARED) ELLIPSE -- the BASELINE configs 2 and 5;
 //                 no dispatch, and the fields of slot m+1 are in flight while slot m is evaluated
+//   SPEC_ELLIPSE_PREP  every slot is a per-vehicle ELLIPSE_PREP with the same STATIC flag: 6 (static)
+//                 or 8 loads and ~25 fma per row, nothing else -- the HBM-bound form of the operator
 // ------------------------------------------------------------------------------------------
 #define SCCAV_SPEC_GENERIC 0
 #define SCCAV_SPEC_ELLIPSE 1
+#define SCCAV_SPEC_ELLIPSE_PREP 2
 
 // row of one slot into shared memory + running feasibility test of the reference point
 // (qp_check(r) of qp2_solve, evaluated on the fly with the same operations)
@@ -534,13 +574,6 @@ __device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc
                 put_row<T>(P, p, sth, cth, v, alpha, r0, r1, rows, stride, m, hmin, worst, feas, nz);
             }
         } else {
-#ifdef SCCAV_EXP_NO_PIPE
-            for (int m = 0; m < M; ++m, f += ss) {
-                T cx = f[0], cy = f[N], a = f[2 * N], b = f[3 * N], t = f[4 * N], vx = f[5 * N], vy = f[6 * N];
-                Partials<T> p = ellipse_partials<T>(x, y, cx, cy, a, b, t, vx, vy);
-                put_row<T>(P, p, sth, cth, v, alpha, r0, r1, rows, stride, m, hmin, worst, feas, nz);
-            }
-#else
             T cx = f[0], cy = f[N], a = f[2 * N], b = f[3 * N], t = f[4 * N], vx = f[5 * N], vy = f[6 * N];
             for (int m = 0; m < M; ++m) {
                 f += ss;
@@ -550,7 +583,21 @@ __device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc
                 put_row<T>(P, p, sth, cth, v, alpha, r0, r1, rows, stride, m, hmin, worst, feas, nz);
                 cx = ncx; cy = ncy; a = na; b = nb; t = nt; vx = nvx; vy = nvy;
             }
+        }
+    } else if (SPEC == SCCAV_SPEC_ELLIPSE_PREP) {
+        const int64_t ss = (int64_t)SCCAV_NFIELD * N;
+        const T* f = obst + n;
+        const bool is_static = (sd.d[0] & SCCAV_SLOT_STATIC) != 0;
+#ifndef SCCAV_PREP_UNROLL
+#define SCCAV_PREP_UNROLL 2
 #endif
+        constexpr int kPrepUnroll = SCCAV_PREP_UNROLL;
+#pragma unroll kPrepUnroll
+        for (int m = 0; m < M; ++m, f += ss) {
+            T wx = T(0), wy = T(0);
+            if (!is_static) { wx = f[6 * N]; wy = f[7 * N]; }
+            Partials<T> p = ellipse_prep_partials<T>(x, y, f[0], f[N], f[2 * N], f[3 * N], f[4 * N], f[5 * N], wx, wy);
+            put_row<T>(P, p, sth, cth, v, alpha, r0, r1, rows, stride, m, hmin, worst, feas, nz);
         }
     } else {
         for (int m = 0; m < M; ++m) {
@@ -558,21 +605,17 @@ __device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc
             const int64_t nn = (desc & SCCAV_SLOT_SHARED) ? 0 : n;
             const T* f = obst + (int64_t)m * SCCAV_NFIELD * N + nn;
             const T* pr = pre ? pre + (int64_t)m * SCCAV_NPRE * N + n : nullptr;
-            Partials<T> p = slot_partials<T>(desc & 0x7f, f, N, x, y, th, v, sth, cth, pr, N);
+            Partials<T> p = slot_partials<T>(desc, f, N, x, y, th, v, sth, cth, pr, N);
             put_row<T>(P, p, sth, cth, v, alpha, r0, r1, rows, stride, m, hmin, worst, feas, nz);
         }
     }
     T q0 = r0, q1 = r1;
     int status = SCCAV_STATUS_INACTIVE;
     mask = 0u;
-#ifndef SCCAV_EXP_NO_QP
     if (!feas) {
         RowView<T> rv{rows, stride};
         status = qp2_solve_active<T>(rv, M, nz, r0, r1, R00, R01, R10, R11, worst, q0, q1, mask);
     }
-#else
-    if (!feas) { status = SCCAV_STATUS_ACTIVE; mask = 1u; }
-#endif
     u0 = q0;
     u1raw = q1;
     if (P.model == SCCAV_MODEL_KBM) {
@@ -584,15 +627,23 @@ __device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc
     return status;
 }
 
-// true when every slot is a per-vehicle ELLIPSE (host-side choice of SCCAV_SPEC_ELLIPSE)
-__host__ __device__ inline bool all_private_ellipses(const uint8_t* d, int M) {
-    if (M < 1) return false;
-#ifdef SCCAV_EXP_NO_SPEC
-    return false;
-#endif
-    for (int m = 0; m < M; ++m)
-        if (d[m] != SCCAV_SLOT_ELLIPSE) return false;
-    return true;
+// host-side choice of the slot-loop specialisation
+__host__ __device__ inline int choose_spec(const uint8_t* d, int M) {
+    if (M < 1) return SCCAV_SPEC_GENERIC;
+    const int first = d[0];
+    const int type = first & SCCAV_SLOT_TYPE_MASK;
+    if (first & SCCAV_SLOT_SHARED) return SCCAV_SPEC_GENERIC;
+    if (type == SCCAV_SLOT_ELLIPSE) {
+        for (int m = 0; m < M; ++m)
+            if (d[m] != SCCAV_SLOT_ELLIPSE) return SCCAV_SPEC_GENERIC;      // (a STATIC canonical ellipse takes the generic loop)
+        return SCCAV_SPEC_ELLIPSE;
+    }
+    if (type == SCCAV_SLOT_ELLIPSE_PREP) {
+        for (int m = 0; m < M; ++m)
+            if (d[m] != first) return SCCAV_SPEC_GENERIC;
+        return SCCAV_SPEC_ELLIPSE_PREP;
+    }
+    return SCCAV_SPEC_GENERIC;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -292,6 +292,30 @@ def launch_count() -> int:
     return int(nv.lib().sccav_launch_count())
 
 
+def prepare_obstacles(slot_desc, obst: torch.Tensor, out: Optional[torch.Tensor] = None):
+    """KP: obstacle ingest for repeated solves -- every ELLIPSE slot of ``obst`` [M,8,N] becomes an
+    ELLIPSE_PREP slot (the batched counterpart of constructing the Ellipse2D objects once,
+    cbf/obstacles.py:146-165, and calling solve_cbf every tick).  Returns (new slot_desc list,
+    prepared obst); ``out`` may be ``obst`` itself (in place)."""
+    L = nv.lib()
+    nv.require_cuda()
+    sd = slot_bytes(slot_desc)
+    M, N = len(sd), obst.shape[-1]
+    dt, dev = obst.dtype, obst.device
+    if dev.type != "cuda":
+        raise ValueError("prepare_obstacles works on device tensors")
+    obst = _chk(obst, (M, nv.NFIELD, N), dt, dev, "obst")
+    if not obst.is_contiguous():
+        raise ValueError("obst must be contiguous")
+    if out is None:
+        out = torch.empty_like(obst)
+    out = _chk(out, (M, nv.NFIELD, N), dt, dev, "out")
+    sd_out = (C.c_uint8 * max(M, 1))()
+    with torch.cuda.device(dev):
+        nv.check(getattr(L, "sccav_prepare_obstacles_" + _SFX[dt])(sd, M, N, _ptr(obst), _ptr(out), C.addressof(sd_out), _stream(dev)))
+    return [int(sd_out[m]) for m in range(M)], out
+
+
 def rollout_launch_info(slot_desc, N: int, P: int, dtype=torch.float64) -> Dict[str, int]:
     """Launch shape of the rollout kernel for (slot_desc, N, P) on the current device (no launch).
     `slot_desc`: the slot descriptors of the batch, or an int M meaning M per-vehicle ellipses."""

@@ -49,6 +49,15 @@ def main():
             ms, solves / ms * 1e3, int(res["n_active"].sum().item()), int(res["n_infeasible"].sum().item()),
             float(res["n_evals"].double().sum().item()) / float(res["steps"].sum().item()),
             ops.rollout_launch_info(batch.slot_desc, batch.N, 2034, dtype)))
+        b2 = sc.config2(n_total=a.vehicles, M=M, T=a.T, seed=0, lo=0, hi=a.vehicles)
+        b2.params = dict(b2.params, flags=1)
+        cl2 = ClosedLoopRollout(b2, dtype=dtype, device=dev)
+        for _ in range(2):
+            res2 = cl2.run()
+        ms2 = timed(cl2.run, 5)
+        same = (res2["steps"] == res["steps"]) & (res2["target_idx"] == res["target_idx"]) & (res2["n_active"] == res["n_active"])
+        out.append("rollout[prepared rows] %.3f ms  %.4g solves/s  (identical bookkeeping vs canonical %.5f)" % (
+            ms2, solves / ms2 * 1e3, float(same.double().mean().item())))
     if not a.no_operator:
         n_op = 2 * 1024 * 1024
         gen = torch.Generator(device=dev); gen.manual_seed(1234)
@@ -70,6 +79,18 @@ def main():
         out.append("operator %.4f ms  %.1f GB/s algorithmic  %.4g solves/s  (active %.3f%%, infeasible %.4f%%)" % (
             ms, bps * n_op * M / ms / 1e6, n_op * M / ms * 1e3,
             100.0 * float((status == 1).sum().item()) / n_op, 100.0 * float((status == 2).sum().item()) / n_op))
+        for static in (0, 0x40):
+            sdp, obp = ops.prepare_obstacles([static] * M, ob)
+            for _ in range(3):
+                u2, mask2, status2, _ = ops.filter_step(prm, sdp, st, obp, ur)
+            ms = timed(lambda: ops.filter_step(prm, sdp, st, obp, ur), 7)
+            nf = 6 if static else 8
+            bps = nf * es + (4 * es + 2 * es + 2 * es + 4 + 1) / M
+            out.append("operator[prepared%s] %.4f ms  %.1f GB/s algorithmic (%.1f B/solve)  %.4g solves/s  masks equal %.6f  max|du| %.2e" % (
+                ", static" if static else "", ms, bps * n_op * M / ms / 1e6, bps, n_op * M / ms * 1e3,
+                float((mask2 == mask).double().mean().item()), float((u2 - u).abs().max().item())))
+        msp = timed(lambda: ops.prepare_obstacles([0] * M, ob, out=obp), 5)
+        out.append("prepare %.4f ms  %.1f GB/s (128 B per slot)" % (msp, 128.0 * n_op * M / msp / 1e6))
     print("\n".join(out), flush=True)
 
 

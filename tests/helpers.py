@@ -21,7 +21,7 @@ def random_slots(rng, N, slot_types, s, near=True):
     M = len(slot_types)
     ob = np.zeros((M, NF, N))
     for m, t in enumerate(slot_types):
-        t &= 0x7F
+        t &= 0x3F
         ahead = rng.uniform(2, 30, N) if near else rng.uniform(20, 60, N)
         lat = rng.uniform(-6, 6, N)
         cx = s[0] + ahead * np.cos(s[2]) - lat * np.sin(s[2])

@@ -397,3 +397,99 @@ def test_fp32_rollout_runs_and_tracks_fp64():
     assert (g32["steps"] == 300).all()
     close_idx = np.abs(g32["target_idx"].astype(int) - g64["target_idx"].astype(int)) <= 30
     assert close_idx.mean() > 0.9
+
+
+# ------------------------------------------------------------------------------------------------
+# prepared obstacles (ELLIPSE_PREP): ingest once, solve many times
+# ------------------------------------------------------------------------------------------------
+def _prepare_np(slots, ob):
+    """numpy restatement of sccav_prepare_obstacles_* (oracle.prepare_ellipse, vectorised)."""
+    out = ob.copy()
+    sd = list(slots)
+    for m, d in enumerate(slots):
+        if (d & o.SLOT_TYPE_MASK) != o.SLOT_ELLIPSE:
+            continue
+        a, b, th, vx, vy = ob[m, 2], ob[m, 3], ob[m, 4], ob[m, 5], ob[m, 6]
+        ct, st = np.cos(th), np.sin(th)
+        out[m, 2], out[m, 3], out[m, 4], out[m, 5] = ct / a, st / a, -st / b, ct / b
+        out[m, 6], out[m, 7] = vx / (a * a), vy / (b * b)
+        sd[m] = (d & ~o.SLOT_TYPE_MASK) | o.SLOT_ELLIPSE_PREP
+    return sd, out
+
+
+@pytest.mark.parametrize("static", [False, True])
+@pytest.mark.parametrize("model", [o.MODEL_DBM, o.MODEL_KBM])
+def test_prepared_ellipse_operator(static, model):
+    """KP + K12 on ELLIPSE_PREP slots: the ingest kernel against its numpy restatement, the solve
+    against the oracle on the prepared slots AND against the canonical ELLIPSE solve (controls
+    to 1e-9, identical active sets and statuses)."""
+    from sccav_cbf_b200 import ops
+    N, M = 4096, 8
+    flag = o.SLOT_STATIC if static else 0
+    slots = [o.SLOT_ELLIPSE | flag] * M
+    rng = np.random.default_rng(77 + model + 2 * static)
+    s = H.random_states(rng, N)
+    ob = H.random_slots(rng, N, slots, s)
+    ur = H.random_uref(rng, N, kbm=(model == o.MODEL_KBM))
+    sd_np, ob_np = _prepare_np(slots, ob)
+    sd_p, ob_p = ops.prepare_obstacles(slots, T(ob))
+    assert sd_p == sd_np == [o.SLOT_ELLIPSE_PREP | flag] * M
+    assert close(ob_p, ob_np, rtol=1e-13) < 1.0
+    prm = ops.make_params(model=model, alpha=0.8)
+    cp = co.default_params(model=model, alpha=0.8)
+    u, mask, status, hmin = ops.filter_step(prm, sd_p, T(s), ob_p, T(ur))
+    ref_p = co.filter_step(cp, sd_p, s, ob_p.cpu().numpy(), ur, rows=True)
+    ref_c = co.filter_step(cp, slots, s, ob, ur)
+    A, b, _ = ops.barrier_rows(prm, sd_p, T(s), ob_p)
+    assert close(A, ref_p["A"]) < 1.0 and close(b, ref_p["b"]) < 1.0
+    m_ = mask.cpu().numpy().view(np.uint32)
+    for ref in (ref_p, ref_c):
+        same = (m_ == ref["mask"]) & (status.cpu().numpy() == ref["status"])
+        assert same.all(), "active set / status mismatch on %d of %d" % ((~same).sum(), N)
+        assert close(u, ref["u"]) < 1.0
+        assert close(hmin, ref["h_min"]) < 1.0
+    assert (ref_c["mask"] != 0).mean() > 0.02
+    # in place ingest gives the same buffer
+    ob_i = T(ob)
+    sd_i, ob_i2 = ops.prepare_obstacles(slots, ob_i, out=ob_i)
+    assert ob_i2.data_ptr() == ob_i.data_ptr() and torch.equal(ob_i, ob_p) and sd_i == sd_p
+
+
+def test_prepared_mixed_slots_and_partials():
+    """ELLIPSE_PREP next to other slot types (generic slot loop) and through K0."""
+    from sccav_cbf_b200 import ops
+    N = 2048
+    slots = [o.SLOT_ELLIPSE, o.SLOT_CONE, o.SLOT_ELLIPSE | o.SLOT_STATIC, o.SLOT_RADIAL, o.SLOT_LANE]
+    rng = np.random.default_rng(5)
+    s = H.random_states(rng, N); ob = H.random_slots(rng, N, slots, s); ur = H.random_uref(rng, N)
+    sd_p, ob_p = ops.prepare_obstacles(slots, T(ob))
+    assert [d & o.SLOT_TYPE_MASK for d in sd_p] == [o.SLOT_ELLIPSE_PREP, o.SLOT_CONE, o.SLOT_ELLIPSE_PREP, o.SLOT_RADIAL, o.SLOT_LANE]
+    assert torch.equal(ob_p[1], T(ob)[1]) and torch.equal(ob_p[3:], T(ob)[3:])
+    prm = ops.make_params()
+    u, mask, status, _ = ops.filter_step(prm, sd_p, T(s), ob_p, T(ur))
+    ref = co.filter_step(co.default_params(), slots, s, ob, ur)
+    assert np.array_equal(mask.cpu().numpy().view(np.uint32), ref["mask"]) and np.array_equal(status.cpu().numpy(), ref["status"])
+    assert close(u, ref["u"]) < 1.0
+    part_p = ops.barrier_partials(sd_p, T(s), ob_p).cpu().numpy()
+    part_c = ops.barrier_partials(slots, T(s), T(ob)).cpu().numpy()
+    assert close(part_p, part_c) < 1.0
+
+
+def test_rollout_prepared_rows_flag():
+    """SCCAV_FLAG_PREPARED_ROWS: the closed loop on prepared ellipses against the (canonical) oracle,
+    same bars as test_rollout_config2_vs_oracle."""
+    from sccav_cbf_b200 import scenarios as sc
+    b = sc.config2(n_total=65536, M=8, T=1000, lo=0, hi=2048)
+    r = _oracle(b, record_stride=50)
+    b.params = dict(b.params, flags=o.FLAG_PREPARED_ROWS)
+    g = _run(b, record_stride=50)
+    frac = _compare_rollout(g, r, b.N, b.T, course=b.course)
+    same_tr = (g["traj_idx"] == r["traj_idx"]).all(axis=0) & (g["traj_mask"].view(np.uint32) == r["traj_mask"]).all(axis=0)
+    assert same_tr.mean() >= 0.999
+    # lanes + prepared ellipses (generic slot loop in the persistent kernel)
+    b4 = sc.config4(n_total=1048576, M=8, T=300, lo=0, hi=512)
+    r4 = _oracle(b4, record_stride=25)
+    b4.params = dict(b4.params, flags=o.FLAG_PREPARED_ROWS)
+    g4 = _run(b4, record_stride=25)
+    _compare_rollout(g4, r4, b4.N, b4.T, min_exact=0.995, state_tol=1e-5, course=b4.course)
+    print("prepared rows: identical bookkeeping fraction", frac)

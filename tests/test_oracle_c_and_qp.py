@@ -143,3 +143,33 @@ def test_c_oracle_qp_degenerate_cases_match_python():
         assert mask == int(c["mask"][n]) and status == int(c["status"][n]), n
         n_inf += status == o.STATUS_INFEASIBLE
     assert n_inf > 5          # all rows here constrain beta only: conflicts are common
+
+
+def test_prepared_ellipse_equals_canonical_ellipse_in_both_oracles():
+    """ELLIPSE_PREP (ingest once, solve many): the regrouped functions equal Ellipse2D's
+    (cbf/obstacles.py:193,218,229,316) to a few ulp, in the Python and in the C oracle, with and
+    without the STATIC flag."""
+    rng = np.random.default_rng(9)
+    N = 200
+    s = H.random_states(rng, N)
+    slots = [o.SLOT_ELLIPSE, o.SLOT_ELLIPSE | o.SLOT_STATIC, o.SLOT_CONE]
+    ob = H.random_slots(rng, N, slots, s)
+    ur = H.random_uref(rng, N)
+    prep = ob.copy()
+    sd_p = list(slots)
+    for m in (0, 1):
+        for n in range(N):
+            prep[m, :, n] = o.prepare_ellipse(ob[m, :, n])
+        sd_p[m] = (slots[m] & ~o.SLOT_TYPE_MASK) | o.SLOT_ELLIPSE_PREP
+    for n in range(0, N, 7):
+        st = tuple(s[:, n])
+        for m in (0, 1):
+            pc = o.slot_partials(slots[m], ob[m, :, n], st)
+            pp = o.slot_partials(sd_p[m], prep[m, :, n], st)
+            assert np.allclose(pc, pp, rtol=1e-12, atol=1e-13), (m, n)
+        assert o.slot_partials(sd_p[1], prep[1, :, n], st)[5] == 0.0          # STATIC: h_t = 0 although wx, wy != 0
+    c_can = co.filter_step(co.default_params(alpha=0.9), slots, s, ob, ur, rows=True)
+    c_pre = co.filter_step(co.default_params(alpha=0.9), sd_p, s, prep, ur, rows=True)
+    assert np.allclose(c_can["A"], c_pre["A"], rtol=1e-11, atol=1e-12) and np.allclose(c_can["b"], c_pre["b"], rtol=1e-11, atol=1e-11)
+    assert np.array_equal(c_can["mask"], c_pre["mask"]) and np.array_equal(c_can["status"], c_pre["status"])
+    assert np.allclose(c_can["u"], c_pre["u"], rtol=1e-10, atol=1e-12)
