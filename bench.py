@@ -209,6 +209,9 @@ def main():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--ref-seconds", type=float, default=4.0, help="CPU seconds per reference step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU seconds for the cpu_baseline sample")
+    ap.add_argument("--rows", default="prepared", choices=["prepared", "canonical"],
+                    help="ellipse rows of the rollout: 'prepared' = SCCAV_FLAG_PREPARED_ROWS (obstacles ingested once per "
+                         "launch, evaluated in their prepared form); 'canonical' = the reference's operation order at every step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-operator", action="store_true", help="skip the regime-(i) operator roofline leg")
     args = ap.parse_args()
@@ -237,6 +240,8 @@ def main():
     n_total = NV * world
     lo, hi = sc.shard_range(n_total, rank, world)
     batch = sc.config2(n_total=n_total, M=M, T=T, seed=0, lo=lo, hi=hi)
+    if args.rows == "prepared":
+        batch.params = dict(batch.params, flags=1)               # SCCAV_FLAG_PREPARED_ROWS
     cl = ClosedLoopRollout(batch, dtype=dtype, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
@@ -271,6 +276,28 @@ def main():
     value = solves_per_step * args.steps / (ms_total * 1e-3)
     checksum = sh.sum(float(res["n_active"].sum().item()))
 
+    # ---- the other row mode, for the record (untimed region; 3 launches, same events)
+    other = None
+    if rank == 0 or world > 1:
+        b2 = sc.config2(n_total=n_total, M=M, T=T, seed=0, lo=lo, hi=hi)
+        if args.rows != "prepared":
+            b2.params = dict(b2.params, flags=1)
+        cl2 = ClosedLoopRollout(b2, dtype=dtype, device=dev, pin=False)
+        cl2.run()
+        ms2 = []
+        for _ in range(3):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r2 = cl2.run(); e1.record()
+            torch.cuda.synchronize()
+            ms2.append(e0.elapsed_time(e1))
+        same = (r2["steps"] == res["steps"]) & (r2["target_idx"] == res["target_idx"]) & (r2["n_active"] == res["n_active"]) \
+            & (r2["n_infeasible"] == res["n_infeasible"])
+        other = {"rows": "canonical" if args.rows == "prepared" else "prepared", "ms_per_step": statistics.mean(ms2),
+                 "value_this_rank": float(r2["steps"].sum().item()) * M / (statistics.mean(ms2) * 1e-3),
+                 "identical_bookkeeping_frac_vs_timed_mode": float(same.double().mean().item())}
+        del cl2
+
     # ---- timed region 2: end to end through the C-ABI host entry point (sccav_rollout_host_*):
     #      pinned HOST buffers in, H2D + kernel + D2H inside the call, HOST results out -- every step
     for _ in range(2):
@@ -297,8 +324,8 @@ def main():
     roofline = {
         "bound": "fp64" if args.dtype == "f64" else "fp32", "kernel": "rollout_kernel<%s>" % tname,
         "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None,
-        "peak_source": "measured live: sccav_measure_fma_peak (unrolled FMA chains, FMA = 2 flop; the fp64 path is "
-                       "compiled without FMA contraction for parity, so 0.5 is its ceiling)",
+        "peak_source": "measured live: sccav_measure_fma_peak (unrolled FMA chains, FMA = 2 flop; the reference-order fp64 "
+                       "arithmetic is compiled without FMA contraction for parity -- only the prepared ellipse rows use fma)",
         "algorithmic_flops_per_launch": flops_per_launch,
         "algorithmic_flops_per_solve": flops_per_launch / solves_per_step_rank,
         "flops_model": "7 x n_evals (counted by the kernel) + vehicle_steps x (34 M + 27); %d transcendental calls per "
@@ -349,7 +376,32 @@ def main():
             "workload": "%d vehicles x %d ellipses, inputs %.0f MB (> L2)" % (n_op, M, obytes / 1e6),
             "traffic": ncu_op.get("dram_bytes"),
         }
-        del st, ob, ur
+        # the same solve on prepared obstacles (ingest once with sccav_prepare_obstacles_*, solve every tick):
+        # 6 fields per static (vehicle, obstacle) instead of 7, no sincos / division per row
+        sdp, obp = ops.prepare_obstacles([d | 0x40 for d in batch.slot_desc], ob)
+        for _ in range(3):
+            ops.filter_step(prm, sdp, st, obp, ur)
+        pevs = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); ops.filter_step(prm, sdp, st, obp, ur); e1.record()
+            pevs.append((e0, e1))
+        torch.cuda.synchronize()
+        pms = statistics.mean(e0.elapsed_time(e1) for e0, e1 in pevs)
+        pbps = 6 * esize + ((4 + 2 + 2) * esize + 5) / M
+        roofline_op["prepared"] = {
+            "kernel": "filter_step_kernel<%s, ELLIPSE_PREP> (static)" % tname, "algorithmic_bytes_per_solve": pbps,
+            "achieved": pbps * n_op * M / (pms * 1e-3) / 1e9, "frac": pbps * n_op * M / (pms * 1e-3) / 1e9 / hbm_peak,
+            "solves_per_s": n_op * M / (pms * 1e-3), "ms": pms,
+        }
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ops.prepare_obstacles(batch.slot_desc, ob, out=obp); e1.record()
+        torch.cuda.synchronize()
+        ims = e0.elapsed_time(e1)
+        roofline_op["ingest"] = {"kernel": "prepare_obstacles_kernel<%s>" % tname, "bytes_per_slot": 16 * esize,
+                                 "achieved": 16 * esize * n_op * M / (ims * 1e-3) / 1e9,
+                                 "frac": 16 * esize * n_op * M / (ims * 1e-3) / 1e9 / hbm_peak, "ms": ims}
+        del st, ob, ur, obp
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the box's host cores, bounded sample
     cpu = None
@@ -373,6 +425,7 @@ def main():
             "config": {"workload": workload_name(args), "vehicles_total": n_total, "obstacles": M, "timesteps": T,
                        "solves_per_step": solves_per_step, "parallelism": "scenario shards x%d, no collective" % world,
                        "l2": "flushed (256 MB write) between timed iterations; inputs 36 MB/GPU",
+                       "rows": args.rows, "other_row_mode": other,
                        "seed": 0, "active_step_checksum": checksum},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cl.h2d_bytes(), "d2h_bytes_per_step": cl.d2h_bytes(),
                     "ms_per_step": 1e3 * e2e_s / args.steps,

@@ -29,6 +29,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 struct DevAttr {
     int sms = 0;
     int smem = 0;
+    bool pool = false;
 };
 static DevAttr g_attr[64];
 
@@ -45,6 +46,23 @@ static DevAttr& attr() {
         a.sms = sms > 0 ? sms : 148;
     }
     return a;
+}
+
+// The entry points take their scratch from the device's stream-ordered pool (cudaMallocAsync).  By
+// default the pool hands freed memory back to the driver at every synchronisation, so each call would
+// map tens of MB again (milliseconds); keep what was used once.
+void keep_pool_memory() {
+    DevAttr& a = attr();
+    if (a.pool) return;
+    a.pool = true;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
 }
 
 int sm_count() { return attr().sms; }

@@ -9,6 +9,7 @@ void set_error(const char* fmt, ...);
 void count_launch();
 int sm_count();          // SMs of the current device (cached per device)
 int max_smem_optin();    // max opt-in dynamic shared memory per block of the current device
+void keep_pool_memory(); // once per device: the stream-ordered pool keeps freed scratch for the next call
 }  // namespace sccav
 
 #define SCCAV_CUDA_CHECK(expr)                                                              \

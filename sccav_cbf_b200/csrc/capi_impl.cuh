@@ -280,6 +280,7 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
     if (M > 0 && !obst) { set_error("obst is NULL"); return SCCAV_EINVAL; }
     const bool stan = p->nominal == SCCAV_NOMINAL_STANLEY;
     if (stan && (P < 1 || !cx || !cy || !cyaw)) { set_error("Stanley nominal control needs a course (P >= 1)"); return SCCAV_EINVAL; }
+    keep_pool_memory();
     RolloutArgs<real> a;
     a.P = convert(p); a.sd = make_desc(slot_desc, M); a.M = M; a.N = N; a.T_steps = T; a.np = stan ? P : 0;
     a.state = state; a.obst = obst; a.cx = cx; a.cy = cy; a.cyaw = cyaw; a.pv = make_pv(pv);
@@ -424,6 +425,7 @@ int SCCAV_FN(sccav_filter_step_host_)(const sccav_params* p, const uint8_t* slot
     if (N == 0) return SCCAV_OK;
     if (!state || !obst || !u_ref || !u_out) { set_error("NULL array argument"); return SCCAV_EINVAL; }
     const size_t n = (size_t)N;
+    keep_pool_memory();
     DevBuf d_state(st), d_obst(st), d_uref(st), d_alpha(st), d_R(st), d_u(st), d_mask(st), d_status(st), d_hmin(st);
     SCCAV_CUDA_CHECK(d_state.upload(state, 4 * n * sizeof(real)));
     SCCAV_CUDA_CHECK(d_obst.upload(obst, (size_t)M * SCCAV_NFIELD * n * sizeof(real)));

@@ -543,12 +543,20 @@ __device__ __forceinline__ void put_row(const Params<T>& P, const Partials<T>& p
     if (!(rk >= -tol)) feas = false;
 }
 
+// what the row phase of one vehicle leaves behind for the QP
+template <typename T> struct RowPhase {
+    T r0, r1;        // reference point in QP coordinates (a | v, beta | omega)
+    T worst;         // its largest row violation
+    RowNz nz;
+    bool feas;       // the reference point satisfies every row: u = u_ref, no solve
+};
+
+// phase 1: u_ref -> QP coordinates, rows of all slots -> shared memory, feasibility of the reference point
 template <typename T, int SPEC>
-__device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc& sd, int M, int64_t N, int64_t n,
-                                              const T* __restrict__ obst, T x, T y, T th, T v, T sth, T cth,
-                                              T alpha, T R00, T R01, T R10, T R11, T uref0, T uref1,
-                                              T* rows, int stride, T& u0, T& u1, T& u1raw, uint32_t& mask, T& hmin,
-                                              const T* __restrict__ pre = nullptr, uint32_t moving = 0xffffffffu) {
+__device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const SlotDesc& sd, int M, int64_t N, int64_t n,
+                                                   const T* __restrict__ obst, T x, T y, T th, T v, T sth, T cth,
+                                                   T alpha, T uref0, T uref1, T* rows, int stride, T& hmin,
+                                                   const T* __restrict__ pre = nullptr, uint32_t moving = 0xffffffffu) {
     typedef Real<T> R;
     hmin = R::inf();
     T r0 = uref0, r1;
@@ -609,21 +617,41 @@ __device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc
             put_row<T>(P, p, sth, cth, v, alpha, r0, r1, rows, stride, m, hmin, worst, feas, nz);
         }
     }
-    T q0 = r0, q1 = r1;
+    RowPhase<T> ph;
+    ph.r0 = r0; ph.r1 = r1; ph.worst = worst; ph.nz = nz; ph.feas = feas;
+    return ph;
+}
+
+// phase 3: QP coordinates -> (a | v, delta)
+template <typename T>
+__device__ __forceinline__ T filter_convert(const Params<T>& P, T q0, T q1, T r0) {
+    typedef Real<T> R;
+    if (P.model == SCCAV_MODEL_KBM) {
+        if (P.kbm_driver_delta) return R::atan_((q1 * P.L) / q0);                        // sce.py:652
+        return R::atan2_(q1 * P.L, r0);                                                  // cbf.py:109
+    }
+    return R::atan2_((P.lf + P.lr) * R::tan_(q1), P.lr);                                 // cbf.py:216
+}
+
+// all three phases by one thread (the persistent rollout kernel; K12 compacts phase 2 across the CTA)
+template <typename T, int SPEC>
+__device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc& sd, int M, int64_t N, int64_t n,
+                                              const T* __restrict__ obst, T x, T y, T th, T v, T sth, T cth,
+                                              T alpha, T R00, T R01, T R10, T R11, T uref0, T uref1,
+                                              T* rows, int stride, T& u0, T& u1, T& u1raw, uint32_t& mask, T& hmin,
+                                              const T* __restrict__ pre = nullptr, uint32_t moving = 0xffffffffu) {
+    const RowPhase<T> ph = filter_rows<T, SPEC>(P, sd, M, N, n, obst, x, y, th, v, sth, cth, alpha, uref0, uref1,
+                                                rows, stride, hmin, pre, moving);
+    T q0 = ph.r0, q1 = ph.r1;
     int status = SCCAV_STATUS_INACTIVE;
     mask = 0u;
-    if (!feas) {
+    if (!ph.feas) {
         RowView<T> rv{rows, stride};
-        status = qp2_solve_active<T>(rv, M, nz, r0, r1, R00, R01, R10, R11, worst, q0, q1, mask);
+        status = qp2_solve_active<T>(rv, M, ph.nz, ph.r0, ph.r1, R00, R01, R10, R11, ph.worst, q0, q1, mask);
     }
     u0 = q0;
     u1raw = q1;
-    if (P.model == SCCAV_MODEL_KBM) {
-        if (P.kbm_driver_delta) u1 = R::atan_((q1 * P.L) / q0);                          // sce.py:652
-        else u1 = R::atan2_(q1 * P.L, r0);                                               // cbf.py:109
-    } else {
-        u1 = R::atan2_((P.lf + P.lr) * R::tan_(q1), P.lr);                               // cbf.py:216
-    }
+    u1 = filter_convert<T>(P, q0, q1, ph.r0);
     return status;
 }
 
