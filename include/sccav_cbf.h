@@ -120,6 +120,10 @@ typedef struct sccav_pervehicle {
     const void* alpha;         /* [N]    overrides params.alpha                                */
     const void* R;             /* [4][N] overrides params.R                                    */
     const void* target_speed;  /* [N]    overrides params.target_speed                         */
+    const int32_t* count;      /* [N]    obstacles of vehicle n = its first count[n] slots (0..M); the rest
+                                  are empty.  The batched form of a per-vehicle ObstacleList2D whose length
+                                  varies (cbf/obstacles.py:798-858).  count[n] = 0: u = u_ref, the guard
+                                  callers put around solve_cbf (carla_ml.py:935-936)           */
 } sccav_pervehicle;
 
 /* Outputs of a rollout; any pointer except `state` may be NULL.  dev pointers.                */
@@ -247,6 +251,35 @@ int sccav_prepare_obstacles_f64(const uint8_t* slot_desc, int32_t M, int64_t N, 
                                 uint8_t* slot_desc_out, void* stream);
 int sccav_prepare_obstacles_f32(const uint8_t* slot_desc, int32_t M, int64_t N, const float* obst_in, float* obst_out,
                                 uint8_t* slot_desc_out, void* stream);
+
+/* KB -- batched ObstacleList2D.update_by_bounding_box (cbf/obstacles.py:833-858) for N vehicles that
+ * each keep their own obstacle list of up to M entries, fed every tick with up to K bounding boxes
+ * (the on-wire obstacle format of the CARLA drivers: actor id, extent, location, yaw, speed --
+ * multi_obstacle_CBF_local_with_lanes.py:906-932, obstacle_map.py:144-156).
+ *   box_id  [K][N] int32   actor id per box, < 0 = no box (padding); ids are unique per vehicle
+ *   box     [K][6][N]      SCCAV_BOX_*: extent.x, extent.y, location.x, location.y, rotation.yaw, velocity
+ *   slot_id [M][N] int32   in/out: id held by slot m (the dict key), -1 = empty
+ *   obst    [M][8][N]      in/out: the slots, ELLIPSE or CONE layout (obs_type)
+ *   count   [N]   int32    in/out: entries of vehicle n = its first count[n] slots (-> sccav_pervehicle.count)
+ *   dropped [N]   int32    out (may be NULL): new ids that found no free slot
+ * SCCAV_INGEST_UPDATE: an id already held is updated in place by <obstacle>.update_by_bounding_box
+ *   (Ellipse2D obstacles.py:294-302: a, b, centre, theta <- extent, location, yaw, buffer NOT re-applied;
+ *   CollisionCone2D :512-530: a <- hypot(extent), s_obs <- [x, y, 0, velocity]); ids not in the boxes are
+ *   removed; new ids are appended in box order by <obstacle>.from_bounding_box (a + buffer,
+ *   :319-331, :532-543).  The resulting order -- surviving entries in their old order, then the new
+ *   ones -- is the dict order of the reference, i.e. the constraint index of every row.
+ * SCCAV_INGEST_REBUILD: the list is rebuilt from the boxes alone, every entry made by from_bounding_box
+ *   (what the CARLA driver does each tick, multi_obstacle_CBF_local_with_lanes.py:918-928).
+ * DEVICE pointers, asynchronous on `stream`; M <= 32, K <= 32. */
+#define SCCAV_BOX_FIELDS 6
+#define SCCAV_INGEST_UPDATE 0
+#define SCCAV_INGEST_REBUILD 1
+int sccav_ingest_boxes_f64(int32_t obs_type, int32_t mode, double buffer, int32_t M, int32_t K, int64_t N,
+                           const int32_t* box_id, const double* box, int32_t* slot_id, double* obst, int32_t* count,
+                           int32_t* dropped, void* stream);
+int sccav_ingest_boxes_f32(int32_t obs_type, int32_t mode, double buffer, int32_t M, int32_t K, int64_t N,
+                           const int32_t* box_id, const float* box, int32_t* slot_id, float* obst, int32_t* count,
+                           int32_t* dropped, void* stream);
 
 /* Measurement helpers used by bench.py (not part of the reference-facing path). */
 /* Launches an unrolled FMA chain kernel and returns the achieved TFLOP/s (FMA = 2 flop) on the

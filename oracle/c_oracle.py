@@ -28,7 +28,7 @@ class Params(C.Structure):
 
 
 class PerVehicle(C.Structure):
-    _fields_ = [("alpha", C.c_void_p), ("R", C.c_void_p), ("target_speed", C.c_void_p)]
+    _fields_ = [("alpha", C.c_void_p), ("R", C.c_void_p), ("target_speed", C.c_void_p), ("count", C.c_void_p)]
 
 
 class RolloutOut(C.Structure):
@@ -84,9 +84,11 @@ def _p(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
 
 
-def _pv(alpha, R, target_speed):
+def _pv(alpha, R, target_speed, count=None):
     pv = PerVehicle()
-    keep = [_f64(alpha), _f64(R), _f64(target_speed)]
+    keep = [_f64(alpha), _f64(R), _f64(target_speed), None if count is None else np.ascontiguousarray(count, dtype=np.int32)]
+    if keep[3] is not None:
+        pv.count = keep[3].ctypes.data
     if keep[0] is not None:
         pv.alpha = keep[0].ctypes.data
     if keep[1] is not None:
@@ -96,14 +98,14 @@ def _pv(alpha, R, target_speed):
     return pv, keep
 
 
-def filter_step(params: Params, slot_desc, state, obst, u_ref, alpha=None, R=None, rows=False, nthreads=0):
+def filter_step(params: Params, slot_desc, state, obst, u_ref, alpha=None, R=None, rows=False, nthreads=0, count=None):
     sd = bytes(int(d) & 0xFF for d in slot_desc)
     state, obst, u_ref = _f64(state), _f64(obst), _f64(u_ref)
     M, N = len(sd), state.shape[1]
     u = np.empty((2, N)); mask = np.empty(N, dtype=np.uint32); status = np.empty(N, dtype=np.uint8); hmin = np.empty(N)
     A = np.empty((2, M, N)) if rows else None
     b = np.empty((M, N)) if rows else None
-    pv, keep = _pv(alpha, R, None)
+    pv, keep = _pv(alpha, R, None, count)
     rc = lib().orc_filter_step(C.byref(params), sd, C.c_int32(M), C.c_int64(N), _p(state), _p(obst), _p(u_ref), C.byref(pv),
                                _p(u), _p(mask), _p(status), _p(hmin), _p(A), _p(b), C.c_int(nthreads))
     if rc != 0:
@@ -115,7 +117,7 @@ def filter_step(params: Params, slot_desc, state, obst, u_ref, alpha=None, R=Non
 
 
 def rollout(params: Params, slot_desc, state, obst, course, T, alpha=None, R=None, target_speed=None,
-            record_stride=0, nthreads=0):
+            record_stride=0, nthreads=0, count=None):
     import copy
     sd = bytes(int(d) & 0xFF for d in slot_desc)
     state = _f64(state)
@@ -140,7 +142,7 @@ def rollout(params: Params, slot_desc, state, obst, course, T, alpha=None, R=Non
     ro = RolloutOut()
     for k, v in res.items():
         setattr(ro, k, v.ctypes.data)
-    pv, keep = _pv(alpha, R, target_speed)
+    pv, keep = _pv(alpha, R, target_speed, count)
     rc = lib().orc_rollout(C.byref(prm), sd, C.c_int32(M), C.c_int64(N), C.c_int32(int(T)), _p(state), _p(obst), _p(cx), _p(cy),
                            _p(cyaw), C.c_int32(P), C.byref(pv), C.byref(ro), C.c_int(nthreads))
     if rc != 0:

@@ -299,6 +299,13 @@ static int filter_vehicle(const sccav_params* p, const uint8_t* sd, int M, int64
     return st;
 }
 
+/* obstacles of vehicle n: its first count[n] slots (sccav_pervehicle.count), all M without it */
+static int slot_count(const sccav_pervehicle* pv, int M, int64_t n) {
+    if (!pv || !pv->count) return M;
+    int c = pv->count[n];
+    return c < 0 ? 0 : (c > M ? M : c);
+}
+
 static void weights(const sccav_params* p, const sccav_pervehicle* pv, int64_t N, int64_t n, double* alpha, double* R) {
     *alpha = (pv && pv->alpha) ? ((const double*)pv->alpha)[n] : p->alpha;
     if (pv && pv->R) { const double* r = (const double*)pv->R; R[0] = r[n]; R[1] = r[N + n]; R[2] = r[2 * N + n]; R[3] = r[3 * N + n]; }
@@ -353,8 +360,13 @@ static void filter_body(void* vctx, int64_t n) {
     double A0[SCCAV_MAX_ROWS], A1[SCCAV_MAX_ROWS], b[SCCAV_MAX_ROWS], alpha, R[4], u0, u1, hmin;
     uint32_t mask;
     weights(c->p, c->pv, N, n, &alpha, R);
-    int st = filter_vehicle(c->p, c->sd, M, N, n, c->obst, c->state[n], c->state[N + n], c->state[2 * N + n],
+    const int Mv = slot_count(c->pv, M, n);
+    int st = SCCAV_STATUS_INACTIVE;
+    for (int m = Mv; m < M; ++m) { A0[m] = 0.0; A1[m] = 0.0; b[m] = -INFINITY; }      /* empty slots: vacuous rows */
+    if (Mv > 0)
+        st = filter_vehicle(c->p, c->sd, Mv, N, n, c->obst, c->state[n], c->state[N + n], c->state[2 * N + n],
                             c->state[3 * N + n], alpha, R, c->u_ref[n], c->u_ref[N + n], &u0, &u1, &mask, &hmin, A0, A1, b);
+    else { u0 = c->u_ref[n]; u1 = c->u_ref[N + n]; mask = 0; hmin = INFINITY; }      /* carla_ml.py:935-936 */
     c->u_out[n] = u0; c->u_out[N + n] = u1;
     if (c->mask_out) c->mask_out[n] = mask;
     if (c->status_out) c->status_out[n] = (uint8_t)st;
@@ -420,6 +432,7 @@ static void rollout_body(void* vctx, int64_t n) {
         double alpha, R[4];
         weights(p, pv, N, n, &alpha, R);
         double tspeed = (pv && pv->target_speed) ? ((const double*)pv->target_speed)[n] : p->target_speed;
+        const int Mv = slot_count(pv, M, n);
         int last_idx = P - 1, target_idx = 0, steps = 0, nact = 0, ninf = 0;
         double time = 0.0, e;
         double hmin_all = INFINITY, bmin = INFINITY, bmax = -INFINITY, bint = 0.0;
@@ -440,9 +453,9 @@ static void rollout_body(void* vctx, int64_t n) {
             double u0 = ur0, u1 = ur1, hmin = INFINITY;
             uint32_t mask = 0;
             int status = SCCAV_STATUS_INACTIVE;
-            if (M > 0 && p->model != SCCAV_MODEL_NONE) {
+            if (Mv > 0 && p->model != SCCAV_MODEL_NONE) {
                 double A0[SCCAV_MAX_ROWS], A1[SCCAV_MAX_ROWS], b[SCCAV_MAX_ROWS];
-                status = filter_vehicle(p, sd, M, N, n, obst, x, y, yaw, v, alpha, R, ur0, ur1, &u0, &u1, &mask, &hmin, A0, A1, b);
+                status = filter_vehicle(p, sd, Mv, N, n, obst, x, y, yaw, v, alpha, R, ur0, ur1, &u0, &u1, &mask, &hmin, A0, A1, b);
             }
             double px = x, py = y, pyaw = yaw, pv_ = v, beta = 0.0;
             double delta = u1;
@@ -463,7 +476,7 @@ static void rollout_body(void* vctx, int64_t n) {
                 if (p->model == SCCAV_MODEL_KBM) v = u0; else v += u0 * p->dt;
             }
             if (p->seeker)
-                for (int m = 0; m < M; ++m)
+                for (int m = 0; m < Mv; ++m)
                     if ((sd[m] & SCCAV_SLOT_TYPE_MASK) == SCCAV_SLOT_RADIAL && !(sd[m] & SCCAV_SLOT_SHARED))
                         seeker_update(obst + (int64_t)m * SCCAV_NFIELD * N + n, N, x, y, p->dt, p->seeker_k, p->seeker_vmin);
             if (p->record_stride > 0 && (steps % p->record_stride) == 0) {

@@ -297,6 +297,69 @@ def slot_partials(slot_desc, f, s):
 
 
 # --------------------------------------------------------------------------------------
+# obstacle ingest from bounding boxes (the step BEFORE the path in the CARLA deployment)
+# --------------------------------------------------------------------------------------
+INGEST_UPDATE = 0
+INGEST_REBUILD = 1
+
+
+def box_to_fields(obs_type, create, buffer, box, old=None):
+    """Slot fields of one obstacle from its bounding box (extent.x, extent.y, location.x, location.y, yaw,
+    velocity).  create: <obstacle>.from_bounding_box (cbf/obstacles.py:319-331 ellipse, :532-543 cone; the
+    buffer is added to a / b); else <obstacle>.update_by_bounding_box on the fields ``old``
+    (:294-302 ellipse -- a, b, centre, theta replaced, buffer NOT re-applied, velocity kept; :512-530 cone --
+    a = hypot(extent), s_obs = [x, y, 0.0, velocity], beta kept)."""
+    ex, ey, lx, ly, yaw, sp = (float(v) for v in box)
+    f = [0.0] * 8 if create else [float(v) for v in old]
+    if obs_type == SLOT_ELLIPSE:
+        f[0], f[1], f[4] = lx, ly, yaw
+        f[2] = ex + buffer if create else ex
+        f[3] = ey + buffer if create else ey
+    elif obs_type == SLOT_CONE:
+        a = float(np.hypot(ex, ey))
+        f[0], f[1], f[2], f[3] = lx, ly, 0.0, sp
+        f[4] = a + buffer if create else a
+    else:
+        raise ValueError("update_by_bounding_box makes Ellipse2D or CollisionCone2D obstacles")
+    return f
+
+
+def ingest_boxes(obs_type, mode, buffer, M, box_ids, boxes, slot_ids, fields, count):
+    """ObstacleList2D.update_by_bounding_box (cbf/obstacles.py:833-858) for ONE vehicle whose list lives in
+    M slots: ``slot_ids[m]`` / ``fields[m]`` for m < count.  Boxes: ``box_ids[k]`` (< 0 = none), ``boxes[k]``.
+    The reference walks the boxes (update the ids it holds, append the new ones -- :839-846), then pops the
+    ids that are gone (:851-853): surviving entries keep their order, new ones follow in box order.  With
+    INGEST_REBUILD the list is rebuilt from the boxes alone (multi_obstacle_CBF_local_with_lanes.py:918-928).
+    Only M entries fit: the last new ids are dropped (counted).  Returns (slot_ids, fields, count, dropped)."""
+    mapping = {}
+    if mode == INGEST_UPDATE:
+        for j in range(min(max(int(count), 0), M)):
+            if slot_ids[j] >= 0:
+                mapping[int(slot_ids[j])] = [float(v) for v in fields[j]]
+    bbox = {}
+    for k, key in enumerate(box_ids):
+        if key >= 0 and int(key) not in bbox:
+            bbox[int(key)] = boxes[k]
+    for key, box in bbox.items():                                          # obstacles.py:838-846
+        if key in mapping:
+            mapping[key] = box_to_fields(obs_type, False, buffer, box, mapping[key])
+        else:
+            mapping[key] = box_to_fields(obs_type, True, buffer, box)
+    for key in list(mapping.keys()):                                       # obstacles.py:851-853
+        if key not in bbox:
+            mapping.pop(key)
+    keys = list(mapping.keys())
+    dropped = max(0, len(keys) - M)
+    keys = keys[:M]
+    out_ids = [-1] * M
+    out_f = [[float(v) for v in fields[m]] for m in range(M)]
+    for m, key in enumerate(keys):
+        out_ids[m] = key
+        out_f[m] = mapping[key]
+    return out_ids, out_f, len(keys), dropped
+
+
+# --------------------------------------------------------------------------------------
 # row assembly: constraint  A0*u0 + A1*u1 >= b
 # --------------------------------------------------------------------------------------
 def dbm_row(part, th, v, alpha, lr):

@@ -12,13 +12,13 @@ from .cbf import DBM_CBF_2DS, KBM_VC_CBF2D
 from .controllers import PID1, LateralStanley
 from .euclid import Point2, Point3, Vector2, Vector3
 from .geometry import Rotation, Transform
-from .obstacles import (BoundingBox, CollisionCone2D, Ellipse2D, Obstacle2DBase, Obstacle2DTypes, ObstacleList2D,
-                        PolyLane)
+from .obstacles import (BatchedObstacleList2D, BoundingBox, CollisionCone2D, Ellipse2D, Obstacle2DBase, Obstacle2DTypes,
+                        ObstacleList2D, PolyLane)
 from .utils import ZERO_TOL, Timer, TimerError, normalize_angle, saturation, sigmoid, vec_norm
 
 __all__ = [
     "DBM_CBF_2DS", "KBM_VC_CBF2D", "LateralStanley", "PID1", "Vector2", "Point2", "Vector3", "Point3", "Rotation",
-    "Transform", "BoundingBox", "CollisionCone2D", "Ellipse2D", "Obstacle2DBase", "Obstacle2DTypes", "ObstacleList2D",
+    "Transform", "BatchedObstacleList2D", "BoundingBox", "CollisionCone2D", "Ellipse2D", "Obstacle2DBase", "Obstacle2DTypes", "ObstacleList2D",
     "PolyLane", "ZERO_TOL", "Timer", "TimerError", "normalize_angle", "saturation", "sigmoid", "vec_norm",
 ]
 __version__ = "0.1.0"

@@ -21,6 +21,8 @@ SLOT_TYPE_MASK = 0x3F
 SLOT_STATIC = 0x40
 SLOT_SHARED = 0x80
 FLAG_PREPARED_ROWS = 1
+BOX_FIELDS = 6
+INGEST_UPDATE, INGEST_REBUILD = 0, 1
 MODEL_DBM, MODEL_KBM, MODEL_NONE = 0, 1, 2
 NOMINAL_STANLEY, NOMINAL_CONST = 0, 1
 STATUS_INACTIVE, STATUS_ACTIVE, STATUS_INFEASIBLE = 0, 1, 2
@@ -41,7 +43,7 @@ class Params(C.Structure):
 
 
 class PerVehicle(C.Structure):
-    _fields_ = [("alpha", C.c_void_p), ("R", C.c_void_p), ("target_speed", C.c_void_p)]
+    _fields_ = [("alpha", C.c_void_p), ("R", C.c_void_p), ("target_speed", C.c_void_p), ("count", C.c_void_p)]
 
 
 class RolloutOut(C.Structure):
@@ -68,7 +70,7 @@ SYMBOLS = [
     "sccav_measure_fma_peak", "sccav_launch_count", "sccav_debug_course_index_host",
     "sccav_rollout_launch_info_f64", "sccav_rollout_launch_info_f32",
     "sccav_barrier_partials_f64", "sccav_barrier_partials_f32", "sccav_stanley_control_f64", "sccav_stanley_control_f32",
-    "sccav_prepare_obstacles_f64", "sccav_prepare_obstacles_f32",
+    "sccav_prepare_obstacles_f64", "sccav_prepare_obstacles_f32", "sccav_ingest_boxes_f64", "sccav_ingest_boxes_f32",
 ]
 
 
@@ -99,6 +101,8 @@ def lib() -> C.CDLL:
         f.argtypes = [C.c_char_p, i32, i64, vp, vp, vp, vp]
         f = getattr(L, "sccav_prepare_obstacles_" + sfx)
         f.argtypes = [C.c_char_p, i32, i64, vp, vp, vp, vp]
+        f = getattr(L, "sccav_ingest_boxes_" + sfx)
+        f.argtypes = [i32, i32, C.c_double, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp]
         f = getattr(L, "sccav_stanley_control_" + sfx)
         f.argtypes = [PP, i64, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]
         f = getattr(L, "sccav_rollout_launch_info_" + sfx)

@@ -103,7 +103,8 @@ class _FilterBase:
         Rv = None
         if isinstance(self._R, torch.Tensor):
             Rv = self._R.to(device=state.device, dtype=state.dtype).contiguous()
-        u, mask, status, hmin = ops.filter_step(params, slot_desc, state, obst, ur, alpha=alpha, R=Rv)
+        u, mask, status, hmin = ops.filter_step(params, slot_desc, state, obst, ur, alpha=alpha, R=Rv,
+                                                count=getattr(self.obstacle_list2d, "count", None))
         scalar = scalar_state and scalar_obs and scalar_u and N == 1
         info = {"status": status, "active_mask": mask, "h_min": hmin, "u_ref": ur}
         self.last_info = info

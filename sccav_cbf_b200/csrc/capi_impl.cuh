@@ -66,11 +66,12 @@ SlotDesc make_desc(const uint8_t* slot_desc, int M) {
 }
 
 PerVehicle<real> make_pv(const sccav_pervehicle* pv) {
-    PerVehicle<real> q{nullptr, nullptr, nullptr};
+    PerVehicle<real> q{nullptr, nullptr, nullptr, nullptr};
     if (pv) {
         q.alpha = (const real*)pv->alpha;
         q.R = (const real*)pv->R;
         q.target_speed = (const real*)pv->target_speed;
+        q.count = pv->count;
     }
     return q;
 }
@@ -112,6 +113,30 @@ int do_prepare(const uint8_t* slot_desc, int32_t M, int64_t N, const real* in, r
     return SCCAV_OK;
 }
 
+int do_ingest(int32_t type, int32_t mode, double buffer, int32_t M, int32_t K, int64_t N, const int32_t* box_id, const real* box,
+              int32_t* slot_id, real* obst, int32_t* count, int32_t* dropped, cudaStream_t st) {
+    if (type != SCCAV_SLOT_ELLIPSE && type != SCCAV_SLOT_CONE) {
+        // ObstacleList2D.update_by_bounding_box makes Ellipse2D or CollisionCone2D entries (obstacles.py:843-846)
+        set_error("obs_type must be SCCAV_SLOT_ELLIPSE or SCCAV_SLOT_CONE, got %d", type);
+        return SCCAV_EINVAL;
+    }
+    if (mode != SCCAV_INGEST_UPDATE && mode != SCCAV_INGEST_REBUILD) { set_error("unknown ingest mode %d", mode); return SCCAV_EINVAL; }
+    if (M < 1 || M > SCCAV_MAX_ROWS) { set_error("M must be in [1, %d], got %d", SCCAV_MAX_ROWS, M); return SCCAV_EINVAL; }
+    if (K < 0 || K > 32) { set_error("K must be in [0, 32], got %d", K); return SCCAV_EINVAL; }
+    if (N < 0) { set_error("N < 0"); return SCCAV_EINVAL; }
+    if (N == 0) return SCCAV_OK;
+    if ((K > 0 && (!box_id || !box)) || !slot_id || !obst || !count) { set_error("NULL array argument"); return SCCAV_EINVAL; }
+    IngestArgs<real> a;
+    a.type = type; a.mode = mode; a.M = M; a.K = K; a.N = N; a.buffer = (real)buffer;
+    a.box_id = box_id; a.box = box; a.slot_id = slot_id; a.obst = obst; a.count = count; a.dropped = dropped;
+    const int block = 128;
+    const size_t smem = (size_t)(K > 0 ? K : 1) * block * sizeof(int32_t);
+    ingest_boxes_kernel<real><<<stream_grid(N, block), block, smem, st>>>(a);
+    count_launch();
+    SCCAV_CUDA_CHECK(cudaGetLastError());
+    return SCCAV_OK;
+}
+
 int do_barrier_rows(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N, const real* state,
                     const real* obst, const sccav_pervehicle* pv, real* A, real* b, real* h, cudaStream_t st) {
     int rc = check_common(p, slot_desc, M, N, false);
@@ -137,7 +162,7 @@ int do_barrier_partials(const uint8_t* slot_desc, int32_t M, int64_t N, const re
     if (N == 0) return SCCAV_OK;
     if (!state || !obst || !out) { set_error("NULL array argument"); return SCCAV_EINVAL; }
     PartialsArgs<real> a;
-    a.sd = make_desc(slot_desc, M); a.M = M; a.N = N; a.state = state; a.obst = obst; a.out = out;
+    a.sd = make_desc(slot_desc, M); a.M = M; a.N = N; a.state = state; a.obst = obst; a.out = out; a.count = nullptr;
     const int block = 256;
     barrier_partials_kernel<real><<<stream_grid(N, block), block, 0, st>>>(a);
     count_launch();
@@ -359,6 +384,12 @@ int SCCAV_FN(sccav_prepare_obstacles_)(const uint8_t* slot_desc, int32_t M, int6
     return sccav::do_prepare(slot_desc, M, N, obst_in, obst_out, slot_desc_out, (cudaStream_t)stream);
 }
 
+int SCCAV_FN(sccav_ingest_boxes_)(int32_t obs_type, int32_t mode, double buffer, int32_t M, int32_t K, int64_t N,
+                                   const int32_t* box_id, const SCCAV_REAL* box, int32_t* slot_id, SCCAV_REAL* obst,
+                                   int32_t* count, int32_t* dropped, void* stream) {
+    return sccav::do_ingest(obs_type, mode, buffer, M, K, N, box_id, box, slot_id, obst, count, dropped, (cudaStream_t)stream);
+}
+
 int SCCAV_FN(sccav_barrier_partials_)(const uint8_t* slot_desc, int32_t M, int64_t N, const SCCAV_REAL* state,
                                       const SCCAV_REAL* obst, SCCAV_REAL* out, void* stream) {
     return sccav::do_barrier_partials(slot_desc, M, N, state, obst, out, (cudaStream_t)stream);
@@ -426,13 +457,14 @@ int SCCAV_FN(sccav_filter_step_host_)(const sccav_params* p, const uint8_t* slot
     if (!state || !obst || !u_ref || !u_out) { set_error("NULL array argument"); return SCCAV_EINVAL; }
     const size_t n = (size_t)N;
     keep_pool_memory();
-    DevBuf d_state(st), d_obst(st), d_uref(st), d_alpha(st), d_R(st), d_u(st), d_mask(st), d_status(st), d_hmin(st);
+    DevBuf d_state(st), d_obst(st), d_uref(st), d_alpha(st), d_R(st), d_cnt(st), d_u(st), d_mask(st), d_status(st), d_hmin(st);
     SCCAV_CUDA_CHECK(d_state.upload(state, 4 * n * sizeof(real)));
     SCCAV_CUDA_CHECK(d_obst.upload(obst, (size_t)M * SCCAV_NFIELD * n * sizeof(real)));
     SCCAV_CUDA_CHECK(d_uref.upload(u_ref, 2 * n * sizeof(real)));
-    sccav_pervehicle dpv = {nullptr, nullptr, nullptr};
+    sccav_pervehicle dpv = {nullptr, nullptr, nullptr, nullptr};
     if (pv && pv->alpha) { SCCAV_CUDA_CHECK(d_alpha.upload(pv->alpha, n * sizeof(real))); dpv.alpha = d_alpha.p; }
     if (pv && pv->R) { SCCAV_CUDA_CHECK(d_R.upload(pv->R, 4 * n * sizeof(real))); dpv.R = d_R.p; }
+    if (pv && pv->count) { SCCAV_CUDA_CHECK(d_cnt.upload(pv->count, n * sizeof(int32_t))); dpv.count = (const int32_t*)d_cnt.p; }
     SCCAV_CUDA_CHECK(d_u.alloc(2 * n * sizeof(real)));
     if (active_out) SCCAV_CUDA_CHECK(d_mask.alloc(n * sizeof(uint32_t)));
     if (status_out) SCCAV_CUDA_CHECK(d_status.alloc(n));
@@ -465,7 +497,7 @@ int SCCAV_FN(sccav_rollout_host_)(const sccav_params* p, const uint8_t* slot_des
     const bool stan = p->nominal == SCCAV_NOMINAL_STANLEY;
     if (stan && (P < 1 || !course_x || !course_y || !course_yaw)) { set_error("Stanley nominal control needs a course"); return SCCAV_EINVAL; }
     const size_t trec = p->record_stride > 0 ? ((size_t)T + p->record_stride - 1) / p->record_stride : 0;
-    DevBuf d_state(st), d_obst(st), d_cx(st), d_cy(st), d_cyaw(st), d_alpha(st), d_R(st), d_ts(st);
+    DevBuf d_state(st), d_obst(st), d_cx(st), d_cy(st), d_cyaw(st), d_alpha(st), d_R(st), d_ts(st), d_cnt(st);
     DevBuf o_state(st), o_steps(st), o_tidx(st), o_nact(st), o_ninf(st), o_hmin(st), o_bmin(st), o_bmax(st), o_bint(st),
         o_traj(st), o_tridx(st), o_trmask(st), o_evals(st);
     SCCAV_CUDA_CHECK(d_state.upload(state, 4 * n * sizeof(real)));
@@ -476,9 +508,10 @@ int SCCAV_FN(sccav_rollout_host_)(const sccav_params* p, const uint8_t* slot_des
         SCCAV_CUDA_CHECK(d_cy.upload(course_y, (size_t)P * sizeof(real)));
         SCCAV_CUDA_CHECK(d_cyaw.upload(course_yaw, (size_t)P * sizeof(real)));
     }
-    sccav_pervehicle dpv = {nullptr, nullptr, nullptr};
+    sccav_pervehicle dpv = {nullptr, nullptr, nullptr, nullptr};
     if (pv && pv->alpha) { SCCAV_CUDA_CHECK(d_alpha.upload(pv->alpha, n * sizeof(real))); dpv.alpha = d_alpha.p; }
     if (pv && pv->R) { SCCAV_CUDA_CHECK(d_R.upload(pv->R, 4 * n * sizeof(real))); dpv.R = d_R.p; }
+    if (pv && pv->count) { SCCAV_CUDA_CHECK(d_cnt.upload(pv->count, n * sizeof(int32_t))); dpv.count = (const int32_t*)d_cnt.p; }
     if (pv && pv->target_speed) { SCCAV_CUDA_CHECK(d_ts.upload(pv->target_speed, n * sizeof(real))); dpv.target_speed = d_ts.p; }
     sccav_rollout_out dout;
     memset(&dout, 0, sizeof(dout));

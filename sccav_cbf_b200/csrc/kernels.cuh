@@ -19,7 +19,15 @@ template <typename T> struct PerVehicle {
     const T* alpha;
     const T* R;
     const T* target_speed;
+    const int32_t* count;    // obstacles of vehicle n = its first count[n] slots (sccav_pervehicle.count)
 };
+
+template <typename T>
+__device__ __forceinline__ int slot_count(const PerVehicle<T>& pv, int M, int64_t n) {
+    if (!pv.count) return M;
+    const int c = pv.count[n];
+    return c < 0 ? 0 : (c > M ? M : c);
+}
 
 template <typename T>
 __device__ __forceinline__ void load_weights(const Params<T>& P, const PerVehicle<T>& pv, int64_t N, int64_t n,
@@ -63,6 +71,92 @@ __global__ void __launch_bounds__(256) prepare_obstacles_kernel(const __grid_con
     }
 }
 
+// ------------------------------------------------------------------------------------------ KB
+// Batched ObstacleList2D.update_by_bounding_box (include/sccav_cbf.h): one thread = one vehicle's list.
+// Integer bookkeeping (which id sits in which slot) is exact; the only arithmetic is a + buffer and
+// hypot(extent).  HBM-bound: reads K (4 + 48) + M (4 + 64) + 4, writes up to M (4 + 64) + 8 bytes per vehicle.
+template <typename T> struct IngestArgs {
+    int type, mode, M, K;
+    int64_t N;
+    T buffer;
+    const int32_t* box_id;
+    const T* box;
+    int32_t* slot_id;
+    T* obst;
+    int32_t* count;
+    int32_t* dropped;
+};
+
+// fields of one obstacle from its bounding box; create = from_bounding_box, else update_by_bounding_box
+template <typename T>
+__device__ __forceinline__ void box_to_slot(int type, bool create, T buffer, const T* __restrict__ bx, int64_t N, T (&f)[SCCAV_NFIELD]) {
+    typedef Real<T> R;
+    const T ex = bx[0], ey = bx[N], lx = bx[2 * N], ly = bx[3 * N], yaw = bx[4 * N], sp = bx[5 * N];
+    if (type == SCCAV_SLOT_ELLIPSE) {
+        f[0] = lx; f[1] = ly; f[4] = yaw;                                   // obstacles.py:298-302,326-330
+        f[2] = create ? ex + buffer : ex;                                   // Ellipse2D.__init__ :159-160 / update(a=, b=)
+        f[3] = create ? ey + buffer : ey;
+        if (create) { f[5] = T(0); f[6] = T(0); f[7] = T(0); }              // vel = Vector2()   :158
+    } else {
+        const T a = R::hypot_(ex, ey);                                      // obstacles.py:528,541
+        f[0] = lx; f[1] = ly; f[2] = T(0); f[3] = sp;                       // s_obs = [x, y, 0.0, velocity]   :529,542
+        f[4] = create ? a + buffer : a;                                     // CollisionCone2D.__init__ :357 / self.a = hypot
+        if (create) { f[5] = T(0); f[6] = T(0); f[7] = T(0); }              // beta = 0   :352
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) ingest_boxes_kernel(const __grid_constant__ IngestArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int32_t* s_bid = reinterpret_cast<int32_t*>(smem_raw) + threadIdx.x;     // [K][blockDim]
+    const int B = blockDim.x, M = a.M, K = a.K;
+    const int64_t N = a.N;
+    for (int64_t n = (int64_t)blockIdx.x * B + threadIdx.x; n < N; n += (int64_t)gridDim.x * B) {
+        for (int k = 0; k < K; ++k) s_bid[k * B] = a.box_id[(int64_t)k * N + n];
+        int cnt = a.mode == SCCAV_INGEST_REBUILD ? 0 : a.count[n];
+        cnt = cnt < 0 ? 0 : (cnt > M ? M : cnt);
+        uint32_t matched = 0u;                       // boxes whose id was found among the held entries
+        int w = 0;                                   // write cursor of the stable compaction
+        T f[SCCAV_NFIELD];
+        for (int j = 0; j < cnt; ++j) {
+            const int32_t id = a.slot_id[(int64_t)j * N + n];
+            int kf = -1;
+            if (id >= 0)
+                for (int k = 0; k < K; ++k)
+                    if (s_bid[k * B] == id) { if (kf < 0) kf = k; matched |= 1u << k; }
+            if (kf < 0) continue;                    // id left the scene: entry removed   obstacles.py:851-853
+            const T* src = a.obst + (int64_t)j * SCCAV_NFIELD * N + n;
+#pragma unroll
+            for (int q = 0; q < SCCAV_NFIELD; ++q) f[q] = src[q * N];
+            box_to_slot<T>(a.type, false, a.buffer, a.box + (int64_t)kf * SCCAV_BOX_FIELDS * N + n, N, f);   // :840-841
+            T* dst = a.obst + (int64_t)w * SCCAV_NFIELD * N + n;
+#pragma unroll
+            for (int q = 0; q < SCCAV_NFIELD; ++q) dst[q * N] = f[q];
+            a.slot_id[(int64_t)w * N + n] = id;
+            ++w;
+        }
+        int drop = 0;
+        for (int k = 0; k < K; ++k) {
+            const int32_t id = s_bid[k * B];
+            if (id < 0 || ((matched >> k) & 1u)) continue;
+            bool dup = false;                        // a repeated new id: the first box wins
+            for (int k2 = 0; k2 < k; ++k2) dup |= s_bid[k2 * B] == id;
+            if (dup) continue;
+            if (w >= M) { ++drop; continue; }
+            box_to_slot<T>(a.type, true, a.buffer, a.box + (int64_t)k * SCCAV_BOX_FIELDS * N + n, N, f);     // :843-846
+            T* dst = a.obst + (int64_t)w * SCCAV_NFIELD * N + n;
+#pragma unroll
+            for (int q = 0; q < SCCAV_NFIELD; ++q) dst[q * N] = f[q];
+            a.slot_id[(int64_t)w * N + n] = id;
+            ++w;
+        }
+        const int old = a.mode == SCCAV_INGEST_REBUILD ? M : cnt;
+        for (int j = w; j < old; ++j) a.slot_id[(int64_t)j * N + n] = -1;
+        a.count[n] = w;
+        if (a.dropped) a.dropped[n] = drop;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ K1
 template <typename T> struct RowsArgs {
     Params<T> P;
@@ -86,14 +180,19 @@ __global__ void __launch_bounds__(256) barrier_rows_kernel(const __grid_constant
         T alpha = a.pv.alpha ? a.pv.alpha[n] : a.P.alpha;
         T sth, cth;
         R::sincos_(th, &sth, &cth);
+        const int Mv = slot_count<T>(a.pv, a.M, n);
         for (int m = 0; m < a.M; ++m) {
-            const int desc = a.sd.d[m];
-            const int64_t nn = (desc & SCCAV_SLOT_SHARED) ? 0 : n;
-            const T* f = a.obst + (int64_t)m * SCCAV_NFIELD * N + nn;
-            Partials<T> p = slot_partials<T>(desc, f, N, x, y, th, v, sth, cth);
-            T A0, A1, b;
-            if (a.P.model == SCCAV_MODEL_KBM) kbm_row<T>(p, sth, cth, alpha, A0, A1, b);
-            else dbm_row<T>(p, sth, cth, v, alpha, a.P.lr, A0, A1, b);
+            T A0 = T(0), A1 = T(0), b = -R::inf();             // empty slot: a vacuous row
+            Partials<T> p;
+            p.h = R::inf();
+            if (m < Mv) {
+                const int desc = a.sd.d[m];
+                const int64_t nn = (desc & SCCAV_SLOT_SHARED) ? 0 : n;
+                const T* f = a.obst + (int64_t)m * SCCAV_NFIELD * N + nn;
+                p = slot_partials<T>(desc, f, N, x, y, th, v, sth, cth);
+                if (a.P.model == SCCAV_MODEL_KBM) kbm_row<T>(p, sth, cth, alpha, A0, A1, b);
+                else dbm_row<T>(p, sth, cth, v, alpha, a.P.lr, A0, A1, b);
+            }
             a.A[(int64_t)m * N + n] = A0;
             a.A[((int64_t)a.M + m) * N + n] = A1;
             a.b[(int64_t)m * N + n] = b;
@@ -111,6 +210,7 @@ template <typename T> struct PartialsArgs {
     int64_t N;
     const T* state;
     const T* obst;
+    const int32_t* count;
     T* out;
 };
 
@@ -122,11 +222,17 @@ __global__ void __launch_bounds__(256) barrier_partials_kernel(const __grid_cons
         T x = a.state[n], y = a.state[N + n], th = a.state[2 * N + n], v = a.state[3 * N + n];
         T sth, cth;
         R::sincos_(th, &sth, &cth);
+        int Mv = a.M;
+        if (a.count) { Mv = a.count[n]; Mv = Mv < 0 ? 0 : (Mv > a.M ? a.M : Mv); }
         for (int m = 0; m < a.M; ++m) {
-            const int desc = a.sd.d[m];
-            const int64_t nn = (desc & SCCAV_SLOT_SHARED) ? 0 : n;
-            const T* f = a.obst + (int64_t)m * SCCAV_NFIELD * N + nn;
-            Partials<T> p = slot_partials<T>(desc, f, N, x, y, th, v, sth, cth);
+            Partials<T> p;
+            p.h = R::inf(); p.hx = p.hy = p.hth = p.hv = p.ht = T(0);      // empty slot
+            if (m < Mv) {
+                const int desc = a.sd.d[m];
+                const int64_t nn = (desc & SCCAV_SLOT_SHARED) ? 0 : n;
+                const T* f = a.obst + (int64_t)m * SCCAV_NFIELD * N + nn;
+                p = slot_partials<T>(desc, f, N, x, y, th, v, sth, cth);
+            }
             T* o = a.out + (int64_t)m * 6 * N + n;
             o[0] = p.h; o[N] = p.hx; o[2 * N] = p.hy; o[3 * N] = p.hth; o[4 * N] = p.hv; o[5 * N] = p.ht;
         }
@@ -154,7 +260,8 @@ __global__ void __launch_bounds__(256) qp2_kernel(const __grid_constant__ QpArgs
     const int stride = blockDim.x;
     const int64_t N = a.N;
     for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
-        for (int m = 0; m < a.M; ++m) {
+        const int Mv = slot_count<T>(a.pv, a.M, n);
+        for (int m = 0; m < Mv; ++m) {
             rows[(3 * m + 0) * stride] = a.A[(int64_t)m * N + n];
             rows[(3 * m + 1) * stride] = a.A[((int64_t)a.M + m) * N + n];
             rows[(3 * m + 2) * stride] = a.b[(int64_t)m * N + n];
@@ -164,7 +271,7 @@ __global__ void __launch_bounds__(256) qp2_kernel(const __grid_constant__ QpArgs
         RowView<T> rv{rows, stride};
         T u0, u1;
         uint32_t mask;
-        int st = qp2_solve<T>(rv, a.M, a.r[n], a.r[N + n], R00, R01, R10, R11, u0, u1, mask);
+        int st = qp2_solve<T>(rv, Mv, a.r[n], a.r[N + n], R00, R01, R10, R11, u0, u1, mask);
         a.u[n] = u0;
         a.u[N + n] = u1;
         if (a.mask) a.mask[n] = mask;
@@ -196,12 +303,12 @@ __global__ void __launch_bounds__(256) qp2_warp_kernel(const __grid_constant__ Q
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t N = a.N;
-    const int M = a.M;
     for (int64_t n = warp; n < N; n += nwarps) {
+        const int M = slot_count<T>(a.pv, a.M, n);
         const bool own = lane < M;
         // lanes >= M hold a vacuous row 0*u >= -inf
         T a0 = own ? a.A[(int64_t)lane * N + n] : T(0);
-        T a1 = own ? a.A[((int64_t)M + lane) * N + n] : T(0);
+        T a1 = own ? a.A[((int64_t)a.M + lane) * N + n] : T(0);
         T bk = own ? a.b[(int64_t)lane * N + n] : -R::inf();
         T alpha, R00, R01, R10, R11;
         load_weights<T>(a.P, a.pv, N, n, alpha, R00, R01, R10, R11);
@@ -306,8 +413,12 @@ __global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_kernel(const 
         R::sincos_(th, &sth, &cth);
         T u0, u1, u1raw, hmin;
         uint32_t mask;
-        int st = filter_vehicle<T, SPEC>(a.P, a.sd, a.M, N, n, a.obst, x, y, th, v, sth, cth, alpha, R00, R01, R10, R11,
+        const int Mv = slot_count<T>(a.pv, a.M, n);
+        int st = SCCAV_STATUS_INACTIVE;
+        if (Mv > 0)
+            st = filter_vehicle<T, SPEC>(a.P, a.sd, Mv, N, n, a.obst, x, y, th, v, sth, cth, alpha, R00, R01, R10, R11,
                                          ur0, ur1, rows, stride, u0, u1, u1raw, mask, hmin);
+        else { u0 = ur0; u1 = ur1; mask = 0u; hmin = R::inf(); }           // empty obstacle list: u = u_ref
         a.u[n] = u0;
         a.u[N + n] = u1;
         if (a.mask) a.mask[n] = mask;
@@ -444,13 +555,14 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
     load_weights<T>(P, a.pv, N, n, alpha, R00, R01, R10, R11);
     const T tspeed = a.pv.target_speed ? a.pv.target_speed[n] : P.target_speed;
     const int last_idx = np - 1;
-    const bool filt = a.M > 0 && P.model != SCCAV_MODEL_NONE;
+    const int Mv = slot_count<T>(a.pv, a.M, n);
+    const bool filt = Mv > 0 && P.model != SCCAV_MODEL_NONE;
 
     // loop-invariant obstacle terms (ellipses): once per (vehicle, slot) into the scratch; `moving`
     // = slots whose ellipse has a velocity (their h_t needs vx, vy, a^2, b^2 every step)
     uint32_t moving = 0u;
     if (a.pre && filt) {
-        for (int m = 0; m < a.M; ++m) {
+        for (int m = 0; m < Mv; ++m) {
             const int desc = a.sd.d[m];
             if ((desc & SCCAV_SLOT_TYPE_MASK) != SCCAV_SLOT_ELLIPSE) continue;
             const int64_t nn = (desc & SCCAV_SLOT_SHARED) ? 0 : n;
@@ -515,7 +627,7 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
         uint32_t mask = 0u;
         int status = SCCAV_STATUS_INACTIVE;
         if (filt)
-            status = filter_vehicle<T, SPEC>(P, a.sd, a.M, N, n, a.obst, x, y, yaw, v, syaw, cyw, alpha, R00, R01, R10, R11,
+            status = filter_vehicle<T, SPEC>(P, a.sd, Mv, N, n, a.obst, x, y, yaw, v, syaw, cyw, alpha, R00, R01, R10, R11,
                                              ur0, ur1, rows, stride, u0, u1, u1raw, mask, hmin, a.pre, moving);
         // ---- plant
         T px = x, py = y, pyaw = yaw, pv_ = v;
@@ -542,7 +654,7 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
         R::sincos_(yaw, &syaw, &cyw);
         // ---- moving obstacles
         if (P.seeker) {
-            for (int m = 0; m < a.M; ++m) {
+            for (int m = 0; m < Mv; ++m) {
                 const int desc = a.sd.d[m];
                 if ((desc & SCCAV_SLOT_TYPE_MASK) == SCCAV_SLOT_RADIAL && !(desc & SCCAV_SLOT_SHARED))
                     seeker_update<T>(a.obst + (int64_t)m * SCCAV_NFIELD * N + n, N, x, y, P.dt, P.seeker_k, P.seeker_vmin);

@@ -554,3 +554,57 @@ class ObstacleList2D(MutableMapping):
         if all(not isinstance(v, torch.Tensor) for v in g):
             return torch.tensor(g, dtype=torch.float64).reshape(-1, 4)
         return torch.stack([torch.as_tensor(v) for v in g])
+
+
+class BatchedObstacleList2D:
+    """N per-vehicle ``ObstacleList2D``'s whose obstacles come and go (the CARLA deployment: every ego sees
+    its own set of actors, cbf/obstacles.py:833-858, multi_obstacle_CBF_local_with_lanes.py:906-932), kept in
+    the structure-of-arrays layout of the kernels: vehicle n holds ``count[n]`` obstacles of ONE type in its
+    first slots -- ``ids`` [M, N] int32 (the dict keys, -1 = empty), ``obst`` [M, 8, N].
+
+    ``update_by_bounding_box(box_id, box)`` is one launch of the ingest kernel (KB): ids already held are
+    updated in place, ids that left the scene are removed, new ids are appended, exactly in the order the
+    reference's dict would hold them.  Assign an instance to ``DBM_CBF_2DS.obstacle_list2d`` and call
+    ``solve_cbf`` as usual; a vehicle with no obstacle gets u = u_ref."""
+
+    def __init__(self, n_vehicles: int, capacity: int = 8, obs_type: Obstacle2DTypes = Obstacle2DTypes.ELLIPSE2D,
+                 dtype: torch.dtype = torch.float64, device=None):
+        if obs_type not in (Obstacle2DTypes.ELLIPSE2D, Obstacle2DTypes.COLLISION_CONE2D):
+            raise TypeError("update_by_bounding_box makes Ellipse2D or CollisionCone2D obstacles")      # obstacles.py:843-846
+        if not 1 <= capacity <= nv.MAX_ROWS:
+            raise ValueError("capacity must be in [1, %d]" % nv.MAX_ROWS)
+        self.device = cuda_device() if device is None else torch.device(device)
+        self.obs_type = obs_type
+        self.slot_type = nv.SLOT_ELLIPSE if obs_type == Obstacle2DTypes.ELLIPSE2D else nv.SLOT_CONE
+        self.N, self.M = int(n_vehicles), int(capacity)
+        self.ids = torch.full((self.M, self.N), -1, dtype=torch.int32, device=self.device)
+        self.obst = torch.zeros((self.M, nv.NFIELD, self.N), dtype=dtype, device=self.device)
+        self.count = torch.zeros((self.N,), dtype=torch.int32, device=self.device)
+        self.dropped = torch.zeros((self.N,), dtype=torch.int32, device=self.device)
+
+    def __len__(self):
+        return self.M
+
+    @property
+    def slot_desc(self) -> List[int]:
+        return [self.slot_type] * self.M
+
+    def update_by_bounding_box(self, box_id: torch.Tensor, box: torch.Tensor, buffer: float = 0.5, rebuild: bool = False):
+        """``box_id`` [K, N] int32 (< 0 = no box), ``box`` [K, 6, N] = extent.x, extent.y, location.x, location.y,
+        rotation.yaw, velocity of ``BoundingBox`` (cbf/obstacles.py:59-64).  ``rebuild``: make every obstacle
+        afresh as the CARLA driver does each tick (multi_obstacle_CBF_local_with_lanes.py:918-928).
+        Returns ``dropped`` [N]: new ids that did not fit the capacity."""
+        ops.ingest_boxes(self.slot_type, box_id.to(self.device), box.to(device=self.device, dtype=self.obst.dtype), self.ids,
+                         self.obst, self.count, buffer=buffer, mode=nv.INGEST_REBUILD if rebuild else nv.INGEST_UPDATE,
+                         dropped=self.dropped)
+        return self.dropped
+
+    def update_state(self, s=None, s_obs_dict=None, buffer=None, **kwargs):
+        """The ego state reaches the kernels with ``solve_cbf``; nothing is stored per obstacle."""
+        if s_obs_dict is not None or buffer is not None:
+            raise ValueError("BatchedObstacleList2D takes obstacle updates through update_by_bounding_box")
+
+    def pack(self, state: torch.Tensor):
+        if state.shape[1] != self.N:
+            raise ValueError("the ego batch has %d vehicles, the obstacle lists %d" % (state.shape[1], self.N))
+        return self.slot_desc, self.obst if self.obst.dtype == state.dtype else self.obst.to(state.dtype), False

@@ -64,9 +64,11 @@ def _stream(device: torch.device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def _pv(N, dtype, device, alpha=None, R=None, target_speed=None):
+def _pv(N, dtype, device, alpha=None, R=None, target_speed=None, count=None):
     pv = nv.PerVehicle()
     keep = []
+    if count is not None:
+        count = _chk(count, (N,), torch.int32, device, "count"); keep.append(count); pv.count = count.data_ptr()
     if alpha is not None:
         alpha = _chk(alpha, (N,), dtype, device, "alpha"); keep.append(alpha); pv.alpha = alpha.data_ptr()
     if R is not None:
@@ -82,7 +84,7 @@ def _need_cuda_lib():
     return nv.lib()
 
 
-def barrier_rows(params: Params, slot_desc, state: torch.Tensor, obst: torch.Tensor, alpha=None):
+def barrier_rows(params: Params, slot_desc, state: torch.Tensor, obst: torch.Tensor, alpha=None, count=None):
     """K1: rows (A [2,M,N], b [M,N]) and barrier values h [M,N] -- ObstacleList2D.f/dx/.. +
     the assembly of cbf/cbf.py:194-207."""
     L = _need_cuda_lib()
@@ -93,7 +95,7 @@ def barrier_rows(params: Params, slot_desc, state: torch.Tensor, obst: torch.Ten
         raise ValueError("barrier_rows takes CUDA tensors")
     state = _chk(state, (4, N), dt, dev, "state")
     obst = _chk(obst, (M, nv.NFIELD, N), dt, dev, "obst")
-    pv, keep = _pv(N, dt, dev, alpha=alpha)
+    pv, keep = _pv(N, dt, dev, alpha=alpha, count=count)
     A = torch.empty((2, M, N), dtype=dt, device=dev)
     b = torch.empty((M, N), dtype=dt, device=dev)
     h = torch.empty((M, N), dtype=dt, device=dev)
@@ -147,7 +149,7 @@ def stanley_control(params: Params, state: torch.Tensor, course, target_idx: tor
     return (delta, err) if want_error else delta
 
 
-def qp2_solve(params: Params, A: torch.Tensor, b: torch.Tensor, r: torch.Tensor, R=None, warp_per_problem=False):
+def qp2_solve(params: Params, A: torch.Tensor, b: torch.Tensor, r: torch.Tensor, R=None, warp_per_problem=False, count=None):
     """K2: exact optimum of min (u-r)^T R (u-r) s.t. A u >= b (what cvxopt.solvers.cp approximates
     at cbf/cbf.py:213).  Returns u [2,N], active mask int32 [N] (bit k = row k), status uint8 [N]."""
     L = _need_cuda_lib()
@@ -158,7 +160,7 @@ def qp2_solve(params: Params, A: torch.Tensor, b: torch.Tensor, r: torch.Tensor,
     A = _chk(A, (2, M, N), dt, dev, "A")
     b = _chk(b, (M, N), dt, dev, "b")
     r = _chk(r, (2, N), dt, dev, "r")
-    pv, keep = _pv(N, dt, dev, R=R)
+    pv, keep = _pv(N, dt, dev, R=R, count=count)
     u = torch.empty((2, N), dtype=dt, device=dev)
     mask = torch.empty((N,), dtype=torch.int32, device=dev)
     status = torch.empty((N,), dtype=torch.uint8, device=dev)
@@ -170,7 +172,7 @@ def qp2_solve(params: Params, A: torch.Tensor, b: torch.Tensor, r: torch.Tensor,
 
 
 def filter_step(params: Params, slot_desc, state: torch.Tensor, obst: torch.Tensor, u_ref: torch.Tensor,
-                alpha=None, R=None):
+                alpha=None, R=None, count=None):
     """K1+K2 fused: one batched ``solve_cbf(u_ref)`` (cbf/cbf.py:166-220 / :67-110).
     CUDA tensors -> device entry point on the current stream; CPU tensors -> host entry point.
     Returns u [2,N] = (a|v, delta), active mask int32 [N], status uint8 [N], h_min [N]."""
@@ -182,7 +184,7 @@ def filter_step(params: Params, slot_desc, state: torch.Tensor, obst: torch.Tens
     state = _chk(state, (4, N), dt, dev, "state")
     obst = _chk(obst, (M, nv.NFIELD, N), dt, dev, "obst")
     u_ref = _chk(u_ref, (2, N), dt, dev, "u_ref")
-    pv, keep = _pv(N, dt, dev, alpha=alpha, R=R)
+    pv, keep = _pv(N, dt, dev, alpha=alpha, R=R, count=count)
     u = torch.empty((2, N), dtype=dt, device=dev)
     mask = torch.empty((N,), dtype=torch.int32, device=dev)
     status = torch.empty((N,), dtype=torch.uint8, device=dev)
@@ -205,7 +207,7 @@ ROLLOUT_SUMMARY = ("steps", "target_idx", "n_active", "n_infeasible", "h_min", "
 
 
 def rollout(params: Params, slot_desc, state: torch.Tensor, obst: Optional[torch.Tensor], course, T: int,
-            alpha=None, R=None, target_speed=None, record_stride: int = 0, summary: bool = True,
+            alpha=None, R=None, target_speed=None, count=None, record_stride: int = 0, summary: bool = True,
             out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
     """K3: persistent closed-loop rollout of T steps (stanley_controller_ellipse.py:630-830 /
     radial_dynamic_obstacles.py:427-507).
@@ -236,7 +238,7 @@ def rollout(params: Params, slot_desc, state: torch.Tensor, obst: Optional[torch
     else:
         cx = cy = cyaw = None
         P = 0
-    pv, keep = _pv(N, dt, dev, alpha=alpha, R=R, target_speed=target_speed)
+    pv, keep = _pv(N, dt, dev, alpha=alpha, R=R, target_speed=target_speed, count=count)
     import copy
     prm = copy.copy(params)
     prm.record_stride = int(record_stride)
@@ -314,6 +316,37 @@ def prepare_obstacles(slot_desc, obst: torch.Tensor, out: Optional[torch.Tensor]
     with torch.cuda.device(dev):
         nv.check(getattr(L, "sccav_prepare_obstacles_" + _SFX[dt])(sd, M, N, _ptr(obst), _ptr(out), C.addressof(sd_out), _stream(dev)))
     return [int(sd_out[m]) for m in range(M)], out
+
+
+def ingest_boxes(obs_type: int, box_id: torch.Tensor, box: torch.Tensor, slot_id: torch.Tensor, obst: torch.Tensor,
+                 count: torch.Tensor, buffer: float = 0.5, mode: int = nv.INGEST_UPDATE,
+                 dropped: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """KB: batched ``ObstacleList2D.update_by_bounding_box`` (cbf/obstacles.py:833-858) -- N vehicles,
+    each with its own list of up to M obstacles held in ``slot_id`` [M,N] int32 (-1 = empty) / ``obst``
+    [M,8,N] / ``count`` [N] int32, fed with up to K boxes ``box_id`` [K,N] int32 (< 0 = none) / ``box`` [K,6,N]
+    (extent.x, extent.y, location.x, location.y, yaw, velocity).  All three list tensors are updated in
+    place; ``count`` is what the filter kernels take as their per-vehicle ``count``."""
+    L = nv.lib()
+    nv.require_cuda()
+    dt, dev = obst.dtype, obst.device
+    if dev.type != "cuda":
+        raise ValueError("ingest_boxes works on device tensors")
+    M, N = obst.shape[0], obst.shape[-1]
+    K = box_id.shape[0]
+    for t, name in ((obst, "obst"), (slot_id, "slot_id"), (count, "count")):
+        if not t.is_contiguous():
+            raise ValueError("%s must be contiguous (it is updated in place)" % name)
+    obst = _chk(obst, (M, nv.NFIELD, N), dt, dev, "obst")
+    box = _chk(box, (K, nv.BOX_FIELDS, N), dt, dev, "box")
+    box_id = _chk(box_id, (K, N), torch.int32, dev, "box_id")
+    slot_id = _chk(slot_id, (M, N), torch.int32, dev, "slot_id")
+    count = _chk(count, (N,), torch.int32, dev, "count")
+    if dropped is not None:
+        dropped = _chk(dropped, (N,), torch.int32, dev, "dropped")
+    with torch.cuda.device(dev):
+        nv.check(getattr(L, "sccav_ingest_boxes_" + _SFX[dt])(int(obs_type), int(mode), float(buffer), M, K, N, _ptr(box_id), _ptr(box),
+                                                             _ptr(slot_id), _ptr(obst), _ptr(count), _ptr(dropped), _stream(dev)))
+    return dropped
 
 
 def rollout_launch_info(slot_desc, N: int, P: int, dtype=torch.float64) -> Dict[str, int]:

@@ -1,0 +1,185 @@
+"""Obstacle ingest from bounding boxes: the batched ObstacleList2D.update_by_bounding_box.
+
+CPU: the oracle's slot-array restatement against the reference's literal dict semantics
+(cbf/obstacles.py:833-858, written out here on plain dicts).  GPU: the ingest kernel (KB) against the
+oracle -- ids / order / counts bit-exact -- and the filter on lists of different length (per-vehicle count)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle as co
+from oracle import oracle as o
+from tests import helpers as H
+
+
+def random_scene(rng, N, M, K, n_ticks, p_leave=0.3, id_pool=40):
+    """Per vehicle a population of actor ids drifting in and out of range: tick t -> (box_id [K,N], box [K,6,N])."""
+    ticks = []
+    cur = [list(rng.choice(id_pool, size=rng.integers(0, K + 1), replace=False)) for _ in range(N)]
+    for _ in range(n_ticks):
+        bid = -np.ones((K, N), np.int32)
+        box = np.zeros((K, 6, N))
+        for n in range(N):
+            keep = [i for i in cur[n] if rng.uniform() > p_leave]
+            new = [i for i in rng.permutation(id_pool) if i not in keep][: rng.integers(0, K - len(keep) + 1)]
+            ids = list(rng.permutation(keep + [int(i) for i in new]))
+            cur[n] = ids
+            pos = rng.permutation(K)[: len(ids)]                  # boxes sit at arbitrary positions, padding in between
+            for k, i in zip(sorted(pos), ids):
+                bid[k, n] = i
+                box[k, :, n] = [rng.uniform(1.5, 3), rng.uniform(0.8, 1.5), rng.uniform(-30, 120), rng.uniform(-40, 10),
+                                rng.uniform(-3, 3), rng.uniform(0, 12)]
+        ticks.append((bid, box))
+    return ticks
+
+
+def reference_dict_update(mapping, bbox_dict, obs_type, buffer):
+    """cbf/obstacles.py:833-858 on a plain dict id -> fields (Python dicts keep insertion order)."""
+    for key, bbox in bbox_dict.items():
+        if key in mapping:
+            mapping[key] = o.box_to_fields(obs_type, False, buffer, bbox, mapping[key])        # .update_by_bounding_box
+        else:
+            mapping[key] = o.box_to_fields(obs_type, True, buffer, bbox)                        # .from_bounding_box
+    for key in list(mapping.keys()):
+        if key not in list(bbox_dict.keys()):
+            mapping.pop(key)
+
+
+@pytest.mark.parametrize("obs_type", [o.SLOT_ELLIPSE, o.SLOT_CONE])
+def test_oracle_ingest_equals_reference_dict_semantics(obs_type):
+    rng = np.random.default_rng(3 + obs_type)
+    N, M, K = 40, 12, 12                                          # M >= K: nothing is ever dropped
+    ticks = random_scene(rng, N, M, K, 8)
+    for n in range(N):
+        mapping = {}
+        ids, fields, cnt = [-1] * M, [[0.0] * 8 for _ in range(M)], 0
+        for bid, box in ticks:
+            bbox_dict = {int(bid[k, n]): box[k, :, n] for k in range(K) if bid[k, n] >= 0}
+            reference_dict_update(mapping, bbox_dict, obs_type, 0.5)
+            ids, fields, cnt, dropped = o.ingest_boxes(obs_type, o.INGEST_UPDATE, 0.5, M, bid[:, n], box[:, :, n].T.reshape(K, 6) if False else [box[k, :, n] for k in range(K)], ids, fields, cnt)
+            assert dropped == 0 and cnt == len(mapping)
+            assert ids[:cnt] == list(mapping.keys())              # dict order == constraint order
+            assert all(i == -1 for i in ids[cnt:])
+            for m, key in enumerate(mapping):
+                assert fields[m] == mapping[key]
+
+
+def test_oracle_ingest_capacity_and_rebuild():
+    box = [np.array([2.0, 1.0, 10.0 + k, -3.0, 0.1 * k, 4.0]) for k in range(5)]
+    ids, f, cnt, dropped = o.ingest_boxes(o.SLOT_CONE, o.INGEST_UPDATE, 1.5, 3, [7, -1, 9, 4, 2], box, [-1] * 3, [[0.0] * 8] * 3, 0)
+    assert ids == [7, 9, 4] and cnt == 3 and dropped == 1
+    assert f[0][4] == float(np.hypot(2.0, 1.0)) + 1.5 and f[0][3] == 4.0 and f[0][2] == 0.0
+    # update keeps the order and drops the buffer (obstacles.py:528: self.a = hypot(...)); rebuild re-applies it
+    ids2, f2, cnt2, _ = o.ingest_boxes(o.SLOT_CONE, o.INGEST_UPDATE, 1.5, 3, [4, 7, -1, -1, -1], box, ids, f, cnt)
+    assert ids2 == [7, 4, -1] and cnt2 == 2 and f2[0][4] == float(np.hypot(2.0, 1.0))
+    ids3, f3, cnt3, _ = o.ingest_boxes(o.SLOT_CONE, o.INGEST_REBUILD, 1.5, 3, [4, 7, -1, -1, -1], box, ids2, f2, cnt2)
+    assert ids3 == [4, 7, -1] and cnt3 == 2 and f3[0][4] == float(np.hypot(2.0, 1.0)) + 1.5
+
+
+def test_c_oracle_per_vehicle_count():
+    """count[n] obstacles per vehicle: the C oracle on M slots with a count equals itself on the truncated list."""
+    rng = np.random.default_rng(8)
+    N, M = 64, 6
+    slots = [o.SLOT_ELLIPSE] * M
+    s = H.random_states(rng, N); ob = H.random_slots(rng, N, slots, s); ur = H.random_uref(rng, N)
+    count = rng.integers(0, M + 1, N).astype(np.int32)
+    full = co.filter_step(co.default_params(), slots, s, ob, ur, rows=True, count=count)
+    for n in range(N):
+        c = int(count[n])
+        if c == 0:
+            assert np.array_equal(full["u"][:, n], ur[:, n]) and full["mask"][n] == 0 and full["status"][n] == 0
+            continue
+        one = co.filter_step(co.default_params(), slots[:c], s[:, n:n + 1], ob[:c, :, n:n + 1], ur[:, n:n + 1], rows=True)
+        assert np.array_equal(full["u"][:, n], one["u"][:, 0]) and full["mask"][n] == one["mask"][0]
+        assert np.array_equal(full["b"][:c, n], one["b"][:, 0]) and np.all(full["b"][c:, n] == -np.inf)
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def T(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(torch.device("cuda", 0))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("obs_type,M,K", [(o.SLOT_ELLIPSE, 8, 8), (o.SLOT_CONE, 5, 12), (o.SLOT_CONE, 32, 32)])
+def test_ingest_kernel_vs_oracle_over_ticks(obs_type, M, K):
+    from sccav_cbf_b200 import ops
+    rng = np.random.default_rng(100 + M)
+    N = 700
+    ticks = random_scene(rng, N, M, K, 6, id_pool=3 * K)
+    ids_g = torch.full((M, N), -1, dtype=torch.int32, device="cuda")
+    ob_g = torch.zeros((M, 8, N), dtype=torch.float64, device="cuda")
+    cnt_g = torch.zeros(N, dtype=torch.int32, device="cuda")
+    drop_g = torch.zeros(N, dtype=torch.int32, device="cuda")
+    ids_o = [[-1] * M for _ in range(N)]
+    f_o = [[[0.0] * 8 for _ in range(M)] for _ in range(N)]
+    cnt_o = [0] * N
+    any_drop = 0
+    for t, (bid, box) in enumerate(ticks):
+        mode = o.INGEST_REBUILD if t == 3 else o.INGEST_UPDATE
+        ops.ingest_boxes(obs_type, T(bid), T(box), ids_g, ob_g, cnt_g, buffer=0.5, mode=mode, dropped=drop_g)
+        ig, og, cg, dg = ids_g.cpu().numpy(), ob_g.cpu().numpy(), cnt_g.cpu().numpy(), drop_g.cpu().numpy()
+        for n in range(N):
+            ids_o[n], f_o[n], cnt_o[n], d = o.ingest_boxes(obs_type, mode, 0.5, M, bid[:, n], [box[k, :, n] for k in range(K)],
+                                                          ids_o[n], f_o[n], cnt_o[n])
+            assert cg[n] == cnt_o[n] and dg[n] == d, (t, n)
+            assert list(ig[:, n]) == ids_o[n], (t, n)                                  # ids and their order: exact
+            c = cnt_o[n]
+            ref = np.array(f_o[n][:c]).reshape(c, 8)
+            assert np.allclose(og[:c, :, n], ref, rtol=1e-15, atol=0.0), (t, n)         # hypot: <= 1 ulp
+            any_drop += d
+    if M < K:
+        assert any_drop > 0
+
+
+@pytest.mark.gpu
+def test_filter_with_per_vehicle_count_and_batched_list_class():
+    from sccav_cbf_b200 import DBM_CBF_2DS, BatchedObstacleList2D, Obstacle2DTypes, ops
+    rng = np.random.default_rng(21)
+    N, M, K = 3000, 8, 8
+    s = H.random_states(rng, N)
+    ur = H.random_uref(rng, N)
+    # boxes placed ahead of each vehicle so that a good share of the rows is active
+    near = H.random_slots(rng, N, [o.SLOT_CONE] * K, s)
+    bid = np.where(rng.uniform(size=(K, N)) < 0.6, rng.permuted(np.tile(np.arange(K, dtype=np.int32)[:, None], (1, N)), axis=0), -1).astype(np.int32)
+    box = np.zeros((K, 6, N))
+    box[:, 0], box[:, 1] = rng.uniform(1.5, 3, (K, N)), rng.uniform(0.8, 1.5, (K, N))
+    box[:, 2], box[:, 3] = near[:, 0], near[:, 1]
+    box[:, 5] = rng.uniform(0, 6, (K, N))
+    lst = BatchedObstacleList2D(N, capacity=M, obs_type=Obstacle2DTypes.COLLISION_CONE2D)
+    lst.update_by_bounding_box(T(bid), T(box), buffer=1.5)
+    cnt = lst.count.cpu().numpy()
+    assert cnt.min() == 0 and cnt.max() >= 6                      # lists of different length, some empty
+    cbf = DBM_CBF_2DS(alpha=1.0)
+    cbf.obstacle_list2d = lst
+    cbf.set_model_params(lr=1.45, lf=1.45)
+    cbf.update_state(T(s))
+    info, u = cbf.solve_cbf(T(ur), return_solver=True)
+    ref = co.filter_step(co.default_params(), lst.slot_desc, s, lst.obst.cpu().numpy(), ur, count=cnt, rows=True)
+    assert np.array_equal(info["active_mask"].cpu().numpy().view(np.uint32), ref["mask"])
+    assert np.array_equal(info["status"].cpu().numpy(), ref["status"])
+    assert np.abs(u.cpu().numpy() - ref["u"]).max() <= 1e-9 * (1 + np.abs(ref["u"]).max())
+    assert np.array_equal(u.cpu().numpy()[:, cnt == 0], ur[:, cnt == 0])          # no obstacle: u = u_ref exactly
+    assert (ref["mask"] != 0).mean() > 0.02
+    # rows / QP entry points honour the count as well
+    prm = ops.make_params()
+    A, b, h = ops.barrier_rows(prm, lst.slot_desc, T(s), lst.obst, count=lst.count)
+    assert np.allclose(A.cpu().numpy(), ref["A"], rtol=1e-9, atol=1e-12)
+    bb = b.cpu().numpy()
+    for m in range(M):
+        assert np.all(bb[m, cnt <= m] == -np.inf)
+    r = T(np.stack([ur[0], np.arctan2(1.45 * np.tan(ur[1]), 2.9)]))
+    for warp in (False, True):
+        u2, mask2, status2 = ops.qp2_solve(prm, A, b, r, warp_per_problem=warp, count=lst.count)
+        assert np.array_equal(mask2.cpu().numpy().view(np.uint32), ref["mask"]) and np.array_equal(status2.cpu().numpy(), ref["status"])
+    # closed loop with lists of different length
+    from sccav_cbf_b200 import scenarios as sc
+    b2 = sc.config2(n_total=65536, M=8, T=300, lo=0, hi=512)
+    c2 = rng.integers(0, 9, b2.N).astype(np.int32)
+    g = ops.rollout(ops.make_params(), b2.slot_desc, T(b2.state), T(b2.obst), tuple(T(c) for c in b2.course), b2.T, count=T(c2))
+    r2 = co.rollout(co.default_params(), b2.slot_desc, b2.state, b2.obst, b2.course, b2.T, count=c2)
+    same = (g["n_active"].cpu().numpy() == r2["n_active"]) & (g["target_idx"].cpu().numpy() == r2["target_idx"])
+    assert same.mean() >= 0.995
+    assert (g["n_active"].cpu().numpy()[c2 == 0] == 0).all()
