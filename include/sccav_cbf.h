@@ -72,6 +72,9 @@ extern "C" {
 #define SCCAV_MODEL_DBM 0          /* DBM_CBF_2DS,  u = (a, beta),  cbf/cbf.py:112-220 */
 #define SCCAV_MODEL_KBM 1          /* KBM_VC_CBF2D, u = (v, omega), cbf/cbf.py:33-110  */
 #define SCCAV_MODEL_NONE 2         /* rollout only: USE_CBF = False, plant State.update (sce.py:86-101,828) */
+#define SCCAV_MODEL_DUM 3          /* DUM_CBF_2DS, dynamic unicycle, u = (a, omega) in and out, cbf/cbf.py:222-298
+                                      (g_c columns [0,0,0,1], [0,0,1,0]; its fc is taken as the 4-vector it lists,
+                                      the reference declares it 5x1 and raises).  Filter entry points only.  */
 
 #define SCCAV_NOMINAL_STANLEY 0    /* Stanley + P speed, stanley_controller_ellipse.py:135-212 */
 #define SCCAV_NOMINAL_CONST 1      /* constant u_ref, radial_dynamic_obstacles.py:444          */
@@ -280,6 +283,23 @@ int sccav_ingest_boxes_f64(int32_t obs_type, int32_t mode, double buffer, int32_
 int sccav_ingest_boxes_f32(int32_t obs_type, int32_t mode, double buffer, int32_t M, int32_t K, int64_t N,
                            const int32_t* box_id, const float* box, int32_t* slot_id, float* obst, int32_t* count,
                            int32_t* dropped, void* stream);
+
+/* KA -- actuator shaping after the filter, the step that follows solve_cbf in the CARLA drivers
+ * (multi_obstacle_CBF_local_with_lanes.py:955-980): u = (a, delta) -> (throttle, brake, steer).
+ *   a > 0 : throttle = clamp(tanh(a), 0, 1), raised by at most `rate` per tick above throttle_prev;
+ *           brake keeps its previous value (the driver does not reset it, :958-968) unless
+ *           SCCAV_ACT_RESET_BRAKE is set, which zeroes it
+ *   a <= 0: throttle = 0, brake = clamp(-tanh(a), 0, 1), raised by at most `rate` per tick above brake_prev
+ *   steer = delta clamped to [0, max_steer] (delta > 0) or [-max_steer, 0]           (:973-976)
+ * throttle_prev / brake_prev [N] are read and then overwritten with the new values (:970-971).
+ * DEVICE pointers, asynchronous on `stream`. */
+#define SCCAV_ACT_RESET_BRAKE 1
+int sccav_actuator_shaping_f64(int64_t N, const double* u, double max_steer, double rate, int32_t flags,
+                               double* throttle_prev, double* brake_prev, double* throttle_out, double* brake_out,
+                               double* steer_out, void* stream);
+int sccav_actuator_shaping_f32(int64_t N, const float* u, double max_steer, double rate, int32_t flags,
+                               float* throttle_prev, float* brake_prev, float* throttle_out, float* brake_out,
+                               float* steer_out, void* stream);
 
 /* Measurement helpers used by bench.py (not part of the reference-facing path). */
 /* Launches an unrolled FMA chain kernel and returns the achieved TFLOP/s (FMA = 2 flop) on the

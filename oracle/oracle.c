@@ -208,6 +208,11 @@ static void make_row(int model, const part_t* p, double th, double v, double alp
         *A0 = p->hx * c + p->hy * s;
         *A1 = p->hth;
         *b = -(alpha * p->h);
+    } else if (model == SCCAV_MODEL_DUM) {                                         /* cbf/cbf.py:237-245,277-286 */
+        *A0 = p->hv;
+        *A1 = p->hth;
+        double Lf = p->hx * (v * c) + p->hy * (v * s);
+        *b = -((Lf + alpha * p->h) + p->ht);
     } else {
         *A0 = p->hv;
         *A1 = (p->hx * (-v * s) + p->hy * (v * c)) + p->hth * (v / lr);
@@ -285,12 +290,15 @@ static int filter_vehicle(const sccav_params* p, const uint8_t* sd, int M, int64
         if (pt.h < *hmin) *hmin = pt.h;
     }
     double r0 = ur0, r1;
-    if (p->model == SCCAV_MODEL_KBM) r1 = ur0 * tan(ur1) / p->L;                /* cbf.py:75 */
+    if (p->model == SCCAV_MODEL_DUM) r1 = ur1;                                 /* cbf.py:253 */
+    else if (p->model == SCCAV_MODEL_KBM) r1 = ur0 * tan(ur1) / p->L;           /* cbf.py:75 */
     else r1 = atan2(p->lr * tan(ur1), p->lf + p->lr);                          /* cbf.py:175 */
     double q0, q1;
     int st = qp2_exact(M, A0, A1, b, r0, r1, R, &q0, &q1, mask);
     *u0 = q0;
-    if (p->model == SCCAV_MODEL_KBM) {
+    if (p->model == SCCAV_MODEL_DUM) {
+        *u1 = q1;                                                              /* cbf.py:293 */
+    } else if (p->model == SCCAV_MODEL_KBM) {
         if (p->kbm_driver_delta) *u1 = atan(q1 * p->L / q0);                   /* sce.py:652 */
         else *u1 = atan2(q1 * p->L, r0);                                       /* cbf.py:109 */
     } else {

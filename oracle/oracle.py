@@ -65,6 +65,7 @@ NFIELD = 8
 MODEL_DBM = 0      # DBM_CBF_2DS  (cbf/cbf.py:112-220)
 MODEL_KBM = 1      # KBM_VC_CBF2D (cbf/cbf.py:33-110)
 MODEL_NONE = 2     # rollout only: USE_CBF = False -> State.update (stanley_controller_ellipse.py:828)
+MODEL_DUM = 3      # DUM_CBF_2DS  (cbf/cbf.py:222-298), filter step only
 
 STATUS_INACTIVE = 0    # u == u_ref (no row active)
 STATUS_ACTIVE = 1      # optimum with 1 or 2 active rows
@@ -360,6 +361,34 @@ def ingest_boxes(obs_type, mode, buffer, M, box_ids, boxes, slot_ids, fields, co
 
 
 # --------------------------------------------------------------------------------------
+# actuator shaping (the step AFTER the path in the CARLA deployment)
+# --------------------------------------------------------------------------------------
+def actuator_shaping(u_a, delta, throttle_previous, brake_previous, max_steer=1.0, rate=0.1, reset_brake=False):
+    """multi_obstacle_CBF_local_with_lanes.py:955-976, literally.  ``brake_previous`` doubles as the driver's
+    ``brake`` variable of the last tick: the throttle branch does not touch it (:958-962), so it keeps its
+    value unless ``reset_brake``.  Returns (throttle, brake, steer)."""
+    brake = brake_previous
+    if u_a > 0:
+        throttle = float(np.tanh(u_a))
+        throttle = max(0.0, min(1.0, throttle))
+        if throttle - throttle_previous > rate:
+            throttle = throttle_previous + rate
+        if reset_brake:
+            brake = 0.0
+    else:
+        throttle = 0
+        brake = -float(np.tanh(u_a))
+        brake = max(0.0, min(1.0, brake))
+        if brake - brake_previous > rate:
+            brake = brake_previous + rate
+    if delta > 0:
+        delta = max(0.0, min(delta, max_steer))
+    else:
+        delta = max(-max_steer, min(delta, 0.0))
+    return float(throttle), float(brake), float(delta)
+
+
+# --------------------------------------------------------------------------------------
 # row assembly: constraint  A0*u0 + A1*u1 >= b
 # --------------------------------------------------------------------------------------
 def dbm_row(part, th, v, alpha, lr):
@@ -371,6 +400,20 @@ def dbm_row(part, th, v, alpha, lr):
     s = float(np.sin(th))
     A0 = h_v
     A1 = (h_x * (-v * s) + h_y * (v * c)) + h_th * (v / lr)
+    Lf = h_x * (v * c) + h_y * (v * s)
+    b = -((Lf + alpha * h) + h_t)
+    return A0, A1, b
+
+
+def dum_row(part, th, v, alpha):
+    """DUM_CBF_2DS.gc/fc + F -- cbf/cbf.py:237-245,277-286.  g_c columns [0,0,0,1], [0,0,1,0] (u = [v_dot,
+    theta_dot]); f_c = [v cos, v sin, 0, 0] (the reference declares this 4-element list as 5 x 1, which cvxopt
+    rejects -- the 4-vector it lists is meant)."""
+    h, h_x, h_y, h_th, h_v, h_t = part
+    c = float(np.cos(th))
+    s = float(np.sin(th))
+    A0 = h_v
+    A1 = h_th
     Lf = h_x * (v * c) + h_y * (v * s)
     b = -((Lf + alpha * h) + h_t)
     return A0, A1, b
@@ -516,6 +559,8 @@ def barrier_rows(model, s, slot_types, fields, alpha, lr):
         part = slot_partials(st, fields[m], s)
         if model == MODEL_DBM:
             r = dbm_row(part, s[2], s[3], alpha, lr)
+        elif model == MODEL_DUM:
+            r = dum_row(part, s[2], s[3], alpha)
         else:
             r = kbm_row(part, s[2], alpha)
         A0.append(r[0]); A1.append(r[1]); b.append(r[2]); hs.append(part[0])
@@ -532,12 +577,16 @@ def filter_step(model, s, u_ref, slot_types, fields, alpha, lr, lf, L, R, kbm_dr
     if model == MODEL_DBM:
         r0 = u_ref[0]
         r1 = delta_to_beta(u_ref[1], lr, lf)
+    elif model == MODEL_DUM:
+        r0, r1 = u_ref[0], u_ref[1]                           # cbf/cbf.py:253: u_ref = [a, omega] as given
     else:
         r0 = u_ref[0]
         r1 = u_ref[0] * float(np.tan(u_ref[1])) / L           # cbf/cbf.py:75
     u0, u1, mask, status = qp2_exact(A0, A1, b, r0, r1, R)
     if model == MODEL_DBM:
         out1 = beta_to_delta(u1, lr, lf)
+    elif model == MODEL_DUM:
+        out1 = u1                                            # cbf/cbf.py:293
     elif kbm_driver_delta:
         out1 = float(np.arctan(u1 * L / u0))                 # stanley_controller_ellipse.py:652
     else:

@@ -23,7 +23,8 @@ SLOT_SHARED = 0x80
 FLAG_PREPARED_ROWS = 1
 BOX_FIELDS = 6
 INGEST_UPDATE, INGEST_REBUILD = 0, 1
-MODEL_DBM, MODEL_KBM, MODEL_NONE = 0, 1, 2
+ACT_RESET_BRAKE = 1
+MODEL_DBM, MODEL_KBM, MODEL_NONE, MODEL_DUM = 0, 1, 2, 3
 NOMINAL_STANLEY, NOMINAL_CONST = 0, 1
 STATUS_INACTIVE, STATUS_ACTIVE, STATUS_INFEASIBLE = 0, 1, 2
 OK, EINVAL, ECUDA, ENOMEM = 0, -1, -2, -3
@@ -71,6 +72,7 @@ SYMBOLS = [
     "sccav_rollout_launch_info_f64", "sccav_rollout_launch_info_f32",
     "sccav_barrier_partials_f64", "sccav_barrier_partials_f32", "sccav_stanley_control_f64", "sccav_stanley_control_f32",
     "sccav_prepare_obstacles_f64", "sccav_prepare_obstacles_f32", "sccav_ingest_boxes_f64", "sccav_ingest_boxes_f32",
+    "sccav_actuator_shaping_f64", "sccav_actuator_shaping_f32",
 ]
 
 
@@ -101,6 +103,8 @@ def lib() -> C.CDLL:
         f.argtypes = [C.c_char_p, i32, i64, vp, vp, vp, vp]
         f = getattr(L, "sccav_prepare_obstacles_" + sfx)
         f.argtypes = [C.c_char_p, i32, i64, vp, vp, vp, vp]
+        f = getattr(L, "sccav_actuator_shaping_" + sfx)
+        f.argtypes = [i64, vp, C.c_double, C.c_double, i32, vp, vp, vp, vp, vp, vp]
         f = getattr(L, "sccav_ingest_boxes_" + sfx)
         f.argtypes = [i32, i32, C.c_double, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp]
         f = getattr(L, "sccav_stanley_control_" + sfx)

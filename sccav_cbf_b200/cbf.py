@@ -11,8 +11,8 @@ Scalars (one scenario, Python floats in / a length-2 CPU tensor out, as the refe
 matrix) or batches ([4, N] state, [2, N] references in / [2, N] CUDA tensor out) -- see
 ``sccav_cbf_b200._batch``.  There is no CPU fallback.
 
-Not provided: ``DUM_CBF_2DS`` (its ``fc`` raises in the reference, cbf/cbf.py:243-245) and
-``SADBM_CBF_2DS`` (wall-clock dt + debug prints, cbf/cbf.py:333,357-433) -- out of scope per SURVEY 8f.
+``DUM_CBF_2DS`` (cbf/cbf.py:222-298) is provided with the 4-vector ``fc`` its code lists (the reference declares
+it 5 x 1 and raises).  Not provided: ``SADBM_CBF_2DS`` (wall-clock dt + debug prints, cbf/cbf.py:333,357-433).
 """
 from __future__ import annotations
 
@@ -186,3 +186,19 @@ class KBM_VC_CBF2D(_FilterBase):
         state, scalar = as_state(self.s)
         params = self._params(L=float(self._L))
         return self._solve(state, scalar, u_ref, params, True)
+
+
+class DUM_CBF_2DS(DBM_CBF_2DS):
+    """Dynamic unicycle model filter (cbf/cbf.py:222-298): state s = [x, y, theta, v], control u = [a, omega]
+    in and out -- g_c selects (v_dot, theta_dot), so Lg h = [h_v, h_theta]; no delta <-> beta conversion.
+    Ellipse / lane barriers have h_v = h_theta = 0 and cannot be influenced by this model's controls;
+    it is meant for the collision cone."""
+    MODEL = nv.MODEL_DUM
+
+    def solve_cbf(self, u_ref, return_solver=False):
+        if len(self.obstacle_list2d) < 1:
+            raise ValueError(EMPTY_MSG)
+        if self.s is None:
+            raise AttributeError("update_state(s) has not been called")
+        state, scalar = as_state(self.s)
+        return self._solve(state, scalar, u_ref, self._params(), return_solver)

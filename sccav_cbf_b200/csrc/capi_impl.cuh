@@ -34,7 +34,7 @@ int check_common(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int
         int t = slot_desc[m] & SCCAV_SLOT_TYPE_MASK;
         if (t > SCCAV_SLOT_ELLIPSE_PREP) { set_error("slot %d: unknown type %d", m, t); return SCCAV_EINVAL; }
     }
-    if (p->model < 0 || p->model > SCCAV_MODEL_NONE) { set_error("unknown model %d", p->model); return SCCAV_EINVAL; }
+    if (p->model < 0 || p->model > SCCAV_MODEL_DUM) { set_error("unknown model %d", p->model); return SCCAV_EINVAL; }
     double det = p->R[0] * p->R[3] - p->R[1] * p->R[2];
     if (!(p->R[0] > 0.0) || !(det > 0.0)) {
         // set_qp_cost_weight (cbf.py:154-157) expects a symmetric positive definite 2x2
@@ -300,6 +300,7 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
     if (rc) return rc;
     if (T < 0) { set_error("T < 0"); return SCCAV_EINVAL; }
     if (p->record_stride < 0) { set_error("record_stride < 0"); return SCCAV_EINVAL; }
+    if (p->model == SCCAV_MODEL_DUM) { set_error("model DUM has no closed loop (the reference has no unicycle plant on this path)"); return SCCAV_EINVAL; }
     if (N == 0) return SCCAV_OK;
     if (!state || !out || !out->state) { set_error("state / out->state is NULL"); return SCCAV_EINVAL; }
     if (M > 0 && !obst) { set_error("obst is NULL"); return SCCAV_EINVAL; }
@@ -388,6 +389,23 @@ int SCCAV_FN(sccav_ingest_boxes_)(int32_t obs_type, int32_t mode, double buffer,
                                    const int32_t* box_id, const SCCAV_REAL* box, int32_t* slot_id, SCCAV_REAL* obst,
                                    int32_t* count, int32_t* dropped, void* stream) {
     return sccav::do_ingest(obs_type, mode, buffer, M, K, N, box_id, box, slot_id, obst, count, dropped, (cudaStream_t)stream);
+}
+
+int SCCAV_FN(sccav_actuator_shaping_)(int64_t N, const SCCAV_REAL* u, double max_steer, double rate, int32_t flags,
+                                       SCCAV_REAL* throttle_prev, SCCAV_REAL* brake_prev, SCCAV_REAL* throttle_out,
+                                       SCCAV_REAL* brake_out, SCCAV_REAL* steer_out, void* stream) {
+    using namespace sccav;
+    if (N < 0) { set_error("N < 0"); return SCCAV_EINVAL; }
+    if (N == 0) return SCCAV_OK;
+    if (!u || !throttle_prev || !brake_prev) { set_error("NULL array argument"); return SCCAV_EINVAL; }
+    ActuatorArgs<SCCAV_REAL> a;
+    a.N = N; a.u = u; a.max_steer = (SCCAV_REAL)max_steer; a.rate = (SCCAV_REAL)rate; a.flags = flags;
+    a.thr_prev = throttle_prev; a.brk_prev = brake_prev; a.thr = throttle_out; a.brk = brake_out; a.steer = steer_out;
+    const int block = 256;
+    actuator_kernel<SCCAV_REAL><<<stream_grid(N, block), block, 0, (cudaStream_t)stream>>>(a);
+    count_launch();
+    SCCAV_CUDA_CHECK(cudaGetLastError());
+    return SCCAV_OK;
 }
 
 int SCCAV_FN(sccav_barrier_partials_)(const uint8_t* slot_desc, int32_t M, int64_t N, const SCCAV_REAL* state,

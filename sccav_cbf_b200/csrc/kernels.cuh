@@ -157,6 +157,50 @@ __global__ void __launch_bounds__(128) ingest_boxes_kernel(const __grid_constant
     }
 }
 
+// ------------------------------------------------------------------------------------------ KA
+// Actuator shaping after the filter (multi_obstacle_CBF_local_with_lanes.py:955-980), element-wise.
+template <typename T> struct ActuatorArgs {
+    int64_t N;
+    const T* u;
+    T max_steer, rate;
+    int flags;
+    T* thr_prev;
+    T* brk_prev;
+    T* thr;
+    T* brk;
+    T* steer;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) actuator_kernel(const __grid_constant__ ActuatorArgs<T> a) {
+    typedef Real<T> R;
+    const int64_t N = a.N;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        const T ua = a.u[n];
+        T d = a.u[N + n];
+        const T tp = a.thr_prev[n], bp = a.brk_prev[n];
+        T throttle, brake = bp;                                   // `brake` is the driver's variable of the last tick
+        if (ua > T(0)) {
+            throttle = R::tanh_(ua);
+            throttle = fmax(T(0), fmin(T(1), throttle));          // :959-960
+            if (throttle - tp > a.rate) throttle = tp + a.rate;   // :961-962
+            if (a.flags & SCCAV_ACT_RESET_BRAKE) brake = T(0);
+        } else {
+            throttle = T(0);                                      // :964
+            brake = -R::tanh_(ua);
+            brake = fmax(T(0), fmin(T(1), brake));                // :965-966
+            if (brake - bp > a.rate) brake = bp + a.rate;         // :967-968
+        }
+        if (d > T(0)) d = fmax(T(0), fmin(d, a.max_steer));       // :973-976
+        else d = fmax(-a.max_steer, fmin(d, T(0)));
+        a.thr_prev[n] = throttle;                                 // :970-971
+        a.brk_prev[n] = brake;
+        if (a.thr) a.thr[n] = throttle;
+        if (a.brk) a.brk[n] = brake;
+        if (a.steer) a.steer[n] = d;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ K1
 template <typename T> struct RowsArgs {
     Params<T> P;
@@ -190,8 +234,7 @@ __global__ void __launch_bounds__(256) barrier_rows_kernel(const __grid_constant
                 const int64_t nn = (desc & SCCAV_SLOT_SHARED) ? 0 : n;
                 const T* f = a.obst + (int64_t)m * SCCAV_NFIELD * N + nn;
                 p = slot_partials<T>(desc, f, N, x, y, th, v, sth, cth);
-                if (a.P.model == SCCAV_MODEL_KBM) kbm_row<T>(p, sth, cth, alpha, A0, A1, b);
-                else dbm_row<T>(p, sth, cth, v, alpha, a.P.lr, A0, A1, b);
+                model_row<T>(a.P, p, sth, cth, v, alpha, A0, A1, b);
             }
             a.A[(int64_t)m * N + n] = A0;
             a.A[((int64_t)a.M + m) * N + n] = A1;

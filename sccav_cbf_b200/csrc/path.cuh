@@ -36,6 +36,7 @@ template <> struct Real<double> {
     static __device__ __forceinline__ double hypot_(double x, double y) { return ::hypot(x, y); }
     static __device__ __forceinline__ double abs_(double x) { return ::fabs(x); }
     static __device__ __forceinline__ double rint_(double x) { return ::rint(x); }
+    static __device__ __forceinline__ double tanh_(double x) { return ::tanh(x); }
     static __device__ __forceinline__ T2 make2(double a, double b) { return make_double2(a, b); }
 };
 
@@ -56,6 +57,7 @@ template <> struct Real<float> {
     static __device__ __forceinline__ float hypot_(float x, float y) { return ::hypotf(x, y); }
     static __device__ __forceinline__ float abs_(float x) { return ::fabsf(x); }
     static __device__ __forceinline__ float rint_(float x) { return ::rintf(x); }
+    static __device__ __forceinline__ float tanh_(float x) { return ::tanhf(x); }
     static __device__ __forceinline__ T2 make2(float a, float b) { return make_float2(a, b); }
 };
 
@@ -375,6 +377,23 @@ __device__ __forceinline__ void kbm_row(const Partials<T>& p, T sth, T cth, T al
     b = -(alpha * p.h);
 }
 
+// DUM_CBF_2DS gc/fc + F -- cbf/cbf.py:237-245,277-286: Lg h = [h_v, h_theta], Lf h = v cos h_x + v sin h_y
+template <typename T>
+__device__ __forceinline__ void dum_row(const Partials<T>& p, T sth, T cth, T v, T alpha, T& A0, T& A1, T& b) {
+    A0 = p.hv;
+    A1 = p.hth;
+    T Lf = p.hx * (v * cth) + p.hy * (v * sth);
+    b = -((Lf + alpha * p.h) + p.ht);
+}
+
+// row of the configured model
+template <typename T>
+__device__ __forceinline__ void model_row(const Params<T>& P, const Partials<T>& p, T sth, T cth, T v, T alpha, T& A0, T& A1, T& b) {
+    if (P.model == SCCAV_MODEL_KBM) kbm_row<T>(p, sth, cth, alpha, A0, A1, b);
+    else if (P.model == SCCAV_MODEL_DUM) dum_row<T>(p, sth, cth, v, alpha, A0, A1, b);
+    else dbm_row<T>(p, sth, cth, v, alpha, P.lr, A0, A1, b);
+}
+
 // ------------------------------------------------------------------------------------------
 // 2-variable QP on rows held in shared memory: row k at rows[(3k + {0,1,2}) * stride]
 // Same enumeration order / tolerances as oracle.qp2_exact: {} , singles, pairs; first KKT point.
@@ -528,8 +547,7 @@ __device__ __forceinline__ void put_row(const Params<T>& P, const Partials<T>& p
                                         T* rows, int stride, int m, T& hmin, T& worst, bool& feas, RowNz& nz) {
     typedef Real<T> R;
     T A0, A1, b;
-    if (P.model == SCCAV_MODEL_KBM) kbm_row<T>(p, sth, cth, alpha, A0, A1, b);
-    else dbm_row<T>(p, sth, cth, v, alpha, P.lr, A0, A1, b);
+    model_row<T>(P, p, sth, cth, v, alpha, A0, A1, b);
     rows[(3 * m + 0) * stride] = A0;
     rows[(3 * m + 1) * stride] = A1;
     rows[(3 * m + 2) * stride] = b;
@@ -561,6 +579,7 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
     hmin = R::inf();
     T r0 = uref0, r1;
     if (P.model == SCCAV_MODEL_KBM) r1 = (uref0 * R::tan_(uref1)) / P.L;                // cbf.py:75
+    else if (P.model == SCCAV_MODEL_DUM) r1 = uref1;                                     // cbf.py:253: u_ref as given
     else r1 = R::atan2_(P.lr * R::tan_(uref1), P.lf + P.lr);                             // cbf.py:175
     // rows -> shared memory; an inactive step never re-reads them
     bool feas = true;
@@ -630,6 +649,7 @@ __device__ __forceinline__ T filter_convert(const Params<T>& P, T q0, T q1, T r0
         if (P.kbm_driver_delta) return R::atan_((q1 * P.L) / q0);                        // sce.py:652
         return R::atan2_(q1 * P.L, r0);                                                  // cbf.py:109
     }
+    if (P.model == SCCAV_MODEL_DUM) return q1;                                           // cbf.py:293: u as solved
     return R::atan2_((P.lf + P.lr) * R::tan_(q1), P.lr);                                 // cbf.py:216
 }
 

@@ -349,6 +349,32 @@ def ingest_boxes(obs_type: int, box_id: torch.Tensor, box: torch.Tensor, slot_id
     return dropped
 
 
+def actuator_shaping(u: torch.Tensor, throttle_prev: torch.Tensor, brake_prev: torch.Tensor, max_steer: float = 1.0,
+                     rate: float = 0.1, reset_brake: bool = False):
+    """KA: (a, delta) -> (throttle, brake, steer) as the CARLA drivers do after ``solve_cbf``
+    (multi_obstacle_CBF_local_with_lanes.py:955-980): tanh map, saturation to [0, 1], increase limited to
+    ``rate`` per tick, steering clamp.  ``throttle_prev`` / ``brake_prev`` [N] are updated in place.
+    ``reset_brake`` zeroes the brake while throttling (the driver keeps its last value)."""
+    L = nv.lib()
+    nv.require_cuda()
+    N = u.shape[-1]
+    dt, dev = u.dtype, u.device
+    if dev.type != "cuda":
+        raise ValueError("actuator_shaping works on device tensors")
+    for t, name in ((throttle_prev, "throttle_prev"), (brake_prev, "brake_prev")):
+        if not t.is_contiguous():
+            raise ValueError("%s must be contiguous (it is updated in place)" % name)
+    u = _chk(u, (2, N), dt, dev, "u")
+    throttle_prev = _chk(throttle_prev, (N,), dt, dev, "throttle_prev")
+    brake_prev = _chk(brake_prev, (N,), dt, dev, "brake_prev")
+    out = torch.empty((3, N), dtype=dt, device=dev)
+    with torch.cuda.device(dev):
+        nv.check(getattr(L, "sccav_actuator_shaping_" + _SFX[dt])(N, _ptr(u), float(max_steer), float(rate),
+                                                                 nv.ACT_RESET_BRAKE if reset_brake else 0, _ptr(throttle_prev),
+                                                                 _ptr(brake_prev), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _stream(dev)))
+    return out[0], out[1], out[2]
+
+
 def rollout_launch_info(slot_desc, N: int, P: int, dtype=torch.float64) -> Dict[str, int]:
     """Launch shape of the rollout kernel for (slot_desc, N, P) on the current device (no launch).
     `slot_desc`: the slot descriptors of the batch, or an int M meaning M per-vehicle ellipses."""

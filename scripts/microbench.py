@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--dtype", default="f64")
     ap.add_argument("--no-rollout", action="store_true")
     ap.add_argument("--no-operator", action="store_true")
+    ap.add_argument("--ingest", action="store_true", help="time the bounding-box ingest kernel (KB)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     dtype = torch.float64 if a.dtype == "f64" else torch.float32
@@ -91,6 +92,30 @@ def main():
                 float((mask2 == mask).double().mean().item()), float((u2 - u).abs().max().item())))
         msp = timed(lambda: ops.prepare_obstacles([0] * M, ob, out=obp), 5)
         out.append("prepare %.4f ms  %.1f GB/s (128 B per slot)" % (msp, 128.0 * n_op * M / msp / 1e6))
+    if a.ingest:
+        n_v, K = 2 * 1024 * 1024, 8
+        gen = torch.Generator(device=dev); gen.manual_seed(7)
+        ids = torch.full((M, n_v), -1, dtype=torch.int32, device=dev)
+        ob = torch.zeros((M, 8, n_v), dtype=dtype, device=dev)
+        cnt = torch.zeros(n_v, dtype=torch.int32, device=dev)
+        box = torch.rand((K, 6, n_v), dtype=dtype, device=dev, generator=gen) * 10 + 1
+        es = 8 if a.dtype == "f64" else 4
+
+        def tick(seed):
+            gen.manual_seed(seed)
+            bid = torch.randint(0, 24, (K, n_v), dtype=torch.int32, device=dev, generator=gen)
+            bid = torch.where(torch.rand((K, n_v), device=dev, generator=gen) < 0.7, bid, torch.full_like(bid, -1))
+            return bid
+        bids = [tick(s) for s in range(6)]
+        for b in bids[:2]:
+            ops.ingest_boxes(0, b, box, ids, ob, cnt)
+        ms = []
+        for b in bids[2:]:
+            ms.append(timed(lambda: ops.ingest_boxes(0, b, box, ids, ob, cnt), 1))
+        ms = statistics.median(ms)
+        byt = n_v * (K * (4 + 6 * es) + M * (4 + 8 * es) * 2 + 8)
+        out.append("ingest %.4f ms  %.1f GB/s (upper-bound bytes: K boxes read, M slots read + written)  %.3g vehicle-lists/s  mean count %.2f" % (
+            ms, byt / ms / 1e6, n_v / ms * 1e3, float(cnt.double().mean().item())))
     print("\n".join(out), flush=True)
 
 

@@ -493,3 +493,35 @@ def test_rollout_prepared_rows_flag():
     g4 = _run(b4, record_stride=25)
     _compare_rollout(g4, r4, b4.N, b4.T, min_exact=0.995, state_tol=1e-5, course=b4.course)
     print("prepared rows: identical bookkeeping fraction", frac)
+
+
+def test_dum_model_filter_vs_oracle():
+    """DUM_CBF_2DS (cbf/cbf.py:222-298): u = (a, omega), rows Lg h = [h_v, h_theta]; cones make both non-zero."""
+    from sccav_cbf_b200 import ops
+    slots = [o.SLOT_CONE] * 4 + [o.SLOT_RADIAL]
+    N = 4096
+    rng = np.random.default_rng(31)
+    s = H.random_states(rng, N); ob = H.random_slots(rng, N, slots, s)
+    ur = np.stack([rng.uniform(-2, 2, N), rng.uniform(-0.5, 0.5, N)])
+    R = [1.0, 0.2, 0.2, 3.0]
+    ref = co.filter_step(co.default_params(model=o.MODEL_DUM, R=R), slots, s, ob, ur, rows=True)
+    prm = ops.make_params(model=o.MODEL_DUM, R=R)
+    u, mask, status, _ = ops.filter_step(prm, slots, T(s), T(ob), T(ur))
+    A, b, _ = ops.barrier_rows(prm, slots, T(s), T(ob))
+    assert close(A, ref["A"]) < 1.0 and close(b, ref["b"]) < 1.0
+    assert np.array_equal(mask.cpu().numpy().view(np.uint32), ref["mask"]) and np.array_equal(status.cpu().numpy(), ref["status"])
+    assert close(u, ref["u"]) < 1.0
+    inactive = ref["mask"] == 0
+    assert np.array_equal(u.cpu().numpy()[:, inactive], ur[:, inactive])        # no conversion: u_ref passes through bit for bit
+    assert (ref["mask"] != 0).mean() > 0.02
+    # python oracle == C oracle on a few problems
+    for n in range(0, 60):
+        fields = [list(ob[m, :, n]) for m in range(len(slots))]
+        u0, u1, m_, st_, _, _ = o.filter_step(o.MODEL_DUM, list(s[:, n]), list(ur[:, n]), slots, fields, 1.0, 1.45, 1.45, 2.9, R)
+        assert m_ == int(ref["mask"][n]) and st_ == int(ref["status"][n])
+        assert abs(u0 - ref["u"][0, n]) <= 1e-9 * (1 + abs(u0)) and abs(u1 - ref["u"][1, n]) <= 1e-9 * (1 + abs(u1))
+    with pytest.raises(ValueError):
+        from sccav_cbf_b200 import scenarios as sc
+        b2 = sc.config2(n_total=65536, M=8, T=10, lo=0, hi=64)
+        b2.params = dict(model=o.MODEL_DUM)
+        _run(b2)

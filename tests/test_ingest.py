@@ -183,3 +183,40 @@ def test_filter_with_per_vehicle_count_and_batched_list_class():
     same = (g["n_active"].cpu().numpy() == r2["n_active"]) & (g["target_idx"].cpu().numpy() == r2["target_idx"])
     assert same.mean() >= 0.995
     assert (g["n_active"].cpu().numpy()[c2 == 0] == 0).all()
+
+
+def test_oracle_actuator_shaping_follows_the_driver():
+    # one braking episode followed by throttle: the driver's brake variable is never reset (:958-968)
+    thr_p = brk_p = 0.0
+    seq = []
+    for ua in (2.0, 2.0, -3.0, -3.0, 0.5):
+        thr, brk, st = o.actuator_shaping(ua, 0.3, thr_p, brk_p, max_steer=1.0)
+        seq.append((thr, brk))
+        thr_p, brk_p = thr, brk
+    assert seq[0] == (0.1, 0.0) and seq[1] == (0.2, 0.0)                # rate limit 0.1 per tick
+    assert seq[2] == (0.0, 0.1) and seq[3] == (0.0, 0.2)
+    assert seq[4][0] == 0.1 and seq[4][1] == 0.2                          # stale brake kept while throttling
+    assert o.actuator_shaping(0.5, 0.3, 0.0, 0.2, reset_brake=True)[1] == 0.0
+    assert o.actuator_shaping(0.0, 1.7, 0.0, 0.0)[2] == 1.0 and o.actuator_shaping(0.0, -1.7, 0.0, 0.0)[2] == -1.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("reset", [False, True])
+def test_actuator_kernel_vs_oracle_over_ticks(reset):
+    from sccav_cbf_b200 import ops
+    rng = np.random.default_rng(4)
+    N = 5000
+    tp = torch.zeros(N, dtype=torch.float64, device="cuda")
+    bp = torch.zeros(N, dtype=torch.float64, device="cuda")
+    tp_o = np.zeros(N); bp_o = np.zeros(N)
+    for t in range(6):
+        u = np.stack([rng.normal(0, 1.5, N), rng.normal(0, 0.8, N)])
+        u[0, :10] = 0.0
+        thr, brk, st = ops.actuator_shaping(T(u), tp, bp, max_steer=0.6, rate=0.1, reset_brake=reset)
+        ref = np.array([o.actuator_shaping(u[0, n], u[1, n], tp_o[n], bp_o[n], 0.6, 0.1, reset) for n in range(N)]).T
+        tp_o, bp_o = ref[0], ref[1]
+        assert np.allclose(thr.cpu().numpy(), ref[0], rtol=1e-14, atol=1e-16)     # tanh: CUDA vs numpy, <= 2 ulp
+        assert np.allclose(brk.cpu().numpy(), ref[1], rtol=1e-14, atol=1e-16)
+        assert np.array_equal(st.cpu().numpy(), ref[2])                            # clamp: exact
+        assert np.allclose(tp.cpu().numpy(), tp_o, rtol=1e-14, atol=1e-16) and np.allclose(bp.cpu().numpy(), bp_o, rtol=1e-14, atol=1e-16)
+        tp_o, bp_o = tp.cpu().numpy(), bp.cpu().numpy()                            # teacher-force the previous values
