@@ -301,6 +301,22 @@ int sccav_actuator_shaping_f32(int64_t N, const float* u, double max_steer, doub
                                float* throttle_prev, float* brake_prev, float* throttle_out, float* brake_out,
                                float* steer_out, void* stream);
 
+/* KC -- course generation for C roads at once, the step before the Stanley controller:
+ * calc_spline_course (test_scripts/PathPlanning/CubicSpline/cubic_spline_planner.py:178-190) = two natural
+ * cubic splines x(s), y(s) over the cumulative chord length (Spline2D :118-175, Spline :12-115; the
+ * tridiagonal system of :95-115 solved by the Thomas recurrence instead of np.linalg.solve), sampled at
+ * t_j = j ds, j < np = ceil(s_end / ds) (np.arange, :180), yaw = atan2(y', x') (:167-173), curvature (:156-165).
+ *   wx, wy  [C][K]      way-points (K >= 2 per course, K <= 64)
+ *   cx, cy, cyaw, ck [C][P_max]   samples; ck may be NULL; only the first min(np, P_max) of a course are written
+ *   np_out  [C] int32   number of samples course c HAS (compare with P_max)
+ * DEVICE pointers, asynchronous on `stream`.  Per-scenario roads: generate C courses, then launch one
+ * rollout per group of vehicles with its course (each launch takes course pointers). */
+#define SCCAV_MAX_KNOTS 64
+int sccav_spline_course_f64(int32_t C, int32_t K, const double* wx, const double* wy, double ds, int32_t P_max,
+                            double* cx, double* cy, double* cyaw, double* ck, int32_t* np_out, void* stream);
+int sccav_spline_course_f32(int32_t C, int32_t K, const float* wx, const float* wy, double ds, int32_t P_max,
+                            float* cx, float* cy, float* cyaw, float* ck, int32_t* np_out, void* stream);
+
 /* Measurement helpers used by bench.py (not part of the reference-facing path). */
 /* Launches an unrolled FMA chain kernel and returns the achieved TFLOP/s (FMA = 2 flop) on the
  * current device; `dtype` 64 or 32.  Used as the measured FP64/FP32 CUDA-core peak. */

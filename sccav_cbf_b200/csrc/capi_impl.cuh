@@ -408,6 +408,25 @@ int SCCAV_FN(sccav_actuator_shaping_)(int64_t N, const SCCAV_REAL* u, double max
     return SCCAV_OK;
 }
 
+int SCCAV_FN(sccav_spline_course_)(int32_t C, int32_t K, const SCCAV_REAL* wx, const SCCAV_REAL* wy, double ds, int32_t P_max,
+                                    SCCAV_REAL* cx, SCCAV_REAL* cy, SCCAV_REAL* cyaw, SCCAV_REAL* ck, int32_t* np_out, void* stream) {
+    using namespace sccav;
+    if (C < 0 || P_max < 1) { set_error("C < 0 or P_max < 1"); return SCCAV_EINVAL; }
+    if (K < 2 || K > SCCAV_MAX_KNOTS) { set_error("a course needs 2 .. %d way-points, got %d", SCCAV_MAX_KNOTS, K); return SCCAV_EINVAL; }
+    if (!(ds > 0.0)) { set_error("ds must be positive"); return SCCAV_EINVAL; }
+    if (C == 0) return SCCAV_OK;
+    if (C > 65535) { set_error("at most 65535 courses per call"); return SCCAV_EINVAL; }
+    if (!wx || !wy || !cx || !cy || !cyaw || !np_out) { set_error("NULL array argument"); return SCCAV_EINVAL; }
+    CourseArgs<SCCAV_REAL> a;
+    a.C = C; a.K = K; a.P_max = P_max; a.ds = (SCCAV_REAL)ds; a.wx = wx; a.wy = wy;
+    a.cx = cx; a.cy = cy; a.cyaw = cyaw; a.ck = ck; a.np_out = np_out;
+    dim3 grid((unsigned)((P_max + 255) / 256), (unsigned)C);
+    spline_course_kernel<SCCAV_REAL><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    count_launch();
+    SCCAV_CUDA_CHECK(cudaGetLastError());
+    return SCCAV_OK;
+}
+
 int SCCAV_FN(sccav_barrier_partials_)(const uint8_t* slot_desc, int32_t M, int64_t N, const SCCAV_REAL* state,
                                       const SCCAV_REAL* obst, SCCAV_REAL* out, void* stream) {
     return sccav::do_barrier_partials(slot_desc, M, N, state, obst, out, (cudaStream_t)stream);

@@ -201,6 +201,92 @@ __global__ void __launch_bounds__(256) actuator_kernel(const __grid_constant__ A
     }
 }
 
+// ------------------------------------------------------------------------------------------ KC
+// Course generation (include/sccav_cbf.h): CTA (chunk, c) samples 256 points of course c.  Every CTA
+// first rebuilds the spline coefficients of its course in shared memory (K <= 64 knots: a few hundred
+// flops by one thread) -- cheaper than a second kernel and a round trip through HBM.
+template <typename T> struct CourseArgs {
+    int C, K, P_max;
+    T ds;
+    const T* wx;
+    const T* wy;
+    T* cx;
+    T* cy;
+    T* cyaw;
+    T* ck;
+    int32_t* np_out;
+};
+
+// natural cubic spline through (s_k, a_k): coefficients b, c, d per segment (cubic_spline_planner.py:17-42,95-115)
+template <typename T>
+__device__ void natural_spline(int K, const T* s, const T* a, T* b, T* c, T* d, T* cp, T* dp) {
+    // interior rows i = 1 .. K-2:  h[i-1] c[i-1] + 2 (h[i-1] + h[i]) c[i] + h[i] c[i+1] = rhs_i ;  c[0] = c[K-1] = 0
+    cp[0] = T(0); dp[0] = T(0);
+    for (int i = 1; i + 1 < K; ++i) {
+        const T h0 = s[i] - s[i - 1], h1 = s[i + 1] - s[i];
+        const T rhs = T(3) * (a[i + 1] - a[i]) / h1 - T(3) * (a[i] - a[i - 1]) / h0;
+        const T m = T(2) * (h0 + h1) - h0 * cp[i - 1];
+        cp[i] = h1 / m;
+        dp[i] = (rhs - h0 * dp[i - 1]) / m;
+    }
+    c[K - 1] = T(0);
+    for (int i = K - 2; i >= 1; --i) c[i] = dp[i] - cp[i] * c[i + 1];
+    c[0] = T(0);
+    for (int i = 0; i + 1 < K; ++i) {
+        const T h = s[i + 1] - s[i];
+        d[i] = (c[i + 1] - c[i]) / (T(3) * h);
+        b[i] = (a[i + 1] - a[i]) / h - h * (c[i + 1] + T(2) * c[i]) / T(3);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) spline_course_kernel(const __grid_constant__ CourseArgs<T> a) {
+    typedef Real<T> R;
+    __shared__ T s[SCCAV_MAX_KNOTS], ax[SCCAV_MAX_KNOTS], ay[SCCAV_MAX_KNOTS];
+    __shared__ T bx[SCCAV_MAX_KNOTS], cx_[SCCAV_MAX_KNOTS], dx_[SCCAV_MAX_KNOTS];
+    __shared__ T by[SCCAV_MAX_KNOTS], cy_[SCCAV_MAX_KNOTS], dy_[SCCAV_MAX_KNOTS];
+    __shared__ T cp[SCCAV_MAX_KNOTS], dp[SCCAV_MAX_KNOTS];
+    __shared__ int s_np;
+    const int c = blockIdx.y, K = a.K;
+    if (threadIdx.x < K) {
+        ax[threadIdx.x] = a.wx[(int64_t)c * K + threadIdx.x];
+        ay[threadIdx.x] = a.wy[(int64_t)c * K + threadIdx.x];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s[0] = T(0);                                                             // Spline2D.__calc_s  :129-136
+        for (int k = 0; k + 1 < K; ++k) s[k + 1] = s[k] + R::hypot_(ax[k + 1] - ax[k], ay[k + 1] - ay[k]);
+        s_np = (int)R::ceil_(s[K - 1] / a.ds);                                   // len(np.arange(0, s[-1], ds))  :180
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) natural_spline<T>(K, s, ax, bx, cx_, dx_, cp, dp);
+    if (threadIdx.x == 32) {
+        __shared__ T cp2[SCCAV_MAX_KNOTS], dp2[SCCAV_MAX_KNOTS];
+        natural_spline<T>(K, s, ay, by, cy_, dy_, cp2, dp2);
+    }
+    __syncthreads();
+    const int np = s_np;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.np_out[c] = np;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= np || j >= a.P_max) return;
+    const T t = (T)j * a.ds;                                                     // np.arange: start + j * step
+    int i = 0;
+    while (i + 2 < K && t >= s[i + 1]) ++i;                                       // bisect.bisect(x, t) - 1   :88-92
+    const T u = t - s[i];
+    const T u2 = u * u, u3 = u2 * u;
+    const int64_t o = (int64_t)c * a.P_max + j;
+    a.cx[o] = ax[i] + bx[i] * u + cx_[i] * u2 + dx_[i] * u3;                      // Spline.calc  :44-60
+    a.cy[o] = ay[i] + by[i] * u + cy_[i] * u2 + dy_[i] * u3;
+    const T gx = bx[i] + T(2) * cx_[i] * u + T(3) * dx_[i] * u2;                  // Spline.calcd :62-76
+    const T gy = by[i] + T(2) * cy_[i] * u + T(3) * dy_[i] * u2;
+    a.cyaw[o] = R::atan2_(gy, gx);                                               // calc_yaw :167-173
+    if (a.ck) {
+        const T hx = T(2) * cx_[i] + T(6) * dx_[i] * u;                           // Spline.calcdd :78-90
+        const T hy = T(2) * cy_[i] + T(6) * dy_[i] * u;
+        a.ck[o] = (hy * gx - hx * gy) / R::pow_(gx * gx + gy * gy, T(1.5));       // calc_curvature :156-165
+    }
+}
+
 // ------------------------------------------------------------------------------------------ K1
 template <typename T> struct RowsArgs {
     Params<T> P;

@@ -37,6 +37,8 @@ template <> struct Real<double> {
     static __device__ __forceinline__ double abs_(double x) { return ::fabs(x); }
     static __device__ __forceinline__ double rint_(double x) { return ::rint(x); }
     static __device__ __forceinline__ double tanh_(double x) { return ::tanh(x); }
+    static __device__ __forceinline__ double pow_(double x, double y) { return ::pow(x, y); }
+    static __device__ __forceinline__ double ceil_(double x) { return ::ceil(x); }
     static __device__ __forceinline__ T2 make2(double a, double b) { return make_double2(a, b); }
 };
 
@@ -58,6 +60,8 @@ template <> struct Real<float> {
     static __device__ __forceinline__ float abs_(float x) { return ::fabsf(x); }
     static __device__ __forceinline__ float rint_(float x) { return ::rintf(x); }
     static __device__ __forceinline__ float tanh_(float x) { return ::tanhf(x); }
+    static __device__ __forceinline__ float pow_(float x, float y) { return ::powf(x, y); }
+    static __device__ __forceinline__ float ceil_(float x) { return ::ceilf(x); }
     static __device__ __forceinline__ T2 make2(float a, float b) { return make_float2(a, b); }
 };
 

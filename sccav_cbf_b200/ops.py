@@ -349,6 +349,30 @@ def ingest_boxes(obs_type: int, box_id: torch.Tensor, box: torch.Tensor, slot_id
     return dropped
 
 
+def spline_courses(wx: torch.Tensor, wy: torch.Tensor, ds: float = 0.1, P_max: Optional[int] = None, curvature: bool = False):
+    """KC: C courses at once from way-points ``wx``, ``wy`` [C, K] (calc_spline_course,
+    cubic_spline_planner.py:178-190).  Returns (cx, cy, cyaw [C, P_max], np [C] int32[, ck]); course c has
+    ``np[c]`` samples, rows are padded with NaN beyond.  ``P_max`` defaults to a bound from the way-point
+    polygon length (the spline is longer than its chords only through rounding of ceil)."""
+    L = nv.lib()
+    nv.require_cuda()
+    dt, dev = wx.dtype, wx.device
+    if dev.type != "cuda":
+        raise ValueError("spline_courses works on device tensors")
+    C_, K = wx.shape
+    wx = _chk(wx, (C_, K), dt, dev, "wx")
+    wy = _chk(wy, (C_, K), dt, dev, "wy")
+    if P_max is None:
+        seg = torch.hypot(wx[:, 1:] - wx[:, :-1], wy[:, 1:] - wy[:, :-1]).sum(dim=1)
+        P_max = int(torch.ceil(seg.max() / ds).item()) + 1
+    out = torch.full((4 if curvature else 3, C_, int(P_max)), float("nan"), dtype=dt, device=dev)
+    npts = torch.zeros((C_,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nv.check(getattr(L, "sccav_spline_course_" + _SFX[dt])(C_, K, _ptr(wx), _ptr(wy), float(ds), int(P_max), _ptr(out[0]), _ptr(out[1]),
+                                                              _ptr(out[2]), _ptr(out[3]) if curvature else None, _ptr(npts), _stream(dev)))
+    return (out[0], out[1], out[2], npts) + ((out[3],) if curvature else ())
+
+
 def actuator_shaping(u: torch.Tensor, throttle_prev: torch.Tensor, brake_prev: torch.Tensor, max_steer: float = 1.0,
                      rate: float = 0.1, reset_brake: bool = False):
     """KA: (a, delta) -> (throttle, brake, steer) as the CARLA drivers do after ``solve_cbf``

@@ -525,3 +525,34 @@ def test_dum_model_filter_vs_oracle():
         b2 = sc.config2(n_total=65536, M=8, T=10, lo=0, hi=64)
         b2.params = dict(model=o.MODEL_DUM)
         _run(b2)
+
+
+@pytest.mark.parametrize("prepared", [False, True])
+def test_full_size_config2_rollout_properties_and_oracle_sample(prepared):
+    """BASELINE config #2 at its FULL size (65,536 vehicles x 8 ellipses x 1,000 steps, one launch):
+    size-independent properties -- every vehicle runs all steps, counters are consistent, never-infeasible
+    vehicles stay outside their obstacles -- and 256 vehicles drawn from inside the batch re-run alone by
+    the CPU oracle (a vehicle's result does not depend on the batch around it)."""
+    from sccav_cbf_b200 import scenarios as sc
+    b = sc.config2(n_total=65536, M=8, T=1000)
+    if prepared:
+        b.params = dict(b.params, flags=o.FLAG_PREPARED_ROWS)
+    g = _run(b)
+    steps = g["steps"]
+    assert (steps == 1000).all()
+    assert (g["n_active"] <= steps).all() and (g["n_infeasible"] <= steps).all() and (g["n_active"] >= 0).all()
+    assert np.isfinite(g["state"]).all()
+    assert (g["target_idx"] >= 0).all() and (g["target_idx"] < len(b.course[0])).all()
+    ok = g["n_infeasible"] == 0
+    assert ok.mean() > 0.2 and (g["h_min"][ok] >= -0.05).all()
+    assert 0.05 < g["n_active"].sum() / steps.sum() < 0.3
+    idx = np.sort(np.random.default_rng(99).choice(b.N, size=256, replace=False))
+    sub = sc.ScenarioBatch("sample", np.ascontiguousarray(b.state[:, idx]), list(b.slot_desc), np.ascontiguousarray(b.obst[:, :, idx]),
+                           b.course, {}, T=b.T)
+    r = _oracle(sub)
+    same = np.ones(len(idx), bool)
+    for k in ("steps", "target_idx", "n_active", "n_infeasible"):
+        same &= g[k][idx] == r[k]
+    assert same.mean() >= 0.99, same.mean()
+    err = _relerr(g["state"][:, idx], r["state"]).max(axis=0)
+    assert np.median(err) <= 1e-12 and (err[same] <= 1e-6).mean() >= 0.9

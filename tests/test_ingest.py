@@ -220,3 +220,60 @@ def test_actuator_kernel_vs_oracle_over_ticks(reset):
         assert np.array_equal(st.cpu().numpy(), ref[2])                            # clamp: exact
         assert np.allclose(tp.cpu().numpy(), tp_o, rtol=1e-14, atol=1e-16) and np.allclose(bp.cpu().numpy(), bp_o, rtol=1e-14, atol=1e-16)
         tp_o, bp_o = tp.cpu().numpy(), bp.cpu().numpy()                            # teacher-force the previous values
+
+
+@pytest.mark.gpu
+def test_device_course_generation_vs_reference_planner_restatement():
+    """KC against sccav_cbf_b200.course.spline_course (bit-exact with the reference's planner on its own
+    way-points, tests/test_course*.py): same number of samples, points / yaw to 1e-12, and closed loops on
+    device-generated roads (one rollout launch per road) against the oracle on the same roads."""
+    from sccav_cbf_b200 import ops, scenarios as sc
+    from sccav_cbf_b200.course import CONFIG1_WAYPOINTS, spline_course
+    rng = np.random.default_rng(12)
+    K = 5
+    roads = [CONFIG1_WAYPOINTS]
+    for _ in range(7):
+        wx = np.cumsum(rng.uniform(15, 45, K)); wy = rng.uniform(-25, 25, K)
+        roads.append((list(wx), list(wy)))
+    wx = np.array([r[0] for r in roads]); wy = np.array([r[1] for r in roads])
+    cx, cy, cyaw, npts, ck = ops.spline_courses(T(wx), T(wy), ds=0.1, curvature=True)
+    npts = npts.cpu().numpy()
+    for c, (rx, ry) in enumerate(roads):
+        hx, hy, hyaw = spline_course(rx, ry, 0.1)
+        assert npts[c] == len(hx), (c, npts[c], len(hx))                                  # sample count: exact
+        n = len(hx)
+        assert np.allclose(cx[c, :n].cpu().numpy(), hx, rtol=1e-12, atol=1e-11)
+        assert np.allclose(cy[c, :n].cpu().numpy(), hy, rtol=1e-12, atol=1e-11)
+        dyaw = np.angle(np.exp(1j * (cyaw[c, :n].cpu().numpy() - hyaw)))
+        assert np.abs(dyaw).max() <= 1e-10
+        assert torch.isnan(cx[c, n:]).all()
+        # curvature: calc_curvature (cubic_spline_planner.py:156-165) from the host spline coefficients
+        from sccav_cbf_b200.course import _natural_spline
+        seg = np.hypot(np.diff(rx), np.diff(ry))
+        sk = np.concatenate([[0.0], np.cumsum(seg)])
+        _, bx_, cx_, dx_ = _natural_spline(list(sk), rx)
+        _, by_, cy_, dy_ = _natural_spline(list(sk), ry)
+        ts = np.arange(0, sk[-1], 0.1)
+        ii = np.clip(np.searchsorted(sk, ts, side="right") - 1, 0, len(sk) - 2)
+        u = ts - sk[ii]
+        gx = np.array(bx_)[ii] + 2.0 * np.array(cx_)[ii] * u + 3.0 * np.array(dx_)[ii] * u ** 2
+        gy = np.array(by_)[ii] + 2.0 * np.array(cy_)[ii] * u + 3.0 * np.array(dy_)[ii] * u ** 2
+        hx2 = 2.0 * np.array(cx_)[ii] + 6.0 * np.array(dx_)[ii] * u
+        hy2 = 2.0 * np.array(cy_)[ii] + 6.0 * np.array(dy_)[ii] * u
+        kref = (hy2 * gx - hx2 * gy) / ((gx ** 2 + gy ** 2) ** (3 / 2))
+        assert np.allclose(ck[c, :n].cpu().numpy(), kref, rtol=1e-9, atol=1e-12)
+    assert npts[0] == 2034
+    # closed loop: a group of vehicles per road, one launch each, course tensors straight from KC
+    b = sc.config2(n_total=65536, M=8, T=250, lo=0, hi=3 * 128)
+    for g in range(3):
+        c = g + 1
+        n = int(npts[c])
+        course_d = (cx[c, :n].contiguous(), cy[c, :n].contiguous(), cyaw[c, :n].contiguous())
+        course_h = tuple(t.cpu().numpy() for t in course_d)
+        sl = slice(g * 128, (g + 1) * 128)
+        st = np.ascontiguousarray(b.state[:, sl]); ob = np.ascontiguousarray(b.obst[:, :, sl])
+        st[0] += course_h[0][0]; st[1] += course_h[1][0] - 5.0                               # start near this road's first point
+        out = ops.rollout(ops.make_params(), b.slot_desc, T(st), T(ob), course_d, b.T)
+        ref = co.rollout(co.default_params(), b.slot_desc, st, ob, course_h, b.T)
+        same = (out["target_idx"].cpu().numpy() == ref["target_idx"]) & (out["n_active"].cpu().numpy() == ref["n_active"])
+        assert same.mean() >= 0.99
