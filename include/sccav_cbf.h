@@ -83,6 +83,11 @@ extern "C" {
 /* rollout: ELLIPSE slots are ingested once per launch (sccav_prepare_obstacles_*) and evaluated in
  * their prepared form at every step -- same results to a few ulp, no division or sincos per row   */
 #define SCCAV_FLAG_PREPARED_ROWS 1
+/* QP: always run the full active-set enumeration ({} -> singles -> pairs, first KKT point).  By default a
+ * one-scan shortcut answers the problems whose optimum has one active row (the most violated row in the
+ * metric of R) and hands every other problem -- and every near-tie -- to the enumeration; results are
+ * bit-identical, the flag exists so that tests can prove it.                                      */
+#define SCCAV_FLAG_QP_ENUMERATE 2
 
 #define SCCAV_STATUS_INACTIVE 0    /* u == u_ref                                               */
 #define SCCAV_STATUS_ACTIVE 1      /* KKT optimum with 1 or 2 active rows                      */

@@ -1,5 +1,6 @@
 // capi_common.cu -- precision-independent part of the C-ABI: version, errors, defaults, device
 // attribute cache, launch counter and the FMA-peak microbenchmark used by bench.py.
+#include <cstdlib>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -29,6 +30,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 struct DevAttr {
     int sms = 0;
     int smem = 0;
+    int smem_sm = 0;
     bool pool = false;
 };
 static DevAttr g_attr[64];
@@ -43,6 +45,9 @@ static DevAttr& attr() {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         a.smem = smem;
+        int smem_sm = 0;
+        cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        a.smem_sm = smem_sm;
         a.sms = sms > 0 ? sms : 148;
     }
     return a;
@@ -67,6 +72,12 @@ void keep_pool_memory() {
 
 int sm_count() { return attr().sms; }
 int max_smem_optin() { return attr().smem; }
+int max_smem_per_sm() { return attr().smem_sm; }
+// debugging knob: SCCAV_K12_PIPE=0 selects the direct-load filter-step kernel (A/B measurements)
+bool k12_pipe_enabled() {
+    const char* e = getenv("SCCAV_K12_PIPE");      // read per call: tests flip it between launches
+    return !(e && e[0] == '0');
+}
 
 // ---- FMA peak: NCHAIN independent dependent-FMA chains per thread, fully unrolled.
 template <typename T, int NCHAIN>

@@ -53,6 +53,10 @@ Params<real> convert(const sccav_params* p) {
     q.ks_stanley = (real)p->ks_stanley; q.Kp = (real)p->Kp; q.target_speed = (real)p->target_speed;
     q.t_max = (real)p->t_max;
     for (int i = 0; i < 4; ++i) q.R[i] = (real)p->R[i];
+    {   // same operations, same precision as the device's RInv: bit-identical
+        const volatile real det = q.R[0] * q.R[3] - q.R[1] * q.R[2];
+        q.Ri[0] = q.R[3] / det; q.Ri[1] = (-q.R[1]) / det; q.Ri[2] = (-q.R[2]) / det; q.Ri[3] = q.R[0] / det;
+    }
     q.seeker_k = (real)p->seeker_k; q.seeker_vmin = (real)p->seeker_vmin;
     q.uref0 = (real)p->uref0; q.uref1 = (real)p->uref1;
     return q;
@@ -235,6 +239,20 @@ int do_filter_step(const sccav_params* p, const uint8_t* slot_desc, int32_t M, i
     const int block = rows_block(M, smem);
     typedef void (*filter_fn)(FilterArgs<real>);
     const int spec = choose_spec(slot_desc, M);
+    const int nf = spec == SCCAV_SPEC_ELLIPSE ? 7 : ((slot_desc[0] & SCCAV_SLOT_STATIC) ? 6 : 8);
+    const size_t staged = (size_t)nf * M * 256 * sizeof(real);
+    if (spec != SCCAV_SPEC_GENERIC && nf < 8 && k12_pipe_enabled() &&
+        2 * (staged + 1024) <= (size_t)max_smem_per_sm()) {
+        // staged kernel: every field of a vehicle requested at once (cp.async), rows overlay the staged slots; two CTAs per SM
+        typedef void (*staged_fn)(FilterArgs<real>);
+        const staged_fn sk = spec == SCCAV_SPEC_ELLIPSE ? filter_step_staged_kernel<real, SCCAV_SPEC_ELLIPSE, 7>
+                                                        : filter_step_staged_kernel<real, SCCAV_SPEC_ELLIPSE_PREP, 6>;
+        SCCAV_CUDA_CHECK(cudaFuncSetAttribute((const void*)sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged));
+        sk<<<stream_grid(N, 256), 256, staged, st>>>(a);
+        count_launch();
+        SCCAV_CUDA_CHECK(cudaGetLastError());
+        return SCCAV_OK;
+    }
     const filter_fn kern = spec == SCCAV_SPEC_ELLIPSE ? filter_step_kernel<real, SCCAV_SPEC_ELLIPSE>
                          : spec == SCCAV_SPEC_ELLIPSE_PREP ? filter_step_kernel<real, SCCAV_SPEC_ELLIPSE_PREP>
                                                            : filter_step_kernel<real, SCCAV_SPEC_GENERIC>;

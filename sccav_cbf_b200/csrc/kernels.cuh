@@ -37,6 +37,16 @@ __device__ __forceinline__ void load_weights(const Params<T>& P, const PerVehicl
     else { R00 = P.R[0]; R01 = P.R[1]; R10 = P.R[2]; R11 = P.R[3]; }
 }
 
+// inverse of the cost weight of vehicle n: the launch-wide one was formed on the host with the same IEEE
+// operations (convert(), capi_impl.cuh); per-vehicle weights are inverted here, once per vehicle
+template <typename T>
+__device__ __forceinline__ RInv<T> load_rinv(const Params<T>& P, const PerVehicle<T>& pv, T R00, T R01, T R10, T R11) {
+    if (pv.R) return RInv<T>(R00, R01, R10, R11);
+    RInv<T> q;
+    q.i00 = P.Ri[0]; q.i01 = P.Ri[1]; q.i10 = P.Ri[2]; q.i11 = P.Ri[3];
+    return q;
+}
+
 // ------------------------------------------------------------------------------------------ KP
 // Obstacle ingest: ELLIPSE slots -> ELLIPSE_PREP (include/sccav_cbf.h), other slots copied.
 // HBM-bound: 64 B read + 64 B written per (vehicle, slot).  in == out is allowed (every thread
@@ -310,6 +320,7 @@ __global__ void __launch_bounds__(256) barrier_rows_kernel(const __grid_constant
         T alpha = a.pv.alpha ? a.pv.alpha[n] : a.P.alpha;
         T sth, cth;
         R::sincos_(th, &sth, &cth);
+        const T vlr = v / a.P.lr;
         const int Mv = slot_count<T>(a.pv, a.M, n);
         for (int m = 0; m < a.M; ++m) {
             T A0 = T(0), A1 = T(0), b = -R::inf();             // empty slot: a vacuous row
@@ -320,7 +331,7 @@ __global__ void __launch_bounds__(256) barrier_rows_kernel(const __grid_constant
                 const int64_t nn = (desc & SCCAV_SLOT_SHARED) ? 0 : n;
                 const T* f = a.obst + (int64_t)m * SCCAV_NFIELD * N + nn;
                 p = slot_partials<T>(desc, f, N, x, y, th, v, sth, cth);
-                model_row<T>(a.P, p, sth, cth, v, alpha, A0, A1, b);
+                model_row<T>(a.P, p, sth, cth, v, alpha, vlr, A0, A1, b);
             }
             a.A[(int64_t)m * N + n] = A0;
             a.A[((int64_t)a.M + m) * N + n] = A1;
@@ -384,27 +395,58 @@ template <typename T> struct QpArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(256) qp2_kernel(const __grid_constant__ QpArgs<T> a) {
+    typedef Real<T> R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
     T* rows = reinterpret_cast<T*>(smem_raw) + threadIdx.x;
+    const T* warp_rows = rows - lane;
     const int stride = blockDim.x;
     const int64_t N = a.N;
-    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
-        const int Mv = slot_count<T>(a.pv, a.M, n);
-        for (int m = 0; m < Mv; ++m) {
-            rows[(3 * m + 0) * stride] = a.A[(int64_t)m * N + n];
-            rows[(3 * m + 1) * stride] = a.A[((int64_t)a.M + m) * N + n];
-            rows[(3 * m + 2) * stride] = a.b[(int64_t)m * N + n];
+    const bool enumerate = (a.P.flags & SCCAV_FLAG_QP_ENUMERATE) != 0;
+    // warp-uniform trip count (the warp's first vehicle decides): the active solve below is warp-cooperative
+    for (int64_t nw = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); nw < N; nw += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = nw + lane;
+        const bool valid = n < N;
+        int Mv = 0;
+        T r0 = T(0), r1 = T(0), worst = -R::inf();
+        T alpha, R00 = T(1), R01 = T(0), R10 = T(0), R11 = T(1);
+        RowNz nz{0u, 0u};
+        bool feas = true;
+        QpScan<T> scan;
+        scan.reset();
+        RInv<T> Ri;
+        Ri.i00 = T(1); Ri.i01 = T(0); Ri.i10 = T(0); Ri.i11 = T(1);
+        if (valid) {
+            Mv = slot_count<T>(a.pv, a.M, n);
+            load_weights<T>(a.P, a.pv, N, n, alpha, R00, R01, R10, R11);
+            Ri = load_rinv<T>(a.P, a.pv, R00, R01, R10, R11);
+            r0 = a.r[n]; r1 = a.r[N + n];
+            for (int m = 0; m < Mv; ++m) {
+                const T a0 = a.A[(int64_t)m * N + n], a1 = a.A[((int64_t)a.M + m) * N + n], bk = a.b[(int64_t)m * N + n];
+                rows[(3 * m + 0) * stride] = a0;
+                rows[(3 * m + 1) * stride] = a1;
+                rows[(3 * m + 2) * stride] = bk;
+                if (a0 != T(0)) nz.nz0 |= 1u << m;
+                if (a1 != T(0)) nz.nz1 |= 1u << m;
+                T t0 = a0 * r0, t1 = a1 * r1;
+                T rk = (t0 + t1) - bk;
+                if (-rk > worst) worst = -rk;
+                T tol = R::feas_eps() * ((R::abs_(t0) + R::abs_(t1)) + R::abs_(bk));
+                if (!(rk >= -tol)) feas = false;
+                scan.row(m, a0, a1, rk, Ri);
+            }
         }
-        T alpha, R00, R01, R10, R11;
-        load_weights<T>(a.P, a.pv, N, n, alpha, R00, R01, R10, R11);
-        RowView<T> rv{rows, stride};
-        T u0, u1;
-        uint32_t mask;
-        int st = qp2_solve<T>(rv, Mv, a.r[n], a.r[N + n], R00, R01, R10, R11, u0, u1, mask);
-        a.u[n] = u0;
-        a.u[N + n] = u1;
-        if (a.mask) a.mask[n] = mask;
-        if (a.status) a.status[n] = (uint8_t)st;
+        T u0 = r0, u1 = r1;
+        uint32_t mask = 0u;
+        const int st = qp2_solve_active_warp<T>(!feas, warp_rows, stride, lane, Mv, nz, r0, r1, R00, R01, R10, R11, Ri,
+                                                a.pv.R == nullptr, worst, scan, u0, u1, mask, enumerate);
+        __syncwarp();                          // the next problem's rows overwrite the columns read above
+        if (valid) {
+            a.u[n] = u0;
+            a.u[N + n] = u1;
+            if (a.mask) a.mask[n] = mask;
+            if (a.status) a.status[n] = (uint8_t)st;
+        }
     }
 }
 
@@ -412,19 +454,6 @@ __global__ void __launch_bounds__(256) qp2_kernel(const __grid_constant__ QpArgs
 // lanes and checked by all lanes at once (one ballot per candidate); the enumeration order and
 // acceptance rule are those of qp2_solve, so results are identical.  Meant for small batches of
 // large problems (latency), the thread-per-problem kernel for throughput.
-template <typename T> __device__ __forceinline__ T shfl(T v, int src);
-template <> __device__ __forceinline__ double shfl<double>(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-template <> __device__ __forceinline__ float shfl<float>(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-
-template <typename T> __device__ __forceinline__ T warp_max(T v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        T w = __shfl_xor_sync(0xffffffffu, v, o);
-        v = (w > v) ? w : v;
-    }
-    return v;
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256) qp2_warp_kernel(const __grid_constant__ QpArgs<T> a) {
     typedef Real<T> R;
@@ -442,61 +471,15 @@ __global__ void __launch_bounds__(256) qp2_warp_kernel(const __grid_constant__ Q
         T alpha, R00, R01, R10, R11;
         load_weights<T>(a.P, a.pv, N, n, alpha, R00, R01, R10, R11);
         const T r0 = a.r[n], r1 = a.r[N + n];
-        // check(u, skip mask): every lane tests its own row
-        auto check = [&](T u0, T u1, uint32_t skip, T& worst) -> bool {
-            T t0 = a0 * u0, t1 = a1 * u1;
-            T rk = (t0 + t1) - bk;
-            T tol = R::feas_eps() * ((R::abs_(t0) + R::abs_(t1)) + R::abs_(bk));
-            bool bad = own && !((skip >> lane) & 1u) && !(rk >= -tol);
-            worst = warp_max<T>(own ? -rk : -R::inf());
-            return __ballot_sync(0xffffffffu, bad) == 0u;
-        };
         T u0 = r0, u1 = r1, worst;
         uint32_t mask = 0u;
         int status = SCCAV_STATUS_INACTIVE;
-        if (!check(r0, r1, 0u, worst)) {
-            status = -1;
-            T fbw = worst, fb0 = r0, fb1 = r1;
-            uint32_t fbm = 0u;
-            const T det = R00 * R11 - R01 * R10;
-            const T Ri00 = R11 / det, Ri01 = (-R01) / det, Ri10 = (-R10) / det, Ri11 = R00 / det;
-            // singles: each lane prepares its own candidate, then they are tried in index order
-            T rk = (a0 * r0 + a1 * r1) - bk;
-            T g0 = Ri00 * a0 + Ri01 * a1, g1 = Ri10 * a0 + Ri11 * a1;
-            T den = a0 * g0 + a1 * g1;
-            bool cand = own && (rk < T(0)) && (den > T(0));
-            T t = cand ? (-rk) / den : T(0);
-            T c0 = r0 + g0 * t, c1 = r1 + g1 * t;
-            uint32_t todo = __ballot_sync(0xffffffffu, cand);
-            while (todo && status < 0) {
-                int k = __ffs(todo) - 1;
-                todo &= todo - 1;
-                T s0 = shfl<T>(c0, k), s1 = shfl<T>(c1, k);
-                if (check(s0, s1, 1u << k, worst)) { u0 = s0; u1 = s1; mask = 1u << k; status = SCCAV_STATUS_ACTIVE; }
-                else if (worst < fbw - R::tie_eps() * (R::abs_(worst) + R::abs_(fbw))) { fbw = worst; fb0 = s0; fb1 = s1; fbm = 1u << k; }
-            }
-            // pairs, lexicographic (j < k): rows are broadcast from their owners
-            for (int j = 0; j < M && status < 0; ++j) {
-                T aj0 = shfl<T>(a0, j), aj1 = shfl<T>(a1, j), bj = shfl<T>(bk, j);
-                for (int k = j + 1; k < M && status < 0; ++k) {
-                    T ak0 = shfl<T>(a0, k), ak1 = shfl<T>(a1, k), bkk = shfl<T>(bk, k);
-                    T t1 = aj0 * ak1, t2 = aj1 * ak0;
-                    T det2 = t1 - t2;
-                    if (!(R::abs_(det2) > R::par_eps() * (R::abs_(t1) + R::abs_(t2)))) continue;
-                    T p0 = (bj * ak1 - aj1 * bkk) / det2;
-                    T p1 = (aj0 * bkk - bj * ak0) / det2;
-                    T e0 = p0 - r0, e1 = p1 - r1;
-                    T w0 = T(2) * (R00 * e0 + R01 * e1);
-                    T w1 = T(2) * (R10 * e0 + R11 * e1);
-                    T lj = (w0 * ak1 - ak0 * w1) / det2;
-                    T lk = (aj0 * w1 - w0 * aj1) / det2;
-                    uint32_t pm = (1u << j) | (1u << k);
-                    bool feas = check(p0, p1, pm, worst);
-                    if (feas && lj >= T(0) && lk >= T(0)) { u0 = p0; u1 = p1; mask = pm; status = SCCAV_STATUS_ACTIVE; }
-                    else if (worst < fbw - R::tie_eps() * (R::abs_(worst) + R::abs_(fbw))) { fbw = worst; fb0 = p0; fb1 = p1; fbm = pm; }
-                }
-            }
-            if (status < 0) { u0 = fb0; u1 = fb1; mask = fbm; status = SCCAV_STATUS_INFEASIBLE; }
+        if (!qp_check_coop<T>(lane, own, a0, a1, bk, r0, r1, 0u, worst)) {
+            RowNz nz;
+            nz.nz0 = __ballot_sync(0xffffffffu, own && a0 != T(0));
+            nz.nz1 = __ballot_sync(0xffffffffu, own && a1 != T(0));
+            const RInv<T> Ri = load_rinv<T>(a.P, a.pv, R00, R01, R10, R11);
+            status = qp2_coop_active<T>(lane, M, a0, a1, bk, nz, r0, r1, R00, R01, R10, R11, Ri, worst, u0, u1, mask);
         }
         if (lane == 0) {
             a.u[n] = u0;
@@ -530,29 +513,145 @@ template <typename T, int SPEC>
 __global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_kernel(const __grid_constant__ FilterArgs<T> a) {
     typedef Real<T> R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
     T* rows = reinterpret_cast<T*>(smem_raw) + threadIdx.x;
+    const T* warp_rows = rows - lane;
     const int stride = blockDim.x;
     const int64_t N = a.N;
-    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
-        T x = a.state[n], y = a.state[N + n], th = a.state[2 * N + n], v = a.state[3 * N + n];
-        T ur0 = a.u_ref[n], ur1 = a.u_ref[N + n];
-        T alpha, R00, R01, R10, R11;
-        load_weights<T>(a.P, a.pv, N, n, alpha, R00, R01, R10, R11);
+    const bool enumerate = (a.P.flags & SCCAV_FLAG_QP_ENUMERATE) != 0;
+    // warp-uniform trip count (the warp's first vehicle decides): the active solve is warp-cooperative
+    for (int64_t nw = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); nw < N; nw += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = nw + lane;
+        const bool valid = n < N;
+        T ur0 = T(0), ur1 = T(0), hmin = R::inf();
+        T alpha = T(0), R00 = T(1), R01 = T(0), R10 = T(0), R11 = T(1);
+        int Mv = 0;
+        RowPhase<T> ph;
+        ph.r0 = T(0); ph.r1 = T(0); ph.worst = -R::inf(); ph.nz.nz0 = 0u; ph.nz.nz1 = 0u; ph.feas = true;
+        ph.scan.reset();
+        RInv<T> Ri;
+        Ri.i00 = T(1); Ri.i01 = T(0); Ri.i10 = T(0); Ri.i11 = T(1);
+        if (valid) {
+            T x = a.state[n], y = a.state[N + n], th = a.state[2 * N + n], v = a.state[3 * N + n];
+            ur0 = a.u_ref[n]; ur1 = a.u_ref[N + n];
+            load_weights<T>(a.P, a.pv, N, n, alpha, R00, R01, R10, R11);
+            Ri = load_rinv<T>(a.P, a.pv, R00, R01, R10, R11);
+            Mv = slot_count<T>(a.pv, a.M, n);
+            if (Mv > 0) {
+                T sth, cth;
+                R::sincos_(th, &sth, &cth);
+                ph = filter_rows<T, SPEC, true>(a.P, a.sd, Mv, N, n, a.obst, x, y, th, v, sth, cth, alpha, ur0, ur1, rows, stride,
+                                                hmin, nullptr, 0xffffffffu, &Ri);
+            }
+        }
+        T q0 = ph.r0, q1 = ph.r1;
+        uint32_t mask = 0u;
+        const int st = qp2_solve_active_warp<T>(!ph.feas, warp_rows, stride, lane, Mv, ph.nz, ph.r0, ph.r1, R00, R01, R10, R11, Ri,
+                                                a.pv.R == nullptr, ph.worst, ph.scan, q0, q1, mask, enumerate);
+        __syncwarp();                          // the next vehicle's rows overwrite the columns read above
+        if (valid) {
+            T u0 = ur0, u1 = ur1;                                           // empty obstacle list: u = u_ref
+            if (Mv > 0) { u0 = q0; u1 = filter_convert<T>(a.P, q0, q1, ph.r0); }
+            a.u[n] = u0;
+            a.u[N + n] = u1;
+            if (a.mask) a.mask[n] = mask;
+            if (a.status) a.status[n] = (uint8_t)st;
+            if (a.h_min) a.h_min[n] = hmin;
+        }
+    }
+}
+
+// K12, staged (all per-vehicle ELLIPSE or static ELLIPSE_PREP slots, M * NF * 8 B <= 448 B per vehicle).
+// The direct-load kernel above stalls on HBM latency: its 16 resident warps (fp64 pairs: 128 registers)
+// have no registers left to hold more than two slots of loads in flight.  Here a thread requests ALL
+// fields of its vehicle at once with cp.async (LDGSTS, one coalesced 256 B request per warp and field,
+// no register until the value is used) into its own column of shared memory, converts u_ref while they
+// fly (sincos, tan, atan2: ~400 instructions), waits once, and evaluates the slots out of shared memory.
+// Row m then overwrites the first three staged fields of slot m, which nobody reads again, so the
+// staging area doubles as the row store: M * NF * 256 * 8 B = 96 KB (NF = 6) per CTA, two CTAs per SM.
+// A thread only reads what it requested itself: no barrier beyond cp.async.wait_group; the warp-level
+// sync at the end of the iteration is the one the cooperative QP needs anyway.  Arithmetic = filter_vehicle.
+template <typename T> __device__ __forceinline__ void cp_async_elem(T* smem_dst, const T* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(s), "l"(gmem_src), "n"((int)sizeof(T)) : "memory");
+}
+
+template <typename T, int SPEC, int NF>
+__global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_staged_kernel(const __grid_constant__ FilterArgs<T> a) {
+    typedef Real<T> R;
+    static_assert(NF >= 3 && NF <= SCCAV_NFIELD, "row m lives in the first three staged fields of slot m");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int B = blockDim.x;
+    const int M = a.M;
+    const int lane = threadIdx.x & 31;
+    T* stage = reinterpret_cast<T*>(smem_raw) + threadIdx.x;       // stage[(m * NF + f) * B]; rows: f = 0, 1, 2
+    const T* warp_rows = stage - lane;
+    const int64_t N = a.N;
+    const Params<T>& P = a.P;
+    const bool enumerate = (P.flags & SCCAV_FLAG_QP_ENUMERATE) != 0;
+    // warp-uniform trip count (the warp's first vehicle decides): the active solve is warp-cooperative
+    for (int64_t nw = (int64_t)blockIdx.x * B + (threadIdx.x - lane); nw < N; nw += (int64_t)gridDim.x * B) {
+        const int64_t n = nw + lane;
+        const bool valid = n < N;
+        T x = T(0), y = T(0), th = T(0), v = T(0), ur0 = T(0), ur1 = T(0);
+        T alpha = T(0), R00 = T(1), R01 = T(0), R10 = T(0), R11 = T(1);
+        RInv<T> Ri;
+        Ri.i00 = T(1); Ri.i01 = T(0); Ri.i10 = T(0); Ri.i11 = T(1);
+        int Mv = 0;
+        if (valid) {
+            Mv = slot_count<T>(a.pv, M, n);
+            const T* src = a.obst + n;
+            T* dst = stage;
+            for (int m = 0; m < Mv; ++m, src += (int64_t)SCCAV_NFIELD * N, dst += NF * B) {
+#pragma unroll
+                for (int f = 0; f < NF; ++f) cp_async_elem<T>(dst + f * B, src + (int64_t)f * N);
+            }
+            x = a.state[n]; y = a.state[N + n]; th = a.state[2 * N + n]; v = a.state[3 * N + n];
+            ur0 = a.u_ref[n]; ur1 = a.u_ref[N + n];
+            load_weights<T>(P, a.pv, N, n, alpha, R00, R01, R10, R11);
+            Ri = load_rinv<T>(P, a.pv, R00, R01, R10, R11);
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
         T sth, cth;
         R::sincos_(th, &sth, &cth);
-        T u0, u1, u1raw, hmin;
-        uint32_t mask;
-        const int Mv = slot_count<T>(a.pv, a.M, n);
-        int st = SCCAV_STATUS_INACTIVE;
-        if (Mv > 0)
-            st = filter_vehicle<T, SPEC>(a.P, a.sd, Mv, N, n, a.obst, x, y, th, v, sth, cth, alpha, R00, R01, R10, R11,
-                                         ur0, ur1, rows, stride, u0, u1, u1raw, mask, hmin);
-        else { u0 = ur0; u1 = ur1; mask = 0u; hmin = R::inf(); }           // empty obstacle list: u = u_ref
-        a.u[n] = u0;
-        a.u[N + n] = u1;
-        if (a.mask) a.mask[n] = mask;
-        if (a.status) a.status[n] = (uint8_t)st;
-        if (a.h_min) a.h_min[n] = hmin;
+        const T vlr = v / P.lr;
+        T r0 = ur0, r1;
+        if (P.model == SCCAV_MODEL_KBM) r1 = (ur0 * R::tan_(ur1)) / P.L;                    // cbf.py:75
+        else if (P.model == SCCAV_MODEL_DUM) r1 = ur1;                                       // cbf.py:253
+        else r1 = R::atan2_(P.lr * R::tan_(ur1), P.lf + P.lr);                               // cbf.py:175
+        T hmin = R::inf(), worst = -R::inf();
+        bool feas = true;
+        RowNz nz{0u, 0u};
+        QpScan<T> scan;
+        scan.reset();
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        {
+            const T* f = stage;
+            for (int m = 0; m < Mv; ++m, f += NF * B) {
+                T g[NF];
+#pragma unroll
+                for (int i = 0; i < NF; ++i) g[i] = f[i * B];
+                Partials<T> p;
+                if (SPEC == SCCAV_SPEC_ELLIPSE) p = ellipse_partials<T>(x, y, g[0], g[1], g[2], g[3], g[4], g[5], g[NF - 1]);
+                else if (NF >= 8) p = ellipse_prep_partials<T>(x, y, g[0], g[1], g[2], g[3], g[4], g[5], g[NF - 2], g[NF - 1]);
+                else p = ellipse_prep_partials<T>(x, y, g[0], g[1], g[2], g[3], g[4], g[5], T(0), T(0));
+                put_row<T, true, NF>(P, p, sth, cth, v, alpha, vlr, r0, r1, stage, B, m, hmin, worst, feas, nz, &scan, &Ri);
+            }
+        }
+        T q0 = r0, q1 = r1;
+        uint32_t mask = 0u;
+        const int st = qp2_solve_active_warp<T>(!feas, warp_rows, B, lane, Mv, nz, r0, r1, R00, R01, R10, R11, Ri,
+                                                a.pv.R == nullptr, worst, scan, q0, q1, mask, enumerate, NF);
+        __syncwarp();                          // the next vehicle's fields overwrite the columns read above
+        if (valid) {
+            T u0 = ur0, u1 = ur1;                                           // empty obstacle list: u = u_ref
+            if (Mv > 0) { u0 = q0; u1 = filter_convert<T>(P, q0, q1, r0); }
+            a.u[n] = u0;
+            a.u[N + n] = u1;
+            if (a.mask) a.mask[n] = mask;
+            if (a.status) a.status[n] = (uint8_t)st;
+            if (a.h_min) a.h_min[n] = hmin;
+        }
     }
 }
 
@@ -756,7 +855,7 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
         uint32_t mask = 0u;
         int status = SCCAV_STATUS_INACTIVE;
         if (filt)
-            status = filter_vehicle<T, SPEC>(P, a.sd, Mv, N, n, a.obst, x, y, yaw, v, syaw, cyw, alpha, R00, R01, R10, R11,
+            status = filter_vehicle<T, SPEC>(P, a.sd, Mv, N, n, a.obst, x, y, yaw, v, syaw, cyw, alpha, R00, R01, R10, R11, a.pv.R == nullptr,
                                              ur0, ur1, rows, stride, u0, u1, u1raw, mask, hmin, a.pre, moving);
         // ---- plant
         T px = x, py = y, pyaw = yaw, pv_ = v;

@@ -26,6 +26,8 @@ template <> struct Real<double> {
     static __device__ __forceinline__ double feas_eps() { return 1e-12; }
     static __device__ __forceinline__ double par_eps() { return 1e-12; }
     static __device__ __forceinline__ double tie_eps() { return 1e-9; }
+    static __device__ __forceinline__ double qp_tie_margin() { return 1e-6; }
+    static __device__ __forceinline__ double qp_res_margin() { return 1e-4; }
     static __device__ __forceinline__ double lane_xtol() { return 1e-12; }
     static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
     static __device__ __forceinline__ void sincos_(double x, double* s, double* c) { ::sincos(x, s, c); }
@@ -49,6 +51,8 @@ template <> struct Real<float> {
     static __device__ __forceinline__ float feas_eps() { return 1e-5f; }
     static __device__ __forceinline__ float par_eps() { return 1e-5f; }
     static __device__ __forceinline__ float tie_eps() { return 1e-4f; }
+    static __device__ __forceinline__ float qp_tie_margin() { return 1e-2f; }
+    static __device__ __forceinline__ float qp_res_margin() { return 1e-2f; }
     static __device__ __forceinline__ float lane_xtol() { return 1e-6f; }
     static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
     static __device__ __forceinline__ void sincos_(float x, float* s, float* c) { ::sincosf(x, s, c); }
@@ -70,6 +74,7 @@ template <typename T> struct Params {
     int model, nominal, terminate, seeker, kbm_driver_delta, record_stride, flags;
     T alpha, lr, lf, L, max_steer, dt, k_stanley, ks_stanley, Kp, target_speed, t_max;
     T R[4];
+    T Ri[4];             // inverse of R, formed on the host with the operations of RInv below
     T seeker_k, seeker_vmin, uref0, uref1;
 };
 
@@ -366,9 +371,11 @@ __device__ __forceinline__ Partials<T> slot_partials(int desc, const T* __restri
 // ------------------------------------------------------------------------------------------
 // DBM_CBF_2DS gc/fc + F -- cbf/cbf.py:159-164,200-207
 template <typename T>
-__device__ __forceinline__ void dbm_row(const Partials<T>& p, T sth, T cth, T v, T alpha, T lr, T& A0, T& A1, T& b) {
+__device__ __forceinline__ void dbm_row(const Partials<T>& p, T sth, T cth, T v, T alpha, T vlr, T& A0, T& A1, T& b) {
+    // vlr = v / lr, formed once per vehicle by the caller: a division inside the slot loop is not hoisted
+    // by the compiler (it cannot fold h_theta * (v / lr) even where h_theta is the constant 0 -- inf, NaN)
     A0 = p.hv;
-    A1 = (p.hx * ((-v) * sth) + p.hy * (v * cth)) + p.hth * (v / lr);
+    A1 = (p.hx * ((-v) * sth) + p.hy * (v * cth)) + p.hth * vlr;
     T Lf = p.hx * (v * cth) + p.hy * (v * sth);
     b = -((Lf + alpha * p.h) + p.ht);
 }
@@ -392,10 +399,10 @@ __device__ __forceinline__ void dum_row(const Partials<T>& p, T sth, T cth, T v,
 
 // row of the configured model
 template <typename T>
-__device__ __forceinline__ void model_row(const Params<T>& P, const Partials<T>& p, T sth, T cth, T v, T alpha, T& A0, T& A1, T& b) {
+__device__ __forceinline__ void model_row(const Params<T>& P, const Partials<T>& p, T sth, T cth, T v, T alpha, T vlr, T& A0, T& A1, T& b) {
     if (P.model == SCCAV_MODEL_KBM) kbm_row<T>(p, sth, cth, alpha, A0, A1, b);
     else if (P.model == SCCAV_MODEL_DUM) dum_row<T>(p, sth, cth, v, alpha, A0, A1, b);
-    else dbm_row<T>(p, sth, cth, v, alpha, P.lr, A0, A1, b);
+    else dbm_row<T>(p, sth, cth, v, alpha, vlr, A0, A1, b);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -405,9 +412,10 @@ __device__ __forceinline__ void model_row(const Params<T>& P, const Partials<T>&
 template <typename T> struct RowView {
     const T* rows;
     int stride;
-    __device__ __forceinline__ T A0(int k) const { return rows[(3 * k + 0) * stride]; }
-    __device__ __forceinline__ T A1(int k) const { return rows[(3 * k + 1) * stride]; }
-    __device__ __forceinline__ T b(int k) const { return rows[(3 * k + 2) * stride]; }
+    int pitch = 3;       // elements between consecutive rows of one problem (3, or NF where rows overlay staged slots)
+    __device__ __forceinline__ T A0(int k) const { return rows[(pitch * k + 0) * stride]; }
+    __device__ __forceinline__ T A1(int k) const { return rows[(pitch * k + 1) * stride]; }
+    __device__ __forceinline__ T b(int k) const { return rows[(pitch * k + 2) * stride]; }
 };
 
 template <typename T>
@@ -439,25 +447,31 @@ struct RowNz {
     }
 };
 
+// inverse of the cost weight, with the operations of oracle.qp2_exact (cbf/cbf.py:182-186 builds P = 2R)
+template <typename T> struct RInv {
+    T i00, i01, i10, i11;
+    __host__ __device__ __forceinline__ RInv() {}
+    __host__ __device__ __forceinline__ RInv(T R00, T R01, T R10, T R11) {
+        const T det = R00 * R11 - R01 * R10;
+        i00 = R11 / det; i01 = (-R01) / det; i10 = (-R10) / det; i11 = R00 / det;
+    }
+};
+
 // Enumeration with the least-violation bookkeeping of oracle.qp2_exact (every candidate checked against
 // every row), minus the pairs that RowNz proves degenerate.
-// (Measured on B200: a cheaper first pass with early exits does not pay -- a warp runs as long as its
-// slowest lane, and nearly every warp of the benchmark batches holds an infeasible problem.)
 template <typename T>
 __device__ __forceinline__ int qp2_solve_active_full(const RowView<T>& rv, int m, RowNz nz, T r0, T r1, T R00, T R01, T R10, T R11,
-                                                  T worst0, T& u0o, T& u1o, uint32_t& masko) {
+                                                  const RInv<T>& Ri, T worst0, T& u0o, T& u1o, uint32_t& masko) {
     typedef Real<T> R;
     T worst;
     T fbw = worst0, fb0 = r0, fb1 = r1;
     uint32_t fbm = 0u;
-    const T det = R00 * R11 - R01 * R10;
-    const T Ri00 = R11 / det, Ri01 = (-R01) / det, Ri10 = (-R10) / det, Ri11 = R00 / det;
     for (int k = 0; k < m; ++k) {
         T a0 = rv.A0(k), a1 = rv.A1(k), bk = rv.b(k);
         T rk = (a0 * r0 + a1 * r1) - bk;
         if (!(rk < T(0))) continue;
-        T g0 = Ri00 * a0 + Ri01 * a1;
-        T g1 = Ri10 * a0 + Ri11 * a1;
+        T g0 = Ri.i00 * a0 + Ri.i01 * a1;
+        T g1 = Ri.i10 * a0 + Ri.i11 * a1;
         T den = a0 * g0 + a1 * g1;
         if (!(den > T(0))) continue;
         T t = (-rk) / den;
@@ -497,11 +511,189 @@ __device__ __forceinline__ int qp2_solve_active_full(const RowView<T>& rv, int m
     return SCCAV_STATUS_INFEASIBLE;
 }
 
-// The reference point r violates at least one row (worst0 = its largest violation): singles, pairs.
+// Shortcut before the enumeration.  If the optimum has ONE active row k, it is the projection of r onto
+// that half-plane in the metric of the cost, at distance d_k = -rk / sqrt(A_k R^-1 A_k^T); it satisfies
+// every other row j, so d_k >= d_j for every row j that r violates: k is the row with the largest
+// rk^2 / den.  One scan finds it (ratios compared by cross-multiplication, no division), its candidate
+// is formed with the operations of the enumeration and checked against every row.  The enumeration --
+// which returns the FIRST accepted single in index order -- is still run whenever its answer could
+// differ: the candidate fails (optimum on a pair, or infeasible rows), another violated row is within
+// 1e-6 of the largest ratio (a tie: the earlier row may be accepted within the feasibility tolerance),
+// or the winning residual is within 1e-4 of its own rounding scale.  Otherwise a row j != k has
+// d_j < d_k (1 - 5e-7): its candidate misses row k by more than 5e-7 |rk|, 5 orders above the
+// acceptance tolerance, so the enumeration rejects it and accepts k -- same point, same bits.
+// tests/test_gpu_parity.py::test_qp_shortcut_equals_enumeration compares the two bit for bit.
+// The scan runs inside the row loop (QpScan::row, all lanes converged, predicated); finish() forms and
+// checks the winner's candidate and returns true (and the solution) if the shortcut answers the problem.
+template <typename T> struct QpScan {
+    T bn, bd;      // largest ratio  rk^2 / den  as a fraction
+    T sn, sd;      // runner-up
+    int kb;
+    __device__ __forceinline__ void reset() { bn = T(0); bd = T(1); sn = T(0); sd = T(1); kb = -1; }
+    // rk = (a0 r0 + a1 r1) - bk of row k, as computed by the feasibility test of the reference point
+    __device__ __forceinline__ void row(int k, T a0, T a1, T rk, const RInv<T>& Ri) {
+        T g0 = Ri.i00 * a0 + Ri.i01 * a1;
+        T g1 = Ri.i10 * a0 + Ri.i11 * a1;
+        T den = a0 * g0 + a1 * g1;
+        if (rk < T(0) && den > T(0)) {
+            T sc = rk * rk;
+            if (sc * bd > bn * den) { sn = bn; sd = bd; bn = sc; bd = den; kb = k; }
+            else if (sc * sd >= sn * den) { sn = sc; sd = den; }
+        }
+    }
+    __device__ __forceinline__ bool finish(const RowView<T>& rv, int m, T r0, T r1, const RInv<T>& Ri,
+                                           T& u0o, T& u1o, uint32_t& masko) const {
+        typedef Real<T> R;
+        if (!(kb >= 0 && sn * bd < (T(1) - R::qp_tie_margin()) * (bn * sd))) return false;
+        T a0 = rv.A0(kb), a1 = rv.A1(kb), bk = rv.b(kb);
+        T t0 = a0 * r0, t1 = a1 * r1;
+        T rk = (t0 + t1) - bk;
+        T g0 = Ri.i00 * a0 + Ri.i01 * a1;
+        T g1 = Ri.i10 * a0 + Ri.i11 * a1;
+        T den = a0 * g0 + a1 * g1;
+        T t = (-rk) / den;
+        T u0 = r0 + g0 * t, u1 = r1 + g1 * t;
+        if (!(-rk * R::qp_res_margin() > R::feas_eps() * ((R::abs_(t0) + R::abs_(t1)) + R::abs_(bk)))) return false;
+        T worst;
+        if (!qp_check(rv, m, u0, u1, kb, -1, worst)) return false;
+        u0o = u0; u1o = u1; masko = 1u << kb;
+        return true;
+    }
+};
+
+// The reference point r violates at least one row (worst0 = its largest violation): one thread, one problem.
+// (The persistent rollout uses this form: plain enumeration, no shortcut -- its warps are not converged.)
 template <typename T>
 __device__ __forceinline__ int qp2_solve_active(const RowView<T>& rv, int m, RowNz nz, T r0, T r1,
-                                                T R00, T R01, T R10, T R11, T worst0, T& u0o, T& u1o, uint32_t& masko) {
-    return qp2_solve_active_full<T>(rv, m, nz, r0, r1, R00, R01, R10, R11, worst0, u0o, u1o, masko);
+                                                T R00, T R01, T R10, T R11, const RInv<T>& Ri, T worst0,
+                                                T& u0o, T& u1o, uint32_t& masko) {
+    return qp2_solve_active_full<T>(rv, m, nz, r0, r1, R00, R01, R10, R11, Ri, worst0, u0o, u1o, masko);
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp-cooperative enumeration of ONE problem: lane k owns row k (m <= 32; lanes >= m hold the vacuous
+// row 0 u >= -inf).  Every candidate is checked by all lanes at once (one ballot); order, acceptance rule
+// and least-violation bookkeeping are those of qp2_solve_active_full, so the results are identical.
+// All 32 lanes must call it with the same m, nz, r, R, worst0.
+// ------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T shfl(T v, int src);
+template <> __device__ __forceinline__ double shfl<double>(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+template <> __device__ __forceinline__ float shfl<float>(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+template <typename T> __device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        T w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = (w > v) ? w : v;
+    }
+    return v;
+}
+
+template <typename T>
+__device__ __forceinline__ bool qp_check_coop(int lane, bool own, T a0, T a1, T bk, T u0, T u1, uint32_t skip, T& worst) {
+    typedef Real<T> R;
+    T t0 = a0 * u0, t1 = a1 * u1;
+    T rk = (t0 + t1) - bk;
+    T tol = R::feas_eps() * ((R::abs_(t0) + R::abs_(t1)) + R::abs_(bk));
+    bool bad = own && !((skip >> lane) & 1u) && !(rk >= -tol);
+    worst = warp_max<T>(own ? -rk : -R::inf());
+    return __ballot_sync(0xffffffffu, bad) == 0u;
+}
+
+template <typename T>
+__device__ __forceinline__ int qp2_coop_active(int lane, int m, T a0, T a1, T bk, RowNz nz, T r0, T r1,
+                                               T R00, T R01, T R10, T R11, const RInv<T>& Ri, T worst0,
+                                               T& u0o, T& u1o, uint32_t& masko) {
+    typedef Real<T> R;
+    const bool own = lane < m;
+    int status = -1;
+    T worst;
+    T fbw = worst0, fb0 = r0, fb1 = r1;
+    uint32_t fbm = 0u;
+    // singles: each lane prepares its own candidate, then they are tried in index order
+    T rk = (a0 * r0 + a1 * r1) - bk;
+    T g0 = Ri.i00 * a0 + Ri.i01 * a1, g1 = Ri.i10 * a0 + Ri.i11 * a1;
+    T den = a0 * g0 + a1 * g1;
+    const bool cand = own && (rk < T(0)) && (den > T(0));
+    T t = cand ? (-rk) / den : T(0);
+    T c0 = r0 + g0 * t, c1 = r1 + g1 * t;
+    uint32_t todo = __ballot_sync(0xffffffffu, cand);
+    while (todo && status < 0) {
+        const int k = __ffs(todo) - 1;
+        todo &= todo - 1;
+        T s0 = shfl<T>(c0, k), s1 = shfl<T>(c1, k);
+        if (qp_check_coop<T>(lane, own, a0, a1, bk, s0, s1, 1u << k, worst)) { u0o = s0; u1o = s1; masko = 1u << k; status = SCCAV_STATUS_ACTIVE; }
+        else if (worst < fbw - R::tie_eps() * (R::abs_(worst) + R::abs_(fbw))) { fbw = worst; fb0 = s0; fb1 = s1; fbm = 1u << k; }
+    }
+    // pairs, lexicographic (j < k): rows are broadcast from their owners
+    if (status < 0 && nz.any_pair()) {
+        for (int j = 0; j < m && status < 0; ++j) {
+            T aj0 = shfl<T>(a0, j), aj1 = shfl<T>(a1, j), bj = shfl<T>(bk, j);
+            for (int k = j + 1; k < m && status < 0; ++k) {
+                if (!nz.pair(j, k)) continue;
+                T ak0 = shfl<T>(a0, k), ak1 = shfl<T>(a1, k), bkk = shfl<T>(bk, k);
+                T t1 = aj0 * ak1, t2 = aj1 * ak0;
+                T det2 = t1 - t2;
+                if (!(R::abs_(det2) > R::par_eps() * (R::abs_(t1) + R::abs_(t2)))) continue;
+                T p0 = (bj * ak1 - aj1 * bkk) / det2;
+                T p1 = (aj0 * bkk - bj * ak0) / det2;
+                T e0 = p0 - r0, e1 = p1 - r1;
+                T w0 = T(2) * (R00 * e0 + R01 * e1);
+                T w1 = T(2) * (R10 * e0 + R11 * e1);
+                T lj = (w0 * ak1 - ak0 * w1) / det2;
+                T lk = (aj0 * w1 - w0 * aj1) / det2;
+                const uint32_t pm = (1u << j) | (1u << k);
+                const bool feas = qp_check_coop<T>(lane, own, a0, a1, bk, p0, p1, pm, worst);
+                if (feas && lj >= T(0) && lk >= T(0)) { u0o = p0; u1o = p1; masko = pm; status = SCCAV_STATUS_ACTIVE; }
+                else if (worst < fbw - R::tie_eps() * (R::abs_(worst) + R::abs_(fbw))) { fbw = worst; fb0 = p0; fb1 = p1; fbm = pm; }
+            }
+        }
+    }
+    if (status < 0) { u0o = fb0; u1o = fb1; masko = fbm; status = SCCAV_STATUS_INFEASIBLE; }
+    return status;
+}
+
+// Active solves of a CONVERGED warp whose lanes hold one problem each (rows of lane L in the column
+// warp_rows + L of shared memory).  `need` = this lane's reference point violates a row.  Lanes first try
+// the shortcut on their own; what is left (pairs, infeasible rows, ties) is enumerated by the whole warp,
+// one problem after the other -- 32 lanes on one problem instead of one lane on it and 31 waiting.
+template <typename T>
+__device__ __forceinline__ int qp2_solve_active_warp(bool need, const T* warp_rows, int stride, int lane, int m, RowNz nz,
+                                                     T r0, T r1, T R00, T R01, T R10, T R11, const RInv<T>& Ri, bool uniform_R,
+                                                     T worst0, const QpScan<T>& scan, T& u0o, T& u1o, uint32_t& masko, bool enumerate,
+                                                     int pitch = 3) {
+    int status = SCCAV_STATUS_INACTIVE;
+    if (need && !enumerate) {
+        const RowView<T> rv{warp_rows + lane, stride, pitch};
+        if (scan.finish(rv, m, r0, r1, Ri, u0o, u1o, masko)) { status = SCCAV_STATUS_ACTIVE; need = false; }
+    }
+    uint32_t todo = __ballot_sync(0xffffffffu, need);
+    if (todo) __syncwarp();                    // rows written by their lanes are read by the whole warp below
+    while (todo) {
+        const int L = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int pm = __shfl_sync(0xffffffffu, m, L);
+        RowNz pnz;
+        pnz.nz0 = __shfl_sync(0xffffffffu, nz.nz0, L);
+        pnz.nz1 = __shfl_sync(0xffffffffu, nz.nz1, L);
+        const T p0 = shfl<T>(r0, L), p1 = shfl<T>(r1, L), pw = shfl<T>(worst0, L);
+        T q00 = R00, q01 = R01, q10 = R10, q11 = R11;
+        RInv<T> qi = Ri;
+        if (!uniform_R) {
+            q00 = shfl<T>(R00, L); q01 = shfl<T>(R01, L); q10 = shfl<T>(R10, L); q11 = shfl<T>(R11, L);
+            qi.i00 = shfl<T>(Ri.i00, L); qi.i01 = shfl<T>(Ri.i01, L); qi.i10 = shfl<T>(Ri.i10, L); qi.i11 = shfl<T>(Ri.i11, L);
+        }
+        const T* col = warp_rows + L;
+        const bool own = lane < pm;
+        const T a0 = own ? col[(pitch * lane + 0) * stride] : T(0);
+        const T a1 = own ? col[(pitch * lane + 1) * stride] : T(0);
+        const T bk = own ? col[(pitch * lane + 2) * stride] : -Real<T>::inf();
+        T s0, s1;
+        uint32_t sm;
+        const int st = qp2_coop_active<T>(lane, pm, a0, a1, bk, pnz, p0, p1, q00, q01, q10, q11, qi, pw, s0, s1, sm);
+        if (lane == L) { u0o = s0; u1o = s1; masko = sm; status = st; }
+    }
+    return status;
 }
 
 // rows already in shared memory (K2): reference-point check, masks, then the active solve
@@ -526,7 +718,8 @@ __device__ __forceinline__ int qp2_solve(const RowView<T>& rv, int m, T r0, T r1
         u0o = r0; u1o = r1; masko = 0u;
         return SCCAV_STATUS_INACTIVE;
     }
-    return qp2_solve_active<T>(rv, m, nz, r0, r1, R00, R01, R10, R11, worst, u0o, u1o, masko);
+    const RInv<T> Ri(R00, R01, R10, R11);
+    return qp2_solve_active<T>(rv, m, nz, r0, r1, R00, R01, R10, R11, Ri, worst, u0o, u1o, masko);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -546,15 +739,16 @@ __device__ __forceinline__ int qp2_solve(const RowView<T>& rv, int m, T r0, T r1
 
 // row of one slot into shared memory + running feasibility test of the reference point
 // (qp_check(r) of qp2_solve, evaluated on the fly with the same operations)
-template <typename T>
-__device__ __forceinline__ void put_row(const Params<T>& P, const Partials<T>& p, T sth, T cth, T v, T alpha, T r0, T r1,
-                                        T* rows, int stride, int m, T& hmin, T& worst, bool& feas, RowNz& nz) {
+template <typename T, bool SCAN = false, int PITCH = 3>
+__device__ __forceinline__ void put_row(const Params<T>& P, const Partials<T>& p, T sth, T cth, T v, T alpha, T vlr, T r0, T r1,
+                                        T* rows, int stride, int m, T& hmin, T& worst, bool& feas, RowNz& nz,
+                                        QpScan<T>* scan = nullptr, const RInv<T>* Ri = nullptr) {
     typedef Real<T> R;
     T A0, A1, b;
-    model_row<T>(P, p, sth, cth, v, alpha, A0, A1, b);
-    rows[(3 * m + 0) * stride] = A0;
-    rows[(3 * m + 1) * stride] = A1;
-    rows[(3 * m + 2) * stride] = b;
+    model_row<T>(P, p, sth, cth, v, alpha, vlr, A0, A1, b);
+    rows[(PITCH * m + 0) * stride] = A0;
+    rows[(PITCH * m + 1) * stride] = A1;
+    rows[(PITCH * m + 2) * stride] = b;
     if (p.h < hmin) hmin = p.h;
     if (A0 != T(0)) nz.nz0 |= 1u << m;
     if (A1 != T(0)) nz.nz1 |= 1u << m;
@@ -563,6 +757,7 @@ __device__ __forceinline__ void put_row(const Params<T>& P, const Partials<T>& p
     if (-rk > worst) worst = -rk;
     T tol = R::feas_eps() * ((R::abs_(t0) + R::abs_(t1)) + R::abs_(b));
     if (!(rk >= -tol)) feas = false;
+    if (SCAN) scan->row(m, A0, A1, rk, *Ri);
 }
 
 // what the row phase of one vehicle leaves behind for the QP
@@ -571,16 +766,19 @@ template <typename T> struct RowPhase {
     T worst;         // its largest row violation
     RowNz nz;
     bool feas;       // the reference point satisfies every row: u = u_ref, no solve
+    QpScan<T> scan;  // most violated row in the metric of R (only filled when filter_rows<.., SCAN = true>)
 };
 
 // phase 1: u_ref -> QP coordinates, rows of all slots -> shared memory, feasibility of the reference point
-template <typename T, int SPEC>
+template <typename T, int SPEC, bool SCAN = false>
 __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const SlotDesc& sd, int M, int64_t N, int64_t n,
                                                    const T* __restrict__ obst, T x, T y, T th, T v, T sth, T cth,
                                                    T alpha, T uref0, T uref1, T* rows, int stride, T& hmin,
-                                                   const T* __restrict__ pre = nullptr, uint32_t moving = 0xffffffffu) {
+                                                   const T* __restrict__ pre = nullptr, uint32_t moving = 0xffffffffu,
+                                                   const RInv<T>* Ri = nullptr) {
     typedef Real<T> R;
     hmin = R::inf();
+    const T vlr = v / P.lr;                                                             // cbf.py:160 (g_c[2][1])
     T r0 = uref0, r1;
     if (P.model == SCCAV_MODEL_KBM) r1 = (uref0 * R::tan_(uref1)) / P.L;                // cbf.py:75
     else if (P.model == SCCAV_MODEL_DUM) r1 = uref1;                                     // cbf.py:253: u_ref as given
@@ -589,6 +787,8 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
     bool feas = true;
     T worst = -R::inf();
     RowNz nz{0u, 0u};
+    QpScan<T> scan;
+    scan.reset();
     if (SPEC == SCCAV_SPEC_ELLIPSE) {
         const int64_t ss = (int64_t)SCCAV_NFIELD * N;          // slot stride
         const T* f = obst + n;
@@ -602,7 +802,7 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
                 T vx = T(0), vy = T(0);
                 if ((moving >> m) & 1u) { vx = f[5 * N]; vy = f[6 * N]; }
                 Partials<T> p = ellipse_partials_pre<T>(x, y, cx, cy, a, b, vx, vy, q, N);
-                put_row<T>(P, p, sth, cth, v, alpha, r0, r1, rows, stride, m, hmin, worst, feas, nz);
+                put_row<T, SCAN>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
             }
         } else {
             T cx = f[0], cy = f[N], a = f[2 * N], b = f[3 * N], t = f[4 * N], vx = f[5 * N], vy = f[6 * N];
@@ -611,7 +811,7 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
                 T ncx = cx, ncy = cy, na = a, nb = b, nt = t, nvx = vx, nvy = vy;
                 if (m + 1 < M) { ncx = f[0]; ncy = f[N]; na = f[2 * N]; nb = f[3 * N]; nt = f[4 * N]; nvx = f[5 * N]; nvy = f[6 * N]; }
                 Partials<T> p = ellipse_partials<T>(x, y, cx, cy, a, b, t, vx, vy);
-                put_row<T>(P, p, sth, cth, v, alpha, r0, r1, rows, stride, m, hmin, worst, feas, nz);
+                put_row<T, SCAN>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
                 cx = ncx; cy = ncy; a = na; b = nb; t = nt; vx = nvx; vy = nvy;
             }
         }
@@ -628,7 +828,7 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
             T wx = T(0), wy = T(0);
             if (!is_static) { wx = f[6 * N]; wy = f[7 * N]; }
             Partials<T> p = ellipse_prep_partials<T>(x, y, f[0], f[N], f[2 * N], f[3 * N], f[4 * N], f[5 * N], wx, wy);
-            put_row<T>(P, p, sth, cth, v, alpha, r0, r1, rows, stride, m, hmin, worst, feas, nz);
+            put_row<T, SCAN>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
         }
     } else {
         for (int m = 0; m < M; ++m) {
@@ -637,11 +837,11 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
             const T* f = obst + (int64_t)m * SCCAV_NFIELD * N + nn;
             const T* pr = pre ? pre + (int64_t)m * SCCAV_NPRE * N + n : nullptr;
             Partials<T> p = slot_partials<T>(desc, f, N, x, y, th, v, sth, cth, pr, N);
-            put_row<T>(P, p, sth, cth, v, alpha, r0, r1, rows, stride, m, hmin, worst, feas, nz);
+            put_row<T, SCAN>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
         }
     }
     RowPhase<T> ph;
-    ph.r0 = r0; ph.r1 = r1; ph.worst = worst; ph.nz = nz; ph.feas = feas;
+    ph.r0 = r0; ph.r1 = r1; ph.worst = worst; ph.nz = nz; ph.feas = feas; ph.scan = scan;
     return ph;
 }
 
@@ -661,7 +861,7 @@ __device__ __forceinline__ T filter_convert(const Params<T>& P, T q0, T q1, T r0
 template <typename T, int SPEC>
 __device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc& sd, int M, int64_t N, int64_t n,
                                               const T* __restrict__ obst, T x, T y, T th, T v, T sth, T cth,
-                                              T alpha, T R00, T R01, T R10, T R11, T uref0, T uref1,
+                                              T alpha, T R00, T R01, T R10, T R11, bool uniform_R, T uref0, T uref1,
                                               T* rows, int stride, T& u0, T& u1, T& u1raw, uint32_t& mask, T& hmin,
                                               const T* __restrict__ pre = nullptr, uint32_t moving = 0xffffffffu) {
     const RowPhase<T> ph = filter_rows<T, SPEC>(P, sd, M, N, n, obst, x, y, th, v, sth, cth, alpha, uref0, uref1,
@@ -671,7 +871,12 @@ __device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc
     mask = 0u;
     if (!ph.feas) {
         RowView<T> rv{rows, stride};
-        status = qp2_solve_active<T>(rv, M, ph.nz, ph.r0, ph.r1, R00, R01, R10, R11, ph.worst, q0, q1, mask);
+        // inverse weight: the launch-wide one comes from the host (constant bank, no registers held across
+        // the time loop); per-vehicle weights are inverted on the spot
+        RInv<T> Ri;
+        if (uniform_R) { Ri.i00 = P.Ri[0]; Ri.i01 = P.Ri[1]; Ri.i10 = P.Ri[2]; Ri.i11 = P.Ri[3]; }
+        else Ri = RInv<T>(R00, R01, R10, R11);
+        status = qp2_solve_active<T>(rv, M, ph.nz, ph.r0, ph.r1, R00, R01, R10, R11, Ri, ph.worst, q0, q1, mask);
     }
     u0 = q0;
     u1raw = q1;

@@ -96,6 +96,67 @@ def test_k1_k2_equal_fused_and_warp_variant():
     assert int((status == 2).sum()) > 0, "want some infeasible problems in this set"
 
 
+@pytest.mark.parametrize("name,model", [("ellipse8", o.MODEL_DBM), ("ellipse8", o.MODEL_KBM), ("mixed", o.MODEL_DBM),
+                                        ("cone5", o.MODEL_DBM), ("radial16", o.MODEL_DBM)])
+def test_qp_shortcut_equals_enumeration(name, model):
+    """The one-scan shortcut of the QP (most violated row in the metric of R, csrc/path.cuh) against the
+    full enumeration (SCCAV_FLAG_QP_ENUMERATE) on 262,144 problems per mix, with duplicated and
+    near-duplicated rows (exact and 1e-9 ties): controls, active sets and statuses bit for bit."""
+    from sccav_cbf_b200 import ops
+    slots = SLOTSETS[name]
+    N = 262144
+    rng = np.random.default_rng(zlib.crc32(name.encode()) + 7 * model)
+    s = H.random_states(rng, N)
+    ob = H.random_slots(rng, N, slots, s)
+    if len(slots) >= 4 and (slots[0] & 0x3F) == (slots[3] & 0x3F):
+        ob[3, :, : N // 8] = ob[0, :, : N // 8]                                   # exact ties
+        ob[3, :, N // 8: N // 4] = ob[0, :, N // 8: N // 4] * (1 + 1e-9)           # near ties
+    ur = H.random_uref(rng, N, kbm=(model == o.MODEL_KBM))
+    R = [1.0, 0.3, 0.3, 2.5]
+    outs = []
+    for flags in (0, 2):
+        prm = ops.make_params(model=model, R=R, alpha=1.3, flags=flags)
+        u, mask, status, hmin = ops.filter_step(prm, slots, T(s), T(ob), T(ur))
+        A, b, _ = ops.barrier_rows(prm, slots, T(s), T(ob))
+        r = T(ur)
+        u2, mask2, status2 = ops.qp2_solve(prm, A, b, r)
+        outs.append((u, mask, status, u2, mask2, status2))
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)
+    st = outs[0][2]
+    assert int((st == 1).sum()) > N // 50, "want active problems"
+
+
+@pytest.mark.parametrize("slot,static,dtype", [(o.SLOT_ELLIPSE, False, torch.float64), (o.SLOT_ELLIPSE_PREP, True, torch.float64),
+                                               (o.SLOT_ELLIPSE_PREP, False, torch.float64), (o.SLOT_ELLIPSE, False, torch.float32)])
+def test_filter_step_pipelined_equals_direct_load_kernel(slot, static, dtype, monkeypatch):
+    """The software-pipelined K12 (cp.async ring per thread, persistent grid) against the direct-load K12
+    (SCCAV_K12_PIPE=0): identical arithmetic, so identical bits -- ragged N (tail tile), M < ring depth,
+    per-vehicle obstacle counts."""
+    from sccav_cbf_b200 import ops
+    for M, N in ((8, 300001), (2, 77), (8, 148 * 2 * 256 + 5), (5, 4096)):
+        rng = np.random.default_rng(M * 1000 + N % 97)
+        s = H.random_states(rng, N)
+        ob = H.random_slots(rng, N, [o.SLOT_ELLIPSE] * M, s)
+        ur = H.random_uref(rng, N)
+        slots = [o.SLOT_ELLIPSE | (o.SLOT_STATIC if static else 0)] * M
+        if static:
+            ob[:, 5:7] = 0.0
+        obst = T(ob, dtype)
+        if slot == o.SLOT_ELLIPSE_PREP:
+            slots, obst = ops.prepare_obstacles(slots, obst)
+        count = torch.from_numpy(rng.integers(0, M + 1, N).astype(np.int32)).to(dev()) if M == 5 else None
+        prm = ops.make_params(alpha=0.8)
+        got = []
+        for pipe in ("1", "0"):
+            monkeypatch.setenv("SCCAV_K12_PIPE", pipe)
+            got.append(ops.filter_step(prm, slots, T(s, dtype), obst, T(ur, dtype), count=count))
+            torch.cuda.synchronize()
+        for x, y in zip(*got):
+            assert torch.equal(x, y), (M, N)
+        assert int((got[0][2] == 1).sum()) > 0
+
+
 def test_qp_kkt_property_full_size():
     """Size-independent property at BASELINE size (65,536 x 8): every returned point is primal
     feasible, stationary on its active set, with non-negative multipliers."""
