@@ -73,10 +73,22 @@ void keep_pool_memory() {
 int sm_count() { return attr().sms; }
 int max_smem_optin() { return attr().smem; }
 int max_smem_per_sm() { return attr().smem_sm; }
-// debugging knob: SCCAV_K12_PIPE=0 selects the direct-load filter-step kernel (A/B measurements)
-bool k12_pipe_enabled() {
-    const char* e = getenv("SCCAV_K12_PIPE");      // read per call: tests flip it between launches
-    return !(e && e[0] == '0');
+// Developer knobs for A/B measurements (read per call: tests flip them between launches).
+// SCCAV_K12_PIPE=0 selects the direct-load filter-step kernel, =1 the staged one wherever it fits; default:
+// staged for prepared slots, direct loads for canonical ellipses (measured).
+bool k12_staged_enabled(int spec) {
+    const char* e = getenv("SCCAV_K12_PIPE");
+    if (e && e[0] == '0') return false;
+    if (e && e[0] == '1') return true;
+    return spec == 2;
+}
+// SCCAV_K12_QP=thread|coop overrides the QP form of the filter-step kernels; default: warp-cooperative
+// (shortcut + cooperative enumeration) in the staged kernel on prepared slots, one thread per problem elsewhere.
+bool k12_coop_enabled(int spec) {
+    const char* e = getenv("SCCAV_K12_QP");
+    if (e && e[0] == 't') return false;
+    if (e && e[0] == 'c') return true;
+    return spec == 2;
 }
 
 // ---- FMA peak: NCHAIN independent dependent-FMA chains per thread, fully unrolled.

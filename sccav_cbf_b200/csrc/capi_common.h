@@ -10,7 +10,8 @@ void count_launch();
 int sm_count();          // SMs of the current device (cached per device)
 int max_smem_optin();    // max opt-in dynamic shared memory per block of the current device
 int max_smem_per_sm();   // shared memory of one SM
-bool k12_pipe_enabled(); // SCCAV_K12_PIPE=0 selects the direct-load filter-step kernel
+bool k12_coop_enabled(int spec);   // SCCAV_K12_QP=thread|coop overrides the staged kernel's QP form
+bool k12_staged_enabled(int spec); // SCCAV_K12_PIPE=0|1 overrides the choice between the direct-load and the staged filter-step kernel
 void keep_pool_memory(); // once per device: the stream-ordered pool keeps freed scratch for the next call
 }  // namespace sccav
 

@@ -241,21 +241,26 @@ int do_filter_step(const sccav_params* p, const uint8_t* slot_desc, int32_t M, i
     const int spec = choose_spec(slot_desc, M);
     const int nf = spec == SCCAV_SPEC_ELLIPSE ? 7 : ((slot_desc[0] & SCCAV_SLOT_STATIC) ? 6 : 8);
     const size_t staged = (size_t)nf * M * 256 * sizeof(real);
-    if (spec != SCCAV_SPEC_GENERIC && nf < 8 && k12_pipe_enabled() &&
+    if (k12_staged_enabled(spec) && spec != SCCAV_SPEC_GENERIC && nf < 8 &&
         2 * (staged + 1024) <= (size_t)max_smem_per_sm()) {
         // staged kernel: every field of a vehicle requested at once (cp.async), rows overlay the staged slots; two CTAs per SM
         typedef void (*staged_fn)(FilterArgs<real>);
-        const staged_fn sk = spec == SCCAV_SPEC_ELLIPSE ? filter_step_staged_kernel<real, SCCAV_SPEC_ELLIPSE, 7>
-                                                        : filter_step_staged_kernel<real, SCCAV_SPEC_ELLIPSE_PREP, 6>;
+        const bool coop = k12_coop_enabled(spec);
+        const staged_fn sk = spec == SCCAV_SPEC_ELLIPSE
+            ? (coop ? filter_step_staged_kernel<real, SCCAV_SPEC_ELLIPSE, 7, true> : filter_step_staged_kernel<real, SCCAV_SPEC_ELLIPSE, 7, false>)
+            : (coop ? filter_step_staged_kernel<real, SCCAV_SPEC_ELLIPSE_PREP, 6, true> : filter_step_staged_kernel<real, SCCAV_SPEC_ELLIPSE_PREP, 6, false>);
         SCCAV_CUDA_CHECK(cudaFuncSetAttribute((const void*)sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged));
         sk<<<stream_grid(N, 256), 256, staged, st>>>(a);
         count_launch();
         SCCAV_CUDA_CHECK(cudaGetLastError());
         return SCCAV_OK;
     }
-    const filter_fn kern = spec == SCCAV_SPEC_ELLIPSE ? filter_step_kernel<real, SCCAV_SPEC_ELLIPSE>
-                         : spec == SCCAV_SPEC_ELLIPSE_PREP ? filter_step_kernel<real, SCCAV_SPEC_ELLIPSE_PREP>
-                                                           : filter_step_kernel<real, SCCAV_SPEC_GENERIC>;
+    const bool dcoop = k12_coop_enabled(-1);
+    const filter_fn kern = spec == SCCAV_SPEC_ELLIPSE
+        ? (dcoop ? filter_step_kernel<real, SCCAV_SPEC_ELLIPSE, true> : filter_step_kernel<real, SCCAV_SPEC_ELLIPSE, false>)
+        : spec == SCCAV_SPEC_ELLIPSE_PREP
+        ? (dcoop ? filter_step_kernel<real, SCCAV_SPEC_ELLIPSE_PREP, true> : filter_step_kernel<real, SCCAV_SPEC_ELLIPSE_PREP, false>)
+        : (dcoop ? filter_step_kernel<real, SCCAV_SPEC_GENERIC, true> : filter_step_kernel<real, SCCAV_SPEC_GENERIC, false>);
     SCCAV_CUDA_CHECK(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<stream_grid(N, block), block, smem, st>>>(a);
     count_launch();

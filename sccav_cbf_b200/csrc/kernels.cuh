@@ -509,7 +509,7 @@ template <typename T> struct FilterArgs {
 #ifndef SCCAV_K12_MINB
 #define SCCAV_K12_MINB 2
 #endif
-template <typename T, int SPEC>
+template <typename T, int SPEC, bool COOP>
 __global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_kernel(const __grid_constant__ FilterArgs<T> a) {
     typedef Real<T> R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -540,15 +540,22 @@ __global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_kernel(const 
             if (Mv > 0) {
                 T sth, cth;
                 R::sincos_(th, &sth, &cth);
-                ph = filter_rows<T, SPEC, true>(a.P, a.sd, Mv, N, n, a.obst, x, y, th, v, sth, cth, alpha, ur0, ur1, rows, stride,
+                ph = filter_rows<T, SPEC, COOP>(a.P, a.sd, Mv, N, n, a.obst, x, y, th, v, sth, cth, alpha, ur0, ur1, rows, stride,
                                                 hmin, nullptr, 0xffffffffu, &Ri);
             }
         }
         T q0 = ph.r0, q1 = ph.r1;
         uint32_t mask = 0u;
-        const int st = qp2_solve_active_warp<T>(!ph.feas, warp_rows, stride, lane, Mv, ph.nz, ph.r0, ph.r1, R00, R01, R10, R11, Ri,
-                                                a.pv.R == nullptr, ph.worst, ph.scan, q0, q1, mask, enumerate);
-        __syncwarp();                          // the next vehicle's rows overwrite the columns read above
+        int st = SCCAV_STATUS_INACTIVE;
+        if (COOP) {
+            st = qp2_solve_active_warp<T>(!ph.feas, warp_rows, stride, lane, Mv, ph.nz, ph.r0, ph.r1, R00, R01, R10, R11, Ri,
+                                          a.pv.R == nullptr, ph.worst, ph.scan, q0, q1, mask, enumerate);
+            __syncwarp();                      // the next vehicle's rows overwrite the columns read above
+        } else if (!ph.feas) {
+            // one thread, one problem: plain enumeration
+            const RowView<T> rv{rows, stride};
+            st = qp2_solve_active<T>(rv, Mv, ph.nz, ph.r0, ph.r1, R00, R01, R10, R11, Ri, ph.worst, q0, q1, mask);
+        }
         if (valid) {
             T u0 = ur0, u1 = ur1;                                           // empty obstacle list: u = u_ref
             if (Mv > 0) { u0 = q0; u1 = filter_convert<T>(a.P, q0, q1, ph.r0); }
@@ -576,7 +583,7 @@ template <typename T> __device__ __forceinline__ void cp_async_elem(T* smem_dst,
     asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(s), "l"(gmem_src), "n"((int)sizeof(T)) : "memory");
 }
 
-template <typename T, int SPEC, int NF>
+template <typename T, int SPEC, int NF, bool COOP>
 __global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_staged_kernel(const __grid_constant__ FilterArgs<T> a) {
     typedef Real<T> R;
     static_assert(NF >= 3 && NF <= SCCAV_NFIELD, "row m lives in the first three staged fields of slot m");
@@ -635,14 +642,21 @@ __global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_staged_kernel
                 if (SPEC == SCCAV_SPEC_ELLIPSE) p = ellipse_partials<T>(x, y, g[0], g[1], g[2], g[3], g[4], g[5], g[NF - 1]);
                 else if (NF >= 8) p = ellipse_prep_partials<T>(x, y, g[0], g[1], g[2], g[3], g[4], g[5], g[NF - 2], g[NF - 1]);
                 else p = ellipse_prep_partials<T>(x, y, g[0], g[1], g[2], g[3], g[4], g[5], T(0), T(0));
-                put_row<T, true, NF>(P, p, sth, cth, v, alpha, vlr, r0, r1, stage, B, m, hmin, worst, feas, nz, &scan, &Ri);
+                put_row<T, COOP, NF>(P, p, sth, cth, v, alpha, vlr, r0, r1, stage, B, m, hmin, worst, feas, nz, &scan, &Ri);
             }
         }
         T q0 = r0, q1 = r1;
         uint32_t mask = 0u;
-        const int st = qp2_solve_active_warp<T>(!feas, warp_rows, B, lane, Mv, nz, r0, r1, R00, R01, R10, R11, Ri,
-                                                a.pv.R == nullptr, worst, scan, q0, q1, mask, enumerate, NF);
-        __syncwarp();                          // the next vehicle's fields overwrite the columns read above
+        int st = SCCAV_STATUS_INACTIVE;
+        if (COOP) {
+            st = qp2_solve_active_warp<T>(!feas, warp_rows, B, lane, Mv, nz, r0, r1, R00, R01, R10, R11, Ri,
+                                          a.pv.R == nullptr, worst, scan, q0, q1, mask, enumerate, NF);
+            __syncwarp();                      // the next vehicle's fields overwrite the columns read above
+        } else if (!feas) {
+            // one thread, one problem: plain enumeration (what pays when the rows themselves are the cost)
+            const RowView<T> rv{stage, B, NF};
+            st = qp2_solve_active<T>(rv, Mv, nz, r0, r1, R00, R01, R10, R11, Ri, worst, q0, q1, mask);
+        }
         if (valid) {
             T u0 = ur0, u1 = ur1;                                           // empty obstacle list: u = u_ref
             if (Mv > 0) { u0 = q0; u1 = filter_convert<T>(P, q0, q1, r0); }

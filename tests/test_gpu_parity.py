@@ -98,11 +98,14 @@ def test_k1_k2_equal_fused_and_warp_variant():
 
 @pytest.mark.parametrize("name,model", [("ellipse8", o.MODEL_DBM), ("ellipse8", o.MODEL_KBM), ("mixed", o.MODEL_DBM),
                                         ("cone5", o.MODEL_DBM), ("radial16", o.MODEL_DBM)])
-def test_qp_shortcut_equals_enumeration(name, model):
+def test_qp_shortcut_equals_enumeration(name, model, monkeypatch):
     """The one-scan shortcut of the QP (most violated row in the metric of R, csrc/path.cuh) against the
     full enumeration (SCCAV_FLAG_QP_ENUMERATE) on 262,144 problems per mix, with duplicated and
-    near-duplicated rows (exact and 1e-9 ties): controls, active sets and statuses bit for bit."""
+    near-duplicated rows (exact and 1e-9 ties): controls, active sets and statuses bit for bit.
+    SCCAV_K12_QP=coop puts the shortcut + cooperative form into every filter-step kernel (by default only
+    the staged kernel on prepared slots and K2 use it); the thread-per-problem enumeration is compared too."""
     from sccav_cbf_b200 import ops
+    monkeypatch.setenv("SCCAV_K12_QP", "coop")
     slots = SLOTSETS[name]
     N = 262144
     rng = np.random.default_rng(zlib.crc32(name.encode()) + 7 * model)
@@ -125,14 +128,18 @@ def test_qp_shortcut_equals_enumeration(name, model):
         assert torch.equal(x, y)
     st = outs[0][2]
     assert int((st == 1).sum()) > N // 50, "want active problems"
+    monkeypatch.setenv("SCCAV_K12_QP", "thread")
+    prm = ops.make_params(model=model, R=R, alpha=1.3)
+    u, mask, status, hmin = ops.filter_step(prm, slots, T(s), T(ob), T(ur))
+    assert torch.equal(u, outs[0][0]) and torch.equal(mask, outs[0][1]) and torch.equal(status, outs[0][2])
 
 
 @pytest.mark.parametrize("slot,static,dtype", [(o.SLOT_ELLIPSE, False, torch.float64), (o.SLOT_ELLIPSE_PREP, True, torch.float64),
                                                (o.SLOT_ELLIPSE_PREP, False, torch.float64), (o.SLOT_ELLIPSE, False, torch.float32)])
 def test_filter_step_pipelined_equals_direct_load_kernel(slot, static, dtype, monkeypatch):
-    """The software-pipelined K12 (cp.async ring per thread, persistent grid) against the direct-load K12
-    (SCCAV_K12_PIPE=0): identical arithmetic, so identical bits -- ragged N (tail tile), M < ring depth,
-    per-vehicle obstacle counts."""
+    """The staged K12 (cp.async of every field of a vehicle into its shared-memory column, rows overlaying
+    the staged slots) against the direct-load K12 (SCCAV_K12_PIPE=0), each with its default QP form:
+    identical arithmetic, so identical bits -- ragged N (tail warp), small M, per-vehicle obstacle counts."""
     from sccav_cbf_b200 import ops
     for M, N in ((8, 300001), (2, 77), (8, 148 * 2 * 256 + 5), (5, 4096)):
         rng = np.random.default_rng(M * 1000 + N % 97)
