@@ -246,9 +246,12 @@ int do_filter_step(const sccav_params* p, const uint8_t* slot_desc, int32_t M, i
         // staged kernel: every field of a vehicle requested at once (cp.async), rows overlay the staged slots; two CTAs per SM
         typedef void (*staged_fn)(FilterArgs<real>);
         const bool coop = k12_coop_enabled(spec);
+        const bool dbm = p->model == SCCAV_MODEL_DBM;                 // the common model gets a dispatch-free slot loop
         const staged_fn sk = spec == SCCAV_SPEC_ELLIPSE
-            ? (coop ? filter_step_staged_kernel<real, SCCAV_SPEC_ELLIPSE, 7, true> : filter_step_staged_kernel<real, SCCAV_SPEC_ELLIPSE, 7, false>)
-            : (coop ? filter_step_staged_kernel<real, SCCAV_SPEC_ELLIPSE_PREP, 6, true> : filter_step_staged_kernel<real, SCCAV_SPEC_ELLIPSE_PREP, 6, false>);
+            ? (coop ? filter_step_staged_kernel<real, SCCAV_SPEC_ELLIPSE, 7, true, -1> : filter_step_staged_kernel<real, SCCAV_SPEC_ELLIPSE, 7, false, -1>)
+            : coop ? (dbm ? filter_step_staged_kernel<real, SCCAV_SPEC_ELLIPSE_PREP, 6, true, SCCAV_MODEL_DBM>
+                          : filter_step_staged_kernel<real, SCCAV_SPEC_ELLIPSE_PREP, 6, true, -1>)
+                   : filter_step_staged_kernel<real, SCCAV_SPEC_ELLIPSE_PREP, 6, false, -1>;
         SCCAV_CUDA_CHECK(cudaFuncSetAttribute((const void*)sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged));
         sk<<<stream_grid(N, 256), 256, staged, st>>>(a);
         count_launch();

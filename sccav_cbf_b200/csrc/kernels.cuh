@@ -583,7 +583,7 @@ template <typename T> __device__ __forceinline__ void cp_async_elem(T* smem_dst,
     asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(s), "l"(gmem_src), "n"((int)sizeof(T)) : "memory");
 }
 
-template <typename T, int SPEC, int NF, bool COOP>
+template <typename T, int SPEC, int NF, bool COOP, int MODEL>
 __global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_staged_kernel(const __grid_constant__ FilterArgs<T> a) {
     typedef Real<T> R;
     static_assert(NF >= 3 && NF <= SCCAV_NFIELD, "row m lives in the first three staged fields of slot m");
@@ -622,9 +622,10 @@ __global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_staged_kernel
         T sth, cth;
         R::sincos_(th, &sth, &cth);
         const T vlr = v / P.lr;
+        const int model = MODEL >= 0 ? MODEL : P.model;
         T r0 = ur0, r1;
-        if (P.model == SCCAV_MODEL_KBM) r1 = (ur0 * R::tan_(ur1)) / P.L;                    // cbf.py:75
-        else if (P.model == SCCAV_MODEL_DUM) r1 = ur1;                                       // cbf.py:253
+        if (model == SCCAV_MODEL_KBM) r1 = (ur0 * R::tan_(ur1)) / P.L;                      // cbf.py:75
+        else if (model == SCCAV_MODEL_DUM) r1 = ur1;                                         // cbf.py:253
         else r1 = R::atan2_(P.lr * R::tan_(ur1), P.lf + P.lr);                               // cbf.py:175
         T hmin = R::inf(), worst = -R::inf();
         bool feas = true;
@@ -642,7 +643,7 @@ __global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_staged_kernel
                 if (SPEC == SCCAV_SPEC_ELLIPSE) p = ellipse_partials<T>(x, y, g[0], g[1], g[2], g[3], g[4], g[5], g[NF - 1]);
                 else if (NF >= 8) p = ellipse_prep_partials<T>(x, y, g[0], g[1], g[2], g[3], g[4], g[5], g[NF - 2], g[NF - 1]);
                 else p = ellipse_prep_partials<T>(x, y, g[0], g[1], g[2], g[3], g[4], g[5], T(0), T(0));
-                put_row<T, COOP, NF>(P, p, sth, cth, v, alpha, vlr, r0, r1, stage, B, m, hmin, worst, feas, nz, &scan, &Ri);
+                put_row<T, COOP, NF, MODEL>(P, p, sth, cth, v, alpha, vlr, r0, r1, stage, B, m, hmin, worst, feas, nz, &scan, &Ri);
             }
         }
         T q0 = r0, q1 = r1;

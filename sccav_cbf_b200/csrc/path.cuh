@@ -398,10 +398,12 @@ __device__ __forceinline__ void dum_row(const Partials<T>& p, T sth, T cth, T v,
 }
 
 // row of the configured model
-template <typename T>
+// (MODEL >= 0: the model is known at compile time -- no dispatch inside the slot loop)
+template <typename T, int MODEL = -1>
 __device__ __forceinline__ void model_row(const Params<T>& P, const Partials<T>& p, T sth, T cth, T v, T alpha, T vlr, T& A0, T& A1, T& b) {
-    if (P.model == SCCAV_MODEL_KBM) kbm_row<T>(p, sth, cth, alpha, A0, A1, b);
-    else if (P.model == SCCAV_MODEL_DUM) dum_row<T>(p, sth, cth, v, alpha, A0, A1, b);
+    const int model = MODEL >= 0 ? MODEL : P.model;
+    if (model == SCCAV_MODEL_KBM) kbm_row<T>(p, sth, cth, alpha, A0, A1, b);
+    else if (model == SCCAV_MODEL_DUM) dum_row<T>(p, sth, cth, v, alpha, A0, A1, b);
     else dbm_row<T>(p, sth, cth, v, alpha, vlr, A0, A1, b);
 }
 
@@ -739,13 +741,13 @@ __device__ __forceinline__ int qp2_solve(const RowView<T>& rv, int m, T r0, T r1
 
 // row of one slot into shared memory + running feasibility test of the reference point
 // (qp_check(r) of qp2_solve, evaluated on the fly with the same operations)
-template <typename T, bool SCAN = false, int PITCH = 3>
+template <typename T, bool SCAN = false, int PITCH = 3, int MODEL = -1>
 __device__ __forceinline__ void put_row(const Params<T>& P, const Partials<T>& p, T sth, T cth, T v, T alpha, T vlr, T r0, T r1,
                                         T* rows, int stride, int m, T& hmin, T& worst, bool& feas, RowNz& nz,
                                         QpScan<T>* scan = nullptr, const RInv<T>* Ri = nullptr) {
     typedef Real<T> R;
     T A0, A1, b;
-    model_row<T>(P, p, sth, cth, v, alpha, vlr, A0, A1, b);
+    model_row<T, MODEL>(P, p, sth, cth, v, alpha, vlr, A0, A1, b);
     rows[(PITCH * m + 0) * stride] = A0;
     rows[(PITCH * m + 1) * stride] = A1;
     rows[(PITCH * m + 2) * stride] = b;

@@ -36,4 +36,7 @@ echo "ncu rollout exit $?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:filter_step_kernel -s 3 -c 1 \
     -f -o "$OUT/prof_filter" python bench.py --steps 1 --warmup 3 --no-cpu --T 10 > "$OUT/ncu_filter.log" 2>&1
 echo "ncu filter exit $?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:filter_step_staged -s 3 -c 1 \
+    -f -o "$OUT/prof_filter_staged" python bench.py --steps 1 --warmup 3 --no-cpu --T 10 > "$OUT/ncu_filter_staged.log" 2>&1
+echo "ncu filter staged exit $?"
 ls -la "$OUT"
