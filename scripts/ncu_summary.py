@@ -112,9 +112,14 @@ def source(path, top=45):
         if hdr is None or cur is None or r[0] in ("Function Name", "Kernel Name") or not r[0].isdigit():
             continue
         d = dict(zip(hdr, r))
-        recs.append((cur, int(r[0]), r[1].strip()[:90], int(d["# Samples"] or 0), int(d["Instructions Executed"] or 0),
-                     int(d["Thread Instructions Executed"] or 0), int(d["L1 Wavefronts Shared"] or 0),
-                     int(d["stall_no_inst"] or 0), int(d["stall_wait"] or 0), int(d["stall_short_sb"] or 0), int(d["stall_long_sb"] or 0)))
+        def num(k):
+            try:
+                return int(d.get(k) or 0)
+            except ValueError:          # ncu prints "-" where a line has no such counter
+                return 0
+        recs.append((cur, int(r[0]), r[1].strip()[:90], num("# Samples"), num("Instructions Executed"),
+                     num("Thread Instructions Executed"), num("L1 Wavefronts Shared"),
+                     num("stall_no_inst"), num("stall_wait"), num("stall_short_sb"), num("stall_long_sb")))
     ts = sum(x[3] for x in recs) or 1
     ti = sum(x[4] for x in recs) or 1
     print("# ncu source page, hottest CUDA source lines of %s" % path)
