@@ -63,6 +63,10 @@ extern "C" {
  *          h = pa^2 + qb^2 - 1, grad h = 2 M^T (pa, qb), h_t = -2 (dx wx + dy wy)
  *          (the same functions as cbf/obstacles.py:193,218,229,316, a few ulp apart)              */
 #define SCCAV_SLOT_ELLIPSE_PREP 5
+/* LANE_SQRT  the distance form of the lane barrier, CBF_lane_sqrt / CBF_lane_cf_sqrt,
+ *          test_scripts/stanley_controller_ellipse.py:465-512,546-579: h = sqrt(d^2) - buffer, and the gradient of
+ *          the LANE barrier divided by 2 (h + buffer).  fields as LANE: buffer, c0, c1, c2, c3, c4, c5, -  */
+#define SCCAV_SLOT_LANE_SQRT 6
 #define SCCAV_SLOT_TYPE_MASK 0x3f
 /* flag: the obstacle does not move -- its velocity fields are not read and h_t = 0            */
 #define SCCAV_SLOT_STATIC 0x40
@@ -72,6 +76,12 @@ extern "C" {
 #define SCCAV_MODEL_DBM 0          /* DBM_CBF_2DS,  u = (a, beta),  cbf/cbf.py:112-220 */
 #define SCCAV_MODEL_KBM 1          /* KBM_VC_CBF2D, u = (v, omega), cbf/cbf.py:33-110  */
 #define SCCAV_MODEL_NONE 2         /* rollout only: USE_CBF = False, plant State.update (sce.py:86-101,828) */
+#define SCCAV_MODEL_SADBM 4        /* SADBM_CBF_2DS, state-augmented steer-rate model, state (x, y, theta, v, beta),
+                                      u = (a, d(beta)/dt) inside, (a, delta) in and out, cbf/cbf.py:300-437.  Filter entry
+                                      points only; stateful: sccav_pervehicle.aug carries (beta, last beta_ref) from call to
+                                      call, sccav_params.sadbm_dt is the FIXED step of the class (its default dt = 0.001;
+                                      the reference's wall-clock mode dt = None is measured by the caller and passed here).
+                                      Every CONE slot uses the vehicle's beta (cbf.py:424-426), not its own field 5.   */
 #define SCCAV_MODEL_DUM 3          /* DUM_CBF_2DS, dynamic unicycle, u = (a, omega) in and out, cbf/cbf.py:222-298
                                       (g_c columns [0,0,0,1], [0,0,1,0]; its fc is taken as the 4-vector it lists,
                                       the reference declares it 5x1 and raises).  Filter entry points only.  */
@@ -121,6 +131,7 @@ typedef struct sccav_params {
     double R[4];               /* QP weight, row-major 2x2 SPD, cbf.py:154                     */
     double seeker_k, seeker_vmin;  /* rdo.py:193                                               */
     double uref0, uref1;       /* NOMINAL_CONST reference                                      */
+    double sadbm_dt;           /* SADBM only: the class's dt, cbf.py:323,367,419 (0 = its default 0.001) */
 } sccav_params;
 
 /* Optional per-vehicle overrides (Monte-Carlo sweeps); any pointer may be NULL.  dev pointers. */
@@ -132,6 +143,8 @@ typedef struct sccav_pervehicle {
                                   are empty.  The batched form of a per-vehicle ObstacleList2D whose length
                                   varies (cbf/obstacles.py:798-858).  count[n] = 0: u = u_ref, the guard
                                   callers put around solve_cbf (carla_ml.py:935-936)           */
+    void* aug;                 /* [2][N]  SADBM only, read AND written: beta (the augmented state, cbf.py:336,419)
+                                  and the converted reference of the previous call (beta_ref_last, cbf.py:335,369) */
 } sccav_pervehicle;
 
 /* Outputs of a rollout; any pointer except `state` may be NULL.  dev pointers.                */

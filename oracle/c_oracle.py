@@ -23,12 +23,13 @@ class Params(C.Structure):
         ("max_steer", C.c_double), ("dt", C.c_double), ("k_stanley", C.c_double), ("ks_stanley", C.c_double),
         ("Kp", C.c_double), ("target_speed", C.c_double), ("t_max", C.c_double),
         ("R", C.c_double * 4), ("seeker_k", C.c_double), ("seeker_vmin", C.c_double),
-        ("uref0", C.c_double), ("uref1", C.c_double),
+        ("uref0", C.c_double), ("uref1", C.c_double), ("sadbm_dt", C.c_double),
     ]
 
 
 class PerVehicle(C.Structure):
-    _fields_ = [("alpha", C.c_void_p), ("R", C.c_void_p), ("target_speed", C.c_void_p), ("count", C.c_void_p)]
+    _fields_ = [("alpha", C.c_void_p), ("R", C.c_void_p), ("target_speed", C.c_void_p), ("count", C.c_void_p),
+                ("aug", C.c_void_p)]
 
 
 class RolloutOut(C.Structure):

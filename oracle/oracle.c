@@ -152,7 +152,7 @@ static double lane_closest_x(const double* c, double px, double py) {
 }
 
 /* PolyLane.update/evaluate/dx/dy -- cbf/obstacles.py:620-636,607-612,681-689 */
-static part_t lane_partials(double x, double y, const double* c, double buffer) {
+static part_t lane_partials(double x, double y, const double* c, double buffer, int sqrt_form) {
     part_t o;
     double cx = lane_closest_x(c, x, y), g, dg, ddg;
     poly3(c, cx, &g, &dg, &ddg);
@@ -162,6 +162,11 @@ static part_t lane_partials(double x, double y, const double* c, double buffer) 
     o.hx = (2 / eta) * ((x - cx) * (eta - 1) - (y - g) * dg);
     o.hy = (2 / eta) * (-(x - cx) * dg + (y - g) * (eta - dg * dg));
     o.hth = o.hv = o.ht = 0.0;
+    if (sqrt_form) {   /* CBF_lane_sqrt -- test_scripts/stanley_controller_ellipse.py:489-492 */
+        o.h = sqrt((cx - x) * (cx - x) + (g - y) * (g - y)) - buffer;
+        o.hx = o.hx / (2 * (o.h + buffer));
+        o.hy = o.hy / (2 * (o.h + buffer));
+    }
     return o;
 }
 
@@ -191,9 +196,10 @@ static part_t slot_partials(int desc, const double* f, int64_t fs, double x, dou
         case SCCAV_SLOT_ELLIPSE_PREP: return ellipse_prep_partials(x, y, f[0], f[fs], f[2 * fs], f[3 * fs], f[4 * fs], f[5 * fs],
                                                                    is_static ? 0.0 : f[6 * fs], is_static ? 0.0 : f[7 * fs]);
         case SCCAV_SLOT_CONE: return cone_partials(x, y, th, v, f[0], f[fs], f[2 * fs], f[3 * fs], f[4 * fs], f[5 * fs]);
-        case SCCAV_SLOT_LANE: {
+        case SCCAV_SLOT_LANE:
+        case SCCAV_SLOT_LANE_SQRT: {
             double c[6] = {f[fs], f[2 * fs], f[3 * fs], f[4 * fs], f[5 * fs], f[6 * fs]};
-            return lane_partials(x, y, c, f[0]);
+            return lane_partials(x, y, c, f[0], type == SCCAV_SLOT_LANE_SQRT);
         }
         case SCCAV_SLOT_RADIAL: return radial_partials(x, y, v, f[0], f[fs], f[2 * fs], f[3 * fs], f[4 * fs], f[5 * fs], f[6 * fs]);
         default: return distance_partials(x, y, f[0], f[fs], f[2 * fs]);

@@ -57,6 +57,7 @@ SLOT_LANE = 2      # f: buffer, c0, c1, c2, c3, c4, c5, -
 SLOT_RADIAL = 3    # f: cx, cy, a, b, kv, vx, vy, -
 SLOT_DISTANCE = 4  # f: cx, cy, Ds, -, -, -, -, -
 SLOT_ELLIPSE_PREP = 5  # f: cx, cy, m00, m01, m10, m11, wx, wy   (prepare_ellipse below)
+SLOT_LANE_SQRT = 6  # f: as LANE; h = sqrt(d^2) - buffer (CBF_lane_sqrt, stanley_controller_ellipse.py:465-512)
 SLOT_TYPE_MASK = 0x3F
 SLOT_STATIC = 0x40  # flag: velocity fields are not read, h_t = 0
 FLAG_PREPARED_ROWS = 1  # sccav_params.flags (GPU rollout only; the oracle's arithmetic is always canonical)
@@ -66,6 +67,7 @@ MODEL_DBM = 0      # DBM_CBF_2DS  (cbf/cbf.py:112-220)
 MODEL_KBM = 1      # KBM_VC_CBF2D (cbf/cbf.py:33-110)
 MODEL_NONE = 2     # rollout only: USE_CBF = False -> State.update (stanley_controller_ellipse.py:828)
 MODEL_DUM = 3      # DUM_CBF_2DS  (cbf/cbf.py:222-298), filter step only
+MODEL_SADBM = 4    # SADBM_CBF_2DS (cbf/cbf.py:300-437) with a fixed dt, filter step only (stateful: beta, last beta_ref)
 
 STATUS_INACTIVE = 0    # u == u_ref (no row active)
 STATUS_ACTIVE = 1      # optimum with 1 or 2 active rows
@@ -253,6 +255,20 @@ def lane_partials(x, y, c, buffer):
     return h, h_x, h_y, 0.0, 0.0, 0.0
 
 
+def lane_sqrt_partials(x, y, c, buffer):
+    """CBF_lane_sqrt / CBF_lane_cf_sqrt -- test_scripts/stanley_controller_ellipse.py:489-492,573-576:
+    h = sqrt(d^2) - buffer and the squared-distance gradient divided by 2 (h + buffer)."""
+    cx = lane_closest_x(c, x, y)
+    g, dg, ddg = _poly3(c, cx)
+    eta = 1 + dg * ddg + dg ** 2 - y * ddg
+    if abs(eta) < ZERO_TOL:
+        eta = ZERO_TOL
+    h = math.sqrt((cx - x) ** 2 + (g - y) ** 2) - buffer
+    h_x = ((2 / eta) * ((x - cx) * (eta - 1) - (y - g) * dg)) / (2 * (h + buffer))
+    h_y = ((2 / eta) * (-(x - cx) * dg + (y - g) * (eta - dg ** 2))) / (2 * (h + buffer))
+    return h, h_x, h_y, 0.0, 0.0, 0.0
+
+
 def prepare_ellipse(f):
     """Ingest-time half of Ellipse2D (include/sccav_cbf.h, ELLIPSE_PREP): canonical fields
     (cx, cy, a, b, theta, vx, vy, -) -> (cx, cy, cos/a, sin/a, -sin/b, cos/b, vx/a^2, vy/b^2)."""
@@ -290,6 +306,8 @@ def slot_partials(slot_desc, f, s):
         return cone_partials(x, y, th, v, f[0], f[1], f[2], f[3], f[4], f[5])
     if slot_type == SLOT_LANE:
         return lane_partials(x, y, [f[1], f[2], f[3], f[4], f[5], f[6]], f[0])
+    if slot_type == SLOT_LANE_SQRT:
+        return lane_sqrt_partials(x, y, [f[1], f[2], f[3], f[4], f[5], f[6]], f[0])
     if slot_type == SLOT_RADIAL:
         return radial_partials(x, y, v, f[0], f[1], f[2], f[3], f[4], f[5], f[6])
     if slot_type == SLOT_DISTANCE:
@@ -565,6 +583,41 @@ def barrier_rows(model, s, slot_types, fields, alpha, lr):
             r = kbm_row(part, s[2], alpha)
         A0.append(r[0]); A1.append(r[1]); b.append(r[2]); hs.append(part[0])
     return A0, A1, b, hs
+
+
+def sadbm_row(p, th, v, beta, alpha, lr):
+    """SADBM_CBF_2DS gc/fc + F -- cbf/cbf.py:337-346,386-397: state (x, y, theta, v, beta), controls
+    (a, d(beta)/dt).  Lg h = [h_v, h_beta]; h_beta = h_theta for the collision cone
+    (cbf/obstacles.py:460-466), 0 for every other obstacle (obstacles.py:124-125) -- only the cone has
+    h_theta != 0, so h_theta serves as h_beta."""
+    h, h_x, h_y, h_th, h_v, h_t = p
+    fc0 = v * float(np.cos(th + beta))
+    fc1 = v * float(np.sin(th + beta))
+    fc2 = v * float(np.sin(beta)) / lr
+    Lf = (h_x * fc0 + h_y * fc1) + h_th * fc2
+    return h_v, h_th, -((Lf + alpha * h) + h_t)
+
+
+def sadbm_filter_step(s, u_ref, beta, beta_ref_last, dt, slot_types, fields, alpha, lr, lf, R):
+    """One ``SADBM_CBF_2DS.solve_cbf`` call with a FIXED dt (cbf/cbf.py:348-437; the reference's default
+    ``dt = 0.001``; its wall-clock mode is not deterministic).  ``beta`` = the augmented state before the
+    call -- also what every CONE slot uses as its beta (cbf.py:424-426 pushes it into the cones after each
+    solve, so the rows of a call see the value left by the previous one); ``beta_ref_last`` = the converted
+    reference of the previous call.  Returns (a, delta, beta_new, beta_ref, mask, status, beta_ref_dot, rows)."""
+    beta_ref = delta_to_beta(u_ref[1], lr, lf)                       # cbf.py:359
+    beta_ref_dot = (beta_ref - beta_ref_last) / dt                    # cbf.py:367
+    A0, A1, b = [], [], []
+    for m, st in enumerate(slot_types):
+        f = list(fields[m])
+        if (int(st) & SLOT_TYPE_MASK) == SLOT_CONE:
+            f[5] = beta
+        part = slot_partials(st, f, s)
+        r = sadbm_row(part, s[2], s[3], beta, alpha, lr)
+        A0.append(r[0]); A1.append(r[1]); b.append(r[2])
+    u0, u1, mask, status = qp2_exact(A0, A1, b, u_ref[0], beta_ref_dot, R)
+    beta_new = beta + u1 * dt                                         # cbf.py:419
+    delta = beta_to_delta(beta_new, lr, lf)                           # cbf.py:429
+    return u0, delta, beta_new, beta_ref, mask, status, beta_ref_dot, (A0, A1, b)
 
 
 def filter_step(model, s, u_ref, slot_types, fields, alpha, lr, lf, L, R, kbm_driver_delta=0):

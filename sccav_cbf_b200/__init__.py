@@ -8,7 +8,7 @@ of the reference.  ``ops`` holds the tensor-level operators, ``rollout.ClosedLoo
 persistent closed-loop kernel front end.  There is no CPU compute path: importing works anywhere
 (so host logic can be tested), every operator raises without the CUDA library and a GPU.
 """
-from .cbf import DBM_CBF_2DS, DUM_CBF_2DS, KBM_VC_CBF2D
+from .cbf import DBM_CBF_2DS, DUM_CBF_2DS, KBM_VC_CBF2D, SADBM_CBF_2DS
 from .controllers import PID1, LateralStanley
 from .euclid import Point2, Point3, Vector2, Vector3
 from .geometry import Rotation, Transform
@@ -17,7 +17,7 @@ from .obstacles import (BatchedObstacleList2D, BoundingBox, CollisionCone2D, Ell
 from .utils import ZERO_TOL, Timer, TimerError, normalize_angle, saturation, sigmoid, vec_norm
 
 __all__ = [
-    "DBM_CBF_2DS", "DUM_CBF_2DS", "KBM_VC_CBF2D", "LateralStanley", "PID1", "Vector2", "Point2", "Vector3", "Point3", "Rotation",
+    "DBM_CBF_2DS", "DUM_CBF_2DS", "KBM_VC_CBF2D", "SADBM_CBF_2DS", "LateralStanley", "PID1", "Vector2", "Point2", "Vector3", "Point3", "Rotation",
     "Transform", "BatchedObstacleList2D", "BoundingBox", "CollisionCone2D", "Ellipse2D", "Obstacle2DBase", "Obstacle2DTypes", "ObstacleList2D",
     "PolyLane", "ZERO_TOL", "Timer", "TimerError", "normalize_angle", "saturation", "sigmoid", "vec_norm",
 ]

@@ -16,7 +16,7 @@ NFIELD = 8
 MAX_ROWS = 32
 TRAJ_FIELDS = 7
 
-SLOT_ELLIPSE, SLOT_CONE, SLOT_LANE, SLOT_RADIAL, SLOT_DISTANCE, SLOT_ELLIPSE_PREP = 0, 1, 2, 3, 4, 5
+SLOT_ELLIPSE, SLOT_CONE, SLOT_LANE, SLOT_RADIAL, SLOT_DISTANCE, SLOT_ELLIPSE_PREP, SLOT_LANE_SQRT = 0, 1, 2, 3, 4, 5, 6
 SLOT_TYPE_MASK = 0x3F
 SLOT_STATIC = 0x40
 SLOT_SHARED = 0x80
@@ -24,7 +24,7 @@ FLAG_PREPARED_ROWS = 1
 BOX_FIELDS = 6
 INGEST_UPDATE, INGEST_REBUILD = 0, 1
 ACT_RESET_BRAKE = 1
-MODEL_DBM, MODEL_KBM, MODEL_NONE, MODEL_DUM = 0, 1, 2, 3
+MODEL_DBM, MODEL_KBM, MODEL_NONE, MODEL_DUM, MODEL_SADBM = 0, 1, 2, 3, 4
 NOMINAL_STANLEY, NOMINAL_CONST = 0, 1
 STATUS_INACTIVE, STATUS_ACTIVE, STATUS_INFEASIBLE = 0, 1, 2
 OK, EINVAL, ECUDA, ENOMEM = 0, -1, -2, -3
@@ -39,12 +39,13 @@ class Params(C.Structure):
         ("max_steer", C.c_double), ("dt", C.c_double), ("k_stanley", C.c_double), ("ks_stanley", C.c_double),
         ("Kp", C.c_double), ("target_speed", C.c_double), ("t_max", C.c_double),
         ("R", C.c_double * 4), ("seeker_k", C.c_double), ("seeker_vmin", C.c_double),
-        ("uref0", C.c_double), ("uref1", C.c_double),
+        ("uref0", C.c_double), ("uref1", C.c_double), ("sadbm_dt", C.c_double),
     ]
 
 
 class PerVehicle(C.Structure):
-    _fields_ = [("alpha", C.c_void_p), ("R", C.c_void_p), ("target_speed", C.c_void_p), ("count", C.c_void_p)]
+    _fields_ = [("alpha", C.c_void_p), ("R", C.c_void_p), ("target_speed", C.c_void_p), ("count", C.c_void_p),
+                ("aug", C.c_void_p)]
 
 
 class RolloutOut(C.Structure):

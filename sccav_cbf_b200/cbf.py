@@ -12,10 +12,12 @@ matrix) or batches ([4, N] state, [2, N] references in / [2, N] CUDA tensor out)
 ``sccav_cbf_b200._batch``.  There is no CPU fallback.
 
 ``DUM_CBF_2DS`` (cbf/cbf.py:222-298) is provided with the 4-vector ``fc`` its code lists (the reference declares
-it 5 x 1 and raises).  Not provided: ``SADBM_CBF_2DS`` (wall-clock dt + debug prints, cbf/cbf.py:333,357-433).
+it 5 x 1 and raises).  ``SADBM_CBF_2DS`` (cbf/cbf.py:300-437) is provided with its fixed ``dt`` (default 0.001) and,
+for ``dt=None``, the reference's wall-clock step measured on the host; its debug prints are dropped.
 """
 from __future__ import annotations
 
+import time
 from typing import Optional
 
 import numpy as np
@@ -25,6 +27,7 @@ from . import _native as nv
 from . import ops
 from ._batch import as_state, as_vec, batch_size, is_scalar
 from .obstacles import ObstacleList2D
+from .utils import ZERO_TOL
 
 EMPTY_MSG = ("Cannot solve CBF for an empty obstacle list. Update the obstacle list so that it is non-empty in order "
              "to move forward.")
@@ -76,6 +79,10 @@ class _FilterBase:
         self._R = R
 
     # ---- shared solve -------------------------------------------------------------------------------
+    def _aug(self, N, state):
+        """carried per-vehicle state of the model (SADBM only)"""
+        return None
+
     def _params(self, **kw):
         R = self._R if isinstance(self._R, np.ndarray) else np.eye(2)
         return ops.make_params(model=self.MODEL, R=R.reshape(-1).tolist(), **kw)
@@ -104,7 +111,7 @@ class _FilterBase:
         if isinstance(self._R, torch.Tensor):
             Rv = self._R.to(device=state.device, dtype=state.dtype).contiguous()
         u, mask, status, hmin = ops.filter_step(params, slot_desc, state, obst, ur, alpha=alpha, R=Rv,
-                                                count=getattr(self.obstacle_list2d, "count", None))
+                                                count=getattr(self.obstacle_list2d, "count", None), aug=self._aug(N, state))
         scalar = scalar_state and scalar_obs and scalar_u and N == 1
         info = {"status": status, "active_mask": mask, "h_min": hmin, "u_ref": ur}
         self.last_info = info
@@ -202,3 +209,49 @@ class DUM_CBF_2DS(DBM_CBF_2DS):
             raise AttributeError("update_state(s) has not been called")
         state, scalar = as_state(self.s)
         return self._solve(state, scalar, u_ref, self._params(), return_solver)
+
+
+class SADBM_CBF_2DS(DBM_CBF_2DS):
+    """State-augmented, steer-rate controlled dynamic bicycle model (cbf/cbf.py:300-437): beta joins the state,
+    its time derivative is the second control, so the small-angle approximation of DBM_CBF_2DS is gone and beta
+    stays continuous.  ``solve_cbf([a_ref, delta_ref])`` converts delta_ref to beta_ref, differentiates it
+    against the previous call (``dt``), solves for (a, d(beta)/dt), integrates beta and returns [a, delta].
+    The object is stateful exactly like the reference's: ``_beta`` and ``beta_ref_last`` ([N] tensors here)
+    carry over between calls; every CollisionCone2D of the list sees the vehicle's beta (cbf.py:424-426).
+
+    ``dt`` is the class's fixed step (default 0.001, cbf.py:323).  ``dt=None`` selects the reference's
+    wall-clock mode (cbf.py:326-328,363-365): the time since the previous call, floored at ZERO_TOL, measured on
+    the host and handed to the kernel -- by nature not reproducible.  The reference's prints are dropped."""
+    MODEL = nv.MODEL_SADBM
+
+    def __init__(self, alpha=1.0, dt=0.001):
+        super().__init__(alpha)
+        self._DT_MODE_AUTO = 1 if dt is None else 0
+        self._dt = 1e-6 if dt is None else dt
+        self.t_last = time.time()
+        self._beta = None              # [N] tensor after the first solve (0.0 before, cbf.py:335-336)
+        self.beta_ref_last = None
+        self._augbuf = None
+
+    def _aug(self, N, state):
+        if self._augbuf is None or self._augbuf.shape[1] != N or self._augbuf.device != state.device or self._augbuf.dtype != state.dtype:
+            self._augbuf = torch.zeros((2, N), dtype=state.dtype, device=state.device)
+        self._beta, self.beta_ref_last = self._augbuf[0], self._augbuf[1]
+        return self._augbuf
+
+    def solve_cbf(self, u_ref, return_solver=False):
+        if len(self.obstacle_list2d) < 1:
+            raise ValueError(EMPTY_MSG)
+        if self._lr is None or self._lf is None:
+            raise AttributeError("set_model_params(lr, lf) has not been called")
+        if self.s is None:
+            raise AttributeError("update_state(s) has not been called")
+        t_current = time.time()
+        if self._DT_MODE_AUTO:
+            self._dt = max(t_current - self.t_last, ZERO_TOL)                      # cbf.py:363-365
+        state, scalar = as_state(self.s)
+        params = self._params(lr=float(self._lr), lf=float(self._lf), L=float(self._lr) + float(self._lf),
+                              sadbm_dt=float(self._dt))
+        out = self._solve(state, scalar, u_ref, params, return_solver)
+        self.t_last = time.time()                                                  # cbf.py:433
+        return out

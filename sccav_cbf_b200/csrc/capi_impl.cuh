@@ -32,9 +32,9 @@ int check_common(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int
     if (M > 0 && !slot_desc) { set_error("slot_desc is NULL"); return SCCAV_EINVAL; }
     for (int m = 0; m < M; ++m) {
         int t = slot_desc[m] & SCCAV_SLOT_TYPE_MASK;
-        if (t > SCCAV_SLOT_ELLIPSE_PREP) { set_error("slot %d: unknown type %d", m, t); return SCCAV_EINVAL; }
+        if (t > SCCAV_SLOT_LANE_SQRT) { set_error("slot %d: unknown type %d", m, t); return SCCAV_EINVAL; }
     }
-    if (p->model < 0 || p->model > SCCAV_MODEL_DUM) { set_error("unknown model %d", p->model); return SCCAV_EINVAL; }
+    if (p->model < 0 || p->model > SCCAV_MODEL_SADBM) { set_error("unknown model %d", p->model); return SCCAV_EINVAL; }
     double det = p->R[0] * p->R[3] - p->R[1] * p->R[2];
     if (!(p->R[0] > 0.0) || !(det > 0.0)) {
         // set_qp_cost_weight (cbf.py:154-157) expects a symmetric positive definite 2x2
@@ -59,6 +59,7 @@ Params<real> convert(const sccav_params* p) {
     }
     q.seeker_k = (real)p->seeker_k; q.seeker_vmin = (real)p->seeker_vmin;
     q.uref0 = (real)p->uref0; q.uref1 = (real)p->uref1;
+    q.sadbm_dt = (real)(p->sadbm_dt > 0.0 ? p->sadbm_dt : 0.001);              // cbf.py:323: dt = 0.001
     return q;
 }
 
@@ -70,8 +71,9 @@ SlotDesc make_desc(const uint8_t* slot_desc, int M) {
 }
 
 PerVehicle<real> make_pv(const sccav_pervehicle* pv) {
-    PerVehicle<real> q{nullptr, nullptr, nullptr, nullptr};
+    PerVehicle<real> q{nullptr, nullptr, nullptr, nullptr, nullptr};
     if (pv) {
+        q.aug = (real*)pv->aug;
         q.alpha = (const real*)pv->alpha;
         q.R = (const real*)pv->R;
         q.target_speed = (const real*)pv->target_speed;
@@ -145,6 +147,7 @@ int do_barrier_rows(const sccav_params* p, const uint8_t* slot_desc, int32_t M, 
                     const real* obst, const sccav_pervehicle* pv, real* A, real* b, real* h, cudaStream_t st) {
     int rc = check_common(p, slot_desc, M, N, false);
     if (rc) return rc;
+    if (p->model == SCCAV_MODEL_SADBM) { set_error("model SADBM: rows depend on the carried beta -- use sccav_filter_step_*"); return SCCAV_EINVAL; }
     if (N == 0) return SCCAV_OK;
     if (!state || !obst || !A || !b) { set_error("NULL array argument"); return SCCAV_EINVAL; }
     RowsArgs<real> a;
@@ -229,6 +232,11 @@ int do_filter_step(const sccav_params* p, const uint8_t* slot_desc, int32_t M, i
     int rc = check_common(p, slot_desc, M, N, false);
     if (rc) return rc;
     if (p->model == SCCAV_MODEL_NONE) { set_error("model NONE has no filter step"); return SCCAV_EINVAL; }
+    const bool sadbm = p->model == SCCAV_MODEL_SADBM;
+    if (sadbm && !(pv && pv->aug) && N > 0) {
+        set_error("model SADBM is stateful: sccav_pervehicle.aug [2][N] (beta, last beta_ref) is required");
+        return SCCAV_EINVAL;
+    }
     if (N == 0) return SCCAV_OK;
     if (!state || !obst || !u_ref || !u) { set_error("NULL array argument"); return SCCAV_EINVAL; }
     FilterArgs<real> a;
@@ -238,7 +246,7 @@ int do_filter_step(const sccav_params* p, const uint8_t* slot_desc, int32_t M, i
     size_t smem;
     const int block = rows_block(M, smem);
     typedef void (*filter_fn)(FilterArgs<real>);
-    const int spec = choose_spec(slot_desc, M);
+    const int spec = sadbm ? SCCAV_SPEC_GENERIC : choose_spec(slot_desc, M);      // SADBM: generic slot loop only
     const int nf = spec == SCCAV_SPEC_ELLIPSE ? 7 : ((slot_desc[0] & SCCAV_SLOT_STATIC) ? 6 : 8);
     const size_t staged = (size_t)nf * M * 256 * sizeof(real);
     if (k12_staged_enabled(spec) && spec != SCCAV_SPEC_GENERIC && nf < 8 &&
@@ -327,6 +335,7 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
     if (T < 0) { set_error("T < 0"); return SCCAV_EINVAL; }
     if (p->record_stride < 0) { set_error("record_stride < 0"); return SCCAV_EINVAL; }
     if (p->model == SCCAV_MODEL_DUM) { set_error("model DUM has no closed loop (the reference has no unicycle plant on this path)"); return SCCAV_EINVAL; }
+    if (p->model == SCCAV_MODEL_SADBM) { set_error("model SADBM has no closed loop here (filter entry points only)"); return SCCAV_EINVAL; }
     if (N == 0) return SCCAV_OK;
     if (!state || !out || !out->state) { set_error("state / out->state is NULL"); return SCCAV_EINVAL; }
     if (M > 0 && !obst) { set_error("obst is NULL"); return SCCAV_EINVAL; }
@@ -524,10 +533,12 @@ int SCCAV_FN(sccav_filter_step_host_)(const sccav_params* p, const uint8_t* slot
     SCCAV_CUDA_CHECK(d_state.upload(state, 4 * n * sizeof(real)));
     SCCAV_CUDA_CHECK(d_obst.upload(obst, (size_t)M * SCCAV_NFIELD * n * sizeof(real)));
     SCCAV_CUDA_CHECK(d_uref.upload(u_ref, 2 * n * sizeof(real)));
-    sccav_pervehicle dpv = {nullptr, nullptr, nullptr, nullptr};
+    sccav_pervehicle dpv = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    DevBuf d_aug(st);
     if (pv && pv->alpha) { SCCAV_CUDA_CHECK(d_alpha.upload(pv->alpha, n * sizeof(real))); dpv.alpha = d_alpha.p; }
     if (pv && pv->R) { SCCAV_CUDA_CHECK(d_R.upload(pv->R, 4 * n * sizeof(real))); dpv.R = d_R.p; }
     if (pv && pv->count) { SCCAV_CUDA_CHECK(d_cnt.upload(pv->count, n * sizeof(int32_t))); dpv.count = (const int32_t*)d_cnt.p; }
+    if (pv && pv->aug) { SCCAV_CUDA_CHECK(d_aug.upload(pv->aug, 2 * n * sizeof(real))); dpv.aug = d_aug.p; }
     SCCAV_CUDA_CHECK(d_u.alloc(2 * n * sizeof(real)));
     if (active_out) SCCAV_CUDA_CHECK(d_mask.alloc(n * sizeof(uint32_t)));
     if (status_out) SCCAV_CUDA_CHECK(d_status.alloc(n));
@@ -539,6 +550,7 @@ int SCCAV_FN(sccav_filter_step_host_)(const sccav_params* p, const uint8_t* slot
     if (active_out) SCCAV_CUDA_CHECK(cudaMemcpyAsync(active_out, d_mask.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     if (status_out) SCCAV_CUDA_CHECK(cudaMemcpyAsync(status_out, d_status.p, n, cudaMemcpyDeviceToHost, st));
     if (h_min_out) SCCAV_CUDA_CHECK(cudaMemcpyAsync(h_min_out, d_hmin.p, n * sizeof(real), cudaMemcpyDeviceToHost, st));
+    if (pv && pv->aug) SCCAV_CUDA_CHECK(cudaMemcpyAsync(pv->aug, d_aug.p, 2 * n * sizeof(real), cudaMemcpyDeviceToHost, st));
     SCCAV_CUDA_CHECK(cudaStreamSynchronize(st));
     return SCCAV_OK;
 }
@@ -571,7 +583,7 @@ int SCCAV_FN(sccav_rollout_host_)(const sccav_params* p, const uint8_t* slot_des
         SCCAV_CUDA_CHECK(d_cy.upload(course_y, (size_t)P * sizeof(real)));
         SCCAV_CUDA_CHECK(d_cyaw.upload(course_yaw, (size_t)P * sizeof(real)));
     }
-    sccav_pervehicle dpv = {nullptr, nullptr, nullptr, nullptr};
+    sccav_pervehicle dpv = {nullptr, nullptr, nullptr, nullptr, nullptr};
     if (pv && pv->alpha) { SCCAV_CUDA_CHECK(d_alpha.upload(pv->alpha, n * sizeof(real))); dpv.alpha = d_alpha.p; }
     if (pv && pv->R) { SCCAV_CUDA_CHECK(d_R.upload(pv->R, 4 * n * sizeof(real))); dpv.R = d_R.p; }
     if (pv && pv->count) { SCCAV_CUDA_CHECK(d_cnt.upload(pv->count, n * sizeof(int32_t))); dpv.count = (const int32_t*)d_cnt.p; }

@@ -20,6 +20,7 @@ template <typename T> struct PerVehicle {
     const T* R;
     const T* target_speed;
     const int32_t* count;    // obstacles of vehicle n = its first count[n] slots (sccav_pervehicle.count)
+    T* aug;                  // [2][N] SADBM: beta, beta_ref_last (read and written)
 };
 
 template <typename T>
@@ -526,6 +527,7 @@ __global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_kernel(const 
         T ur0 = T(0), ur1 = T(0), hmin = R::inf();
         T alpha = T(0), R00 = T(1), R01 = T(0), R10 = T(0), R11 = T(1);
         int Mv = 0;
+        T augv[2] = {T(0), T(0)};
         RowPhase<T> ph;
         ph.r0 = T(0); ph.r1 = T(0); ph.worst = -R::inf(); ph.nz.nz0 = 0u; ph.nz.nz1 = 0u; ph.feas = true;
         ph.scan.reset();
@@ -540,8 +542,9 @@ __global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_kernel(const 
             if (Mv > 0) {
                 T sth, cth;
                 R::sincos_(th, &sth, &cth);
+                if (a.P.model == SCCAV_MODEL_SADBM) { augv[0] = a.pv.aug[n]; augv[1] = a.pv.aug[N + n]; }
                 ph = filter_rows<T, SPEC, COOP>(a.P, a.sd, Mv, N, n, a.obst, x, y, th, v, sth, cth, alpha, ur0, ur1, rows, stride,
-                                                hmin, nullptr, 0xffffffffu, &Ri);
+                                                hmin, nullptr, 0xffffffffu, &Ri, augv);
             }
         }
         T q0 = ph.r0, q1 = ph.r1;
@@ -558,6 +561,14 @@ __global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_kernel(const 
         }
         if (valid) {
             T u0 = ur0, u1 = ur1;                                           // empty obstacle list: u = u_ref
+            if (Mv > 0 && a.P.model == SCCAV_MODEL_SADBM) {
+                // cbf.py:419-429: integrate the solved rate, hand the new beta and this call's beta_ref to the next call
+                const T beta_new = augv[0] + q1 * a.P.sadbm_dt;
+                u0 = q0;
+                u1 = R::atan2_((a.P.lf + a.P.lr) * R::tan_(beta_new), a.P.lr);
+                a.pv.aug[n] = beta_new;
+                a.pv.aug[N + n] = R::atan2_(a.P.lr * R::tan_(ur1), a.P.lf + a.P.lr);
+            } else
             if (Mv > 0) { u0 = q0; u1 = filter_convert<T>(a.P, q0, q1, ph.r0); }
             a.u[n] = u0;
             a.u[N + n] = u1;

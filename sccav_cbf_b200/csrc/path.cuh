@@ -76,6 +76,7 @@ template <typename T> struct Params {
     T R[4];
     T Ri[4];             // inverse of R, formed on the host with the operations of RInv below
     T seeker_k, seeker_vmin, uref0, uref1;
+    T sadbm_dt;          // SADBM_CBF_2DS: the class's fixed dt
 };
 
 struct SlotDesc {
@@ -304,7 +305,7 @@ template <typename T> __device__ T lane_closest_x(const T (&c)[6], T px, T py) {
 
 // PolyLane.update/evaluate/dx/dy -- cbf/obstacles.py:620-636,607-612,681-689
 template <typename T>
-__device__ __forceinline__ Partials<T> lane_partials(T x, T y, const T (&c)[6], T buffer) {
+__device__ __forceinline__ Partials<T> lane_partials(T x, T y, const T (&c)[6], T buffer, bool sqrt_form = false) {
     typedef Real<T> R;
     Partials<T> o;
     T cx = lane_closest_x(c, x, y);
@@ -318,6 +319,13 @@ __device__ __forceinline__ Partials<T> lane_partials(T x, T y, const T (&c)[6], 
     o.hx = te * ((x - cx) * (eta - T(1)) - (y - g) * dg);
     o.hy = te * ((-(x - cx)) * dg + (y - g) * (eta - dg * dg));
     o.hth = o.hv = o.ht = T(0);
+    if (sqrt_form) {
+        // CBF_lane_sqrt -- stanley_controller_ellipse.py:489-492: distance instead of squared distance
+        o.h = R::sqrt_(ex * ex + ey * ey) - buffer;
+        const T den = T(2) * (o.h + buffer);
+        o.hx = o.hx / den;
+        o.hy = o.hy / den;
+    }
     return o;
 }
 
@@ -325,7 +333,8 @@ __device__ __forceinline__ Partials<T> lane_partials(T x, T y, const T (&c)[6], 
 template <typename T>
 __device__ __forceinline__ Partials<T> slot_partials(int desc, const T* __restrict__ f, int64_t fs,
                                                      T x, T y, T th, T v, T sth, T cth,
-                                                     const T* pre = nullptr, int64_t ps = 0) {
+                                                     const T* pre = nullptr, int64_t ps = 0,
+                                                     const T* ego_beta = nullptr) {
     const int type = desc & SCCAV_SLOT_TYPE_MASK;
     const bool is_static = (desc & SCCAV_SLOT_STATIC) != 0;
     // f points at field 0 of this slot for this vehicle; fs = stride between fields (N)
@@ -342,13 +351,16 @@ __device__ __forceinline__ Partials<T> slot_partials(int desc, const T* __restri
             return ellipse_partials<T>(x, y, cx, cy, a, b, t, vx, vy);
         }
         case SCCAV_SLOT_CONE: {
-            T cx = f[0], cy = f[fs], to = f[2 * fs], vo = f[3 * fs], a = f[4 * fs], be = f[5 * fs];
+            T cx = f[0], cy = f[fs], to = f[2 * fs], vo = f[3 * fs], a = f[4 * fs];
+            // SADBM pushes the vehicle's beta into every cone after each solve (cbf.py:424-426)
+            T be = ego_beta ? *ego_beta : f[5 * fs];
             return cone_partials<T>(x, y, th, v, sth, cth, cx, cy, to, vo, a, be);
         }
-        case SCCAV_SLOT_LANE: {
+        case SCCAV_SLOT_LANE:
+        case SCCAV_SLOT_LANE_SQRT: {
             T buf = f[0];
             T c[6] = {f[fs], f[2 * fs], f[3 * fs], f[4 * fs], f[5 * fs], f[6 * fs]};
-            return lane_partials<T>(x, y, c, buf);
+            return lane_partials<T>(x, y, c, buf, type == SCCAV_SLOT_LANE_SQRT);
         }
         case SCCAV_SLOT_RADIAL: {
             T cx = f[0], cy = f[fs], a = f[2 * fs], b = f[3 * fs], kv = f[4 * fs], vx = f[5 * fs], vy = f[6 * fs];
@@ -397,6 +409,18 @@ __device__ __forceinline__ void dum_row(const Partials<T>& p, T sth, T cth, T v,
     b = -((Lf + alpha * p.h) + p.ht);
 }
 
+// SADBM_CBF_2DS gc/fc + F -- cbf/cbf.py:337-346,386-397.  State (x, y, theta, v, beta), controls (a, d(beta)/dt):
+// Lg h = [h_v, h_beta], Lf h = h_x v cos(theta+beta) + h_y v sin(theta+beta) + h_theta v sin(beta) / lr.
+// h_beta = h_theta for the cone (obstacles.py:460-466) and 0 for every other obstacle (obstacles.py:124-125),
+// which have h_theta = 0 too -- so h_theta serves.  The caller passes sin / cos of theta+beta and v sin(beta) / lr.
+template <typename T>
+__device__ __forceinline__ void sadbm_row(const Partials<T>& p, T sthb, T cthb, T v, T alpha, T vsb_lr, T& A0, T& A1, T& b) {
+    A0 = p.hv;
+    A1 = p.hth;
+    T Lf = (p.hx * (v * cthb) + p.hy * (v * sthb)) + p.hth * vsb_lr;
+    b = -((Lf + alpha * p.h) + p.ht);
+}
+
 // row of the configured model
 // (MODEL >= 0: the model is known at compile time -- no dispatch inside the slot loop)
 template <typename T, int MODEL = -1>
@@ -404,6 +428,7 @@ __device__ __forceinline__ void model_row(const Params<T>& P, const Partials<T>&
     const int model = MODEL >= 0 ? MODEL : P.model;
     if (model == SCCAV_MODEL_KBM) kbm_row<T>(p, sth, cth, alpha, A0, A1, b);
     else if (model == SCCAV_MODEL_DUM) dum_row<T>(p, sth, cth, v, alpha, A0, A1, b);
+    else if (model == SCCAV_MODEL_SADBM) sadbm_row<T>(p, sth, cth, v, alpha, vlr, A0, A1, b);
     else dbm_row<T>(p, sth, cth, v, alpha, vlr, A0, A1, b);
 }
 
@@ -777,11 +802,23 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
                                                    const T* __restrict__ obst, T x, T y, T th, T v, T sth, T cth,
                                                    T alpha, T uref0, T uref1, T* rows, int stride, T& hmin,
                                                    const T* __restrict__ pre = nullptr, uint32_t moving = 0xffffffffu,
-                                                   const RInv<T>* Ri = nullptr) {
+                                                   const RInv<T>* Ri = nullptr, const T* aug = nullptr) {
     typedef Real<T> R;
     hmin = R::inf();
-    const T vlr = v / P.lr;                                                             // cbf.py:160 (g_c[2][1])
+    T vlr = v / P.lr;                                                                   // cbf.py:160 (g_c[2][1])
     T r0 = uref0, r1;
+    T ego_beta = T(0);
+    const bool sadbm = P.model == SCCAV_MODEL_SADBM;
+    if (sadbm) {
+        // aug = (beta, beta_ref_last) of this vehicle.  cbf.py:359-372: u_ref[1] -> d(beta_ref)/dt; the rows use
+        // sin / cos(theta + beta) and v sin(beta) / lr where the other models use sin / cos(theta) and v / lr
+        ego_beta = aug[0];
+        const T beta_ref = R::atan2_(P.lr * R::tan_(uref1), P.lf + P.lr);
+        r1 = (beta_ref - aug[1]) / P.sadbm_dt;
+        T sb, cb;
+        R::sincos_(ego_beta, &sb, &cb);
+        vlr = (v * sb) / P.lr;
+    } else
     if (P.model == SCCAV_MODEL_KBM) r1 = (uref0 * R::tan_(uref1)) / P.L;                // cbf.py:75
     else if (P.model == SCCAV_MODEL_DUM) r1 = uref1;                                     // cbf.py:253: u_ref as given
     else r1 = R::atan2_(P.lr * R::tan_(uref1), P.lf + P.lr);                             // cbf.py:175
@@ -833,13 +870,15 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
             put_row<T, SCAN>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
         }
     } else {
+        T rsth = sth, rcth = cth;                              // trig of the row assembly (theta + beta under SADBM)
+        if (sadbm) R::sincos_(th + ego_beta, &rsth, &rcth);
         for (int m = 0; m < M; ++m) {
             const int desc = sd.d[m];
             const int64_t nn = (desc & SCCAV_SLOT_SHARED) ? 0 : n;
             const T* f = obst + (int64_t)m * SCCAV_NFIELD * N + nn;
             const T* pr = pre ? pre + (int64_t)m * SCCAV_NPRE * N + n : nullptr;
-            Partials<T> p = slot_partials<T>(desc, f, N, x, y, th, v, sth, cth, pr, N);
-            put_row<T, SCAN>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
+            Partials<T> p = slot_partials<T>(desc, f, N, x, y, th, v, sth, cth, pr, N, sadbm ? &ego_beta : nullptr);
+            put_row<T, SCAN>(P, p, rsth, rcth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
         }
     }
     RowPhase<T> ph;

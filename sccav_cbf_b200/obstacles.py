@@ -369,6 +369,10 @@ class PolyLane(Obstacle2DBase):
             self.id = kwargs["id"]
         self.beta = kwargs.get("beta", 0.0)
         self.type = Obstacle2DTypes.POLY_LANE
+        # distance_form=True: h = sqrt(d^2) - buffer, the CBF_lane_sqrt / CBF_lane_cf_sqrt barrier of
+        # test_scripts/stanley_controller_ellipse.py:465-512,546-579 (the class itself only has the squared form)
+        if kwargs.get("distance_form", False):
+            self.slot_type = nv.SLOT_LANE_SQRT
         self.update_coeffs(coefficients)
         self.s = s
         self.s_obs = s_obs

@@ -64,9 +64,14 @@ def _stream(device: torch.device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def _pv(N, dtype, device, alpha=None, R=None, target_speed=None, count=None):
+def _pv(N, dtype, device, alpha=None, R=None, target_speed=None, count=None, aug=None):
     pv = nv.PerVehicle()
     keep = []
+    if aug is not None:
+        aug = _chk(aug, (2, N), dtype, device, "aug")
+        if not aug.is_contiguous():
+            raise ValueError("aug must be contiguous (it is updated in place)")
+        keep.append(aug); pv.aug = aug.data_ptr()
     if count is not None:
         count = _chk(count, (N,), torch.int32, device, "count"); keep.append(count); pv.count = count.data_ptr()
     if alpha is not None:
@@ -172,9 +177,10 @@ def qp2_solve(params: Params, A: torch.Tensor, b: torch.Tensor, r: torch.Tensor,
 
 
 def filter_step(params: Params, slot_desc, state: torch.Tensor, obst: torch.Tensor, u_ref: torch.Tensor,
-                alpha=None, R=None, count=None):
+                alpha=None, R=None, count=None, aug=None):
     """K1+K2 fused: one batched ``solve_cbf(u_ref)`` (cbf/cbf.py:166-220 / :67-110).
     CUDA tensors -> device entry point on the current stream; CPU tensors -> host entry point.
+    ``aug`` [2,N] (model SADBM only, cbf/cbf.py:300-437): beta and the last beta_ref, updated IN PLACE.
     Returns u [2,N] = (a|v, delta), active mask int32 [N], status uint8 [N], h_min [N]."""
     L = nv.lib()
     nv.require_cuda()
@@ -184,7 +190,7 @@ def filter_step(params: Params, slot_desc, state: torch.Tensor, obst: torch.Tens
     state = _chk(state, (4, N), dt, dev, "state")
     obst = _chk(obst, (M, nv.NFIELD, N), dt, dev, "obst")
     u_ref = _chk(u_ref, (2, N), dt, dev, "u_ref")
-    pv, keep = _pv(N, dt, dev, alpha=alpha, R=R, count=count)
+    pv, keep = _pv(N, dt, dev, alpha=alpha, R=R, count=count, aug=aug)
     u = torch.empty((2, N), dtype=dt, device=dev)
     mask = torch.empty((N,), dtype=torch.int32, device=dev)
     status = torch.empty((N,), dtype=torch.uint8, device=dev)

@@ -39,7 +39,7 @@ def random_slots(rng, N, slot_types, s, near=True):
             ob[m, 3] = rng.uniform(0, 8, N)
             ob[m, 4] = rng.uniform(1, 4, N) + 1.5
             ob[m, 5] = np.where(rng.uniform(size=N) < 0.7, 0.0, rng.uniform(-0.2, 0.2, N))
-        elif t == o.SLOT_LANE:
+        elif t in (o.SLOT_LANE, o.SLOT_LANE_SQRT):
             ob[m, 0] = 1.5
             c1 = rng.uniform(-0.3, 0.3, N)
             ob[m, 2] = c1

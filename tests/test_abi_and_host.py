@@ -29,7 +29,7 @@ def test_params_struct_layout_matches_header_defaults():
     from oracle import c_oracle as co
     from sccav_cbf_b200 import _native as nv
     from sccav_cbf_b200 import ops
-    assert ctypes.sizeof(nv.Params) == ctypes.sizeof(co.Params) == 8 * 4 + 19 * 8
+    assert ctypes.sizeof(nv.Params) == ctypes.sizeof(co.Params) == 8 * 4 + 20 * 8
     p = nv.default_params()
     q = co.default_params()
     for name, _ in nv.Params._fields_:

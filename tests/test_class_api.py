@@ -7,6 +7,7 @@ same names, argument meaning and error behaviour as cbf/*.py of the reference.
   oracle; scalar calls and batched calls agree bit for bit.
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -390,3 +391,82 @@ def test_reference_driver_loop_with_the_class_api_reproduces_beta_vs_time(golden
         time += dt
     assert len(betas) == 277
     assert np.abs(np.degrees(betas) - np.array(gold["beta_deg"])).max() <= 1e-3
+
+
+@pytest.fixture(scope="module")
+def refvec2(golden_dir):
+    return np.load(os.path.join(golden_dir, "reference_vectors_lane_sadbm.npz"))
+
+
+@gpu
+def test_sadbm_class_sequences_vs_reference_class(refvec2):
+    """SADBM_CBF_2DS used the way the reference's object is (cbf/cbf.py:300-437): 16 sequences of 6 ticks with
+    1-3 collision cones, fixed dt; controls, the carried beta and the active sets against vectors produced by
+    the reference's own class (tests/golden/gen_reference_vectors_lane_sadbm.py)."""
+    from sccav_cbf_b200 import SADBM_CBF_2DS
+    cfg, M, cone = refvec2["sadbm_cfg"], refvec2["sadbm_m"], refvec2["sadbm_cone"]
+    I, out = refvec2["sadbm_in"], refvec2["sadbm_out"]
+    for i in range(cfg.shape[0]):
+        alpha, dt, lr, lf = cfg[i, :4]
+        m = int(M[i])
+        ctl = SADBM_CBF_2DS(alpha=alpha, dt=dt)
+        ctl.set_model_params(lr=lr, lf=lf)
+        ctl.set_qp_cost_weight(cfg[i, 4:8].reshape(2, 2))
+        s0 = I[i, 0, :4]
+        obs = []
+        for j in range(m):
+            c = cone[i, 0, j]
+            ob = CollisionCone2D(c[4] - 1.5, s0, c[:4])                       # default buffer 1.5 (obstacles.py:341)
+            ctl.obstacle_list2d[j] = ob
+            obs.append(ob)
+        for t in range(I.shape[1]):
+            s, ur = I[i, t, :4], I[i, t, 4:6]
+            for j, ob in enumerate(obs):
+                ob.update(s_obs=cone[i, t, j, :4])
+            ctl.update_state(s=s)
+            info, u = ctl.solve_cbf(list(ur), return_solver=True)
+            assert info["active_mask"] == int(out[i, t, 4]) and info["status"] == int(out[i, t, 5]), (i, t)
+            assert abs(float(u[0]) - out[i, t, 0]) <= 1e-9 * (1 + abs(out[i, t, 0]))
+            assert abs(float(u[1]) - out[i, t, 1]) <= 1e-9
+            assert abs(float(ctl._beta[0]) - out[i, t, 2]) <= 1e-10
+    with pytest.raises(ValueError):
+        SADBM_CBF_2DS().solve_cbf([0.0, 0.0])
+
+
+@gpu
+def test_sadbm_batched_ticks_vs_oracle():
+    """model SADBM through the C-ABI on a batch: three consecutive ticks with the carried state (beta, last
+    beta_ref) updated in place, cones + an ellipse + a lane, per-vehicle counts; against oracle.sadbm_filter_step."""
+    from oracle import oracle as o
+    from sccav_cbf_b200 import ops
+    from tests import helpers as H
+    N = 1536
+    slots = [o.SLOT_CONE, o.SLOT_CONE, o.SLOT_ELLIPSE, o.SLOT_CONE, o.SLOT_LANE]
+    rng = np.random.default_rng(99)
+    R = [1.0, 0.2, 0.2, 2.0]
+    dt = 0.02
+    prm = ops.make_params(model=4, R=R, alpha=0.9, sadbm_dt=dt)
+    dev = torch.device("cuda", 0)
+    aug = torch.zeros((2, N), dtype=torch.float64, device=dev)
+    aug_ref = np.zeros((2, N))
+    nact = 0
+    for tick in range(3):
+        s = H.random_states(rng, N)
+        ob = H.random_slots(rng, N, slots, s)
+        ur = H.random_uref(rng, N)
+        u, mask, status, hmin = ops.filter_step(prm, slots, torch.from_numpy(s).to(dev), torch.from_numpy(ob).to(dev),
+                                                torch.from_numpy(ur).to(dev), aug=aug)
+        u_, m_, st_, a_ = u.cpu().numpy(), mask.cpu().numpy().view(np.uint32), status.cpu().numpy(), aug.cpu().numpy()
+        for n in range(N):
+            fields = [list(ob[k, :, n]) for k in range(len(slots))]
+            u0, d, bn, br, mk, st, _, _ = o.sadbm_filter_step(list(s[:, n]), list(ur[:, n]), aug_ref[0, n], aug_ref[1, n], dt, slots,
+                                                              fields, 0.9, 1.45, 1.45, R)
+            assert mk == int(m_[n]) and st == int(st_[n]), (tick, n)
+            assert abs(u0 - u_[0, n]) <= 1e-9 * (1 + abs(u0)) and abs(d - u_[1, n]) <= 1e-9 * (1 + abs(d))
+            assert abs(bn - a_[0, n]) <= 1e-9 * (1 + abs(bn)) and abs(br - a_[1, n]) <= 1e-12
+            aug_ref[0, n], aug_ref[1, n] = bn, br
+            nact += mk != 0
+    assert nact > 100
+    # stateful model: the carried state is mandatory, and there is no closed loop for it
+    with pytest.raises(Exception):
+        ops.filter_step(prm, slots, torch.from_numpy(s).to(dev), torch.from_numpy(ob).to(dev), torch.from_numpy(ur).to(dev))

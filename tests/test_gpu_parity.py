@@ -44,6 +44,7 @@ SLOTSETS = {
     "radial16": [o.SLOT_RADIAL] * 16,
     "mixed": [o.SLOT_ELLIPSE, o.SLOT_CONE, o.SLOT_LANE, o.SLOT_RADIAL, o.SLOT_DISTANCE, o.SLOT_ELLIPSE],
     "single": [o.SLOT_ELLIPSE],
+    "lane_sqrt": [o.SLOT_LANE_SQRT, o.SLOT_LANE_SQRT, o.SLOT_LANE, o.SLOT_ELLIPSE],
     "max32": [o.SLOT_ELLIPSE, o.SLOT_CONE] * 16,
 }
 

@@ -11,7 +11,7 @@ from tests import helpers as H
 
 def test_c_oracle_filter_step_equals_python_oracle():
     rng = np.random.default_rng(42)
-    slots = [o.SLOT_ELLIPSE, o.SLOT_CONE, o.SLOT_LANE, o.SLOT_RADIAL, o.SLOT_DISTANCE, o.SLOT_CONE]
+    slots = [o.SLOT_ELLIPSE, o.SLOT_CONE, o.SLOT_LANE, o.SLOT_RADIAL, o.SLOT_DISTANCE, o.SLOT_CONE, o.SLOT_LANE_SQRT]
     N = 300
     s = H.random_states(rng, N); ob = H.random_slots(rng, N, slots, s); ur = H.random_uref(rng, N)
     R = (1.0, 0.3, 0.3, 2.5)

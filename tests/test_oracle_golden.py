@@ -164,3 +164,55 @@ def test_radial_rows_vs_reference_function(refvec):
         u0, d, mask, status, _, _ = o.filter_step(o.MODEL_DBM, s, uref, [o.SLOT_RADIAL], f, gamma, 1.45, 1.45, 2.9, (1.0, 0.0, 0.0, 1.0))
         assert mask == int(ref[5]) and status == int(ref[6])
         assert abs(u0 - ref[0]) <= 1e-12 * (1 + abs(ref[0])) and abs(d - ref[1]) <= 1e-12 * (1 + abs(ref[1]))
+
+
+@pytest.fixture(scope="module")
+def refvec2(golden_dir):
+    """tests/golden/reference_vectors_lane_sadbm.npz -- produced by gen_reference_vectors_lane_sadbm.py from
+    the reference's CBF_lane / CBF_lane_sqrt driver functions and its SADBM_CBF_2DS class."""
+    return np.load(os.path.join(golden_dir, "reference_vectors_lane_sadbm.npz"))
+
+
+def test_lane_squared_and_distance_rows_vs_reference_functions(refvec2):
+    """CBF_lane / CBF_lane_sqrt (stanley_controller_ellipse.py:416-512): row and solution of the LANE and
+    LANE_SQRT slots.  The closest abscissa comes from scipy's Newton-CG in the reference (xtol 1e-8), hence
+    1e-7; the closed-form variants CBF_lane_cf* (different, mis-parenthesised Lg) are not a target."""
+    I, rows, U = refvec2["lanev_in"], refvec2["lanev_rows"], refvec2["lanev_u"]
+    nact = 0
+    for i in range(I.shape[0]):
+        s = list(I[i, :4]); co = list(I[i, 4:8]) + [0.0, 0.0]; ud = I[i, 8:10]; buf, al = I[i, 10], I[i, 11]
+        for j, t in enumerate((o.SLOT_LANE, o.SLOT_LANE_SQRT)):
+            f = [[buf] + co + [0.0]]
+            A0, A1, b, _ = o.barrier_rows(o.MODEL_DBM, s, [t], f, al, 1.45)
+            assert A0[0] == rows[i, j, 0] == 0.0
+            assert abs(A1[0] - rows[i, j, 1]) <= 1e-7 * (1 + abs(rows[i, j, 1]))
+            assert abs(b[0] - rows[i, j, 2]) <= 1e-7 * (1 + abs(rows[i, j, 2]))
+            u0, u1, mask, status = o.qp2_exact(A0, A1, b, ud[0], ud[1], (1.0, 0.0, 0.0, 1.0))
+            assert abs(u0 - U[i, j, 0]) <= 1e-8 and abs(u1 - U[i, j, 1]) <= 1e-7 * (1 + abs(U[i, j, 1]))
+            nact += mask != 0
+    assert nact > 20
+
+
+def test_sadbm_class_sequences_vs_reference(refvec2):
+    """SADBM_CBF_2DS.solve_cbf (cbf/cbf.py:348-437) with a fixed dt over 16 sequences of 6 ticks: rows as the
+    class assembles them, converted reference, solution, carried beta / beta_ref_last."""
+    cfg, M, cone = refvec2["sadbm_cfg"], refvec2["sadbm_m"], refvec2["sadbm_cone"]
+    I, rows, out = refvec2["sadbm_in"], refvec2["sadbm_rows"], refvec2["sadbm_out"]
+    nact = 0
+    for i in range(cfg.shape[0]):
+        alpha, dt, lr, lf = cfg[i, :4]; R = tuple(cfg[i, 4:8]); m = int(M[i])
+        beta, brl = I[i, 0, 6], I[i, 0, 7]
+        for t in range(I.shape[1]):
+            s = list(I[i, t, :4]); ur = list(I[i, t, 4:6])
+            assert abs(beta - I[i, t, 6]) <= 1e-13 and abs(brl - I[i, t, 7]) <= 1e-13      # carried state
+            fields = [[*cone[i, t, j], 0.0, 0.0, 0.0] for j in range(m)]
+            u0, d, bn, br, mask, st, brd, (A0, A1, b) = o.sadbm_filter_step(s, ur, beta, brl, dt, [o.SLOT_CONE] * m, fields, alpha, lr, lf, R)
+            for j in range(m):
+                for got, ref in ((A0[j], rows[i, t, j, 0]), (A1[j], rows[i, t, j, 1]), (b[j], rows[i, t, j, 2])):
+                    assert abs(got - ref) <= 1e-13 * (1 + abs(ref))
+            assert mask == int(out[i, t, 4]) and st == int(out[i, t, 5])
+            assert abs(u0 - out[i, t, 0]) <= 1e-12 and abs(d - out[i, t, 1]) <= 1e-12 and abs(bn - out[i, t, 2]) <= 1e-12
+            assert abs(brd - out[i, t, 3]) <= 1e-12 * (1 + abs(out[i, t, 3]))
+            nact += mask != 0
+            beta, brl = bn, br
+    assert nact > 30
