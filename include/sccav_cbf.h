@@ -335,6 +335,25 @@ int sccav_spline_course_f64(int32_t C, int32_t K, const double* wx, const double
 int sccav_spline_course_f32(int32_t C, int32_t K, const float* wx, const float* wy, double ds, int32_t P_max,
                             float* cx, float* cy, float* cyaw, float* ck, int32_t* np_out, void* stream);
 
+/* KL -- weighted polynomial lane fit for C lanes at once, the step before the lane barrier:
+ * PolyLane.fit_polynomial_curve (cbf/obstacles.py:715-773: scipy curve_fit of a polynomial with per-point sigma;
+ * fixed points enter as ordinary points with the small sigma `alpha`, :749-756) == PolynomialLaneCurve.lsq_curve
+ * (test_scripts/lane_cbf_test.py:108-138) for equal weights.  The model is linear in its coefficients, so the
+ * least-squares optimum curve_fit iterates to is THE weighted least-squares solution; it is computed in the
+ * centred, scaled abscissa t = (x - mid) / half_range with polynomials orthogonal over the weighted points
+ * (Forsythe's three-term recurrence: no normal equations), then expanded back to powers of x.
+ *   x, y    [K][C]     points of lane c (the caller appends its fixed points, as the reference does)
+ *   sigma   [K][C]     per-point sigma (weight 1 / sigma^2), or NULL = 10 everywhere (obstacles.py:738-739)
+ *   count   [C] int32  lane c uses its first count[c] points (NULL = all K); needs count > degree
+ *   degree  1..5
+ *   coeffs  [6][C]     c0..c5 of y = sum c_i x^i -- the coefficient fields of a LANE slot; unused ones are 0
+ *   status  [C] int32  0 = ok, 1 = too few points / singular system (coeffs = NaN); may be NULL
+ * DEVICE pointers, asynchronous on `stream`. */
+int sccav_fit_lanes_f64(int32_t C, int32_t K, const double* x, const double* y, const double* sigma, const int32_t* count,
+                        int32_t degree, double* coeffs, int32_t* status, void* stream);
+int sccav_fit_lanes_f32(int32_t C, int32_t K, const float* x, const float* y, const float* sigma, const int32_t* count,
+                        int32_t degree, float* coeffs, int32_t* status, void* stream);
+
 /* Measurement helpers used by bench.py (not part of the reference-facing path). */
 /* Launches an unrolled FMA chain kernel and returns the achieved TFLOP/s (FMA = 2 flop) on the
  * current device; `dtype` 64 or 32.  Used as the measured FP64/FP32 CUDA-core peak. */

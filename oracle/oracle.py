@@ -269,6 +269,32 @@ def lane_sqrt_partials(x, y, c, buffer):
     return h, h_x, h_y, 0.0, 0.0, 0.0
 
 
+def fit_polynomial(x_pts, y_pts, n=3, sigma=None):
+    """PolyLane.fit_polynomial_curve -- cbf/obstacles.py:715-773 (scipy ``curve_fit`` of a polynomial with
+    per-point ``sigma``; fixed points are ordinary points with a small sigma, :749-756).  The model is linear
+    in its coefficients: the optimum curve_fit iterates to is the weighted least-squares solution.  It is
+    computed in the centred, scaled abscissa t = (x - mid) / half_range by an orthogonal factorisation (numpy
+    lstsq; the raw Vandermonde matrix of x ~ 50 m at degree 5 is too ill-conditioned for that), then expanded
+    to powers of x.  Returns c0..cn."""
+    x = np.asarray(x_pts, dtype=np.float64).ravel()
+    y = np.asarray(y_pts, dtype=np.float64).ravel()
+    sg = np.full_like(x, 10.0) if sigma is None else np.asarray(sigma, dtype=np.float64).ravel()
+    mid = 0.5 * (x.min() + x.max())
+    half = 0.5 * (x.max() - x.min())
+    t = (x - mid) / half
+    V = np.vander(t, n + 1, increasing=True) / sg[:, None]
+    a, *_ = np.linalg.lstsq(V, y / sg, rcond=1e-15)
+    # p(t) = sum a_j t^j, t = x / half - mid / half: Horner in polynomials of x
+    c = np.zeros(n + 1)
+    for j in range(n, -1, -1):
+        nc = np.zeros(n + 1)
+        nc[1:] = c[:-1] / half
+        nc -= c * (mid / half)
+        nc[0] += a[j]
+        c = nc
+    return c
+
+
 def prepare_ellipse(f):
     """Ingest-time half of Ellipse2D (include/sccav_cbf.h, ELLIPSE_PREP): canonical fields
     (cx, cy, a, b, theta, vx, vy, -) -> (cx, cy, cos/a, sin/a, -sin/b, cos/b, vx/a^2, vy/b^2)."""

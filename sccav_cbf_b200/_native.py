@@ -74,6 +74,7 @@ SYMBOLS = [
     "sccav_barrier_partials_f64", "sccav_barrier_partials_f32", "sccav_stanley_control_f64", "sccav_stanley_control_f32",
     "sccav_prepare_obstacles_f64", "sccav_prepare_obstacles_f32", "sccav_ingest_boxes_f64", "sccav_ingest_boxes_f32",
     "sccav_actuator_shaping_f64", "sccav_actuator_shaping_f32", "sccav_spline_course_f64", "sccav_spline_course_f32",
+    "sccav_fit_lanes_f64", "sccav_fit_lanes_f32",
 ]
 
 
@@ -106,6 +107,8 @@ def lib() -> C.CDLL:
         f.argtypes = [C.c_char_p, i32, i64, vp, vp, vp, vp]
         f = getattr(L, "sccav_spline_course_" + sfx)
         f.argtypes = [i32, i32, vp, vp, C.c_double, i32, vp, vp, vp, vp, vp, vp]
+        f = getattr(L, "sccav_fit_lanes_" + sfx)
+        f.argtypes = [i32, i32, vp, vp, vp, vp, i32, vp, vp, vp]
         f = getattr(L, "sccav_actuator_shaping_" + sfx)
         f.argtypes = [i64, vp, C.c_double, C.c_double, i32, vp, vp, vp, vp, vp, vp]
         f = getattr(L, "sccav_ingest_boxes_" + sfx)

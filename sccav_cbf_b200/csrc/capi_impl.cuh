@@ -462,6 +462,22 @@ int SCCAV_FN(sccav_spline_course_)(int32_t C, int32_t K, const SCCAV_REAL* wx, c
     return SCCAV_OK;
 }
 
+int SCCAV_FN(sccav_fit_lanes_)(int32_t C, int32_t K, const SCCAV_REAL* x, const SCCAV_REAL* y, const SCCAV_REAL* sigma,
+                                const int32_t* count, int32_t degree, SCCAV_REAL* coeffs, int32_t* status, void* stream) {
+    using namespace sccav;
+    if (C < 0 || K < 0) { set_error("C < 0 or K < 0"); return SCCAV_EINVAL; }
+    if (degree < 1 || degree > 5) { set_error("degree must be in [1, 5] (a LANE slot holds 6 coefficients), got %d", degree); return SCCAV_EINVAL; }
+    if (C == 0) return SCCAV_OK;
+    if (!x || !y || !coeffs) { set_error("NULL array argument"); return SCCAV_EINVAL; }
+    LaneFitArgs<SCCAV_REAL> a;
+    a.C = C; a.K = K; a.degree = degree; a.x = x; a.y = y; a.sigma = sigma; a.count = count; a.coeffs = coeffs; a.status = status;
+    const int block = 128;
+    lane_fit_kernel<SCCAV_REAL><<<stream_grid(C, block), block, 0, (cudaStream_t)stream>>>(a);
+    count_launch();
+    SCCAV_CUDA_CHECK(cudaGetLastError());
+    return SCCAV_OK;
+}
+
 int SCCAV_FN(sccav_barrier_partials_)(const uint8_t* slot_desc, int32_t M, int64_t N, const SCCAV_REAL* state,
                                       const SCCAV_REAL* obst, SCCAV_REAL* out, void* stream) {
     return sccav::do_barrier_partials(slot_desc, M, N, state, obst, out, (cudaStream_t)stream);

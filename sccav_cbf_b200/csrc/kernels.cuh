@@ -298,6 +298,95 @@ __global__ void __launch_bounds__(256) spline_course_kernel(const __grid_constan
     }
 }
 
+// ------------------------------------------------------------------------------------------ KL
+// Weighted polynomial lane fit (include/sccav_cbf.h): one thread = one lane; points are read [K][C] (coalesced
+// over lanes, L2-resident across the degree + 2 passes).  Range of x, then orthogonal polynomials in
+// t = (x - mid) / half over the weighted points, then the expansion into powers of x.
+template <typename T> struct LaneFitArgs {
+    int C, K, degree;
+    const T* x;
+    const T* y;
+    const T* sigma;
+    const int32_t* count;
+    T* coeffs;
+    int32_t* status;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) lane_fit_kernel(const __grid_constant__ LaneFitArgs<T> a) {
+    // arithmetic in double for both storage types: powers of x about x = 0 cancel badly in fp32 from degree 4 on,
+    // and the kernel is a few hundred flops per lane
+    typedef double W;
+    typedef Real<W> R;
+    const int C = a.C;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+        const int n = a.degree;
+        int K = a.count ? a.count[c] : a.K;
+        K = K < 0 ? 0 : (K > a.K ? a.K : K);
+        W out[6] = {W(0), W(0), W(0), W(0), W(0), W(0)};
+        bool ok = K > n;
+        W lo = R::inf(), hi = -R::inf();
+        for (int k = 0; k < K; ++k) {
+            const W xv = a.x[(int64_t)k * C + c];
+            lo = xv < lo ? xv : lo;
+            hi = xv > hi ? xv : hi;
+        }
+        const W mid = W(0.5) * (lo + hi);
+        W half = W(0.5) * (hi - lo);
+        if (!(half > W(0))) { half = W(1); ok = false; }           // all abscissae equal (or NaN)
+        const W inv = W(1) / half;
+        // Forsythe's method: polynomials p_0..p_n orthogonal over the weighted points, built by the three-term
+        // recurrence p_{j+1} = (t - al_j) p_j - be_j p_{j-1}; the fit is sum d_j p_j with d_j = <y, p_j> / <p_j, p_j>.
+        // No matrix is formed (the normal equations lose half the digits when the sigmas span 10 .. 0.01);
+        // pass j re-runs the recurrence per point, O(K n^2) flops in all.
+        W al[6], be[6], d[6], nrm[6];
+        for (int j = 0; j <= n && ok; ++j) {
+            W sN = W(0), sA = W(0), sD = W(0);
+            for (int k = 0; k < K; ++k) {
+                const W t = (a.x[(int64_t)k * C + c] - mid) * inv;
+                const W sg = a.sigma ? a.sigma[(int64_t)k * C + c] : W(10);
+                const W w = W(1) / (sg * sg);
+                W pm = W(0), p = W(1);
+                for (int q = 0; q < j; ++q) {
+                    const W pn = (t - al[q]) * p - be[q] * pm;
+                    pm = p; p = pn;
+                }
+                const W wp = w * p;
+                sN += wp * p;
+                sA += wp * p * t;
+                sD += wp * a.y[(int64_t)k * C + c];
+            }
+            if (!(sN > W(0)) || !(sN < R::inf())) { ok = false; break; }      // fewer distinct abscissae than coefficients
+            nrm[j] = sN;
+            al[j] = sA / sN;
+            be[j] = j > 0 ? sN / nrm[j - 1] : W(0);
+            d[j] = sD / sN;
+        }
+        if (ok && n > 0 && !(nrm[n] > nrm[0] * R::feas_eps() * R::feas_eps())) ok = false;
+        if (ok) {
+            // monomial coefficients (in t) of sum d_j p_j through the same recurrence on coefficient vectors
+            W cm[6] = {W(0), W(0), W(0), W(0), W(0), W(0)}, cp[6] = {W(1), W(0), W(0), W(0), W(0), W(0)};
+            W at[6] = {d[0], W(0), W(0), W(0), W(0), W(0)};
+            for (int j = 0; j < n; ++j) {
+                W cn[6];
+                for (int q = 0; q < 6; ++q) cn[q] = (q > 0 ? cp[q - 1] : W(0)) - al[j] * cp[q] - be[j] * cm[q];
+                for (int q = 0; q < 6; ++q) { cm[q] = cp[q]; cp[q] = cn[q]; at[q] += d[j + 1] * cn[q]; }
+            }
+            // p(t) = sum at_j t^j with t = x inv - mid inv: Horner in polynomials of x
+            const W sh = -mid * inv;
+            for (int j = n; j >= 0; --j) {
+                for (int q = n; q >= 1; --q) out[q] = out[q] * sh + out[q - 1] * inv;
+                out[0] = out[0] * sh + at[j];
+            }
+        } else {
+            const W nan = R::inf() - R::inf();
+            for (int q = 0; q < 6; ++q) out[q] = nan;
+        }
+        for (int q = 0; q < 6; ++q) a.coeffs[(int64_t)q * C + c] = (T)out[q];
+        if (a.status) a.status[c] = ok ? 0 : 1;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ K1
 template <typename T> struct RowsArgs {
     Params<T> P;

@@ -440,6 +440,19 @@ class PolyLane(Obstacle2DBase):
         coeffs, *_ = np.linalg.lstsq(V, y_pts / sigma, rcond=None)
         return cls(coeffs)
 
+    @classmethod
+    def fit_polynomial_curves(cls, x_pts: torch.Tensor, y_pts: torch.Tensor, n: int = 3, sigma: Optional[torch.Tensor] = None,
+                              count: Optional[torch.Tensor] = None, **kwargs) -> "PolyLane":
+        """Batched ``fit_polynomial_curve`` on the GPU (kernel KL, ``sccav_fit_lanes_*``): ``x_pts``, ``y_pts`` [K, C] CUDA
+        tensors hold the points of C lanes (fixed points appended with their small sigma, as cbf/obstacles.py:749-756
+        does), ``sigma`` [K, C] (default 10), ``count`` [C] points per lane.  Returns ONE PolyLane whose
+        coefficients are [n + 1, C] tensors -- lane c belongs to vehicle c of a batch."""
+        from . import ops
+        coeffs, status = ops.fit_lanes(x_pts, y_pts, n=n, sigma=sigma, count=count)
+        lane = cls(coeffs[: n + 1], **kwargs)
+        lane.fit_status = status
+        return lane
+
 
 class ObstacleList2D(MutableMapping):
     """Insertion-ordered mapping id -> obstacle (cbf/obstacles.py:798-941); the constraint index of

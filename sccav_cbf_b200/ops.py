@@ -379,6 +379,32 @@ def spline_courses(wx: torch.Tensor, wy: torch.Tensor, ds: float = 0.1, P_max: O
     return (out[0], out[1], out[2], npts) + ((out[3],) if curvature else ())
 
 
+def fit_lanes(x: torch.Tensor, y: torch.Tensor, n: int = 3, sigma: Optional[torch.Tensor] = None,
+              count: Optional[torch.Tensor] = None):
+    """KL: weighted polynomial fits of C lanes at once -- the batched ``PolyLane.fit_polynomial_curve``
+    (cbf/obstacles.py:715-773).  ``x``, ``y`` [K, C] points (fixed points appended by the caller with their small
+    sigma, as the reference does), ``sigma`` [K, C] or None (= 10), ``count`` [C] int32 points per lane or None.
+    Returns (coeffs [6, C] = c0..c5 of y = sum c_i x^i -- the coefficient fields of a LANE slot, status [C] int32)."""
+    L = nv.lib()
+    nv.require_cuda()
+    dt, dev = x.dtype, x.device
+    if dev.type != "cuda":
+        raise ValueError("fit_lanes works on device tensors")
+    K, C_ = x.shape
+    x = _chk(x, (K, C_), dt, dev, "x")
+    y = _chk(y, (K, C_), dt, dev, "y")
+    if sigma is not None:
+        sigma = _chk(sigma, (K, C_), dt, dev, "sigma")
+    if count is not None:
+        count = _chk(count, (C_,), torch.int32, dev, "count")
+    coeffs = torch.empty((6, C_), dtype=dt, device=dev)
+    status = torch.empty((C_,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nv.check(getattr(L, "sccav_fit_lanes_" + _SFX[dt])(C_, K, _ptr(x), _ptr(y), _ptr(sigma), _ptr(count), int(n), _ptr(coeffs),
+                                                         _ptr(status), _stream(dev)))
+    return coeffs, status
+
+
 def actuator_shaping(u: torch.Tensor, throttle_prev: torch.Tensor, brake_prev: torch.Tensor, max_steer: float = 1.0,
                      rate: float = 0.1, reset_brake: bool = False):
     """KA: (a, delta) -> (throttle, brake, steer) as the CARLA drivers do after ``solve_cbf``

@@ -6,7 +6,9 @@
   ``PolynomialLaneCurve`` (``test_scripts/lane_cbf_test.py:10-157``, real scipy Newton-CG);
   rows are captured inside the shimmed ``solvers.cp``;
 * ``cbf/cbf.py``: ``SADBM_CBF_2DS`` (lines 300-437) with a FIXED ``dt`` over sequences of ticks
-  (the class is stateful: beta and the last beta_ref carry over), collision-cone obstacles.
+  (the class is stateful: beta and the last beta_ref carry over), collision-cone obstacles;
+* ``cbf/obstacles.py``: ``PolyLane.fit_polynomial_curve`` (lines 715-773, real scipy ``curve_fit``) with and
+  without fixed points / ``fixed_pts_idx``, degrees 1-5.
 """
 import ast
 import contextlib
@@ -33,7 +35,7 @@ import euclid as euc  # noqa: E402  (the shim)
 from euclid import Point2, Vector2  # noqa: E402
 
 from cbf.cbf import SADBM_CBF_2DS  # noqa: E402
-from cbf.obstacles import CollisionCone2D  # noqa: E402
+from cbf.obstacles import CollisionCone2D, PolyLane  # noqa: E402
 
 
 def extract(path, names, consts, extra):
@@ -151,6 +153,51 @@ out["sadbm_cone"] = sad_cone
 out["sadbm_in"] = sad_in
 out["sadbm_rows"] = sad_rows
 out["sadbm_out"] = sad_out
+
+# ---------------------------------------------------------------- 3. PolyLane.fit_polynomial_curve (class)
+NF_, KMAX = 30, 40
+fit_x = np.full((NF_, KMAX), np.nan)
+fit_y = np.full((NF_, KMAX), np.nan)
+fit_sigma = np.full((NF_, KMAX), np.nan)         # the sigma the reference ends up using per point
+fit_k = np.zeros(NF_, dtype=np.int64)
+fit_n = np.zeros(NF_, dtype=np.int64)
+fit_c = np.zeros((NF_, 6))
+for i in range(NF_):
+    n = 1 + i % 5
+    K = int(rng.integers(n + 3, 28))
+    x0 = rng.uniform(-20, 40)
+    x = np.sort(x0 + rng.uniform(0, 60, K))
+    true = np.array([rng.uniform(-4, 4), rng.uniform(-0.3, 0.3), rng.uniform(-4e-3, 4e-3), rng.uniform(-4e-5, 4e-5),
+                     rng.uniform(-2e-7, 2e-7), rng.uniform(-1e-9, 1e-9)])[: n + 1]
+    y = sum(true[j] * x ** j for j in range(n + 1)) + rng.normal(0, 0.05, K)
+    kw = dict(n=n)
+    sig = np.full(K, 10.0)
+    xs, ys = x, y
+    if i % 3 == 1:                                   # appended fixed points (obstacles.py:749-756)
+        xf = np.array([x[0] - 2.0, x[-1] + 2.0]); yf = sum(true[j] * xf ** j for j in range(n + 1))
+        kw.update(x_fixed_pts=xf, y_fixed_pts=yf, alpha=0.01)
+        xs, ys, sig = np.append(x, xf), np.append(y, yf), np.append(sig, [0.01, 0.01])
+    if i % 3 == 2:                                   # pinned existing points (obstacles.py:758-759)
+        idx = np.array([0, K // 2])
+        kw.update(fixed_pts_idx=idx, alpha=0.05)
+        sig[idx] = 0.05
+    if i % 4 == 0:
+        sg = rng.uniform(0.5, 5.0, K)
+        kw.update(sigma=sg.copy())
+        sig[:K] = sg
+        if i % 3 == 2:
+            sig[idx] = 0.05
+    lane = PolyLane.fit_polynomial_curve(x, y, **kw)
+    co = np.asarray(lane.coeffs, dtype=np.float64).ravel()
+    fit_k[i] = xs.size; fit_n[i] = n
+    fit_x[i, : xs.size] = xs; fit_y[i, : xs.size] = ys; fit_sigma[i, : xs.size] = sig
+    fit_c[i, : n + 1] = co
+out["fit_x"] = fit_x
+out["fit_y"] = fit_y
+out["fit_sigma"] = fit_sigma
+out["fit_k"] = fit_k
+out["fit_n"] = fit_n
+out["fit_c"] = fit_c
 
 dst = os.path.join(HERE, "reference_vectors_lane_sadbm.npz")
 np.savez_compressed(dst, **out)

@@ -277,3 +277,78 @@ def test_device_course_generation_vs_reference_planner_restatement():
         ref = co.rollout(co.default_params(), b.slot_desc, st, ob, course_h, b.T)
         same = (out["target_idx"].cpu().numpy() == ref["target_idx"]) & (out["n_active"].cpu().numpy() == ref["n_active"])
         assert same.mean() >= 0.99
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 1e-4)])
+def test_device_lane_fit_vs_oracle_and_reference_vectors(dtype, tol, golden_dir):
+    """KL (sccav_fit_lanes_*): the batched weighted polynomial lane fit against the oracle's least-squares
+    solution -- the reference's own inputs (PolyLane.fit_polynomial_curve vectors, ragged point counts, mixed
+    degrees launched per degree) and 4,096 random lanes; degenerate lanes report status 1.  (fp32 storage: the
+    kernel computes in double -- powers of x about x = 0 cancel in fp32 -- so only the rounding of the inputs and
+    of the six coefficients is left.)"""
+    import os
+    from sccav_cbf_b200 import ops
+    g = np.load(os.path.join(golden_dir, "reference_vectors_lane_sadbm.npz"))
+    dev = torch.device("cuda", 0)
+    for n in range(1, 6):
+        sel = np.nonzero(g["fit_n"] == n)[0]
+        K = int(g["fit_k"][sel].max())
+        x = np.nan_to_num(g["fit_x"][sel, :K].T.copy()); y = np.nan_to_num(g["fit_y"][sel, :K].T.copy())
+        sg = np.nan_to_num(g["fit_sigma"][sel, :K].T.copy(), nan=1.0)
+        cnt = torch.from_numpy(g["fit_k"][sel].astype(np.int32)).to(dev)
+        c, st = ops.fit_lanes(torch.from_numpy(x).to(dev, dtype), torch.from_numpy(y).to(dev, dtype), n=n,
+                              sigma=torch.from_numpy(sg).to(dev, dtype), count=cnt)
+        assert int(st.sum()) == 0
+        c = c.cpu().double().numpy()
+        for j, i in enumerate(sel):
+            k = int(g["fit_k"][i])
+            ref = o.fit_polynomial(g["fit_x"][i, :k], g["fit_y"][i, :k], n, g["fit_sigma"][i, :k])
+            xx = np.linspace(g["fit_x"][i, :k].min(), g["fit_x"][i, :k].max(), 64)
+            got = np.polyval(c[: n + 1, j][::-1], xx); want = np.polyval(ref[::-1], xx)
+            assert np.abs(got - want).max() <= tol * (1 + np.abs(want).max()), (n, i)
+            assert (c[n + 1:, j] == 0).all()
+    # random cubic lanes, default sigma
+    rng = np.random.default_rng(12)
+    C, K = 4096, 24
+    x = np.sort(rng.uniform(-10, 70, (K, C)), axis=0)
+    true = np.stack([rng.uniform(-4, 4, C), rng.uniform(-0.2, 0.2, C), rng.uniform(-3e-3, 3e-3, C), rng.uniform(-3e-5, 3e-5, C)])
+    y = sum(true[j] * x ** j for j in range(4)) + rng.normal(0, 0.03, (K, C))
+    x[:, 7] = 3.0                                                     # a degenerate lane: one abscissa only
+    c, st = ops.fit_lanes(torch.from_numpy(x).to(dev, dtype), torch.from_numpy(y).to(dev, dtype), n=3)
+    st = st.cpu().numpy(); c = c.cpu().double().numpy()
+    assert st[7] == 1 and np.isnan(c[:, 7]).all() and st.sum() == 1
+    for j in list(range(0, C, 97)):
+        if j == 7:
+            continue
+        ref = o.fit_polynomial(x[:, j], y[:, j], 3)
+        xx = np.linspace(x[:, j].min(), x[:, j].max(), 32)
+        assert np.abs(np.polyval(c[:4, j][::-1], xx) - np.polyval(ref[::-1], xx)).max() <= tol * 10
+
+
+@pytest.mark.gpu
+def test_batched_lane_fit_feeds_the_lane_barrier():
+    """PolyLane.fit_polynomial_curves -> a batched PolyLane in an obstacle list -> solve_cbf: the fitted coefficients
+    go straight from kernel KL into the LANE slot fields, one lane per vehicle."""
+    from sccav_cbf_b200 import DBM_CBF_2DS, PolyLane
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(3)
+    C, K = 64, 16
+    x = np.sort(rng.uniform(0, 60, (K, C)), axis=0)
+    c0 = rng.uniform(2.5, 4.0, C)
+    y = c0 + 0.01 * x + rng.normal(0, 0.01, (K, C))
+    lane = PolyLane.fit_polynomial_curves(torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev), n=1, buffer=1.5)
+    assert int(lane.fit_status.sum()) == 0 and lane.coeffs.shape == (2, C)
+    assert np.abs(lane.coeffs[0].cpu().numpy() - c0).max() < 0.05
+    ctl = DBM_CBF_2DS(alpha=1.0)
+    ctl.set_model_params(lr=1.45, lf=1.45)
+    ctl.obstacle_list2d["left"] = lane
+    s = torch.stack([torch.full((C,), 20.0), torch.full((C,), 1.9), torch.full((C,), 0.25), torch.full((C,), 8.0)]).double().to(dev)
+    ctl.update_state(s)
+    info, u = ctl.solve_cbf(torch.stack([torch.zeros(C), torch.full((C,), 0.1)]).double().to(dev), return_solver=True)
+    ref = []
+    for n_ in range(C):
+        f = [[1.5, float(lane.coeffs[0, n_]), float(lane.coeffs[1, n_]), 0, 0, 0, 0, 0]]
+        ref.append(o.filter_step(o.MODEL_DBM, [20.0, 1.9, 0.25, 8.0], [0.0, 0.1], [o.SLOT_LANE], f, 1.0, 1.45, 1.45, 2.9, (1, 0, 0, 1)))
+    assert np.abs(u[1].cpu().numpy() - np.array([r[1] for r in ref])).max() < 1e-7      # (lane parity proper: test_gpu_parity)
+    assert (info["status"].cpu().numpy() == np.array([r[3] for r in ref])).all() and int((info["status"] == 1).sum()) > C // 2

@@ -216,3 +216,24 @@ def test_sadbm_class_sequences_vs_reference(refvec2):
             nact += mask != 0
             beta, brl = bn, br
     assert nact > 30
+
+
+def _wsse(c, x, y, sg):
+    return float(np.sum(((np.polyval(np.asarray(c)[::-1], x) - y) / sg) ** 2))
+
+
+def test_polynomial_lane_fit_vs_reference_curve_fit(refvec2):
+    """PolyLane.fit_polynomial_curve (cbf/obstacles.py:715-773) runs scipy's Levenberg-Marquardt from zero
+    coefficients; the restatement solves the same weighted least-squares problem directly.  It must never have a
+    LARGER weighted residual than the reference's answer, and the two curves agree to the reference's own
+    convergence (1e-5 m on the data range up to degree 4; LM stalls earlier on some degree-5 fits)."""
+    g = refvec2
+    for i in range(g["fit_k"].shape[0]):
+        K, n = int(g["fit_k"][i]), int(g["fit_n"][i])
+        x, y, sg = g["fit_x"][i, :K], g["fit_y"][i, :K], g["fit_sigma"][i, :K]
+        c = o.fit_polynomial(x, y, n, sg)
+        ref = g["fit_c"][i, : n + 1]
+        assert _wsse(c, x, y, sg) <= _wsse(ref, x, y, sg) * (1 + 1e-9) + 1e-18
+        if n <= 4:
+            xx = np.linspace(x.min(), x.max(), 64)
+            assert np.abs(np.polyval(c[::-1], xx) - np.polyval(ref[::-1], xx)).max() <= 1e-5
