@@ -296,7 +296,10 @@ void rollout_geometry(int64_t N, int& grid, int& block) {
 
 // the six instances of the persistent kernel: course in shared memory or not x slot specialisation
 typedef void (*rollout_fn)(RolloutArgs<real>);
-rollout_fn rollout_instance(bool course_smem, int spec) {
+rollout_fn rollout_instance(bool course_smem, int spec, bool fast = false) {
+    // + the compile-time (DBM, Stanley, no seekers) instances of the two ellipse specialisations
+    if (fast && course_smem && spec == SCCAV_SPEC_ELLIPSE_PREP) return rollout_kernel<real, true, SCCAV_SPEC_ELLIPSE_PREP, true>;
+    if (fast && course_smem && spec == SCCAV_SPEC_ELLIPSE) return rollout_kernel<real, true, SCCAV_SPEC_ELLIPSE, true>;
     if (spec == SCCAV_SPEC_ELLIPSE)
         return course_smem ? rollout_kernel<real, true, SCCAV_SPEC_ELLIPSE> : rollout_kernel<real, false, SCCAV_SPEC_ELLIPSE>;
     if (spec == SCCAV_SPEC_ELLIPSE_PREP)
@@ -380,7 +383,8 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
         if (me != cudaSuccess) { if (prep) cudaFreeAsync(prep, st); SCCAV_CUDA_CHECK(me); }
         a.pre = (real*)scratch;
     }
-    const rollout_fn kern = rollout_instance(course_smem, spec);
+    const bool fast = p->model == SCCAV_MODEL_DBM && stan && !p->seeker;
+    const rollout_fn kern = rollout_instance(course_smem, spec, fast);
     cudaError_t le = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (le == cudaSuccess) { kern<<<grid, block, smem, st>>>(a); le = cudaGetLastError(); }
     count_launch();

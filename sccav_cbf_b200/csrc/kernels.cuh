@@ -843,7 +843,10 @@ template <typename T> struct RolloutSmem {
     }
 };
 
-template <typename T, bool COURSE_SMEM, int SPEC>
+// FAST = the launch is known to be (model DBM, Stanley nominal, no seekers): those three become compile-time
+// constants, which removes the other plants, the seeker loop and the per-row model dispatch from the instance the
+// headline configurations run (a smaller loop body: fewer instructions and fewer instruction-cache misses).
+template <typename T, bool COURSE_SMEM, int SPEC, bool FAST = false>
 __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
     typedef Real<T> R;
     typedef typename R::T2 T2;
@@ -856,7 +859,9 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
     T* s_cyaw = reinterpret_cast<T*>(smem_raw + lay.off_cyaw);
     T* rows = reinterpret_cast<T*>(smem_raw + lay.off_rows) + threadIdx.x;
     const int stride = blockDim.x;
-    const bool stan = a.P.nominal == SCCAV_NOMINAL_STANLEY;
+    const bool stan = FAST ? true : a.P.nominal == SCCAV_NOMINAL_STANLEY;
+    const int model = FAST ? SCCAV_MODEL_DBM : a.P.model;
+    constexpr int MODEL = FAST ? SCCAV_MODEL_DBM : -1;
     CourseIndex<T, T2> ci;
     ci.xy = s_cxy;
     ci.np = np; ci.nleaf = lay.nleaf; ci.nsup = lay.nsup;
@@ -899,7 +904,7 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
     const T tspeed = a.pv.target_speed ? a.pv.target_speed[n] : P.target_speed;
     const int last_idx = np - 1;
     const int Mv = slot_count<T>(a.pv, a.M, n);
-    const bool filt = Mv > 0 && P.model != SCCAV_MODEL_NONE;
+    const bool filt = Mv > 0 && model != SCCAV_MODEL_NONE;
 
     // loop-invariant obstacle terms (ellipses): once per (vehicle, slot) into the scratch; `moving`
     // = slots whose ellipse has a velocity (their h_t needs vx, vy, a^2, b^2 every step)
@@ -959,7 +964,7 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
                 evals += np;
                 d_ref = stanley_law<T, T2>(P, R::make2(a.cx[idx], a.cy[idx]), a.cyaw, idx, fx, fy, yaw, v, target_idx);
             }
-            ur0 = (P.model == SCCAV_MODEL_KBM) ? tspeed : a_ref;                           // sce.py:646-648
+            ur0 = (model == SCCAV_MODEL_KBM) ? tspeed : a_ref;                             // sce.py:646-648
             ur1 = d_ref;
         } else {
             ur0 = P.uref0;
@@ -970,7 +975,7 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
         uint32_t mask = 0u;
         int status = SCCAV_STATUS_INACTIVE;
         if (filt)
-            status = filter_vehicle<T, SPEC>(P, a.sd, Mv, N, n, a.obst, x, y, yaw, v, syaw, cyw, alpha, R00, R01, R10, R11, a.pv.R == nullptr,
+            status = filter_vehicle<T, SPEC, MODEL>(P, a.sd, Mv, N, n, a.obst, x, y, yaw, v, syaw, cyw, alpha, R00, R01, R10, R11, a.pv.R == nullptr,
                                              ur0, ur1, rows, stride, u0, u1, u1raw, mask, hmin, a.pre, moving);
         // ---- plant
         T px = x, py = y, pyaw = yaw, pv_ = v;
@@ -978,7 +983,7 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
         if (delta < -P.max_steer) delta = -P.max_steer;
         if (delta > P.max_steer) delta = P.max_steer;
         T beta = T(0);
-        if (P.model == SCCAV_MODEL_DBM) {
+        if (model == SCCAV_MODEL_DBM) {
             // State.update_com   sce.py:122-131 (no yaw normalisation)
             beta = R::atan2_(P.lr * R::tan_(delta), P.lf + P.lr);
             x = x + (v * cyw - (v * syaw) * beta) * P.dt;
@@ -991,12 +996,12 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
             y = y + (v * syaw) * P.dt;
             yaw = yaw + ((v / P.L) * R::tan_(delta)) * P.dt;
             yaw = normalize_angle<T>(yaw);
-            if (P.model == SCCAV_MODEL_KBM) v = u0;
+            if (model == SCCAV_MODEL_KBM) v = u0;
             else v = v + u0 * P.dt;
         }
         R::sincos_(yaw, &syaw, &cyw);
         // ---- moving obstacles
-        if (P.seeker) {
+        if (FAST ? false : (P.seeker != 0)) {
             for (int m = 0; m < Mv; ++m) {
                 const int desc = a.sd.d[m];
                 if ((desc & SCCAV_SLOT_TYPE_MASK) == SCCAV_SLOT_RADIAL && !(desc & SCCAV_SLOT_SHARED))

@@ -797,7 +797,7 @@ template <typename T> struct RowPhase {
 };
 
 // phase 1: u_ref -> QP coordinates, rows of all slots -> shared memory, feasibility of the reference point
-template <typename T, int SPEC, bool SCAN = false>
+template <typename T, int SPEC, bool SCAN = false, int MODEL = -1>
 __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const SlotDesc& sd, int M, int64_t N, int64_t n,
                                                    const T* __restrict__ obst, T x, T y, T th, T v, T sth, T cth,
                                                    T alpha, T uref0, T uref1, T* rows, int stride, T& hmin,
@@ -808,7 +808,8 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
     T vlr = v / P.lr;                                                                   // cbf.py:160 (g_c[2][1])
     T r0 = uref0, r1;
     T ego_beta = T(0);
-    const bool sadbm = P.model == SCCAV_MODEL_SADBM;
+    const int model = MODEL >= 0 ? MODEL : P.model;
+    const bool sadbm = model == SCCAV_MODEL_SADBM;
     if (sadbm) {
         // aug = (beta, beta_ref_last) of this vehicle.  cbf.py:359-372: u_ref[1] -> d(beta_ref)/dt; the rows use
         // sin / cos(theta + beta) and v sin(beta) / lr where the other models use sin / cos(theta) and v / lr
@@ -819,8 +820,8 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
         R::sincos_(ego_beta, &sb, &cb);
         vlr = (v * sb) / P.lr;
     } else
-    if (P.model == SCCAV_MODEL_KBM) r1 = (uref0 * R::tan_(uref1)) / P.L;                // cbf.py:75
-    else if (P.model == SCCAV_MODEL_DUM) r1 = uref1;                                     // cbf.py:253: u_ref as given
+    if (model == SCCAV_MODEL_KBM) r1 = (uref0 * R::tan_(uref1)) / P.L;                  // cbf.py:75
+    else if (model == SCCAV_MODEL_DUM) r1 = uref1;                                       // cbf.py:253: u_ref as given
     else r1 = R::atan2_(P.lr * R::tan_(uref1), P.lf + P.lr);                             // cbf.py:175
     // rows -> shared memory; an inactive step never re-reads them
     bool feas = true;
@@ -841,7 +842,7 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
                 T vx = T(0), vy = T(0);
                 if ((moving >> m) & 1u) { vx = f[5 * N]; vy = f[6 * N]; }
                 Partials<T> p = ellipse_partials_pre<T>(x, y, cx, cy, a, b, vx, vy, q, N);
-                put_row<T, SCAN>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
+                put_row<T, SCAN, 3, MODEL>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
             }
         } else {
             T cx = f[0], cy = f[N], a = f[2 * N], b = f[3 * N], t = f[4 * N], vx = f[5 * N], vy = f[6 * N];
@@ -850,7 +851,7 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
                 T ncx = cx, ncy = cy, na = a, nb = b, nt = t, nvx = vx, nvy = vy;
                 if (m + 1 < M) { ncx = f[0]; ncy = f[N]; na = f[2 * N]; nb = f[3 * N]; nt = f[4 * N]; nvx = f[5 * N]; nvy = f[6 * N]; }
                 Partials<T> p = ellipse_partials<T>(x, y, cx, cy, a, b, t, vx, vy);
-                put_row<T, SCAN>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
+                put_row<T, SCAN, 3, MODEL>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
                 cx = ncx; cy = ncy; a = na; b = nb; t = nt; vx = nvx; vy = nvy;
             }
         }
@@ -867,7 +868,7 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
             T wx = T(0), wy = T(0);
             if (!is_static) { wx = f[6 * N]; wy = f[7 * N]; }
             Partials<T> p = ellipse_prep_partials<T>(x, y, f[0], f[N], f[2 * N], f[3 * N], f[4 * N], f[5 * N], wx, wy);
-            put_row<T, SCAN>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
+            put_row<T, SCAN, 3, MODEL>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
         }
     } else {
         T rsth = sth, rcth = cth;                              // trig of the row assembly (theta + beta under SADBM)
@@ -878,7 +879,7 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
             const T* f = obst + (int64_t)m * SCCAV_NFIELD * N + nn;
             const T* pr = pre ? pre + (int64_t)m * SCCAV_NPRE * N + n : nullptr;
             Partials<T> p = slot_partials<T>(desc, f, N, x, y, th, v, sth, cth, pr, N, sadbm ? &ego_beta : nullptr);
-            put_row<T, SCAN>(P, p, rsth, rcth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
+            put_row<T, SCAN, 3, MODEL>(P, p, rsth, rcth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
         }
     }
     RowPhase<T> ph;
@@ -887,25 +888,26 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
 }
 
 // phase 3: QP coordinates -> (a | v, delta)
-template <typename T>
+template <typename T, int MODEL = -1>
 __device__ __forceinline__ T filter_convert(const Params<T>& P, T q0, T q1, T r0) {
     typedef Real<T> R;
-    if (P.model == SCCAV_MODEL_KBM) {
+    const int model = MODEL >= 0 ? MODEL : P.model;
+    if (model == SCCAV_MODEL_KBM) {
         if (P.kbm_driver_delta) return R::atan_((q1 * P.L) / q0);                        // sce.py:652
         return R::atan2_(q1 * P.L, r0);                                                  // cbf.py:109
     }
-    if (P.model == SCCAV_MODEL_DUM) return q1;                                           // cbf.py:293: u as solved
+    if (model == SCCAV_MODEL_DUM) return q1;                                             // cbf.py:293: u as solved
     return R::atan2_((P.lf + P.lr) * R::tan_(q1), P.lr);                                 // cbf.py:216
 }
 
 // all three phases by one thread (the persistent rollout kernel; K12 compacts phase 2 across the CTA)
-template <typename T, int SPEC>
+template <typename T, int SPEC, int MODEL = -1>
 __device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc& sd, int M, int64_t N, int64_t n,
                                               const T* __restrict__ obst, T x, T y, T th, T v, T sth, T cth,
                                               T alpha, T R00, T R01, T R10, T R11, bool uniform_R, T uref0, T uref1,
                                               T* rows, int stride, T& u0, T& u1, T& u1raw, uint32_t& mask, T& hmin,
                                               const T* __restrict__ pre = nullptr, uint32_t moving = 0xffffffffu) {
-    const RowPhase<T> ph = filter_rows<T, SPEC>(P, sd, M, N, n, obst, x, y, th, v, sth, cth, alpha, uref0, uref1,
+    const RowPhase<T> ph = filter_rows<T, SPEC, false, MODEL>(P, sd, M, N, n, obst, x, y, th, v, sth, cth, alpha, uref0, uref1,
                                                 rows, stride, hmin, pre, moving);
     T q0 = ph.r0, q1 = ph.r1;
     int status = SCCAV_STATUS_INACTIVE;
@@ -921,7 +923,7 @@ __device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc
     }
     u0 = q0;
     u1raw = q1;
-    u1 = filter_convert<T>(P, q0, q1, ph.r0);
+    u1 = filter_convert<T, MODEL>(P, q0, q1, ph.r0);
     return status;
 }
 
