@@ -373,6 +373,7 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
         any_ellipse = false;
     }
     const int spec = filt ? choose_spec(desc2, M) : SCCAV_SPEC_GENERIC;
+    const bool fast = p->model == SCCAV_MODEL_DBM && stan && !p->seeker;
     rc = rollout_launch_shape(M, N, a.np, stan, spec, grid, block, smem, course_smem);
     if (rc) { if (prep) cudaFreeAsync(prep, st); return rc; }
     // scratch for the loop-invariant terms of canonical ellipses: stream-ordered, lives for this launch
@@ -383,7 +384,6 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
         if (me != cudaSuccess) { if (prep) cudaFreeAsync(prep, st); SCCAV_CUDA_CHECK(me); }
         a.pre = (real*)scratch;
     }
-    const bool fast = p->model == SCCAV_MODEL_DBM && stan && !p->seeker;
     const rollout_fn kern = rollout_instance(course_smem, spec, fast);
     cudaError_t le = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (le == cudaSuccess) { kern<<<grid, block, smem, st>>>(a); le = cudaGetLastError(); }
@@ -525,7 +525,8 @@ int SCCAV_FN(sccav_rollout_launch_info_)(const uint8_t* slot_desc, int32_t M, in
     const int spec = choose_spec(slot_desc, M);
     int rc = rollout_launch_shape(M, N, P, P > 0, spec, grid, block, smem, course_smem);
     if (rc) return rc;
-    const void* kern = (const void*)rollout_instance(course_smem, spec);
+    // (reported for the default parameters -- model DBM, Stanley nominal, no seekers -- i.e. the compile-time instance)
+    const void* kern = (const void*)rollout_instance(course_smem, spec, P > 0);
     cudaFuncAttributes fa;
     SCCAV_CUDA_CHECK(cudaFuncGetAttributes(&fa, kern));
     int occ = 0;

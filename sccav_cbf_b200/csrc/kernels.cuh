@@ -740,7 +740,10 @@ __global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_staged_kernel
 #pragma unroll
                 for (int i = 0; i < NF; ++i) g[i] = f[i * B];
                 Partials<T> p;
-                if (SPEC == SCCAV_SPEC_ELLIPSE) p = ellipse_partials<T>(x, y, g[0], g[1], g[2], g[3], g[4], g[5], g[NF - 1]);
+                if (SPEC == SCCAV_SPEC_ELLIPSE) {
+                    const bool st_ = (a.sd.d[0] & SCCAV_SLOT_STATIC) != 0;
+                    p = ellipse_partials<T>(x, y, g[0], g[1], g[2], g[3], g[4], st_ ? T(0) : g[5], st_ ? T(0) : g[NF - 1]);
+                }
                 else if (NF >= 8) p = ellipse_prep_partials<T>(x, y, g[0], g[1], g[2], g[3], g[4], g[5], g[NF - 2], g[NF - 1]);
                 else p = ellipse_prep_partials<T>(x, y, g[0], g[1], g[2], g[3], g[4], g[5], T(0), T(0));
                 put_row<T, COOP, NF, MODEL>(P, p, sth, cth, v, alpha, vlr, r0, r1, stage, B, m, hmin, worst, feas, nz, &scan, &Ri);

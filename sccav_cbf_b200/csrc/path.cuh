@@ -845,11 +845,15 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
                 put_row<T, SCAN, 3, MODEL>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
             }
         } else {
-            T cx = f[0], cy = f[N], a = f[2 * N], b = f[3 * N], t = f[4 * N], vx = f[5 * N], vy = f[6 * N];
+            const bool st_ = (sd.d[0] & SCCAV_SLOT_STATIC) != 0;      // static: the velocity fields are not read
+            T cx = f[0], cy = f[N], a = f[2 * N], b = f[3 * N], t = f[4 * N], vx = st_ ? T(0) : f[5 * N], vy = st_ ? T(0) : f[6 * N];
             for (int m = 0; m < M; ++m) {
                 f += ss;
                 T ncx = cx, ncy = cy, na = a, nb = b, nt = t, nvx = vx, nvy = vy;
-                if (m + 1 < M) { ncx = f[0]; ncy = f[N]; na = f[2 * N]; nb = f[3 * N]; nt = f[4 * N]; nvx = f[5 * N]; nvy = f[6 * N]; }
+                if (m + 1 < M) {
+                    ncx = f[0]; ncy = f[N]; na = f[2 * N]; nb = f[3 * N]; nt = f[4 * N];
+                    if (!st_) { nvx = f[5 * N]; nvy = f[6 * N]; }
+                }
                 Partials<T> p = ellipse_partials<T>(x, y, cx, cy, a, b, t, vx, vy);
                 put_row<T, SCAN, 3, MODEL>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
                 cx = ncx; cy = ncy; a = na; b = nb; t = nt; vx = nvx; vy = nvy;
@@ -935,7 +939,7 @@ __host__ __device__ inline int choose_spec(const uint8_t* d, int M) {
     if (first & SCCAV_SLOT_SHARED) return SCCAV_SPEC_GENERIC;
     if (type == SCCAV_SLOT_ELLIPSE) {
         for (int m = 0; m < M; ++m)
-            if (d[m] != SCCAV_SLOT_ELLIPSE) return SCCAV_SPEC_GENERIC;      // (a STATIC canonical ellipse takes the generic loop)
+            if (d[m] != first) return SCCAV_SPEC_GENERIC;                   // same STATIC flag on every slot
         return SCCAV_SPEC_ELLIPSE;
     }
     if (type == SCCAV_SLOT_ELLIPSE_PREP) {

@@ -115,7 +115,8 @@ def config2(n_total: int = 65536, M: int = 8, T: int = 1000, seed: int = 0, lo: 
         ob.append(_ellipses_on_course(rng, BLOCK, M, course)[:, :, s:e])
     state = np.ascontiguousarray(np.concatenate(st, axis=1))
     obst = np.ascontiguousarray(np.concatenate(ob, axis=2))
-    return ScenarioBatch("config2", state, [nv.SLOT_ELLIPSE] * M, obst, course, dict(), T=T)
+    # "static ellipses" (BASELINE config 2): the slots say so -- their velocity fields are not read
+    return ScenarioBatch("config2", state, [nv.SLOT_ELLIPSE | nv.SLOT_STATIC] * M, obst, course, dict(), T=T)
 
 
 def config3(n_total: int = 262144, M: int = 16, T: int = 600, seed: int = 1, lo: int = 0, hi: Optional[int] = None,
