@@ -209,9 +209,12 @@ def main():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--ref-seconds", type=float, default=4.0, help="CPU seconds per reference step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU seconds for the cpu_baseline sample")
-    ap.add_argument("--rows", default="prepared", choices=["prepared", "canonical"],
-                    help="ellipse rows of the rollout: 'prepared' = SCCAV_FLAG_PREPARED_ROWS (obstacles ingested once per "
-                         "launch, evaluated in their prepared form); 'canonical' = the reference's operation order at every step")
+    ap.add_argument("--rows", default="fast", choices=["fast", "prepared", "canonical"],
+                    help="arithmetic of the rollout: 'canonical' = the reference's operation order at every step; 'prepared' = "
+                         "SCCAV_FLAG_PREPARED_ROWS (obstacles ingested once per launch, rows evaluated in their prepared form); "
+                         "'fast' = prepared rows + SCCAV_FLAG_FUSED_STEER (beta = clamp(beta*) instead of beta* -> delta -> clip -> "
+                         "beta).  All three are fp64 and compute the same functions -- a few ulp apart; the canonical timing and the "
+                         "fraction of vehicles with identical integer bookkeeping are always reported beside the timed mode")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-operator", action="store_true", help="skip the regime-(i) operator roofline leg")
     args = ap.parse_args()
@@ -240,8 +243,9 @@ def main():
     n_total = NV * world
     lo, hi = sc.shard_range(n_total, rank, world)
     batch = sc.config2(n_total=n_total, M=M, T=T, seed=0, lo=lo, hi=hi)
-    if args.rows == "prepared":
-        batch.params = dict(batch.params, flags=1)               # SCCAV_FLAG_PREPARED_ROWS
+    ROW_FLAGS = {"canonical": 0, "prepared": 1, "fast": 5}       # SCCAV_FLAG_PREPARED_ROWS = 1, SCCAV_FLAG_FUSED_STEER = 4
+    if ROW_FLAGS[args.rows]:
+        batch.params = dict(batch.params, flags=ROW_FLAGS[args.rows])
     cl = ClosedLoopRollout(batch, dtype=dtype, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
@@ -280,8 +284,8 @@ def main():
     other = None
     if rank == 0 or world > 1:
         b2 = sc.config2(n_total=n_total, M=M, T=T, seed=0, lo=lo, hi=hi)
-        if args.rows != "prepared":
-            b2.params = dict(b2.params, flags=1)
+        if args.rows == "canonical":
+            b2.params = dict(b2.params, flags=ROW_FLAGS["fast"])
         cl2 = ClosedLoopRollout(b2, dtype=dtype, device=dev, pin=False)
         cl2.run()
         ms2 = []
@@ -293,7 +297,7 @@ def main():
             ms2.append(e0.elapsed_time(e1))
         same = (r2["steps"] == res["steps"]) & (r2["target_idx"] == res["target_idx"]) & (r2["n_active"] == res["n_active"]) \
             & (r2["n_infeasible"] == res["n_infeasible"])
-        other = {"rows": "canonical" if args.rows == "prepared" else "prepared", "ms_per_step": statistics.mean(ms2),
+        other = {"rows": "canonical" if args.rows != "canonical" else "fast", "ms_per_step": statistics.mean(ms2),
                  "value_this_rank": float(r2["steps"].sum().item()) * M / (statistics.mean(ms2) * 1e-3),
                  "identical_bookkeeping_frac_vs_timed_mode": float(same.double().mean().item())}
         del cl2
@@ -329,7 +333,7 @@ def main():
         "algorithmic_flops_per_launch": flops_per_launch,
         "algorithmic_flops_per_solve": flops_per_launch / solves_per_step_rank,
         "flops_model": "7 x n_evals (counted by the kernel) + vehicle_steps x (34 M + 27); %d transcendental calls per "
-                       "vehicle-step not counted" % TRANSCENDENTALS_PER_VEHICLE_STEP,
+                       "vehicle-step not counted" % (TRANSCENDENTALS_PER_VEHICLE_STEP - (4 if args.rows == "fast" else 0)),
         "nearest_search_evals_per_vehicle_step": evals_rank / max(vehicle_steps_rank, 1.0),
         "exhaustive_scan_flops_per_solve": exhaustive_flops_per_solve(P_COURSE, M),
         "traffic": ncu_roll.get("dram_bytes"),

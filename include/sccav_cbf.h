@@ -98,6 +98,12 @@ extern "C" {
  * metric of R) and hands every other problem -- and every near-tie -- to the enumeration; results are
  * bit-identical, the flag exists so that tests can prove it.                                      */
 #define SCCAV_FLAG_QP_ENUMERATE 2
+/* rollout, model DBM: the plant takes beta = clamp(beta*, +-beta(max_steer)) straight from the QP's beta* instead of
+ * beta* -> delta = atan2(L tan beta*, lr) -> clip(delta, +-max_steer) -> beta = atan2(lr tan delta, L)
+ * (cbf.py:216, sce.py:122-125).  tan and atan are monotone, so it is the same function -- bit-identical whenever the
+ * steering clips, a few ulp apart otherwise (two tan + two atan2 per step are not evaluated); |beta*| >= 1.5 takes the
+ * literal sequence.  delta is still produced for the steps that are recorded.  The reference order stays the default. */
+#define SCCAV_FLAG_FUSED_STEER 4
 
 #define SCCAV_STATUS_INACTIVE 0    /* u == u_ref                                               */
 #define SCCAV_STATUS_ACTIVE 1      /* KKT optimum with 1 or 2 active rows                      */

@@ -21,6 +21,8 @@ SLOT_TYPE_MASK = 0x3F
 SLOT_STATIC = 0x40
 SLOT_SHARED = 0x80
 FLAG_PREPARED_ROWS = 1
+FLAG_QP_ENUMERATE = 2
+FLAG_FUSED_STEER = 4
 BOX_FIELDS = 6
 INGEST_UPDATE, INGEST_REBUILD = 0, 1
 ACT_RESET_BRAKE = 1

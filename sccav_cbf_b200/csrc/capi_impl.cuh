@@ -296,10 +296,12 @@ void rollout_geometry(int64_t N, int& grid, int& block) {
 
 // the six instances of the persistent kernel: course in shared memory or not x slot specialisation
 typedef void (*rollout_fn)(RolloutArgs<real>);
-rollout_fn rollout_instance(bool course_smem, int spec, bool fast = false) {
-    // + the compile-time (DBM, Stanley, no seekers) instances of the two ellipse specialisations
-    if (fast && course_smem && spec == SCCAV_SPEC_ELLIPSE_PREP) return rollout_kernel<real, true, SCCAV_SPEC_ELLIPSE_PREP, true>;
-    if (fast && course_smem && spec == SCCAV_SPEC_ELLIPSE) return rollout_kernel<real, true, SCCAV_SPEC_ELLIPSE, true>;
+rollout_fn rollout_instance(bool course_smem, int spec, bool fast = false, bool fused = false) {
+    // + the compile-time (DBM, Stanley, no seekers; fused steering or not) instances of the two ellipse specialisations
+    if (fast && course_smem && spec == SCCAV_SPEC_ELLIPSE_PREP)
+        return fused ? rollout_kernel<real, true, SCCAV_SPEC_ELLIPSE_PREP, true, 1> : rollout_kernel<real, true, SCCAV_SPEC_ELLIPSE_PREP, true, 0>;
+    if (fast && course_smem && spec == SCCAV_SPEC_ELLIPSE)
+        return fused ? rollout_kernel<real, true, SCCAV_SPEC_ELLIPSE, true, 1> : rollout_kernel<real, true, SCCAV_SPEC_ELLIPSE, true, 0>;
     if (spec == SCCAV_SPEC_ELLIPSE)
         return course_smem ? rollout_kernel<real, true, SCCAV_SPEC_ELLIPSE> : rollout_kernel<real, false, SCCAV_SPEC_ELLIPSE>;
     if (spec == SCCAV_SPEC_ELLIPSE_PREP)
@@ -384,7 +386,7 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
         if (me != cudaSuccess) { if (prep) cudaFreeAsync(prep, st); SCCAV_CUDA_CHECK(me); }
         a.pre = (real*)scratch;
     }
-    const rollout_fn kern = rollout_instance(course_smem, spec, fast);
+    const rollout_fn kern = rollout_instance(course_smem, spec, fast, (p->flags & SCCAV_FLAG_FUSED_STEER) != 0);
     cudaError_t le = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (le == cudaSuccess) { kern<<<grid, block, smem, st>>>(a); le = cudaGetLastError(); }
     count_launch();

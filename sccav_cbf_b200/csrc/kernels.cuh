@@ -849,7 +849,8 @@ template <typename T> struct RolloutSmem {
 // FAST = the launch is known to be (model DBM, Stanley nominal, no seekers): those three become compile-time
 // constants, which removes the other plants, the seeker loop and the per-row model dispatch from the instance the
 // headline configurations run (a smaller loop body: fewer instructions and fewer instruction-cache misses).
-template <typename T, bool COURSE_SMEM, int SPEC, bool FAST = false>
+// FUSED: SCCAV_FLAG_FUSED_STEER known at compile time (1 / 0; the FAST instances) or read from the flags (-1).
+template <typename T, bool COURSE_SMEM, int SPEC, bool FAST = false, int FUSED = -1>
 __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
     typedef Real<T> R;
     typedef typename R::T2 T2;
@@ -945,6 +946,9 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
     int steps = 0, nact = 0, ninf = 0;
     T hmin_all = R::inf(), bmin = R::inf(), bmax = -R::inf(), bint = T(0);
     const int stride_rec = P.record_stride;
+    // SCCAV_FLAG_FUSED_STEER (DBM only): beta(max_steer) with the operations the clipped plant would use
+    const bool fused = (FUSED >= 0 ? FUSED != 0 : (P.flags & SCCAV_FLAG_FUSED_STEER) != 0) && model == SCCAV_MODEL_DBM;
+    const T beta_clip = R::atan2_(P.lr * R::tan_(P.max_steer), P.lf + P.lr);
 
     while (steps < a.T_steps) {
         if (P.terminate && !(P.t_max >= time && last_idx > target_idx)) break;          // sce.py:630
@@ -979,16 +983,28 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
         int status = SCCAV_STATUS_INACTIVE;
         if (filt)
             status = filter_vehicle<T, SPEC, MODEL>(P, a.sd, Mv, N, n, a.obst, x, y, yaw, v, syaw, cyw, alpha, R00, R01, R10, R11, a.pv.R == nullptr,
-                                             ur0, ur1, rows, stride, u0, u1, u1raw, mask, hmin, a.pre, moving);
+                                             ur0, ur1, rows, stride, u0, u1, u1raw, mask, hmin, a.pre, moving, !fused);
         // ---- plant
         T px = x, py = y, pyaw = yaw, pv_ = v;
+        T beta = T(0);
+        // SCCAV_FLAG_FUSED_STEER: beta straight from the QP's beta* (include/sccav_cbf.h); delta only where it is recorded
+        const bool rec_now = stride_rec > 0 && (steps % stride_rec) == 0;
+        bool fused_done = false;
+        if (fused && filt && R::abs_(u1raw) < T(1.5)) {
+            beta = u1raw;
+            if (beta < -beta_clip) beta = -beta_clip;
+            if (beta > beta_clip) beta = beta_clip;
+            if (rec_now) u1 = filter_convert<T, MODEL>(P, u0, u1raw, ur0);
+            fused_done = true;
+        } else if (fused && filt) {
+            u1 = filter_convert<T, MODEL>(P, u0, u1raw, ur0);
+        }
         T delta = u1;
         if (delta < -P.max_steer) delta = -P.max_steer;
         if (delta > P.max_steer) delta = P.max_steer;
-        T beta = T(0);
         if (model == SCCAV_MODEL_DBM) {
             // State.update_com   sce.py:122-131 (no yaw normalisation)
-            beta = R::atan2_(P.lr * R::tan_(delta), P.lf + P.lr);
+            if (!fused_done) beta = R::atan2_(P.lr * R::tan_(delta), P.lf + P.lr);
             x = x + (v * cyw - (v * syaw) * beta) * P.dt;
             y = y + (v * syaw + (v * cyw) * beta) * P.dt;
             yaw = yaw + ((v * beta) / P.lr) * P.dt;
@@ -1012,7 +1028,7 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
             }
         }
         // ---- bookkeeping
-        if (stride_rec > 0 && (steps % stride_rec) == 0) {
+        if (rec_now) {
             const int64_t rec = steps / stride_rec;
             if (a.o_traj) {
                 T* tr = a.o_traj + rec * SCCAV_TRAJ_FIELDS * N + n;

@@ -910,7 +910,8 @@ __device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc
                                               const T* __restrict__ obst, T x, T y, T th, T v, T sth, T cth,
                                               T alpha, T R00, T R01, T R10, T R11, bool uniform_R, T uref0, T uref1,
                                               T* rows, int stride, T& u0, T& u1, T& u1raw, uint32_t& mask, T& hmin,
-                                              const T* __restrict__ pre = nullptr, uint32_t moving = 0xffffffffu) {
+                                              const T* __restrict__ pre = nullptr, uint32_t moving = 0xffffffffu,
+                                              bool convert = true) {
     const RowPhase<T> ph = filter_rows<T, SPEC, false, MODEL>(P, sd, M, N, n, obst, x, y, th, v, sth, cth, alpha, uref0, uref1,
                                                 rows, stride, hmin, pre, moving);
     T q0 = ph.r0, q1 = ph.r1;
@@ -927,7 +928,7 @@ __device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc
     }
     u0 = q0;
     u1raw = q1;
-    u1 = filter_convert<T, MODEL>(P, q0, q1, ph.r0);
+    if (convert) u1 = filter_convert<T, MODEL>(P, q0, q1, ph.r0);      // (the caller converts later, or never, otherwise)
     return status;
 }
 

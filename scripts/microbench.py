@@ -59,6 +59,16 @@ def main():
         same = (res2["steps"] == res["steps"]) & (res2["target_idx"] == res["target_idx"]) & (res2["n_active"] == res["n_active"])
         out.append("rollout[prepared rows] %.3f ms  %.4g solves/s  (identical bookkeeping vs canonical %.5f)" % (
             ms2, solves / ms2 * 1e3, float(same.double().mean().item())))
+        for fl in (4, 5):
+            b3 = sc.config2(n_total=a.vehicles, M=M, T=a.T, seed=0, lo=0, hi=a.vehicles)
+            b3.params = dict(b3.params, flags=fl)
+            cl3 = ClosedLoopRollout(b3, dtype=dtype, device=dev)
+            for _ in range(2):
+                res3 = cl3.run()
+            ms3 = timed(cl3.run, 5)
+            same3 = (res3["steps"] == res["steps"]) & (res3["target_idx"] == res["target_idx"]) & (res3["n_active"] == res["n_active"])
+            out.append("rollout[flags=%d: fused steer%s] %.3f ms  %.4g solves/s  (identical bookkeeping vs canonical %.5f)" % (
+                fl, " + prepared rows" if fl & 1 else "", ms3, solves / ms3 * 1e3, float(same3.double().mean().item())))
     if not a.no_operator:
         n_op = 2 * 1024 * 1024
         gen = torch.Generator(device=dev); gen.manual_seed(1234)

@@ -564,6 +564,29 @@ def test_rollout_prepared_rows_flag():
     print("prepared rows: identical bookkeeping fraction", frac)
 
 
+@pytest.mark.parametrize("flags", [4, 5])
+def test_rollout_fused_steer_flag(flags):
+    """SCCAV_FLAG_FUSED_STEER (alone and with PREPARED_ROWS): beta = clamp(beta*) instead of beta* -> delta -> clip ->
+    beta, against the oracle's literal sequence -- same bars as the canonical closed loop; the recorded delta (u1) and
+    beta of every recorded step included (trajectory fields 5 and 6)."""
+    from sccav_cbf_b200 import scenarios as sc
+    b = sc.config2(n_total=65536, M=8, T=1000, lo=0, hi=2048)
+    r = _oracle(b, record_stride=50)
+    b.params = dict(b.params, flags=flags)
+    g = _run(b, record_stride=50)
+    _compare_rollout(g, r, b.N, b.T, course=b.course)
+    same_tr = (g["traj_idx"] == r["traj_idx"]).all(axis=0) & (g["traj_mask"].view(np.uint32) == r["traj_mask"]).all(axis=0)
+    assert same_tr.mean() >= 0.999
+    # config 1 (one vehicle, the reference's own run): the beta curve of beta_vs_time.mat within its 1e-3 deg
+    c1 = sc.config1("cone")
+    r1 = _oracle(c1, record_stride=1)
+    c1.params = dict(c1.params, flags=flags)
+    g1 = _run(c1, record_stride=1)
+    assert int(g1["steps"][0]) == int(r1["steps"][0]) == 276
+    assert np.array_equal(g1["traj_idx"], r1["traj_idx"]) and np.array_equal(g1["traj_mask"].view(np.uint32), r1["traj_mask"])
+    assert np.abs(g1["traj"][:276, 6] - r1["traj"][:276, 6]).max() < 1e-9 and np.abs(g1["traj"][:276, 5] - r1["traj"][:276, 5]).max() < 1e-9
+
+
 def test_dum_model_filter_vs_oracle():
     """DUM_CBF_2DS (cbf/cbf.py:222-298): u = (a, omega), rows Lg h = [h_v, h_theta]; cones make both non-zero."""
     from sccav_cbf_b200 import ops
