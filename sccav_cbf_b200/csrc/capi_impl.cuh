@@ -302,6 +302,8 @@ rollout_fn rollout_instance(bool course_smem, int spec, bool fast = false, bool 
         return fused ? rollout_kernel<real, true, SCCAV_SPEC_ELLIPSE_PREP, true, 1> : rollout_kernel<real, true, SCCAV_SPEC_ELLIPSE_PREP, true, 0>;
     if (fast && course_smem && spec == SCCAV_SPEC_ELLIPSE)
         return fused ? rollout_kernel<real, true, SCCAV_SPEC_ELLIPSE, true, 1> : rollout_kernel<real, true, SCCAV_SPEC_ELLIPSE, true, 0>;
+    if (fast && course_smem && spec == SCCAV_SPEC_GENERIC)
+        return fused ? rollout_kernel<real, true, SCCAV_SPEC_GENERIC, true, 1> : rollout_kernel<real, true, SCCAV_SPEC_GENERIC, true, 0>;
     if (spec == SCCAV_SPEC_ELLIPSE)
         return course_smem ? rollout_kernel<real, true, SCCAV_SPEC_ELLIPSE> : rollout_kernel<real, false, SCCAV_SPEC_ELLIPSE>;
     if (spec == SCCAV_SPEC_ELLIPSE_PREP)

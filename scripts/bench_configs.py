@@ -48,8 +48,13 @@ def oracle_run(b):
                       alpha=b.alpha, R=b.R, target_speed=b.target_speed)
 
 
+FLAGS = 0
+
+
 def run_config(name, batch, dtype, reps, n_sample, dev):
     t0 = time.time()
+    if FLAGS:
+        batch.params = dict(batch.params, flags=FLAGS)
     cl = ClosedLoopRollout(batch, dtype=dtype, device=dev, pin=False)
     for _ in range(2):
         res = cl.run()
@@ -122,7 +127,10 @@ def main():
     ap.add_argument("--sample", type=int, default=512)
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every N (smoke runs)")
     ap.add_argument("--out", default="")
+    ap.add_argument("--flags", type=int, default=0, help="sccav_params.flags for every config (5 = prepared rows + fused steer)")
     a = ap.parse_args()
+    global FLAGS
+    FLAGS = a.flags
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     want = set(a.configs.split(","))
@@ -132,6 +140,7 @@ def main():
         return max(1024, int(x * a.scale))
 
     def emit(line):
+        line["flags"] = a.flags
         lines.append(line)
         print(json.dumps(line), flush=True)
 
