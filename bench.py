@@ -282,6 +282,7 @@ def main():
 
     # ---- the other row mode, for the record (untimed region; 3 launches, same events)
     other = None
+    fp32_variant = None
     if rank == 0 or world > 1:
         b2 = sc.config2(n_total=n_total, M=M, T=T, seed=0, lo=lo, hi=hi)
         if args.rows == "canonical":
@@ -301,6 +302,29 @@ def main():
                  "value_this_rank": float(r2["steps"].sum().item()) * M / (statistics.mean(ms2) * 1e-3),
                  "identical_bookkeeping_frac_vs_timed_mode": float(same.double().mean().item())}
         del cl2
+        # ---- the fp32 variant of the same rollout (north_star: fp64 by default, fp32 reported): timing and how far
+        # it drifts from the fp64 run of the timed mode (same flags)
+        if args.dtype == "f64":
+            b3 = sc.config2(n_total=n_total, M=M, T=T, seed=0, lo=lo, hi=hi)
+            b3.params = dict(batch.params)
+            cl3 = ClosedLoopRollout(b3, dtype=torch.float32, device=dev, pin=False)
+            cl3.run()
+            ms3 = []
+            for _ in range(3):
+                flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); r3 = cl3.run(); e1.record()
+                torch.cuda.synchronize()
+                ms3.append(e0.elapsed_time(e1))
+            same3 = (r3["steps"] == res["steps"]) & (r3["target_idx"] == res["target_idx"]) & (r3["n_active"] == res["n_active"]) \
+                & (r3["n_infeasible"] == res["n_infeasible"])
+            dpos = (r3["state"][:2].double() - res["state"][:2].double()).norm(dim=0)
+            fp32_variant = {"dtype": "f32", "rows": args.rows, "ms_per_step": statistics.mean(ms3),
+                            "value_this_rank": float(r3["steps"].sum().item()) * M / (statistics.mean(ms3) * 1e-3),
+                            "identical_bookkeeping_frac_vs_f64": float(same3.double().mean().item()),
+                            "final_position_diff_m_median": float(dpos.median().item()),
+                            "final_position_diff_m_p99": float(torch.quantile(dpos, 0.99).item())}
+            del cl3
 
     # ---- timed region 2: end to end through the C-ABI host entry point (sccav_rollout_host_*):
     #      pinned HOST buffers in, H2D + kernel + D2H inside the call, HOST results out -- every step
@@ -456,7 +480,7 @@ def main():
             "config": {"workload": workload_name(args), "vehicles_total": n_total, "obstacles": M, "timesteps": T,
                        "solves_per_step": solves_per_step, "parallelism": "scenario shards x%d, no collective" % world,
                        "l2": "flushed (256 MB write) between timed iterations; inputs 36 MB/GPU",
-                       "rows": args.rows, "other_row_mode": other,
+                       "rows": args.rows, "other_row_mode": other, "fp32_variant": fp32_variant,
                        "seed": 0, "active_step_checksum": checksum},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cl.h2d_bytes(), "d2h_bytes_per_step": cl.d2h_bytes(),
                     "ms_per_step": 1e3 * e2e_s / args.steps,

@@ -136,7 +136,8 @@ def test_qp_shortcut_equals_enumeration(name, model, monkeypatch):
 
 
 @pytest.mark.parametrize("slot,static,dtype", [(o.SLOT_ELLIPSE, False, torch.float64), (o.SLOT_ELLIPSE_PREP, True, torch.float64),
-                                               (o.SLOT_ELLIPSE_PREP, False, torch.float64), (o.SLOT_ELLIPSE, False, torch.float32)])
+                                               (o.SLOT_ELLIPSE_PREP, False, torch.float64), (o.SLOT_ELLIPSE, False, torch.float32),
+                                               (o.SLOT_ELLIPSE_PREP, True, torch.float32)])
 def test_filter_step_pipelined_equals_direct_load_kernel(slot, static, dtype, monkeypatch):
     """The staged K12 (cp.async of every field of a vehicle into its shared-memory column, rows overlaying
     the staged slots) against the direct-load K12 (SCCAV_K12_PIPE=0), each with its default QP form:
