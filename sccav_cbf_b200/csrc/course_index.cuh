@@ -194,7 +194,7 @@ __host__ __device__ inline int course_nearest(const CourseIndex<T, T2>& ci, T fx
         // phase B: which supers can hold a point at distance <= best?  (same trip count for all lanes)
         const int ns = (ci.nsup - s0 < 32) ? ci.nsup - s0 : 32;
         uint32_t smask = 0u;
-#pragma unroll 1
+#pragma unroll 2
         for (int j = 0; j < ns; ++j)
             if (!capsule_skip<T, T2>(ci.sup, s0 + j, fx, fy, reach)) smask |= 1u << j;
         ne += ns;
@@ -205,7 +205,7 @@ __host__ __device__ inline int course_nearest(const CourseIndex<T, T2>& ci, T fx
             if (capsule_skip<T, T2>(ci.sup, s, fx, fy, reach)) { ++ne; continue; }   // bound tightened since phase B
             const int l0 = s * SCCAV_SUPER_LEAVES;
             uint32_t todo = 0u;
-#pragma unroll 1
+#pragma unroll 2
             for (int j = 0; j < SCCAV_SUPER_LEAVES; ++j) {
                 const int l = l0 + j;
                 if (l < ci.nleaf && l != leaf0 && l != leaf1 && !capsule_skip<T, T2>(ci.leaf, l, fx, fy, reach)) todo |= 1u << j;
