@@ -706,6 +706,10 @@ __global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_staged_kernel
         Ri.i00 = T(1); Ri.i01 = T(0); Ri.i10 = T(0); Ri.i11 = T(1);
         int Mv = 0;
         if (valid) {
+            // the vehicle's own six values first: they are needed first (sincos, tan), and the asynchronous copies
+            // below would otherwise queue in front of them (the volatile asm pins the program order)
+            x = a.state[n]; y = a.state[N + n]; th = a.state[2 * N + n]; v = a.state[3 * N + n];
+            ur0 = a.u_ref[n]; ur1 = a.u_ref[N + n];
             Mv = slot_count<T>(a.pv, M, n);
             const T* src = a.obst + n;
             T* dst = stage;
@@ -713,8 +717,6 @@ __global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_staged_kernel
 #pragma unroll
                 for (int f = 0; f < NF; ++f) cp_async_elem<T>(dst + f * B, src + (int64_t)f * N);
             }
-            x = a.state[n]; y = a.state[N + n]; th = a.state[2 * N + n]; v = a.state[3 * N + n];
-            ur0 = a.u_ref[n]; ur1 = a.u_ref[N + n];
             load_weights<T>(P, a.pv, N, n, alpha, R00, R01, R10, R11);
             Ri = load_rinv<T>(P, a.pv, R00, R01, R10, R11);
         }
