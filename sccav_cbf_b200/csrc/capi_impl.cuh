@@ -1,6 +1,7 @@
 // capi_impl.cuh -- the extern "C" entry points for ONE precision.  Included by capi_f64.cu
 // (SCCAV_REAL = double, compiled with -fmad=false) and capi_f32.cu (SCCAV_REAL = float).
 #pragma once
+#include <algorithm>
 #include <cstring>
 #include <new>
 
@@ -261,7 +262,7 @@ int do_filter_step(const sccav_params* p, const uint8_t* slot_desc, int32_t M, i
                           : filter_step_staged_kernel<real, SCCAV_SPEC_ELLIPSE_PREP, 6, true, -1>)
                    : filter_step_staged_kernel<real, SCCAV_SPEC_ELLIPSE_PREP, 6, false, -1>;
         SCCAV_CUDA_CHECK(cudaFuncSetAttribute((const void*)sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged));
-        sk<<<stream_grid(N, 256), 256, staged, st>>>(a);
+        sk<<<(int)std::min<int64_t>((N + 255) / 256, (int64_t)sm_count() * 2), 256, staged, st>>>(a);
         count_launch();
         SCCAV_CUDA_CHECK(cudaGetLastError());
         return SCCAV_OK;
