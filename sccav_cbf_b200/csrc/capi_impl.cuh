@@ -274,7 +274,7 @@ int do_filter_step(const sccav_params* p, const uint8_t* slot_desc, int32_t M, i
         ? (dcoop ? filter_step_kernel<real, SCCAV_SPEC_ELLIPSE_PREP, true> : filter_step_kernel<real, SCCAV_SPEC_ELLIPSE_PREP, false>)
         : (dcoop ? filter_step_kernel<real, SCCAV_SPEC_GENERIC, true> : filter_step_kernel<real, SCCAV_SPEC_GENERIC, false>);
     SCCAV_CUDA_CHECK(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<stream_grid(N, block), block, smem, st>>>(a);
+    kern<<<(int)std::min<int64_t>((N + block - 1) / block, (int64_t)sm_count() * 2 * (256 / block)), block, smem, st>>>(a);
     count_launch();
     SCCAV_CUDA_CHECK(cudaGetLastError());
     return SCCAV_OK;
