@@ -747,7 +747,7 @@ __global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_staged_kernel
                     p = ellipse_partials<T>(x, y, g[0], g[1], g[2], g[3], g[4], st_ ? T(0) : g[5], st_ ? T(0) : g[NF - 1]);
                 }
                 else if (NF >= 8) p = ellipse_prep_partials<T>(x, y, g[0], g[1], g[2], g[3], g[4], g[5], g[NF - 2], g[NF - 1]);
-                else p = ellipse_prep_partials<T>(x, y, g[0], g[1], g[2], g[3], g[4], g[5], T(0), T(0));
+                else p = ellipse_prep_partials<T>(x, y, g[0], g[1], g[2], g[3], g[4], g[5], T(0), T(0), true);
                 put_row<T, COOP, NF, MODEL>(P, p, sth, cth, v, alpha, vlr, r0, r1, stage, B, m, hmin, worst, feas, nz, &scan, &Ri);
             }
         }

@@ -176,8 +176,10 @@ __device__ __forceinline__ void ellipse_prepare(T a, T b, T th, T vx, T vy, T& m
     wx = vx / (a * a); wy = vy / (b * b);
 }
 
+// (is_static: h_t = -2 (dx 0 + dy 0) is not evaluated -- it is a zero whose sign cannot reach u or the active set)
 template <typename T>
-__device__ __forceinline__ Partials<T> ellipse_prep_partials(T x, T y, T cx, T cy, T m00, T m01, T m10, T m11, T wx, T wy) {
+__device__ __forceinline__ Partials<T> ellipse_prep_partials(T x, T y, T cx, T cy, T m00, T m01, T m10, T m11, T wx, T wy,
+                                                             bool is_static = false) {
     Partials<T> o;
     T dx = x - cx, dy = y - cy;
     T pa = fma(m00, dx, m01 * dy);
@@ -187,7 +189,7 @@ __device__ __forceinline__ Partials<T> ellipse_prep_partials(T x, T y, T cx, T c
     o.hy = T(2) * fma(m01, pa, m11 * qb);
     o.hth = T(0);
     o.hv = T(0);
-    o.ht = T(-2) * fma(dx, wx, dy * wy);
+    o.ht = is_static ? T(0) : T(-2) * fma(dx, wx, dy * wy);
     return o;
 }
 
@@ -369,7 +371,7 @@ __device__ __forceinline__ Partials<T> slot_partials(int desc, const T* __restri
         case SCCAV_SLOT_ELLIPSE_PREP: {
             T wx = T(0), wy = T(0);
             if (!is_static) { wx = f[6 * fs]; wy = f[7 * fs]; }
-            return ellipse_prep_partials<T>(x, y, f[0], f[fs], f[2 * fs], f[3 * fs], f[4 * fs], f[5 * fs], wx, wy);
+            return ellipse_prep_partials<T>(x, y, f[0], f[fs], f[2 * fs], f[3 * fs], f[4 * fs], f[5 * fs], wx, wy, is_static);
         }
         default: {
             T cx = f[0], cy = f[fs], Ds = f[2 * fs];
@@ -871,7 +873,7 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
         for (int m = 0; m < M; ++m, f += ss) {
             T wx = T(0), wy = T(0);
             if (!is_static) { wx = f[6 * N]; wy = f[7 * N]; }
-            Partials<T> p = ellipse_prep_partials<T>(x, y, f[0], f[N], f[2 * N], f[3 * N], f[4 * N], f[5 * N], wx, wy);
+            Partials<T> p = ellipse_prep_partials<T>(x, y, f[0], f[N], f[2 * N], f[3 * N], f[4 * N], f[5 * N], wx, wy, is_static);
             put_row<T, SCAN, 3, MODEL>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
         }
     } else {
