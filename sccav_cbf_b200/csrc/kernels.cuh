@@ -1,9 +1,13 @@
-// kernels.cuh -- the four sm_100a kernels of the path and their launchers.
+// kernels.cuh -- the sm_100a kernels of the path (launchers: capi_impl.cuh).
 //
-//   K1  barrier_rows_kernel   HBM-bound: reads state + obstacle SoA, writes rows       (regime i)
-//   K2  qp2_kernel            HBM-bound: reads rows, writes u / active set / status    (regime i)
-//   K12 filter_step_kernel    K1+K2 fused (rows never leave the SM)                    (regime i)
-//   K3  rollout_kernel        persistent closed loop, FP64-pipe bound                  (regime ii)
+//   K0  barrier_partials_kernel      h and its partials per (vehicle, slot)                        HBM-bound
+//   K1  barrier_rows_kernel          reads state + obstacle SoA, writes rows                       HBM-bound   (regime i)
+//   K2  qp2_kernel / qp2_warp_kernel reads rows, writes u / active set / status                    HBM-bound   (regime i)
+//   K12 filter_step_kernel           K1+K2 fused, direct loads (rows never leave the SM)                       (regime i)
+//       filter_step_staged_kernel    the same with all fields of a vehicle staged by cp.async, rows overlaying them
+//   K3  rollout_kernel               persistent closed loop, fp64 issue / latency bound                        (regime ii)
+//   KS  stanley_kernel, KP prepare_obstacles_kernel, KB ingest_boxes_kernel, KA actuator_kernel,
+//   KC  spline_course_kernel, KL lane_fit_kernel        the steps either side of the path
 //
 // Layout: thread == vehicle; all global accesses are SoA with the vehicle index fastest, so a warp
 // reads/writes 32 consecutive elements (256 B for fp64) per request.  Rows live in shared memory

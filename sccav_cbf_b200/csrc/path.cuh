@@ -725,32 +725,6 @@ __device__ __forceinline__ int qp2_solve_active_warp(bool need, const T* warp_ro
     return status;
 }
 
-// rows already in shared memory (K2): reference-point check, masks, then the active solve
-template <typename T>
-__device__ __forceinline__ int qp2_solve(const RowView<T>& rv, int m, T r0, T r1, T R00, T R01, T R10, T R11,
-                                         T& u0o, T& u1o, uint32_t& masko) {
-    typedef Real<T> R;
-    bool feas = true;
-    T worst = -R::inf();
-    RowNz nz{0u, 0u};
-    for (int k = 0; k < m; ++k) {
-        T a0 = rv.A0(k), a1 = rv.A1(k), bk = rv.b(k);
-        if (a0 != T(0)) nz.nz0 |= 1u << k;
-        if (a1 != T(0)) nz.nz1 |= 1u << k;
-        T t0 = a0 * r0, t1 = a1 * r1;
-        T rk = (t0 + t1) - bk;
-        if (-rk > worst) worst = -rk;
-        T tol = R::feas_eps() * ((R::abs_(t0) + R::abs_(t1)) + R::abs_(bk));
-        if (!(rk >= -tol)) feas = false;
-    }
-    if (feas) {
-        u0o = r0; u1o = r1; masko = 0u;
-        return SCCAV_STATUS_INACTIVE;
-    }
-    const RInv<T> Ri(R00, R01, R10, R11);
-    return qp2_solve_active<T>(rv, m, nz, r0, r1, R00, R01, R10, R11, Ri, worst, u0o, u1o, masko);
-}
-
 // ------------------------------------------------------------------------------------------
 // one solve_cbf for one vehicle: rows of all slots -> smem -> QP -> converted output
 // (cbf/cbf.py:166-220 for DBM, :67-110 for KBM).  u_ref = (a|v, delta); returns (a|v, delta).
