@@ -470,3 +470,43 @@ def test_sadbm_batched_ticks_vs_oracle():
     # stateful model: the carried state is mandatory, and there is no closed loop for it
     with pytest.raises(Exception):
         ops.filter_step(prm, slots, torch.from_numpy(s).to(dev), torch.from_numpy(ob).to(dev), torch.from_numpy(ur).to(dev))
+
+
+@gpu
+def test_sadbm_wall_clock_mode_and_lane_distance_form():
+    """SADBM_CBF_2DS(dt=None) measures the step on the host as cbf.py:363-365 does (floored at ZERO_TOL) and still
+    integrates beta consistently; PolyLane(distance_form=True) is the CBF_lane_sqrt barrier
+    (stanley_controller_ellipse.py:465-512) -- class getters and solve_cbf against the oracle."""
+    import time
+    from sccav_cbf_b200 import SADBM_CBF_2DS
+    from sccav_cbf_b200.utils import ZERO_TOL
+    ctl = SADBM_CBF_2DS(alpha=1.0, dt=None)
+    ctl.set_model_params(lr=1.45, lf=1.45)
+    s = [0.0, 0.0, 0.1, 8.0]
+    ctl.obstacle_list2d[0] = CollisionCone2D(2.0, s, [18.0, 1.0, 3.0, 2.0])
+    ctl.update_state(s=s)
+    u1 = ctl.solve_cbf([0.5, 0.05])
+    b1 = float(ctl._beta[0])
+    assert ctl._dt >= ZERO_TOL and math.isfinite(float(u1[1]))
+    time.sleep(0.02)
+    ctl.update_state(s=s)
+    u2 = ctl.solve_cbf([0.5, 0.05])
+    assert ctl._dt >= 0.02                                          # the measured step went into the kernel
+    # same reference twice: beta_ref_dot = 0 on the second call, so beta moves by u[1]-rate * dt only
+    assert abs(float(ctl.beta_ref_last[0]) - math.atan2(1.45 * math.tan(0.05), 2.9)) < 1e-15
+    assert math.isfinite(b1) and math.isfinite(float(ctl._beta[0]))
+    # distance-form lane barrier
+    co = np.array([3.0, 0.02, 0.001])
+    st = [10.0, 1.2, 0.3, 7.0]
+    ln = PolyLane(co, s=st, buffer=1.5, distance_form=True)
+    h, hx, hy, _, _, _ = o.lane_sqrt_partials(st[0], st[1], list(co) + [0.0, 0.0, 0.0], 1.5)
+    assert rel(ln.f(), h) < 1e-9 and rel(ln.dx(), hx) < 1e-9 and rel(ln.dy(), hy) < 1e-9
+    sq = PolyLane(co, s=st, buffer=1.5)
+    assert abs((ln.f() + 1.5) ** 2 - (sq.f() + 1.5)) < 1e-9           # sqrt(d^2) - buffer  vs  d^2 - buffer
+    d = DBM_CBF_2DS(alpha=1.0)
+    d.set_model_params(lr=1.45, lf=1.45)
+    d.obstacle_list2d["l"] = ln
+    d.update_state(st)
+    info, u = d.solve_cbf([0.0, 0.3], return_solver=True)
+    ref = o.filter_step(o.MODEL_DBM, st, [0.0, 0.3], [o.SLOT_LANE_SQRT], [[1.5] + list(co) + [0.0, 0.0, 0.0, 0.0]], 1.0, 1.45, 1.45, 2.9, (1, 0, 0, 1))
+    assert info["status"] == ref[3] and abs(float(u[1]) - ref[1]) < 1e-7 and abs(float(u[0]) - ref[0]) < 1e-9

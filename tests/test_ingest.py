@@ -352,3 +352,22 @@ def test_batched_lane_fit_feeds_the_lane_barrier():
         ref.append(o.filter_step(o.MODEL_DBM, [20.0, 1.9, 0.25, 8.0], [0.0, 0.1], [o.SLOT_LANE], f, 1.0, 1.45, 1.45, 2.9, (1, 0, 0, 1)))
     assert np.abs(u[1].cpu().numpy() - np.array([r[1] for r in ref])).max() < 1e-7      # (lane parity proper: test_gpu_parity)
     assert (info["status"].cpu().numpy() == np.array([r[3] for r in ref])).all() and int((info["status"] == 1).sum()) > C // 2
+
+
+@pytest.mark.gpu
+def test_lane_fit_degenerate_inputs():
+    """KL: too few points for the degree, and argument errors through the C-ABI."""
+    from sccav_cbf_b200 import ops
+    dev = torch.device("cuda", 0)
+    x = torch.tensor([[0.0, 0.0], [1.0, 1.0], [2.0, 2.0]], dtype=torch.float64, device=dev)       # K = 3, C = 2
+    y = torch.tensor([[1.0, 1.0], [2.0, 3.0], [3.0, 5.0]], dtype=torch.float64, device=dev)
+    c, st = ops.fit_lanes(x, y, n=1)
+    assert st.tolist() == [0, 0]
+    assert torch.allclose(c[:2].cpu(), torch.tensor([[1.0, 1.0], [1.0, 2.0]], dtype=torch.float64), atol=1e-12) and (c[2:] == 0).all()
+    c, st = ops.fit_lanes(x, y, n=3)                                   # 3 points cannot fix 4 coefficients
+    assert st.tolist() == [1, 1] and torch.isnan(c).all()
+    cnt = torch.tensor([3, 1], dtype=torch.int32, device=dev)
+    c, st = ops.fit_lanes(x, y, n=1, count=cnt)
+    assert st.tolist() == [0, 1] and torch.isnan(c[:, 1]).all()
+    with pytest.raises(ValueError):                                     # SCCAV_EINVAL -> ValueError, like the other entry points
+        ops.fit_lanes(x, y, n=6)
