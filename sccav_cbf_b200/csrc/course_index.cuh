@@ -175,7 +175,9 @@ __host__ __device__ __forceinline__ int lowest_bit(uint32_t m) {
 // Exact global nearest index (first minimum) of (fx, fy) over the whole course.
 // hint: any index (the previous nearest index; clamped into [0, np)); evals (optional) counts
 // distance evaluations + capsule tests for the roofline accounting.
-template <typename T, typename T2>
+// UNR: unroll factor of the two capsule-test loops (2 lets independent tests interleave in the lean ellipse
+// instances of the rollout; the larger generic instances are better off with 1 -- registers).
+template <typename T, typename T2, int UNR = 2>
 __host__ __device__ inline int course_nearest(const CourseIndex<T, T2>& ci, T fx, T fy, int hint, int* evals) {
     if (hint < 0) hint = 0;
     if (hint >= ci.np) hint = ci.np - 1;
@@ -194,7 +196,7 @@ __host__ __device__ inline int course_nearest(const CourseIndex<T, T2>& ci, T fx
         // phase B: which supers can hold a point at distance <= best?  (same trip count for all lanes)
         const int ns = (ci.nsup - s0 < 32) ? ci.nsup - s0 : 32;
         uint32_t smask = 0u;
-#pragma unroll 2
+#pragma unroll UNR
         for (int j = 0; j < ns; ++j)
             if (!capsule_skip<T, T2>(ci.sup, s0 + j, fx, fy, reach)) smask |= 1u << j;
         ne += ns;
@@ -205,7 +207,7 @@ __host__ __device__ inline int course_nearest(const CourseIndex<T, T2>& ci, T fx
             if (capsule_skip<T, T2>(ci.sup, s, fx, fy, reach)) { ++ne; continue; }   // bound tightened since phase B
             const int l0 = s * SCCAV_SUPER_LEAVES;
             uint32_t todo = 0u;
-#pragma unroll 2
+#pragma unroll UNR
             for (int j = 0; j < SCCAV_SUPER_LEAVES; ++j) {
                 const int l = l0 + j;
                 if (l < ci.nleaf && l != leaf0 && l != leaf1 && !capsule_skip<T, T2>(ci.leaf, l, fx, fy, reach)) todo |= 1u << j;

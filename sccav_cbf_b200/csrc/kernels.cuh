@@ -963,7 +963,7 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
         if (stan) {
             T a_ref = P.Kp * (tspeed - v);                                                 // sce.py:135-143
             T d_ref;
-            if (COURSE_SMEM) d_ref = stanley<T, T2>(P, ci, s_cyaw, x, y, yaw, v, syaw, cyw, target_idx, near_idx, &evals);
+            if (COURSE_SMEM) d_ref = stanley<T, T2, (SPEC == SCCAV_SPEC_GENERIC ? 1 : 2)>(P, ci, s_cyaw, x, y, yaw, v, syaw, cyw, target_idx, near_idx, &evals);
             else {
                 // global-memory course fallback (P too large for shared memory): exhaustive scan
                 T fx = x + P.L * cyw, fy = y + P.L * syaw;

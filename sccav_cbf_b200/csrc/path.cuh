@@ -948,12 +948,12 @@ __device__ __forceinline__ T stanley_law(const Params<T>& P, CXY c, const T* __r
 }
 
 // course staged in shared memory with its bounding-circle index: exact pruned nearest search
-template <typename T, typename T2>
+template <typename T, typename T2, int UNR = 2>
 __device__ __forceinline__ T stanley(const Params<T>& P, const CourseIndex<T, T2>& ci, const T* __restrict__ cyaw,
                                      T x, T y, T yaw, T v, T syaw, T cyw, int& target_idx, int& near_idx, int* evals) {
     T fx = x + P.L * cyw;
     T fy = y + P.L * syaw;
-    int idx = course_nearest<T, T2>(ci, fx, fy, near_idx, evals);
+    int idx = course_nearest<T, T2, UNR>(ci, fx, fy, near_idx, evals);
     near_idx = idx;
     return stanley_law<T, T2>(P, ci.pt(idx), cyaw, idx, fx, fy, yaw, v, target_idx);
 }
