@@ -173,3 +173,44 @@ def test_prepared_ellipse_equals_canonical_ellipse_in_both_oracles():
     assert np.allclose(c_can["A"], c_pre["A"], rtol=1e-11, atol=1e-12) and np.allclose(c_can["b"], c_pre["b"], rtol=1e-11, atol=1e-11)
     assert np.array_equal(c_can["mask"], c_pre["mask"]) and np.array_equal(c_can["status"], c_pre["status"])
     assert np.allclose(c_can["u"], c_pre["u"], rtol=1e-10, atol=1e-12)
+
+
+def test_qp_shortcut_theory_most_violated_row_in_the_metric_of_R():
+    """The statement the kernels' one-scan QP shortcut rests on (csrc/path.cuh, QpScan): if the optimum has exactly ONE
+    active row, that row is the one with the largest rk^2 / (A_k R^-1 A_k^T) among the rows the reference point violates
+    (its projection has to clear every other violated half-plane).  Checked against the enumerating oracle, with a numpy
+    mirror of the scan -- including the direction the kernel relies on: whenever the scan's candidate passes the
+    feasibility test (and is not a near-tie), it IS the oracle's answer."""
+    rng = np.random.default_rng(21)
+    n_single = n_accept = 0
+    for it in range(4000):
+        m = int(rng.integers(1, 9))
+        A0, A1, b, r, Rm = _random_qp(rng, m)
+        if it % 3 == 0:
+            A0[:] = 0.0                                               # the all-ellipse DBM shape: rows constrain u1 only
+        u0, u1, mask, status = o.qp2_exact(list(A0), list(A1), list(b), r[0], r[1], tuple(Rm.ravel()))
+        Ri = np.linalg.inv(Rm)
+        rk = A0 * r[0] + A1 * r[1] - b
+        g = Ri @ np.stack([A0, A1])
+        den = A0 * g[0] + A1 * g[1]
+        viol = (rk < 0) & (den > 0)
+        if not viol.any():
+            continue
+        ratio = np.where(viol, rk * rk / np.where(den > 0, den, 1.0), -1.0)
+        kb = int(np.argmax(ratio))
+        runner = np.partition(ratio, -2)[-2] if m > 1 else -1.0
+        if status == o.STATUS_ACTIVE and bin(mask).count("1") == 1:
+            n_single += 1
+            k = mask.bit_length() - 1
+            assert ratio[k] >= ratio[kb] * (1 - 1e-9), (it, k, kb)    # the active row is the most violated one
+        # the kernel's direction: candidate of kb feasible (and a clear winner) => it is the oracle's answer
+        t = -rk[kb] / den[kb]
+        c = r + g[:, kb] * t
+        res = A0 * c[0] + A1 * c[1] - b
+        tol = 1e-12 * (np.abs(A0 * c[0]) + np.abs(A1 * c[1]) + np.abs(b))
+        ok = all(res[j] >= -tol[j] for j in range(m) if j != kb)
+        if ok and runner < ratio[kb] * (1 - 1e-6):
+            n_accept += 1
+            assert status == o.STATUS_ACTIVE and mask == 1 << kb, (it, mask, kb)
+            assert abs(c[0] - u0) <= 1e-12 * (1 + abs(u0)) and abs(c[1] - u1) <= 1e-12 * (1 + abs(u1))
+    assert n_single > 500 and n_accept > 500
