@@ -6,9 +6,13 @@
  * The reference has no FFI of its own (pure Python); its boundary is the class API
  *     DBM_CBF_2DS.solve_cbf            cbf/cbf.py:166-220
  *     KBM_VC_CBF2D.solve_cbf           cbf/cbf.py:67-110
+ *     DUM_CBF_2DS / SADBM_CBF_2DS.solve_cbf   cbf/cbf.py:247-298, 348-437
  *     ObstacleList2D.f/dx/dy/dtheta/dv/dt   cbf/obstacles.py:879-925
  *     the per-tick loop of             test_scripts/stanley_controller_ellipse.py:630-830
  *                                      test_scripts/radial_dynamic_obstacles.py:427-507
+ * and, either side of the path: ObstacleList2D.update_by_bounding_box (obstacles.py:833-858), calc_spline_course
+ * (cubic_spline_planner.py:178-190), PolyLane.fit_polynomial_curve (obstacles.py:715-773), the actuator block of
+ * carla_scripts/multi_obstacle_CBF_local_with_lanes.py:955-980.
  * Each entry point below names the reference interface it replaces.  INTEGRATION.md shows the
  * ctypes binding a maintainer of the reference would add.
  *
