@@ -237,3 +237,18 @@ def test_polynomial_lane_fit_vs_reference_curve_fit(refvec2):
         if n <= 4:
             xx = np.linspace(x.min(), x.max(), 64)
             assert np.abs(np.polyval(c[::-1], xx) - np.polyval(ref[::-1], xx)).max() <= 1e-5
+
+
+def test_polynomial_lane_fit_equals_numpy_polyfit():
+    """Independent check of the lane-fit restatement: numpy.polyfit with weights 1 / sigma minimises the same weighted
+    residual (on well-conditioned inputs -- polyfit works on the raw Vandermonde matrix)."""
+    rng = np.random.default_rng(4)
+    for n in (1, 2, 3):
+        for _ in range(20):
+            K = int(rng.integers(n + 2, 30))
+            x = np.sort(rng.uniform(-5, 5, K))
+            y = rng.normal(size=n + 1) @ np.vander(x, n + 1, increasing=True).T + rng.normal(0, 0.05, K)
+            sg = rng.uniform(0.5, 3.0, K)
+            c = o.fit_polynomial(x, y, n, sg)
+            ref = np.polyfit(x, y, n, w=1.0 / sg)[::-1]
+            assert np.allclose(c, ref, rtol=1e-9, atol=1e-10)
