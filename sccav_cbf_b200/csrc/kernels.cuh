@@ -503,13 +503,14 @@ __global__ void __launch_bounds__(256) qp2_kernel(const __grid_constant__ QpArgs
         const bool valid = n < N;
         int Mv = 0;
         T r0 = T(0), r1 = T(0), worst = -R::inf();
-        T alpha, R00 = T(1), R01 = T(0), R10 = T(0), R11 = T(1);
+        // (lanes past N take part in the cooperative enumeration of their warp's problems with the launch-wide weight)
+        T alpha, R00 = a.P.R[0], R01 = a.P.R[1], R10 = a.P.R[2], R11 = a.P.R[3];
         RowNz nz{0u, 0u};
         bool feas = true;
         QpScan<T> scan;
         scan.reset();
         RInv<T> Ri;
-        Ri.i00 = T(1); Ri.i01 = T(0); Ri.i10 = T(0); Ri.i11 = T(1);
+        Ri.i00 = a.P.Ri[0]; Ri.i01 = a.P.Ri[1]; Ri.i10 = a.P.Ri[2]; Ri.i11 = a.P.Ri[3];
         if (valid) {
             Mv = slot_count<T>(a.pv, a.M, n);
             load_weights<T>(a.P, a.pv, N, n, alpha, R00, R01, R10, R11);
@@ -618,14 +619,15 @@ __global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_kernel(const 
         const int64_t n = nw + lane;
         const bool valid = n < N;
         T ur0 = T(0), ur1 = T(0), hmin = R::inf();
-        T alpha = T(0), R00 = T(1), R01 = T(0), R10 = T(0), R11 = T(1);
+        // (lanes past N take part in the cooperative enumeration of their warp's problems with the launch-wide weight)
+        T alpha = T(0), R00 = a.P.R[0], R01 = a.P.R[1], R10 = a.P.R[2], R11 = a.P.R[3];
         int Mv = 0;
         T augv[2] = {T(0), T(0)};
         RowPhase<T> ph;
         ph.r0 = T(0); ph.r1 = T(0); ph.worst = -R::inf(); ph.nz.nz0 = 0u; ph.nz.nz1 = 0u; ph.feas = true;
         ph.scan.reset();
         RInv<T> Ri;
-        Ri.i00 = T(1); Ri.i01 = T(0); Ri.i10 = T(0); Ri.i11 = T(1);
+        Ri.i00 = a.P.Ri[0]; Ri.i01 = a.P.Ri[1]; Ri.i10 = a.P.Ri[2]; Ri.i11 = a.P.Ri[3];
         if (valid) {
             T x = a.state[n], y = a.state[N + n], th = a.state[2 * N + n], v = a.state[3 * N + n];
             ur0 = a.u_ref[n]; ur1 = a.u_ref[N + n];
@@ -705,9 +707,10 @@ __global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_staged_kernel
         const int64_t n = nw + lane;
         const bool valid = n < N;
         T x = T(0), y = T(0), th = T(0), v = T(0), ur0 = T(0), ur1 = T(0);
-        T alpha = T(0), R00 = T(1), R01 = T(0), R10 = T(0), R11 = T(1);
+        // (lanes past N take part in the cooperative enumeration of their warp's problems with the launch-wide weight)
+        T alpha = T(0), R00 = P.R[0], R01 = P.R[1], R10 = P.R[2], R11 = P.R[3];
         RInv<T> Ri;
-        Ri.i00 = T(1); Ri.i01 = T(0); Ri.i10 = T(0); Ri.i11 = T(1);
+        Ri.i00 = P.Ri[0]; Ri.i01 = P.Ri[1]; Ri.i10 = P.Ri[2]; Ri.i11 = P.Ri[3];
         int Mv = 0;
         if (valid) {
             // the vehicle's own six values first: they are needed first (sincos, tan), and the asynchronous copies

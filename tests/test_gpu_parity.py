@@ -166,6 +166,42 @@ def test_filter_step_pipelined_equals_direct_load_kernel(slot, static, dtype, mo
         assert int((got[0][2] == 1).sum()) > 0
 
 
+def test_cooperative_qp_tail_warp_with_non_identity_weight(monkeypatch):
+    """A batch whose last warp is only partly filled, with a launch-wide R != I: the lanes past N take part in the
+    cooperative enumeration of their warp's problems and must use the same weight as everybody else.  Staged + cooperative
+    (prepared static slots), direct + cooperative, thread-per-problem and the warp-per-problem K2 all give the same bits."""
+    from sccav_cbf_b200 import ops
+    M = 8
+    for N in (37, 1000 + 7, 256 * 3 + 1):
+        rng = np.random.default_rng(N)
+        s = H.random_states(rng, N)
+        ob = H.random_slots(rng, N, [o.SLOT_ELLIPSE] * M, s)
+        ob[:, 5:7] = 0.0
+        ur = H.random_uref(rng, N)
+        R = [1.5, 0.4, 0.4, 2.0]
+        prm = ops.make_params(R=R, alpha=0.8)
+        sd, obp = ops.prepare_obstacles([o.SLOT_ELLIPSE | o.SLOT_STATIC] * M, T(ob))
+        got = []
+        for pipe, qp in (("1", "coop"), ("0", "coop"), ("0", "thread")):
+            monkeypatch.setenv("SCCAV_K12_PIPE", pipe)
+            monkeypatch.setenv("SCCAV_K12_QP", qp)
+            got.append(ops.filter_step(prm, sd, T(s), obp, T(ur)))
+            torch.cuda.synchronize()
+        for g in got[1:]:
+            for x, y in zip(got[0], g):
+                assert torch.equal(x, y), N
+        ref = co.filter_step(co.default_params(R=R, alpha=0.8), sd, s, obp.cpu().numpy(), ur)
+        assert np.array_equal(got[0][1].cpu().numpy().view(np.uint32), ref["mask"]) and np.array_equal(got[0][2].cpu().numpy(), ref["status"])
+        assert close(got[0][0], ref["u"]) < 1.0
+        A, b, _ = ops.barrier_rows(prm, sd, T(s), obp)
+        r = T(np.stack([ur[0], np.arctan2(1.45 * np.tan(ur[1]), 2.9)]))
+        u2, m2, s2 = ops.qp2_solve(prm, A, b, r)
+        u3, m3, s3 = ops.qp2_solve(prm, A, b, r, warp_per_problem=True)
+        assert torch.equal(u2, u3) and torch.equal(m2, m3) and torch.equal(s2, s3)
+        assert torch.equal(m2, got[0][1]) and torch.equal(s2, got[0][2])
+        assert int((s2 != 0).sum()) > 0
+
+
 def test_qp_kkt_property_full_size():
     """Size-independent property at BASELINE size (65,536 x 8): every returned point is primal
     feasible, stationary on its active set, with non-negative multipliers."""
