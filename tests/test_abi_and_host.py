@@ -85,3 +85,26 @@ def test_scenarios_are_independent_of_sharding():
     assert c3.obst.shape == (16, 8, 10) and c3.params["seeker"] == 1
     c4 = sc.config4(n_total=1000, M=8, T=5, lo=0, hi=10)
     assert c4.M == 10 and c4.slot_desc[-1] == (2 | 0x80)
+
+
+def test_header_constants_match_their_python_mirrors():
+    """Slot types, slot flags, models, parameter flags and status codes of include/sccav_cbf.h against
+    sccav_cbf_b200._native (the product's ctypes layer) and oracle.oracle (the checker)."""
+    from oracle import oracle as o
+    from sccav_cbf_b200 import _native as nv
+    hdr = open(os.path.join(ROOT, "include", "sccav_cbf.h")).read()
+    defs = {k: int(v, 0) for k, v in re.findall(r"#define\s+(SCCAV_[A-Z0-9_]+)\s+(0x[0-9a-fA-F]+|-?\d+)\b", hdr)}
+    pairs = {
+        "SCCAV_SLOT_ELLIPSE": "SLOT_ELLIPSE", "SCCAV_SLOT_CONE": "SLOT_CONE", "SCCAV_SLOT_LANE": "SLOT_LANE",
+        "SCCAV_SLOT_RADIAL": "SLOT_RADIAL", "SCCAV_SLOT_DISTANCE": "SLOT_DISTANCE", "SCCAV_SLOT_ELLIPSE_PREP": "SLOT_ELLIPSE_PREP",
+        "SCCAV_SLOT_LANE_SQRT": "SLOT_LANE_SQRT", "SCCAV_SLOT_STATIC": "SLOT_STATIC",
+        "SCCAV_MODEL_DBM": "MODEL_DBM", "SCCAV_MODEL_KBM": "MODEL_KBM", "SCCAV_MODEL_NONE": "MODEL_NONE", "SCCAV_MODEL_DUM": "MODEL_DUM",
+        "SCCAV_MODEL_SADBM": "MODEL_SADBM", "SCCAV_FLAG_PREPARED_ROWS": "FLAG_PREPARED_ROWS", "SCCAV_FLAG_QP_ENUMERATE": "FLAG_QP_ENUMERATE",
+        "SCCAV_FLAG_FUSED_STEER": "FLAG_FUSED_STEER",
+    }
+    for c_name, py_name in pairs.items():
+        assert c_name in defs, c_name
+        assert getattr(nv, py_name) == defs[c_name], py_name
+        assert getattr(o, py_name) == defs[c_name], py_name
+    assert (o.STATUS_INACTIVE, o.STATUS_ACTIVE, o.STATUS_INFEASIBLE) == (defs["SCCAV_STATUS_INACTIVE"], defs["SCCAV_STATUS_ACTIVE"], defs["SCCAV_STATUS_INFEASIBLE"])
+    assert nv.NFIELD == defs["SCCAV_NFIELD"] == o.NFIELD and nv.MAX_ROWS == defs["SCCAV_MAX_ROWS"]
