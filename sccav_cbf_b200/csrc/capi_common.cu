@@ -189,26 +189,29 @@ template <typename T, typename T2>
 static void debug_course_index(const double* cx, const double* cy, int P, const double* fx, const double* fy,
                                const int32_t* hint, int64_t nq, int32_t* idx, int32_t* idx_full, int64_t* evals) {
     std::vector<T2> xy(course_nslot(P));
-    T ext = T(0);
-    for (int i = 0; i < P; ++i) {
-        xy[course_slot(i)].x = (T)cx[i]; xy[course_slot(i)].y = (T)cy[i];
-        ext = std::max(ext, std::max((T)fabs((T)cx[i]), (T)fabs((T)cy[i])));
-    }
-    const int nleaf = course_nleaf(P), nsup = course_nsup(P);
-    std::vector<T2> lc(3 * nleaf), sc(3 * nsup);
+    for (int i = 0; i < P; ++i) { xy[course_slot(i)].x = (T)cx[i]; xy[course_slot(i)].y = (T)cy[i]; }
+    // same construction as course_stage (kernels.cuh): origin = the middle point of the course
+    T org[2] = {xy[course_slot(P / 2)].x, xy[course_slot(P / 2)].y};
+    double e = 0.0;
+    for (int i = 0; i < P; ++i)
+        e = std::max(e, std::max(fabs((double)xy[course_slot(i)].x - (double)org[0]), fabs((double)xy[course_slot(i)].y - (double)org[1])));
+    const float ext = course_ext_inflate(e);
+    int lev[2 * SCCAV_MAX_LEVELS], units;
+    const int nlev = course_levels(P, lev, &units);
+    std::vector<float4> nodes(units);
     CourseIndex<T, T2> ci;
     ci.xy = xy.data();
-    ci.np = P; ci.nleaf = nleaf; ci.nsup = nsup;
-    ci.leaf.a = lc.data(); ci.leaf.ab = lc.data() + nleaf; ci.leaf.ir = lc.data() + 2 * nleaf;
-    ci.sup.a = sc.data(); ci.sup.ab = sc.data() + nsup; ci.sup.ir = sc.data() + 2 * nsup;
-    for (int l = 0; l < nleaf; ++l) {
-        int lo = l * SCCAV_LEAF, hi = lo + SCCAV_LEAF < P ? lo + SCCAV_LEAF : P;
-        capsule_build<T, T2>(xy.data(), lo, hi, ext, ci.leaf.a[l], ci.leaf.ab[l], ci.leaf.ir[l]);
-    }
-    for (int q = 0; q < nsup; ++q) {
-        int lo = q * SCCAV_LEAF * SCCAV_SUPER_LEAVES, hi = lo + SCCAV_LEAF * SCCAV_SUPER_LEAVES < P ? lo + SCCAV_LEAF * SCCAV_SUPER_LEAVES : P;
-        capsule_build<T, T2>(xy.data(), lo, hi, ext, ci.sup.a[q], ci.sup.ab[q], ci.sup.ir[q]);
-    }
+    ci.node = nodes.data(); ci.lev = lev; ci.org = org; ci.ext = &ext;
+    ci.np = P; ci.nleaf = course_nleaf(P); ci.nlev = nlev;
+    for (int k = 0; k < nlev; ++k)
+        for (int j = 0; j < lev[2 * k + 1]; ++j) {
+            float4 c;
+            float2 r;
+            capsule_build<T, T2>(xy.data(), P, k, j, (double)org[0], (double)org[1], ext, c, r);
+            const int u = CourseIndex<T, T2>::unit(lev[2 * k], j);
+            nodes[u] = c;
+            nodes[u + 1] = make_float4(r.x, r.y, 0.f, 0.f);
+        }
     for (int64_t k = 0; k < nq; ++k) {
         int ne = 0;
         idx[k] = course_nearest<T, T2>(ci, (T)fx[k], (T)fy[k], hint ? hint[k] : 0, &ne);

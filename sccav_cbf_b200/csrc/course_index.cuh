@@ -4,27 +4,30 @@
 // test_scripts/stanley_controller_ellipse.py:188-212: np.hypot over the whole course + np.argmin,
 // first minimum wins).  At P = 2034 that scan is > 80 % of the arithmetic of a closed-loop step.
 // This header returns THE SAME index -- the lexicographic minimum of (d2_i, i), d2_i computed with
-// the same operations as the full scan -- while touching a few dozen points:
+// the same operations as the full scan -- while evaluating 16 points:
 //
-//   * the course is cut into leaves of LEAF consecutive points and supers of SUPER_LEAVES leaves;
-//     every leaf / super carries a CAPSULE: the chord from its first to its last point plus a
-//     radius rho >= max_i dist(p_i, chord) (a few mm for a leaf of a smooth course);
-//   * for every point p_i of a block  |f - p_i| >= dist(f, chord) - rho  (triangle inequality through
-//     the chord point closest to p_i), so a block is skipped only when
-//         dist(f, chord) > sqrt(best) (1 + eps) + rho (1 + 4 eps) + slack ,
-//     with eps and slack (1e-9 and 1e-12 x the course extent in fp64) orders of magnitude above the
-//     rounding error of the few operations involved (a mis-rounded chord parameter t only moves the
-//     foot point ALONG the chord, a second-order effect covered by slack).  Neither a smaller
-//     distance nor an equal one with a smaller index can therefore hide in a skipped block;
-//   * the search starts in the leaf of a hint (the previous tick's nearest index), which makes the
-//     bound tight immediately; any hint gives the same result, only the cost differs.
+//   * the course is cut into leaves of 8 consecutive points; leaves are the bottom level of a tree of
+//     fan-out 8 (node j of level k = nodes 8j .. 8j+7 of level k-1); every node carries a CAPSULE: a
+//     chord from (about) its first to its last point and a radius rho >= max_i dist(p_i, chord);
+//   * for every point p_i of a node  |f - p_i| >= dist(f, chord) - rho  (triangle inequality through the
+//     chord point closest to p_i), so a node is skipped only when  dist(f, chord) > sqrt(best) + rho + slack.
+//     The test is a BOUND, not reference arithmetic, so it is evaluated in single precision relative to
+//     an origin on the course (12 fp32 instructions, 24 bytes per node) with every rounding error charged
+//     to the slack: the chord is whatever its fp32 end points say and rho is measured against THAT chord in
+//     double precision at build time; the query point's conversion, the subtraction, the (mis-rounded)
+//     chord parameter and the final products are covered by  2e-6 (|f - o|_1 + extent)  -- an order of
+//     magnitude above their sum (<= 5e-7 of the same quantity) -- and sqrt(best) is rounded up.  Neither a
+//     smaller distance nor an equal one with a smaller index can therefore hide in a skipped node;
+//   * the search scans the two leaves around a hint (the index predicted from the previous ticks), which
+//     makes the bound tight immediately, then CLIMBS: at every level the siblings of the scanned leaves'
+//     ancestor are tested in ONE unrolled batch of 8 independent tests (the same code, the same trip count
+//     and eight-fold instruction-level parallelism for every lane of a warp).  A sibling that cannot be
+//     excluded is opened: its 8 children are tested in another batch, a surviving leaf is scanned.  Any
+//     hint gives the same result, only the cost differs.
 //
-// Control flow is written so that the lanes of a warp each walk their OWN blocks inside common
-// loops (trip count = per-lane count; a warp pays the maximum over its lanes, not the union).
 // In shared memory every leaf is padded by one point so that lanes scanning different leaves hit
-// different banks.  Functions are __host__ __device__: tests/test_course_index.py runs them on
-// the CPU against the exhaustive scan (sccav_debug_course_index_host); the rollout kernel runs
-// them on shared memory.
+// different banks.  Functions are __host__ __device__: tests/test_course_index.py runs them on the CPU
+// against the exhaustive scan (sccav_debug_course_index_host); the kernels run them on shared memory.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -32,93 +35,176 @@
 
 namespace sccav {
 
-#define SCCAV_LEAF 16
-#define SCCAV_LEAF_SHIFT 4
-#define SCCAV_SUPER_LEAVES 8
-
-template <typename T> struct IndexEps;
-template <> struct IndexEps<double> {
-    static __host__ __device__ __forceinline__ double rel() { return 1e-9; }
-    static __host__ __device__ __forceinline__ double abs_rel() { return 1e-12; }
-    static __host__ __device__ __forceinline__ double tiny() { return 1e-300; }
-};
-template <> struct IndexEps<float> {
-    static __host__ __device__ __forceinline__ float rel() { return 1e-4f; }
-    static __host__ __device__ __forceinline__ float abs_rel() { return 1e-5f; }
-    static __host__ __device__ __forceinline__ float tiny() { return 1e-30f; }
-};
+#define SCCAV_LEAF_SHIFT 3
+#define SCCAV_LEAF (1 << SCCAV_LEAF_SHIFT)
+#define SCCAV_FAN_SHIFT 3
+#define SCCAV_FAN (1 << SCCAV_FAN_SHIFT)
+#define SCCAV_MAX_LEVELS 8          /* 8 levels of fan-out 8 over leaves of 8 points: far more than any course */
+#define SCCAV_TOP_MAX 8             /* the top level holds at most this many nodes (<= 32): all of them are tested.  A flat top
+                                       of 32 tight nodes instead of 4 loose ones + their children was measured: 13.1 vs 12.3 ms */
 
 // position of course point i in the padded point array (one spare slot after every leaf)
 __host__ __device__ __forceinline__ int course_slot(int i) { return i + (i >> SCCAV_LEAF_SHIFT); }
 __host__ __device__ __forceinline__ int course_nleaf(int np) { return (np + SCCAV_LEAF - 1) / SCCAV_LEAF; }
-__host__ __device__ __forceinline__ int course_nsup(int np) {
-    return (course_nleaf(np) + SCCAV_SUPER_LEAVES - 1) / SCCAV_SUPER_LEAVES;
-}
 __host__ __device__ __forceinline__ int course_nslot(int np) { return np + course_nleaf(np); }
 
-// capsule = chord a + t ab (t in [0,1]) with radius; stored as three 2-vectors
-template <typename T2> struct Capsules {
-    T2* a;    // chord start
-    T2* ab;   // chord vector
-    T2* ir;   // (1 / |ab|^2  or 0, inflated radius)
-};
+// Levels of the tree over a course of np points: level 0 = the leaves, level k + 1 has ceil(n_k / 8) nodes; the
+// top level has at most SCCAV_TOP_MAX nodes, all siblings under a root that is never tested (long, curved nodes
+// have loose capsules: a flat top of tight ones is tested in full instead -- the same loads for every lane).  A node is 32 bytes (chord float4,
+// (1/len^2, radius) float2, 8 spare); a group of 8 siblings is followed by 16 spare bytes, so that lanes of a warp
+// reading the same member of DIFFERENT groups hit different banks (the stride between groups is 272 B = 17 x 16 B).
+// lev[2k] = first 16-byte unit of level k in the node storage, lev[2k + 1] = number of nodes of level k.
+// Returns the number of levels (>= 1); *units (optional) = 16-byte units of node storage.  lev may be NULL.
+#define SCCAV_NODE_UNITS 2          /* 16-byte units per node */
+#define SCCAV_GROUP_UNITS 17        /* 16-byte units per group of 8 nodes (8 x 2 + 1 spare) */
+__host__ __device__ inline int course_levels(int np, int* lev, int* units) {
+    int cnt = course_nleaf(np), o = 0, k = 0;
+    for (;;) {
+        if (lev) { lev[2 * k] = o; lev[2 * k + 1] = cnt; }
+        o += ((cnt + SCCAV_FAN - 1) >> SCCAV_FAN_SHIFT) * SCCAV_GROUP_UNITS;
+        ++k;
+        if (cnt <= SCCAV_TOP_MAX || k >= SCCAV_MAX_LEVELS) break;
+        cnt = (cnt + SCCAV_FAN - 1) >> SCCAV_FAN_SHIFT;
+    }
+    if (units) *units = o;
+    return k;
+}
+__host__ __device__ inline int course_node_units(int np) {
+    int u;
+    course_levels(np, nullptr, &u);
+    return u;
+}
 
-// View of a staged course
+// View of a staged course: padded points + the fp32 capsules of the tree nodes
 template <typename T, typename T2> struct CourseIndex {
     const T2* xy;      // [course_nslot(np)] padded points, point i at course_slot(i)
-    Capsules<T2> leaf; // [nleaf]
-    Capsules<T2> sup;  // [nsup]
-    int np, nleaf, nsup;
+    float4* node;      // node storage (16-byte units): chord (start x, y, vector z, w) at +0, (1 / |chord|^2 or 0, radius) at +1
+    const int* lev;    // [2 nlev] first unit and node count of every level
+    const T* org;      // origin (x, y) of the fp32 frame: a point of the course
+    const float* ext;  // [1] inflated max-norm extent of the course around the origin
+    int np, nleaf, nlev;
     __host__ __device__ __forceinline__ T2 pt(int i) const { return xy[course_slot(i)]; }
+    // first unit of node n of the level that starts at unit `base`
+    static __host__ __device__ __forceinline__ int unit(int base, int n) {
+        return base + (n >> SCCAV_FAN_SHIFT) * SCCAV_GROUP_UNITS + (n & (SCCAV_FAN - 1)) * SCCAV_NODE_UNITS;
+    }
 };
 
-// squared distance from f to the chord of a capsule (computed >= true up to the slack, see header)
-template <typename T, typename T2>
-__host__ __device__ __forceinline__ T chord_dist2(T2 a, T2 ab, T inv, T fx, T fy) {
-    // explicit fma: this is a conservative bound, not reference arithmetic (the fp64 unit is
-    // otherwise compiled with -fmad=false)
-    T vx = fx - a.x, vy = fy - a.y;
-    T t = fma(vx, ab.x, vy * ab.y) * inv;
-    t = t < T(0) ? T(0) : (t > T(1) ? T(1) : t);
-    T ex = fma(-t, ab.x, vx), ey = fma(-t, ab.y, vy);
-    return fma(ex, ex, ey * ey);
+// point range [lo, hi) of node j of level k
+__host__ __device__ __forceinline__ void node_range(int np, int k, int j, int& lo, int& hi) {
+    const int sh = SCCAV_FAN_SHIFT * k + SCCAV_LEAF_SHIFT;
+    const int64_t l = (int64_t)j << sh, h = (int64_t)(j + 1) << sh;
+    lo = (int)(l < np ? l : np);
+    hi = (int)(h < np ? h : np);
 }
 
-// Capsule of points [lo, hi) (indices into the padded array through course_slot); `extent` = an
-// upper bound of |coordinates| of the whole course (absolute slack of the radius).
+// fp32 chord of a node from its first and last point (double precision, relative to the origin)
+__host__ __device__ __forceinline__ void capsule_chord(double ax, double ay, double bx, double by, float4& c, double& inv) {
+    c.x = (float)ax; c.y = (float)ay;
+    c.z = (float)(bx - ax); c.w = (float)(by - ay);
+    const double l2 = (double)c.z * (double)c.z + (double)c.w * (double)c.w;
+    inv = l2 > 0.0 ? 1.0 / l2 : 0.0;
+}
+
+// exact (double) squared distance of the point (px, py) to the fp32 chord c
+__host__ __device__ __forceinline__ double chord_dist2(const float4& c, double inv, double px, double py) {
+    const double vx = px - (double)c.x, vy = py - (double)c.y;
+    double t = (vx * (double)c.z + vy * (double)c.w) * inv;
+    t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
+    const double ex = vx - t * (double)c.z, ey = vy - t * (double)c.w;
+    return ex * ex + ey * ey;
+}
+
+// (1 / |chord|^2, radius) of a node from the largest squared chord distance m of its points; the radius is inflated
+// past the double -> float rounding, the sqrt and (for a float course) the rounding of p - o
+__host__ __device__ __forceinline__ float2 capsule_ir(double inv, double m, float ext) {
+    float2 r;
+    r.x = (float)inv;
+    r.y = (float)(sqrt(m) * 1.000001 + 2e-7 * (double)ext + 1e-30);
+    return r;
+}
+
+__host__ __device__ __forceinline__ float course_ext_inflate(double ext) { return (float)(ext * 1.000001 + 1e-30); }
+
+// Capsule of node j of level k, serial form (the kernels build theirs warp-cooperatively with the same functions:
+// the radius is a maximum, so the order of the points does not matter).
 template <typename T, typename T2>
-__host__ __device__ inline void capsule_build(const T2* xy, int lo, int hi, T extent, T2& a, T2& ab, T2& ir) {
-    a = xy[course_slot(lo)];
-    T2 b = xy[course_slot(hi - 1)];
-    ab.x = b.x - a.x;
-    ab.y = b.y - a.y;
-    T l2 = ab.x * ab.x + ab.y * ab.y;
-    T inv = l2 > T(0) ? T(1) / l2 : T(0);
-    T m = T(0);
+__host__ __device__ inline void capsule_build(const T2* xy, int np, int k, int j, double ox, double oy, float ext, float4& c, float2& r) {
+    int lo, hi;
+    node_range(np, k, j, lo, hi);
+    const T2 a = xy[course_slot(lo)], b = xy[course_slot(hi - 1)];
+    double inv;
+    capsule_chord((double)a.x - ox, (double)a.y - oy, (double)b.x - ox, (double)b.y - oy, c, inv);
+    double m = 0.0;
     for (int i = lo; i < hi; ++i) {
-        T2 p = xy[course_slot(i)];
-        T d2 = chord_dist2<T, T2>(a, ab, inv, p.x, p.y);
+        const T2 p = xy[course_slot(i)];
+        const double d2 = chord_dist2(c, inv, (double)p.x - ox, (double)p.y - oy);
         m = d2 > m ? d2 : m;
     }
-    T rho = (T)sqrt((double)m);
-    ir.x = inv;
-    ir.y = rho * (T(1) + T(4) * IndexEps<T>::rel()) + IndexEps<T>::abs_rel() * extent + IndexEps<T>::tiny();
+    r = capsule_ir(inv, m, ext);
 }
 
-// true when no point of the capsule can be at squared distance <= best from f  (reach = sqrt(best)(1+eps))
+// the query in the fp32 frame: point, and (reach + slack) -- everything of the skip test that does not depend on the node
+struct IndexQuery {
+    float qx, qy, slack, base;
+};
+
+template <typename T> __host__ __device__ __forceinline__ float index_reach32(T best) {
+    // sqrt(best) rounded up: conversion and sqrtf are each within 6e-8 relative
+    return sqrtf((float)best) * 1.000002f;
+}
+
 template <typename T, typename T2>
-__host__ __device__ __forceinline__ bool capsule_skip(const Capsules<T2>& c, int k, T fx, T fy, T reach) {
-    T2 ir = c.ir[k];
-    T d2 = chord_dist2<T, T2>(c.a[k], c.ab[k], ir.x, fx, fy);
-    T thr = reach + ir.y;
-    return d2 > thr * thr;
+__host__ __device__ __forceinline__ IndexQuery index_query(const CourseIndex<T, T2>& ci, T fx, T fy, T best) {
+    IndexQuery q;
+    q.qx = (float)(fx - ci.org[0]);
+    q.qy = (float)(fy - ci.org[1]);
+    q.slack = 2e-6f * ((fabsf(q.qx) + fabsf(q.qy)) + ci.ext[0]);
+    q.base = (index_reach32<T>(best) + q.slack) * 1.000002f;
+    return q;
 }
 
-template <typename T> __host__ __device__ __forceinline__ T index_reach(T best) {
-    return (T)sqrt((double)best) * (T(1) + IndexEps<T>::rel());
+__host__ __device__ __forceinline__ float sat01(float t) {
+#ifdef __CUDA_ARCH__
+    return __saturatef(t);
+#else
+    return fminf(fmaxf(t, 0.0f), 1.0f);
+#endif
 }
-template <> __host__ __device__ __forceinline__ float index_reach<float>(float best) {
-    return sqrtf(best) * (1.0f + IndexEps<float>::rel());
+
+// One batch: the (up to) 8 nodes of group `group` of level `level`, except ex0 / ex1.  Returns the bit mask of the
+// nodes that can NOT be excluded (a NaN anywhere keeps the node: conservative).
+template <typename T, typename T2>
+__host__ __device__ __forceinline__ uint32_t index_test8(const CourseIndex<T, T2>& ci, int level, int group, int ex0, int ex1,
+                                                         const IndexQuery& q, int& ne) {
+    const int first = group << SCCAV_FAN_SHIFT;
+    const int left = ci.lev[2 * level + 1] - first;                         // nodes of the level from `first` on
+    // which of the 8 members exist and are wanted (one register -> 8 predicates)
+    uint32_t want = left >= SCCAV_FAN ? 0xffu : ((1u << (left > 0 ? left : 0)) - 1u);
+    const uint32_t e0 = (uint32_t)(ex0 - first), e1 = (uint32_t)(ex1 - first);
+    if (e0 < (uint32_t)SCCAV_FAN) want &= ~(1u << e0);
+    if (e1 < (uint32_t)SCCAV_FAN) want &= ~(1u << e1);
+    const float4* __restrict__ g = ci.node + ci.lev[2 * level] + group * SCCAV_GROUP_UNITS;
+    uint32_t mask = 0u;
+#pragma unroll
+    for (int j = 0; j < SCCAV_FAN; ++j) {
+        if (want & (1u << j)) {
+            const float4 c = g[SCCAV_NODE_UNITS * j];
+            const float2 r = *reinterpret_cast<const float2*>(g + SCCAV_NODE_UNITS * j + 1);
+            const float vx = q.qx - c.x, vy = q.qy - c.y;
+            const float t = sat01(fmaf(vx, c.z, vy * c.w) * r.x);
+            const float ex = fmaf(-t, c.z, vx), ey = fmaf(-t, c.w, vy);
+            const float d2 = fmaf(ex, ex, ey * ey);
+            const float thr = q.base + r.y;
+            if (!(d2 > thr * thr)) mask |= 1u << j;
+        }
+    }
+#ifdef __CUDA_ARCH__
+    ne += __popc(want);
+#else
+    ne += __builtin_popcount(want);
+#endif
+    return mask;
 }
 
 // Scan one leaf in ascending index order (strict <: first minimum inside the leaf), then merge
@@ -164,74 +250,75 @@ __host__ __device__ inline int course_nearest_full(const T2* xy, int np, T fx, T
     return ib;
 }
 
-__host__ __device__ __forceinline__ int lowest_bit(uint32_t m) {
+__host__ __device__ __forceinline__ int lowest_bit64(uint64_t m) {
 #ifdef __CUDA_ARCH__
-    return __ffs((int)m) - 1;
+    return __ffsll((long long)m) - 1;
 #else
-    return __builtin_ctz(m);
+    return __builtin_ctzll(m);
 #endif
 }
 
 // Exact global nearest index (first minimum) of (fx, fy) over the whole course.
-// hint: any index (the previous nearest index; clamped into [0, np)); evals (optional) counts
+// hint: any index (the predicted nearest index; clamped into [0, np)); evals (optional) counts
 // distance evaluations + capsule tests for the roofline accounting.
-// UNR: unroll factor of the two capsule-test loops (2 lets independent tests interleave in the lean ellipse
-// instances of the rollout; the larger generic instances are better off with 1 -- registers).
-template <typename T, typename T2, int UNR = 2>
+template <typename T, typename T2>
 __host__ __device__ inline int course_nearest(const CourseIndex<T, T2>& ci, T fx, T fy, int hint, int* evals) {
     if (hint < 0) hint = 0;
     if (hint >= ci.np) hint = ci.np - 1;
-    // phase A: the hint's leaf and the next one (a vehicle advances about half a leaf per tick)
+    // the two leaves around the hint, inside the hint's group of 8 leaves
     const int leaf0 = hint >> SCCAV_LEAF_SHIFT;
-    const int leaf1 = (leaf0 + 1 < ci.nleaf) ? leaf0 + 1 : leaf0;
+    int lo = ((hint & (SCCAV_LEAF - 1)) >= SCCAV_LEAF / 2) ? leaf0 : leaf0 - 1;
+    if ((lo & (SCCAV_FAN - 1)) == SCCAV_FAN - 1) lo = (lo == leaf0) ? lo - 1 : lo + 1;
+    if (lo > ci.nleaf - 2) lo = ci.nleaf - 2;
+    if (lo < 0) lo = 0;
+    int hi = (lo + 1 < ci.nleaf) ? lo + 1 : lo;
+    if ((hi >> SCCAV_FAN_SHIFT) != (lo >> SCCAV_FAN_SHIFT)) hi = lo;        // (a last group of one leaf)
     T best = (T)INFINITY;
     int ib = ci.np;
     int ne = 2 * SCCAV_LEAF;
-#pragma unroll 1
-    for (int l = leaf0; l <= leaf1; ++l) index_scan_leaf<T, T2>(ci, l, fx, fy, best, ib);
+    index_scan_leaf<T, T2>(ci, lo, fx, fy, best, ib);
+    if (hi != lo) index_scan_leaf<T, T2>(ci, hi, fx, fy, best, ib);
     // NaN / overflowing query (np.argmin of all-NaN is 0): no usable bound, do what the reference does
     if (!(best < (T)INFINITY)) return course_nearest_full<T, T2>(ci.xy, ci.np, fx, fy);
-    T reach = index_reach<T>(best);
-    for (int s0 = 0; s0 < ci.nsup; s0 += 32) {
-        // phase B: which supers can hold a point at distance <= best?  (same trip count for all lanes)
-        const int ns = (ci.nsup - s0 < 32) ? ci.nsup - s0 : 32;
-        uint32_t smask = 0u;
-#pragma unroll UNR
-        for (int j = 0; j < ns; ++j)
-            if (!capsule_skip<T, T2>(ci.sup, s0 + j, fx, fy, reach)) smask |= 1u << j;
-        ne += ns;
-        // phase C: every lane walks its own supers / leaves
-        while (smask) {
-            const int s = s0 + lowest_bit(smask);
-            smask &= smask - 1u;
-            if (capsule_skip<T, T2>(ci.sup, s, fx, fy, reach)) { ++ne; continue; }   // bound tightened since phase B
-            const int l0 = s * SCCAV_SUPER_LEAVES;
-            uint32_t todo = 0u;
-#pragma unroll UNR
-            for (int j = 0; j < SCCAV_SUPER_LEAVES; ++j) {
-                const int l = l0 + j;
-                if (l < ci.nleaf && l != leaf0 && l != leaf1 && !capsule_skip<T, T2>(ci.leaf, l, fx, fy, reach)) todo |= 1u << j;
-            }
-            ne += SCCAV_SUPER_LEAVES;
-            while (todo) {
-                const int l = l0 + lowest_bit(todo);
-                todo &= todo - 1u;
-                const T before = best;
-                index_scan_leaf<T, T2>(ci, l, fx, fy, best, ib);
-                ne += SCCAV_LEAF;
-                if (best < before) {
-                    // tighter bound: drop the remaining leaves of this super that it now excludes
-                    reach = index_reach<T>(best);
-                    uint32_t keep = 0u, rest = todo;
-                    while (rest) {
-                        const int j = lowest_bit(rest);
-                        rest &= rest - 1u;
-                        if (!capsule_skip<T, T2>(ci.leaf, l0 + j, fx, fy, reach)) keep |= 1u << j;
-                        ++ne;
-                    }
-                    todo = keep;
-                }
-            }
+    IndexQuery q = index_query<T, T2>(ci, fx, fy, best);
+    // climb: at every level below the top, the siblings of the scanned leaves' ancestor; at the top, every other node.
+    // pending: byte k = the nodes of level k, in the group of the current position's ancestor, that still have to be
+    // opened; top_pending: the same for the (up to 32) nodes of the top level.
+    uint64_t pending = 0u;
+    uint32_t top_pending = 0u;
+    const int top = ci.nlev - 1;
+    for (int k = 0; k < top; ++k) {
+        const int own = lo >> (SCCAV_FAN_SHIFT * k);
+        const uint32_t m = index_test8<T, T2>(ci, k, own >> SCCAV_FAN_SHIFT, own, k == 0 ? hi : own, q, ne);
+        pending |= (uint64_t)m << (8 * k);
+    }
+    {
+        const int own = lo >> (SCCAV_FAN_SHIFT * top), own2 = hi >> (SCCAV_FAN_SHIFT * top);
+        const int ngrp = (ci.lev[2 * top + 1] + SCCAV_FAN - 1) >> SCCAV_FAN_SHIFT;
+        for (int g = 0; g < ngrp; ++g) top_pending |= index_test8<T, T2>(ci, top, g, own, own2, q, ne) << (8 * g);
+    }
+    // open what could not be excluded, lowest level (= nearest) first
+    int cur = lo;
+    while (pending | top_pending) {
+        int m, node;
+        if (pending) {
+            const int bit = lowest_bit64(pending);
+            pending &= pending - 1u;
+            m = bit >> 3;
+            node = ((cur >> (SCCAV_FAN_SHIFT * (m + 1))) << SCCAV_FAN_SHIFT) + (bit & 7);
+        } else {
+            node = lowest_bit64(top_pending);
+            top_pending &= top_pending - 1u;
+            m = top;
+        }
+        cur = node << (SCCAV_FAN_SHIFT * m);
+        if (m == 0) {
+            const T before = best;
+            index_scan_leaf<T, T2>(ci, node, fx, fy, best, ib);
+            ne += SCCAV_LEAF;
+            if (best < before) q.base = (index_reach32<T>(best) + q.slack) * 1.000002f;
+        } else {
+            pending |= (uint64_t)index_test8<T, T2>(ci, m - 1, node, -1, -1, q, ne) << (8 * (m - 1));
         }
     }
     if (evals) *evals += ne;

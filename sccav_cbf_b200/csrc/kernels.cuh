@@ -836,24 +836,95 @@ __device__ __forceinline__ void seeker_update(T* f, int64_t fs, T ex, T ey, T dt
 #define SCCAV_ROLLOUT_MAXB 448
 
 // Shared-memory layout of the rollout kernel (bytes), shared by the launcher and the kernel:
-//   [ course xy : T2 x nslot (leaf-padded) ][ leaf capsules : 3 x T2 x nleaf ][ super capsules : 3 x T2 x nsup ]
+//   [ course xy : T2 x nslot (leaf-padded) ][ tree nodes : 16 B x units ][ header : level table int x 16, origin T x 2, extent float ]
 //   [ cyaw : T x np_pad ][ rows : T x 3 M block ]
 template <typename T> struct RolloutSmem {
-    int nslot, nleaf, nsup, np_pad;
-    size_t off_leaf, off_sup, off_cyaw, off_rows, course_bytes;
+    int nslot, units, np_pad;
+    size_t off_node, off_hdr, off_cyaw, off_rows, course_bytes;
     __host__ __device__ RolloutSmem(int np, bool course_smem) {
         nslot = course_smem ? course_nslot(np) : 0;
-        nleaf = course_smem ? course_nleaf(np) : 0;
-        nsup = course_smem ? course_nsup(np) : 0;
+        units = course_smem ? course_node_units(np) : 0;
         np_pad = course_smem ? ((np + 1) & ~1) : 0;
         size_t o = (size_t)nslot * 2 * sizeof(T);
-        off_leaf = o; o += (size_t)nleaf * 6 * sizeof(T);
-        off_sup = o;  o += (size_t)nsup * 6 * sizeof(T);
+        o = (o + 15) & ~(size_t)15;
+        off_node = o; o += (size_t)units * 16;
+        off_hdr = o; o += course_smem ? 96 : 0;        // 16 ints | 2 T (at +64) | float (at +80)
         off_cyaw = o; o += (size_t)np_pad * sizeof(T);
         off_rows = o;
         course_bytes = o;
     }
 };
+
+// Stage one course into shared memory (leaf-padded points, optionally cyaw) and build the capsules of its tree
+// (course_index.cuh).  Called by every thread of the CTA; `scratch` = at least 32 doubles of shared memory that are
+// free during the build.  Nodes are built warp-cooperatively: the lanes of a warp share the points of one node and
+// reduce the largest chord distance (a maximum: the same radius as the serial capsule_build).
+template <typename T, typename T2>
+__device__ __forceinline__ CourseIndex<T, T2> course_stage(unsigned char* smem, const RolloutSmem<T>& lay, int np,
+                                                           const T* __restrict__ cx, const T* __restrict__ cy,
+                                                           const T* __restrict__ cyaw, T* s_cyaw, double* scratch) {
+    typedef Real<T> R;
+    T2* s_cxy = reinterpret_cast<T2*>(smem);
+    int* s_lev = reinterpret_cast<int*>(smem + lay.off_hdr);
+    T* s_org = reinterpret_cast<T*>(smem + lay.off_hdr + 64);
+    float* s_ext = reinterpret_cast<float*>(smem + lay.off_hdr + 80);
+    CourseIndex<T, T2> ci;
+    ci.xy = s_cxy;
+    ci.node = reinterpret_cast<float4*>(smem + lay.off_node);
+    ci.lev = s_lev; ci.org = s_org; ci.ext = s_ext;
+    ci.np = np; ci.nleaf = course_nleaf(np);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    // origin of the fp32 frame: the middle point of the course
+    const T ox = cx[np / 2], oy = cy[np / 2];
+    double ext = 0.0;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) {
+        T px = cx[i], py = cy[i];
+        s_cxy[course_slot(i)] = R::make2(px, py);
+        if (s_cyaw) s_cyaw[i] = cyaw[i];
+        ext = fmax(ext, fmax(fabs((double)px - (double)ox), fabs((double)py - (double)oy)));
+    }
+    // extent of the course around the origin: CTA-wide max
+    ext = warp_max<double>(ext);
+    if (lane == 0) scratch[warp] = ext;
+    __syncthreads();
+    ext = 0.0;
+    for (int w = 0; w < nwarp; ++w) ext = fmax(ext, scratch[w]);
+    const float extf = course_ext_inflate(ext);
+    if (threadIdx.x == 0) { s_org[0] = ox; s_org[1] = oy; s_ext[0] = extf; }
+    // level by level (same recurrence as course_levels)
+    int base = 0, cnt = ci.nleaf, k = 0;
+    for (;;) {
+        if (threadIdx.x == 0) { s_lev[2 * k] = base; s_lev[2 * k + 1] = cnt; }
+        for (int j = warp; j < cnt; j += nwarp) {
+            int lo, hi;
+            node_range(np, k, j, lo, hi);
+            const T2 pa = s_cxy[course_slot(lo)], pb = s_cxy[course_slot(hi - 1)];
+            float4 c;
+            double inv;
+            capsule_chord((double)pa.x - (double)ox, (double)pa.y - (double)oy, (double)pb.x - (double)ox, (double)pb.y - (double)oy, c, inv);
+            double m = 0.0;
+            for (int i = lo + lane; i < hi; i += 32) {
+                const T2 p = s_cxy[course_slot(i)];
+                const double d2 = chord_dist2(c, inv, (double)p.x - (double)ox, (double)p.y - (double)oy);
+                m = d2 > m ? d2 : m;
+            }
+            m = warp_max<double>(m);
+            if (lane == 0) {
+                const float2 r = capsule_ir(inv, m, extf);
+                const int u = CourseIndex<T, T2>::unit(base, j);
+                ci.node[u] = c;
+                ci.node[u + 1] = make_float4(r.x, r.y, 0.f, 0.f);
+            }
+        }
+        base += ((cnt + SCCAV_FAN - 1) >> SCCAV_FAN_SHIFT) * SCCAV_GROUP_UNITS;
+        ++k;
+        if (cnt <= SCCAV_TOP_MAX || k >= SCCAV_MAX_LEVELS) break;
+        cnt = (cnt + SCCAV_FAN - 1) >> SCCAV_FAN_SHIFT;
+    }
+    ci.nlev = k;
+    __syncthreads();
+    return ci;
+}
 
 // FAST = the launch is known to be (model DBM, Stanley nominal, no seekers): those three become compile-time
 // constants, which removes the other plants, the seeker loop and the per-row model dispatch from the instance the
@@ -867,8 +938,6 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
     const int np = a.np;
     const RolloutSmem<T> lay(np, COURSE_SMEM);
     T2* s_cxy = reinterpret_cast<T2*>(smem_raw);
-    T2* s_leaf = reinterpret_cast<T2*>(smem_raw + lay.off_leaf);
-    T2* s_sup = reinterpret_cast<T2*>(smem_raw + lay.off_sup);
     T* s_cyaw = reinterpret_cast<T*>(smem_raw + lay.off_cyaw);
     T* rows = reinterpret_cast<T*>(smem_raw + lay.off_rows) + threadIdx.x;
     const int stride = blockDim.x;
@@ -876,36 +945,11 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
     const int model = FAST ? SCCAV_MODEL_DBM : a.P.model;
     constexpr int MODEL = FAST ? SCCAV_MODEL_DBM : -1;
     CourseIndex<T, T2> ci;
-    ci.xy = s_cxy;
-    ci.np = np; ci.nleaf = lay.nleaf; ci.nsup = lay.nsup;
-    ci.leaf.a = s_leaf; ci.leaf.ab = s_leaf + lay.nleaf; ci.leaf.ir = s_leaf + 2 * lay.nleaf;
-    ci.sup.a = s_sup; ci.sup.ab = s_sup + lay.nsup; ci.sup.ir = s_sup + 2 * lay.nsup;
-    if (COURSE_SMEM && stan) {
-        // stage the course once per CTA (leaf-padded), then build the capsules of its leaves / supers
-        T ext = T(0);
-        for (int i = threadIdx.x; i < np; i += blockDim.x) {
-            T px = a.cx[i], py = a.cy[i];
-            s_cxy[course_slot(i)] = R::make2(px, py);
-            s_cyaw[i] = a.cyaw[i];
-            ext = fmax(ext, fmax(R::abs_(px), R::abs_(py)));
-        }
-        // course extent (absolute slack of the capsule radii): CTA-wide max through shared memory
-        T* s_ext = reinterpret_cast<T*>(smem_raw + lay.off_rows);
-        s_ext[threadIdx.x] = ext;
-        __syncthreads();
-        ext = T(0);
-        for (int i = 0; i < (int)blockDim.x; ++i) ext = fmax(ext, s_ext[i]);
-        __syncthreads();
-        for (int l = threadIdx.x; l < lay.nleaf; l += blockDim.x) {
-            const int lo = l * SCCAV_LEAF, hi = min(np, lo + SCCAV_LEAF);
-            capsule_build<T, T2>(s_cxy, lo, hi, ext, ci.leaf.a[l], ci.leaf.ab[l], ci.leaf.ir[l]);
-        }
-        for (int q = threadIdx.x; q < lay.nsup; q += blockDim.x) {
-            const int lo = q * SCCAV_LEAF * SCCAV_SUPER_LEAVES, hi = min(np, lo + SCCAV_LEAF * SCCAV_SUPER_LEAVES);
-            capsule_build<T, T2>(s_cxy, lo, hi, ext, ci.sup.a[q], ci.sup.ab[q], ci.sup.ir[q]);
-        }
-        __syncthreads();
-    }
+    ci.xy = s_cxy; ci.node = nullptr; ci.lev = nullptr; ci.org = nullptr; ci.ext = nullptr;
+    ci.np = np; ci.nleaf = 0; ci.nlev = 0;
+    // stage the course once per CTA (leaf-padded) and build the capsules of its tree
+    if (COURSE_SMEM && stan)
+        ci = course_stage<T, T2>(smem_raw, lay, np, a.cx, a.cy, a.cyaw, s_cyaw, reinterpret_cast<double*>(smem_raw + lay.off_rows));
     const int64_t N = a.N;
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
@@ -934,7 +978,7 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
     }
 
     T time = T(0);
-    int target_idx = 0, near_idx = 0, evals = 0;
+    int target_idx = 0, near_idx = 0, adv = 0, evals = 0;
     T syaw, cyw;
     R::sincos_(yaw, &syaw, &cyw);
     if (stan) {
@@ -966,7 +1010,7 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
         if (stan) {
             T a_ref = P.Kp * (tspeed - v);                                                 // sce.py:135-143
             T d_ref;
-            if (COURSE_SMEM) d_ref = stanley<T, T2, (SPEC == SCCAV_SPEC_GENERIC ? 1 : 2)>(P, ci, s_cyaw, x, y, yaw, v, syaw, cyw, target_idx, near_idx, &evals);
+            if (COURSE_SMEM) d_ref = stanley<T, T2, (FUSED == 1)>(P, ci, s_cyaw, x, y, yaw, v, syaw, cyw, target_idx, near_idx, adv, &evals);
             else {
                 // global-memory course fallback (P too large for shared memory): exhaustive scan
                 T fx = x + P.L * cyw, fy = y + P.L * syaw;
@@ -1093,35 +1137,9 @@ __global__ void __launch_bounds__(256) stanley_kernel(const __grid_constant__ St
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int np = a.np;
     const RolloutSmem<T> lay(np, true);
-    T2* s_cxy = reinterpret_cast<T2*>(smem_raw);
-    T2* s_leaf = reinterpret_cast<T2*>(smem_raw + lay.off_leaf);
-    T2* s_sup = reinterpret_cast<T2*>(smem_raw + lay.off_sup);
-    T* s_ext = reinterpret_cast<T*>(smem_raw + lay.off_cyaw);      // scratch during the build only
-    CourseIndex<T, T2> ci;
-    ci.xy = s_cxy;
-    ci.np = np; ci.nleaf = lay.nleaf; ci.nsup = lay.nsup;
-    ci.leaf.a = s_leaf; ci.leaf.ab = s_leaf + lay.nleaf; ci.leaf.ir = s_leaf + 2 * lay.nleaf;
-    ci.sup.a = s_sup; ci.sup.ab = s_sup + lay.nsup; ci.sup.ir = s_sup + 2 * lay.nsup;
-    T ext = T(0);
-    for (int i = threadIdx.x; i < np; i += blockDim.x) {
-        T px = a.cx[i], py = a.cy[i];
-        s_cxy[course_slot(i)] = R::make2(px, py);
-        ext = fmax(ext, fmax(R::abs_(px), R::abs_(py)));
-    }
-    s_ext[threadIdx.x] = ext;
-    __syncthreads();
-    ext = T(0);
-    for (int i = 0; i < (int)blockDim.x; ++i) ext = fmax(ext, s_ext[i]);
-    __syncthreads();
-    for (int l = threadIdx.x; l < lay.nleaf; l += blockDim.x) {
-        const int lo = l * SCCAV_LEAF, hi = min(np, lo + SCCAV_LEAF);
-        capsule_build<T, T2>(s_cxy, lo, hi, ext, ci.leaf.a[l], ci.leaf.ab[l], ci.leaf.ir[l]);
-    }
-    for (int q = threadIdx.x; q < lay.nsup; q += blockDim.x) {
-        const int lo = q * SCCAV_LEAF * SCCAV_SUPER_LEAVES, hi = min(np, lo + SCCAV_LEAF * SCCAV_SUPER_LEAVES);
-        capsule_build<T, T2>(s_cxy, lo, hi, ext, ci.sup.a[q], ci.sup.ab[q], ci.sup.ir[q]);
-    }
-    __syncthreads();
+    // (cyaw stays in global memory here: one read per vehicle; its region is the build's scratch)
+    const CourseIndex<T, T2> ci = course_stage<T, T2>(smem_raw, lay, np, a.cx, a.cy, nullptr, nullptr,
+                                                      reinterpret_cast<double*>(smem_raw + lay.off_cyaw));
     const int64_t N = a.N;
     for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
         T x = a.state[n], y = a.state[N + n], yaw = a.state[2 * N + n], v = a.state[3 * N + n];
@@ -1133,7 +1151,9 @@ __global__ void __launch_bounds__(256) stanley_kernel(const __grid_constant__ St
             fx = x + a.P.L * cyw;
             fy = y + a.P.L * syaw;
         }
+        // (a target index past the course -- e.g. kept from a longer one -- is clamped: the reference would raise IndexError)
         int tidx = a.target_idx[n];
+        tidx = tidx < 0 ? 0 : (tidx >= np ? np - 1 : tidx);
         const int idx = course_nearest<T, T2>(ci, fx, fy, tidx, nullptr);
         T2 c = ci.pt(idx);
         T s2, c2;

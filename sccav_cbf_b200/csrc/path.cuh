@@ -933,13 +933,21 @@ __host__ __device__ inline int choose_spec(const uint8_t* d, int M) {
 // minimum wins, strict <), over ALL P points, like calc_target_index (:202-205).
 // ------------------------------------------------------------------------------------------
 // cross-track error + steering law once the nearest index is known (sce.py:208-212,159-167)
-template <typename T, typename CXY>
+// NORMAL_IDENTITY (opt-in, the SCCAV_FLAG_FUSED_STEER instances): the front-axle normal
+// [-cos(yaw + pi/2), -sin(yaw + pi/2)] of sce.py:208-209 is taken as [sin yaw, -cos yaw] from the sincos the plant
+// already holds -- the same vector to an ulp or two, one sincos per tick cheaper.
+template <typename T, typename CXY, bool NORMAL_IDENTITY = false>
 __device__ __forceinline__ T stanley_law(const Params<T>& P, CXY c, const T* __restrict__ cyaw, int idx,
-                                         T fx, T fy, T yaw, T v, int& target_idx) {
+                                         T fx, T fy, T yaw, T v, int& target_idx, T syaw = T(0), T cyw = T(0)) {
     typedef Real<T> R;
-    T s2, c2;
-    R::sincos_(yaw + R::pi() / T(2), &s2, &c2);                                          // sce.py:208-209
-    T e = (fx - c.x) * (-c2) + (fy - c.y) * (-s2);
+    T e;
+    if (NORMAL_IDENTITY) {
+        e = (fx - c.x) * syaw + (fy - c.y) * (-cyw);
+    } else {
+        T s2, c2;
+        R::sincos_(yaw + R::pi() / T(2), &s2, &c2);                                      // sce.py:208-209
+        e = (fx - c.x) * (-c2) + (fy - c.y) * (-s2);
+    }
     if (target_idx >= idx) idx = target_idx;                                             // sce.py:159-160
     T theta_e = normalize_angle<T>(cyaw[idx] - yaw);
     T theta_d = R::atan2_(P.k_stanley * e, v + P.ks_stanley);
@@ -947,15 +955,19 @@ __device__ __forceinline__ T stanley_law(const Params<T>& P, CXY c, const T* __r
     return theta_e + theta_d;
 }
 
-// course staged in shared memory with its bounding-circle index: exact pruned nearest search
-template <typename T, typename T2, int UNR = 2>
+// course staged in shared memory with its capsule tree: exact pruned nearest search.  The hint is the previous
+// nearest index advanced by the previous tick's advance (a vehicle moves about as far as it did last tick);
+// any hint gives the same index, a good one makes the search cheap.
+template <typename T, typename T2, bool NORMAL_IDENTITY = false>
 __device__ __forceinline__ T stanley(const Params<T>& P, const CourseIndex<T, T2>& ci, const T* __restrict__ cyaw,
-                                     T x, T y, T yaw, T v, T syaw, T cyw, int& target_idx, int& near_idx, int* evals) {
+                                     T x, T y, T yaw, T v, T syaw, T cyw, int& target_idx, int& near_idx, int& adv, int* evals) {
     T fx = x + P.L * cyw;
     T fy = y + P.L * syaw;
-    int idx = course_nearest<T, T2, UNR>(ci, fx, fy, near_idx, evals);
+    int idx = course_nearest<T, T2>(ci, fx, fy, near_idx + adv, evals);
+    adv = idx - near_idx;
+    adv = adv < -4 * SCCAV_LEAF ? 0 : (adv > 4 * SCCAV_LEAF ? 0 : adv);      // a jump is not a trend
     near_idx = idx;
-    return stanley_law<T, T2>(P, ci.pt(idx), cyaw, idx, fx, fy, yaw, v, target_idx);
+    return stanley_law<T, T2, NORMAL_IDENTITY>(P, ci.pt(idx), cyaw, idx, fx, fy, yaw, v, target_idx, syaw, cyw);
 }
 
 }  // namespace sccav

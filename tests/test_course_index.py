@@ -106,3 +106,42 @@ def test_fp32_variant_matches_its_own_exhaustive_scan():
     fx = cx[base] + rng.normal(0, 1.5, n); fy = cy[base] + rng.normal(0, 1.5, n)
     idx, full, _ = run(cx, cy, fx, fy, np.clip(base - 8, 0, None), dtype=32)
     assert np.array_equal(idx, full)
+
+
+@pytest.mark.parametrize("shift", [0.0, 3.0e3, 5.0e5, 4.0e6])
+def test_single_precision_bounds_stay_conservative(shift):
+    """The capsule tests run in fp32 relative to an origin on the course with every rounding error charged to the
+    slack (course_index.cuh).  Courses far from the coordinate origin (map / UTM coordinates), queries from
+    centimetres to 1e7 m away, near-ties on arcs seen from their centre of curvature, and exact duplicates."""
+    rng = np.random.default_rng(int(shift) % 97)
+    cx, cy, _ = config1_course()
+    cx = cx + shift; cy = cy - 0.5 * shift
+    n = 3000
+    base = rng.integers(0, len(cx), n)
+    for spread in (0.02, 2.0, 50.0, 3.0e3, 1.0e7):
+        fx = cx[base] + rng.normal(0, spread, n); fy = cy[base] + rng.normal(0, spread, n)
+        for hint in (base, rng.integers(0, len(cx), n)):
+            idx, full, _ = run(cx, cy, fx, fy, hint)
+            assert np.array_equal(idx, full), (shift, spread)
+    # an arc of constant radius seen from (almost) its centre: every point is a near-tie
+    t = np.linspace(0.0, 1.5 * np.pi, 1500)
+    ax = shift + 25.0 * np.cos(t); ay = 25.0 * np.sin(t)
+    fx = shift + rng.normal(0, 1e-3, 400); fy = rng.normal(0, 1e-3, 400)
+    idx, full, _ = run(ax, ay, fx, fy, rng.integers(0, len(ax), 400))
+    assert np.array_equal(idx, full)
+    idx, full, _ = run(ax, ay, fx, fy, rng.integers(0, len(ax), 400), dtype=32)
+    assert np.array_equal(idx, full)
+
+
+def test_closed_loop_queries_cost_a_few_dozen_evaluations():
+    """Hints as the rollout kernel makes them (previous index + previous advance) along a sweep of the course."""
+    cx, cy, cyaw = config1_course()
+    k = np.arange(0, len(cx) - 1, 8)
+    off = 1.5 * np.sin(k / 40.0)
+    fx = cx[k] - off * np.sin(cyaw[k]); fy = cy[k] + off * np.cos(cyaw[k])
+    idx0, full, _ = run(cx, cy, fx, fy, k)
+    assert np.array_equal(idx0, full)
+    hint = np.concatenate([[0, idx0[0]], idx0[1:-1] + (idx0[1:-1] - idx0[:-2])])
+    idx, full, ev = run(cx, cy, fx, fy, hint)
+    assert np.array_equal(idx, full)
+    assert ev.mean() < 60, ev.mean()
