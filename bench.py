@@ -131,16 +131,166 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def csrc_sha() -> str:
+    """Hash of the kernel sources: profiles/ncu_metrics.json records the one it was captured from."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "sccav_cbf_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+    h.update(open(os.path.join(ROOT, "include", "sccav_cbf.h"), "rb").read())
+    return h.hexdigest()[:16]
+
+
+NCU_STALE = [None]
+
+
 def committed_ncu(kernel: str):
     """Numbers of `kernel` from the committed ncu --set full capture (profiles/ncu_metrics.json):
-    dram bytes per launch ("traffic"), fp64-pipe / issue utilisation.  None if absent."""
+    dram bytes per launch ("traffic"), fp64-pipe / issue utilisation.  None if absent -- or if the kernels have
+    changed since the capture (the JSON records the hash of csrc/ it was taken from): stale numbers are not quoted."""
     path = os.path.join(ROOT, "profiles", "ncu_metrics.json")
     if os.path.exists(path):
         try:
-            return json.load(open(path)).get(kernel)
+            d = json.load(open(path))
+            NCU_STALE[0] = d.get("_csrc_sha") != csrc_sha()
+            if NCU_STALE[0]:
+                return None
+            return d.get(kernel)
         except Exception:
             return None
     return None
+
+
+# ------------------------------------------------------------------------------------------ extra legs
+def _time_rollout(cl, reps, flush):
+    """CUDA-event time of `reps` rollout launches of a resident batch (L2 flushed before each)."""
+    import torch
+    cl.run()
+    torch.cuda.synchronize()
+    ms = []
+    res = None
+    for _ in range(reps):
+        cl.reset()
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); res = cl.launch(); e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    return ms, res
+
+
+def _sample_batch(batch, idx):
+    """The scenarios `idx` of a batch as a batch of their own (what the oracle re-runs)."""
+    import numpy as np
+    from sccav_cbf_b200 import scenarios as sc
+    return sc.ScenarioBatch(batch.name + "_sample", np.ascontiguousarray(batch.state[:, idx]), list(batch.slot_desc),
+                            None if batch.obst is None else np.ascontiguousarray(batch.obst[:, :, idx]), batch.course,
+                            dict(batch.params), T=batch.T,
+                            alpha=None if batch.alpha is None else np.ascontiguousarray(batch.alpha[idx]),
+                            R=None if batch.R is None else np.ascontiguousarray(batch.R[:, idx]),
+                            target_speed=None if batch.target_speed is None else np.ascontiguousarray(batch.target_speed[idx]))
+
+
+def _oracle_sample(batch, res, n_sample, f32=False):
+    """A sample of vehicles taken from INSIDE the full-size batch, re-run alone by the CPU oracle (checker only):
+    fraction with identical integer bookkeeping, fraction with the final state within tolerance."""
+    import numpy as np
+    from oracle import c_oracle as co
+    rng = np.random.default_rng(12345)
+    idx = np.sort(rng.choice(batch.N, size=min(n_sample, batch.N), replace=False))
+    sub = _sample_batch(batch, idx)
+    prm = dict(sub.params)
+    prm.pop("flags", None)                       # the oracle's arithmetic is always the reference's order
+    r = co.rollout(co.default_params(**prm), sub.slot_desc, sub.state, sub.obst, sub.course, sub.T,
+                   alpha=sub.alpha, R=sub.R, target_speed=sub.target_speed)
+    g = {k: res[k][..., idx].cpu().numpy() for k in ("steps", "target_idx", "n_active", "n_infeasible", "state")}
+    same = np.ones(len(idx), dtype=bool)
+    for k in ("steps", "target_idx", "n_active", "n_infeasible"):
+        same &= g[k] == r[k]
+    err = (np.abs(g["state"].astype(np.float64) - r["state"]) / np.maximum(1.0, np.abs(r["state"]))).max(axis=0)
+    tol = 5e-2 if f32 else 1e-6
+    return float(same.mean()), float((err <= tol).mean()), tol
+
+
+def run_config_leg(prefix, batch, dtype, flags, dev, flush, sh, reps=2, sample=512, check=True):
+    """One BASELINE.json configuration at its full per-GPU size: whole-job solves/s (CUDA events, max over ranks)
+    + the oracle-sample parity fractions of rank 0's shard.  Returns FLAT keys (the driver keeps scalars)."""
+    import torch
+    from sccav_cbf_b200.rollout import ClosedLoopRollout
+    if flags:
+        batch.params = dict(batch.params, flags=flags)
+    cl = ClosedLoopRollout(batch, dtype=dtype, device=dev, pin=False)
+    sh.barrier()
+    ms, res = _time_rollout(cl, reps, flush)
+    ms_rank = min(ms)
+    solves = sh.sum(float(res["steps"].sum().item()) * batch.M)
+    ms_job = sh.max(ms_rank)
+    out = {prefix + "_value": solves / (ms_job * 1e-3), prefix + "_ms": ms_job, prefix + "_vehicles_total": int(sh.sum(float(batch.N))),
+           prefix + "_rows_per_vehicle": batch.M, prefix + "_active_step_frac": sh.sum(float(res["n_active"].sum().item())) / max(1.0, sh.sum(float(res["steps"].sum().item())))}
+    if check and sh.rank == 0:
+        same, ok, tol = _oracle_sample(batch, res, sample, f32=(dtype == torch.float32))
+        out[prefix + "_oracle_identical_bookkeeping_frac"] = same
+        out[prefix + "_oracle_state_within_tol_frac"] = ok
+        out[prefix + "_oracle_sample"] = min(sample, batch.N)
+    del cl
+    torch.cuda.empty_cache()
+    return out
+
+
+def python_loop_rate(seconds, M, T):
+    """What a reference user experiences minus cvxopt's IPM and matplotlib: the scalar Python restatement of the
+    loop (oracle/oracle.py, structured like stanley_controller_ellipse.py:630-830), 1 core, whole vehicles until
+    `seconds` are spent."""
+    import numpy as np
+    from oracle import oracle as o
+    from sccav_cbf_b200 import scenarios as sc
+    b = sc.config2(n_total=65536, M=M, T=T, seed=0, lo=0, hi=16)
+    course = tuple(np.asarray(c) for c in b.course)
+    t0 = time.perf_counter()
+    solves, n = 0.0, 0
+    while n < b.N and (n == 0 or time.perf_counter() - t0 < seconds):
+        r = o.rollout(b.state[:, n], [int(d) & 0x3f for d in b.slot_desc], [b.obst[m, :, n] for m in range(M)], course, T)
+        solves += r["steps"] * M
+        n += 1
+    dt = time.perf_counter() - t0
+    return solves / dt, n, dt
+
+
+def solve_cbf_latency(dev, n, reps=200):
+    """Per-call latency of the class API as the reference uses it: one DBM_CBF_2DS.solve_cbf per tick on a list of
+    8 ellipses (cbf/cbf.py:166-220), batch size n; microseconds per call, result synchronised every call."""
+    import torch
+    from sccav_cbf_b200 import DBM_CBF_2DS, Ellipse2D
+    from sccav_cbf_b200.euclid import Vector2
+    g = torch.Generator(device="cpu"); g.manual_seed(7)
+    cbf = DBM_CBF_2DS(alpha=1.0)
+    cbf.set_model_params(1.45, 1.45)
+    for k in range(8):
+        if n == 1:
+            e = Ellipse2D(3.0 + 0.2 * k, 1.5, Vector2(12.0 + 5.0 * k, 4.0 - k), theta=0.1 * k, buffer=0.5)
+        else:
+            cx = (12.0 + 5.0 * k + torch.rand(n, generator=g, dtype=torch.float64)).to(dev)
+            cy = (4.0 - k + torch.rand(n, generator=g, dtype=torch.float64)).to(dev)
+            e = Ellipse2D(3.0 + 0.2 * k, 1.5, Vector2(cx, cy), theta=0.1 * k, buffer=0.5)
+        cbf.obstacle_list2d[k] = e
+    if n == 1:
+        s = [0.0, 5.0, 0.35, 10.0]
+        u_ref = [0.3, 0.05]
+    else:
+        s = torch.tensor([[0.0], [5.0], [0.35], [10.0]], dtype=torch.float64, device=dev).repeat(1, n)
+        u_ref = torch.tensor([[0.3], [0.05]], dtype=torch.float64, device=dev).repeat(1, n)
+    for _ in range(10):
+        cbf.update_state(s)
+        u = cbf.solve_cbf(u_ref)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        cbf.update_state(s)
+        u = cbf.solve_cbf(u_ref)
+        torch.cuda.synchronize()
+    return 1e6 * (time.perf_counter() - t0) / reps
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -217,6 +367,8 @@ def main():
                          "fraction of vehicles with identical integer bookkeeping are always reported beside the timed mode")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-operator", action="store_true", help="skip the regime-(i) operator roofline leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs 3 / 4 / 5 / 1M-vehicle-target legs")
+    ap.add_argument("--config-scale", type=float, default=1.0, help="shrink the vehicle counts of the extra config legs (smoke runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -340,6 +492,58 @@ def main():
     e2e_value = solves_per_step * args.steps / e2e_s
     assert int(hres["steps"].sum().item()) == int(vehicle_steps_rank)
 
+    # ---- the other BASELINE.json configurations at their full per-GPU sizes (flat keys: whole-job solves/s, ms,
+    #      oracle-sample parity of rank 0's shard).  Every rank runs its shard; no collective on the path.
+    flat = {}
+    if other is not None:
+        canon = other if other["rows"] == "canonical" else None
+        if canon is not None:
+            flat["canonical_ms_per_step"] = sh.max(canon["ms_per_step"])
+            flat["canonical_value"] = solves_per_step / (flat["canonical_ms_per_step"] * 1e-3)
+        flat["identical_bookkeeping_frac"] = other["identical_bookkeeping_frac_vs_timed_mode"]
+    if fp32_variant is not None:
+        flat["fp32_ms_per_step"] = sh.max(fp32_variant["ms_per_step"])
+        flat["fp32_value"] = solves_per_step / (flat["fp32_ms_per_step"] * 1e-3)
+        flat["fp32_identical_bookkeeping_frac_vs_f64"] = fp32_variant["identical_bookkeeping_frac_vs_f64"]
+    if not args.no_configs and args.dtype == "f64":
+        fl = ROW_FLAGS[args.rows]
+        sc_ = args.config_scale
+
+        def per_gpu(n):
+            return max(1024, int(n * sc_))
+        # config 3: 262,144 vehicles x 16 moving circles (radial-dynamic TV-CBF, seekers), 600 frames
+        n3 = per_gpu(262144)
+        lo3, hi3 = sc.shard_range(n3 * world, rank, world)
+        flat.update(run_config_leg("config3", sc.config3(n_total=n3 * world, M=16, T=600, lo=lo3, hi=hi3), dtype, fl, dev, flush, sh))
+        # config 4: 1,048,576 vehicles x (8 ellipses + 2 lanes), fp64 and fp32
+        n4 = per_gpu(1048576)
+        lo4, hi4 = sc.shard_range(n4 * world, rank, world)
+        b4 = sc.config4(n_total=n4 * world, M=8, T=1000, lo=lo4, hi=hi4)
+        flat.update(run_config_leg("config4_f64", b4, dtype, fl, dev, flush, sh))
+        flat.update(run_config_leg("config4_f32", b4, torch.float32, fl, dev, flush, sh))
+        del b4
+        # config 5, weak: 2,097,152 sweep scenarios per GPU (shard `rank` of 8 x that many)
+        n5 = per_gpu(16777216 // 8)
+        b5 = sc.config5(n_total=8 * n5, T=300, lo=rank * n5, hi=(rank + 1) * n5)
+        flat.update(run_config_leg("config5", b5, dtype, fl, dev, flush, sh))
+        del b5
+        # config 5, STRONG: the whole 16,777,216-scenario sweep split over the ranks of this job
+        n5s = per_gpu(16777216)
+        lo5, hi5 = sc.shard_range(n5s, rank, world)
+        flat.update(run_config_leg("config5_strong", sc.config5(n_total=n5s, T=300, lo=lo5, hi=hi5), dtype, fl, dev, flush, sh, check=False))
+        # the north-star target shard: 1,048,576 vehicles x 8 ellipses over 8 GPUs = 131,072 vehicles per GPU
+        nt = per_gpu(131072)
+        lot, hit = sc.shard_range(nt * world, rank, world)
+        flat.update(run_config_leg("target1m", sc.config2(n_total=nt * world, M=8, T=1000, seed=0, lo=lot, hi=hit), dtype, fl, dev, flush, sh))
+        flat["config_legs_flags"] = fl
+    # ---- per-call latency of the class API (one solve_cbf per tick, as the reference uses it)
+    if rank == 0:
+        try:
+            flat["solve_cbf_latency_us_n1"] = solve_cbf_latency(dev, 1)
+            flat["solve_cbf_latency_us_n1024"] = solve_cbf_latency(dev, 1024)
+        except Exception as exc:          # keep the bench line even if the class API leg fails
+            flat["solve_cbf_latency_error"] = repr(exc)[:200]
+
     # ---- roofline of the dominant kernel (rollout): fp64 FMA peak measured on this GPU, now
     peak_tf = ops.measure_fma_peak(dtype)
     flops_per_launch = rollout_flops(evals_rank, vehicle_steps_rank, M)
@@ -449,6 +653,33 @@ def main():
             "active_frac": float((st_cf == 1).double().mean().item()), "infeasible_frac": float((st_cf == 2).double().mean().item()),
         }
         del h_all, ob_cf, obp_cf
+        # the same batch through the CLASS API (what a user of the reference calls every tick): DBM_CBF_2DS with 8
+        # Ellipse2D objects holding [N] tensors; the first call packs and ingests them, later calls reuse the image
+        try:
+            from sccav_cbf_b200 import DBM_CBF_2DS, Ellipse2D
+            from sccav_cbf_b200.euclid import Vector2
+            cbf = DBM_CBF_2DS(alpha=1.0)
+            cbf.set_model_params(1.45, 1.45)
+            for m_ in range(M):
+                cbf.obstacle_list2d[m_] = Ellipse2D(ob[m_, 2], ob[m_, 3], Vector2(ob[m_, 0], ob[m_, 1]), theta=ob[m_, 4], buffer=0)
+            cbf.update_state(st)
+            for _ in range(3):
+                u_c = cbf.solve_cbf(ur)
+            aevs = []
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); cbf.update_state(st); u_c = cbf.solve_cbf(ur); e1.record()
+                aevs.append((e0, e1))
+            torch.cuda.synchronize()
+            ams = statistics.mean(e0.elapsed_time(e1) for e0, e1 in aevs)
+            roofline_op["class_api"] = {
+                "call": "DBM_CBF_2DS.update_state + solve_cbf, 8 Ellipse2D with [N] tensor fields (cached ingested image)",
+                "algorithmic_bytes_per_solve": pbps, "achieved": pbps * n_op * M / (ams * 1e-3) / 1e9,
+                "frac": pbps * n_op * M / (ams * 1e-3) / 1e9 / hbm_peak, "ms": ams,
+                "max_abs_diff_vs_operator": float((u_c - u_p).abs().max().item())}
+            del cbf, u_c
+        except Exception as exc:
+            roofline_op["class_api"] = {"error": repr(exc)[:300]}
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); ops.prepare_obstacles(batch.slot_desc, ob, out=obp); e1.record()
         torch.cuda.synchronize()
@@ -471,7 +702,20 @@ def main():
                          % (n, NV, M, T, dt_cpu, threads),
                "note": "reference loop not runnable here (cvxopt/euclid absent, no network); the port solves each QP exactly "
                        "instead of paying cvxopt's python-callback interior-point iterations, so it flatters the reference"}
+        # what a reference USER runs is a Python loop: the scalar Python restatement (no cvxopt IPM, no matplotlib), 1 core
+        py_rate, py_n, py_dt = python_loop_rate(4.0, M, T)
+        cpu["python_loop_value"] = py_rate
+        cpu["python_loop_sample"] = "%d vehicles x %d ellipses x %d steps in %.1f s, oracle/oracle.py, 1 core" % (py_n, M, T, py_dt)
+        flat["cpu_python_loop_value"] = py_rate
+        flat["cpu_port_value"] = rate
 
+    if roofline_op is not None:
+        flat["operator_canonical_hbm_frac"] = roofline_op["frac"]
+        flat["operator_prepared_hbm_frac"] = roofline_op["prepared"]["frac"]
+        flat["operator_prepared_ms"] = roofline_op["prepared"]["ms"]
+        if "frac" in roofline_op.get("class_api", {}):
+            flat["class_api_hbm_frac"] = roofline_op["class_api"]["frac"]
+            flat["class_api_ms"] = roofline_op["class_api"]["ms"]
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -491,7 +735,10 @@ def main():
             "roofline_operator": roofline_op,
             "cpu_baseline": cpu,
             "wall_s_timed_region": t_wall1 - t_wall0,
+            "vs_reference_note": "N GPUs over ONE host's CPU threads when n_gpus > 1 (the CPU arm does not scale with --gpus)",
         }
+        line.update(flat)
+        line["ncu_metrics_stale"] = NCU_STALE[0]
         print(json.dumps(line), flush=True)
     sh.close()
     return 0

@@ -75,6 +75,24 @@ def as_state(s, dtype=None, device=None) -> Tuple[torch.Tensor, bool]:
     return torch.tensor(vals, dtype=dtype or DEFAULT_DTYPE, device=device).reshape(4, 1), True
 
 
+def state_scalar(s):
+    """The ego state as a float64 numpy [4] when it is given as 4 plain numbers (one scenario), else None."""
+    if isinstance(s, torch.Tensor):
+        return None
+    if isinstance(s, np.ndarray) and s.ndim == 2 and s.shape[1] > 1:
+        return None
+    try:
+        comps = [s[i] for i in range(4)]
+    except Exception:
+        return None
+    if any(isinstance(c, torch.Tensor) for c in comps):
+        return None
+    try:
+        return np.array([float(np.asarray(c).reshape(-1)[0]) for c in comps], dtype=np.float64)
+    except Exception:
+        return None
+
+
 def to_output(t: torch.Tensor, scalar: bool):
     """[N] tensor -> Python float in scalar mode (one D2H read), the tensor itself otherwise."""
     if scalar:

@@ -25,7 +25,7 @@ import torch
 
 from . import _native as nv
 from . import ops
-from ._batch import as_state, as_vec, batch_size, is_scalar
+from ._batch import as_state, as_vec, batch_size, cuda_device, is_scalar, state_scalar
 from .obstacles import ObstacleList2D
 from .utils import ZERO_TOL
 
@@ -58,6 +58,7 @@ class _FilterBase:
         self._R = np.eye(2)                                          # cbf.py:52,134
         self.s = None
         self.last_info = None
+        self._host_scalar = True          # one-scenario calls with Python numbers go through the host entry point
 
     def set_alpha(self, alpha=1.0):
         self._alpha = alpha
@@ -87,10 +88,61 @@ class _FilterBase:
         R = self._R if isinstance(self._R, np.ndarray) else np.eye(2)
         return ops.make_params(model=self.MODEL, R=R.reshape(-1).tolist(), **kw)
 
+    def _state(self):
+        """([4, N] CUDA tensor, False) for a batch; (numpy [4], True) for one scenario given as plain numbers when the
+        host entry point will take the call (no device tensor is made for it)."""
+        if self._host_scalar and self.MODEL != nv.MODEL_SADBM:
+            v = state_scalar(self.s)
+            if v is not None:
+                return v, True
+        return as_state(self.s)
+
+    def _solve_scalar_host(self, state, u_ref, params, return_solver):
+        """One scenario given as Python numbers (the reference's own call): everything is marshalled on the host
+        and handed to the library's host entry point in ONE call -- no torch device op per field."""
+        descs, obst = self.obstacle_list2d.pack_host()
+        M = obst.shape[0]
+        st = torch.from_numpy(np.ascontiguousarray(state, dtype=np.float64).reshape(4, 1))
+        ob = torch.from_numpy(obst.reshape(M, nv.NFIELD, 1))
+        ur = torch.tensor([[float(np.asarray(u_ref[0]).reshape(-1)[0])], [float(np.asarray(u_ref[1]).reshape(-1)[0])]], dtype=torch.float64)
+        params.alpha = float(self._alpha)
+        aug = self._aug(1, st)
+        u, mask, status, hmin = ops.filter_step(params, descs, st, ob, ur, aug=aug)
+        self.last_info = {"status": status, "active_mask": mask, "h_min": hmin, "u_ref": ur}
+        out = u[:, 0].clone()
+        if not return_solver:
+            return out
+        info = {"status": int(status[0]), "active_mask": int(mask[0]) & 0xFFFFFFFF, "h_min": float(hmin[0]), "x": out}
+        return info, out
+
+    def _scalar_call(self, u_ref) -> bool:
+        if isinstance(self._alpha, torch.Tensor) and self._alpha.dim() > 0:
+            return False
+        if isinstance(self._R, torch.Tensor):
+            return False
+        if getattr(self.obstacle_list2d, "count", None) is not None or not hasattr(self.obstacle_list2d, "pack_host"):
+            return False
+        try:
+            if len(u_ref) != 2 or not all(is_scalar(v) for v in (u_ref[0], u_ref[1])):
+                return False
+        except TypeError:
+            return False
+        if isinstance(u_ref, torch.Tensor) and u_ref.dim() == 2:
+            return False
+        return self.obstacle_list2d.all_scalar()
+
     def _solve(self, state, scalar_state, u_ref, params, return_solver):
         if len(self.obstacle_list2d) < 1:
             raise ValueError(EMPTY_MSG)                               # cbf.py:77-80,177-180
-        slot_desc, obst, scalar_obs = self.obstacle_list2d.pack(state)
+        if isinstance(state, np.ndarray):
+            if self._scalar_call(u_ref):
+                return self._solve_scalar_host(state, u_ref, params, return_solver)
+            state = torch.from_numpy(state.reshape(4, 1)).to(cuda_device())
+        prepared = bool(getattr(self.obstacle_list2d, "use_prepared", False)) and self.MODEL != nv.MODEL_SADBM
+        if prepared:
+            slot_desc, obst, scalar_obs = self.obstacle_list2d.pack(state, prepared=True)
+        else:
+            slot_desc, obst, scalar_obs = self.obstacle_list2d.pack(state)
         N = obst.shape[2]
         if state.shape[1] != N:
             state = state.expand(4, N).contiguous()
@@ -153,7 +205,7 @@ class DBM_CBF_2DS(_FilterBase):
             raise AttributeError("set_model_params(lr, lf) has not been called")
         if self.s is None:
             raise AttributeError("update_state(s) has not been called")
-        state, scalar = as_state(self.s)
+        state, scalar = self._state()
         params = self._params(lr=float(self._lr), lf=float(self._lf), L=float(self._lr) + float(self._lf))
         return self._solve(state, scalar, u_ref, params, return_solver)
 
@@ -190,7 +242,7 @@ class KBM_VC_CBF2D(_FilterBase):
             raise AttributeError("set_model_params(L) has not been called")
         if self.s is None:
             raise AttributeError("update_state(p, theta) has not been called")
-        state, scalar = as_state(self.s)
+        state, scalar = self._state()
         params = self._params(L=float(self._L))
         return self._solve(state, scalar, u_ref, params, True)
 
@@ -207,7 +259,7 @@ class DUM_CBF_2DS(DBM_CBF_2DS):
             raise ValueError(EMPTY_MSG)
         if self.s is None:
             raise AttributeError("update_state(s) has not been called")
-        state, scalar = as_state(self.s)
+        state, scalar = self._state()
         return self._solve(state, scalar, u_ref, self._params(), return_solver)
 
 
@@ -249,7 +301,7 @@ class SADBM_CBF_2DS(DBM_CBF_2DS):
         t_current = time.time()
         if self._DT_MODE_AUTO:
             self._dt = max(t_current - self.t_last, ZERO_TOL)                      # cbf.py:363-365
-        state, scalar = as_state(self.s)
+        state, scalar = self._state()
         params = self._params(lr=float(self._lr), lf=float(self._lf), L=float(self._lr) + float(self._lf),
                               sadbm_dt=float(self._dt))
         out = self._solve(state, scalar, u_ref, params, return_solver)

@@ -520,19 +520,101 @@ class ObstacleList2D(MutableMapping):
                 warnings.warn("Unknown key provided in s_obs_dict. Corresponding key not found in the obstacle list. key: %r" % (key,))
 
     # ---- SoA packing + stacked getters ----------------------------------------------------------
-    def pack(self, state: torch.Tensor) -> Tuple[List[int], torch.Tensor, bool]:
-        """(slot_desc, obst [M, 8, N], all_scalar) for the ego batch ``state`` [4, N]."""
-        N = state.shape[1]
-        descs, rows, scalar = [], [], True
+    # ``solve_cbf`` on a list whose ELLIPSE obstacles have not changed since the previous call evaluates them in their
+    # ingested form (ELLIPSE_PREP, include/sccav_cbf.h: everything of Ellipse2D that does not depend on the vehicle is
+    # computed once, sccav_prepare_obstacles_*) -- the same functions as cbf/obstacles.py:193,218,229,316, a few ulp
+    # apart, and the HBM-bound form of the operator.  Set to False for the reference's operation order on every call.
+    use_prepared = True
+
+    def _gather(self):
+        """(descs, rows of 8 field values, all_scalar, cacheable, fingerprint) of the current list."""
+        descs, rows, fp = [], [], []
+        scalar, cacheable = True, True
         for obs in self.mapping.values():
             f = obs.fields()
-            scalar = scalar and all(is_scalar(v) for v in f)
-            N = max([N] + [batch_size(v) for v in f])
             descs.append(obs.slot_type)
             rows.append(f)
-        obst = torch.stack([torch.stack([as_vec(v, N, state.dtype, state.device) for v in f]) for f in rows]) \
-            if rows else torch.empty((0, nv.NFIELD, N), dtype=state.dtype, device=state.device)
-        return descs, obst.contiguous(), scalar
+            fp.append(obs.slot_type)
+            for v in f:
+                if isinstance(v, torch.Tensor):
+                    if v.dim() > 0:
+                        scalar = False
+                    fp.append((id(v), v._version))
+                elif isinstance(v, np.ndarray):
+                    if not (v.ndim == 0 or v.size == 1):
+                        scalar = False
+                    cacheable = False                         # arrays change in place without a trace
+                    fp.append(None)
+                else:
+                    fp.append(float(v))
+        return descs, rows, scalar, cacheable, tuple(fp)
+
+    def pack_host(self) -> Tuple[List[int], np.ndarray]:
+        """(slot_desc, fields [M, 8] float64 numpy) of a list whose fields are all scalars -- the one-scenario call of
+        the reference: no device work at all, the host entry point of the library takes it from here."""
+        descs, rows, scalar, _, _ = self._gather()
+        if not scalar:
+            raise ValueError("pack_host needs scalar obstacle fields")
+        arr = np.array([[float(v) for v in f] for f in rows], dtype=np.float64).reshape(len(rows), nv.NFIELD)
+        return descs, arr
+
+    def all_scalar(self) -> bool:
+        for obs in self.mapping.values():
+            for v in obs.fields():
+                if isinstance(v, torch.Tensor) and v.dim() > 0:
+                    return False
+                if isinstance(v, np.ndarray) and not (v.ndim == 0 or v.size == 1):
+                    return False
+        return True
+
+    def pack(self, state: torch.Tensor, prepared: bool = False) -> Tuple[List[int], torch.Tensor, bool]:
+        """(slot_desc, obst [M, 8, N], all_scalar) for the ego batch ``state`` [4, N].
+
+        The packed buffer is cached: as long as no field of any obstacle has changed (scalars by value, tensors by
+        identity and in-place version) the same device tensor is returned and nothing is launched.  With
+        ``prepared`` the ELLIPSE slots come back in their ingested form (see ``use_prepared``); ellipses whose
+        velocity is exactly (0, 0) are declared STATIC."""
+        descs, rows, scalar, cacheable, fp = self._gather()
+        N = state.shape[1]
+        for f in rows:
+            for v in f:
+                N = max(N, batch_size(v))
+        key = (fp, N, state.dtype, state.device)
+        c = getattr(self, "_pack_cache", None)
+        if c is None or not cacheable or c["key"] != key:
+            M = len(rows)
+            if M == 0:
+                obst = torch.empty((0, nv.NFIELD, N), dtype=state.dtype, device=state.device)
+            else:
+                # scalars go through ONE host array and one copy; tensor-valued fields are written over it
+                host = np.zeros((M, nv.NFIELD), dtype=np.float64)
+                tens = []
+                for m, f in enumerate(rows):
+                    for k, v in enumerate(f):
+                        if isinstance(v, (torch.Tensor, np.ndarray)) and batch_size(v) > 1:
+                            tens.append((m, k, v))
+                        elif isinstance(v, torch.Tensor):
+                            host[m, k] = float(v)
+                        else:
+                            host[m, k] = float(np.asarray(v).reshape(-1)[0])
+                base = torch.from_numpy(host).to(device=state.device, dtype=state.dtype)
+                obst = base.unsqueeze(2).expand(M, nv.NFIELD, N).contiguous()
+                for m, k, v in tens:
+                    obst[m, k].copy_(as_vec(v, N, state.dtype, state.device))
+            c = {"key": key, "descs": descs, "obst": obst, "scalar": scalar, "prep": None,
+                 "keep": [v for f in rows for v in f if isinstance(v, torch.Tensor)]}      # ids stay unique while cached
+            self._pack_cache = c
+        if prepared and c["obst"].shape[0] > 0:
+            if c["prep"] is None:
+                d2 = list(c["descs"])
+                for m, f in enumerate(rows):
+                    vx, vy = f[5], f[6]
+                    if (d2[m] & nv.SLOT_TYPE_MASK) == nv.SLOT_ELLIPSE and not isinstance(vx, (torch.Tensor, np.ndarray)) \
+                            and not isinstance(vy, (torch.Tensor, np.ndarray)) and float(vx) == 0.0 and float(vy) == 0.0:
+                        d2[m] |= nv.SLOT_STATIC
+                c["prep"] = ops.prepare_obstacles(d2, c["obst"])
+            return c["prep"][0], c["prep"][1], c["scalar"]
+        return c["descs"], c["obst"], c["scalar"]
 
     def _stacked(self, k: int):
         vals = [obs._get(k) for obs in self.mapping.values()]

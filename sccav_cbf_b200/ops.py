@@ -68,9 +68,11 @@ def _pv(N, dtype, device, alpha=None, R=None, target_speed=None, count=None, aug
     pv = nv.PerVehicle()
     keep = []
     if aug is not None:
-        aug = _chk(aug, (2, N), dtype, device, "aug")
+        # checked BEFORE _chk (which would hand back a contiguous copy: the kernel would advance the copy's beta /
+        # beta_ref_last and the caller's SADBM state would never move)
         if not aug.is_contiguous():
             raise ValueError("aug must be contiguous (it is updated in place)")
+        aug = _chk(aug, (2, N), dtype, device, "aug")
         keep.append(aug); pv.aug = aug.data_ptr()
     if count is not None:
         count = _chk(count, (N,), torch.int32, device, "count"); keep.append(count); pv.count = count.data_ptr()

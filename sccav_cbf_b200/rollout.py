@@ -57,6 +57,7 @@ class ClosedLoopRollout:
         self.d_tspeed = None if self.h_tspeed is None else self.h_tspeed.to(self.device)
         self.out: Dict[str, torch.Tensor] = {}
         self._host_out: Dict[str, torch.Tensor] = {}
+        self._h_obst0 = None
 
     @property
     def N(self) -> int:
@@ -76,6 +77,10 @@ class ClosedLoopRollout:
 
     def run(self, T: Optional[int] = None, record_stride: int = 0) -> Dict[str, torch.Tensor]:
         self.reset()
+        return self.launch(T, record_stride)
+
+    def launch(self, T: Optional[int] = None, record_stride: int = 0) -> Dict[str, torch.Tensor]:
+        """The rollout launch alone (callers that time it call reset() themselves, outside the timed region)."""
         return ops.rollout(self.params, self.slot_desc, self.d_state, self.d_obst, self.course,
                            self.T if T is None else T, alpha=self.d_alpha, R=self.d_R, target_speed=self.d_tspeed,
                            record_stride=record_stride, out=self.out)
@@ -84,6 +89,13 @@ class ClosedLoopRollout:
         """The end-to-end call: ONE C-ABI call with HOST pointers (sccav_rollout_host_*): the inputs are
         copied from pinned host memory, the rollout kernel runs, the per-vehicle results are copied
         back, and the stream is synchronised inside the call.  Returns pinned host tensors."""
+        if self.h_obst is not None and self.params.seeker:
+            # the host entry point writes the moved obstacles back into the buffer it was given: start every call
+            # from the pristine scenario, not from the previous call's final obstacle positions
+            if self._h_obst0 is None:
+                self._h_obst0 = self.h_obst.clone()
+            else:
+                self.h_obst.copy_(self._h_obst0)
         with torch.cuda.device(self.device):
             res = ops.rollout(self.params, self.slot_desc, self.h_state, self.h_obst, self.h_course,
                               self.T if T is None else T, alpha=self.h_alpha, R=self.h_R, target_speed=self.h_tspeed,

@@ -171,6 +171,9 @@ def metrics(paths, out_json):
                 "registers_per_thread": val("launch__registers_per_thread"),
                 "grid": d["Grid Size"][1], "block": d["Block Size"][1],
             }
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    res["_csrc_sha"] = bench.csrc_sha()            # bench.py refuses to quote these numbers once csrc/ has changed
     json.dump(res, open(out_json, "w"), indent=1, sort_keys=True)
     print(json.dumps(res, indent=1, sort_keys=True))
 

@@ -56,8 +56,9 @@ def test_no_cpu_fallback_without_device():
         ops.filter_step(ops.make_params(), [0], torch.zeros(4, 2, dtype=torch.float64), torch.ones(1, 8, 2, dtype=torch.float64),
                         torch.zeros(2, 2, dtype=torch.float64))
     src = "".join(open(os.path.join(ROOT, "sccav_cbf_b200", f)).read() for f in os.listdir(os.path.join(ROOT, "sccav_cbf_b200")) if f.endswith(".py"))
-    assert "oracle" not in src.replace("the oracle", "").replace("oracle's", "").replace("oracle/", "") or True
-    assert "import oracle" not in src and "from oracle" not in src
+    # no import of the checker anywhere in the product package, in any spelling
+    assert not re.search(r"^\s*(import|from)\s+oracle\b", src, re.M)
+    assert "import_module(\"oracle" not in src and "__import__(\"oracle" not in src and "liboracle" not in src
 
 
 def test_course_matches_reference_planner(refvec):

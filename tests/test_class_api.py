@@ -273,8 +273,17 @@ def test_batched_solve_equals_scalar_solves_and_oracle():
         ctl.obstacle_list2d[j] = e
         fields.append(np.stack([cx, cy, a + 0.5, b + 0.5, th, 0 * a, 0 * a, 0 * a]))
     ctl.update_state(torch.from_numpy(s))
+    # default: unchanged ellipses are evaluated in their ingested form (a few ulp from the reference's operation order)
+    assert ctl.obstacle_list2d.use_prepared
+    info_p, u_p = ctl.solve_cbf(torch.from_numpy(ur), return_solver=True)
+    _, u_p2 = ctl.solve_cbf(torch.from_numpy(ur), return_solver=True)          # second call: the cached image, nothing re-packed
+    assert torch.equal(u_p, u_p2)
+    # the reference's operation order on every call: bit-identical to the one-scenario calls below
+    ctl.obstacle_list2d.use_prepared = False
     info, u = ctl.solve_cbf(torch.from_numpy(ur), return_solver=True)
     assert u.is_cuda and u.shape == (2, N)
+    assert ((u_p - u).abs() <= 1e-12 * (1 + u.abs())).all()
+    assert torch.equal(info_p["active_mask"], info["active_mask"]) and torch.equal(info_p["status"], info["status"])
     u = u.cpu().numpy(); mask = info["active_mask"].cpu().numpy().view(np.uint32); status = info["status"].cpu().numpy()
     assert (status != o.STATUS_INACTIVE).sum() > 10
     for n in range(0, N, 7):
@@ -510,3 +519,48 @@ def test_sadbm_wall_clock_mode_and_lane_distance_form():
     info, u = d.solve_cbf([0.0, 0.3], return_solver=True)
     ref = o.filter_step(o.MODEL_DBM, st, [0.0, 0.3], [o.SLOT_LANE_SQRT], [[1.5] + list(co) + [0.0, 0.0, 0.0, 0.0]], 1.0, 1.45, 1.45, 2.9, (1, 0, 0, 1))
     assert info["status"] == ref[3] and abs(float(u[1]) - ref[1]) < 1e-7 and abs(float(u[0]) - ref[0]) < 1e-9
+
+
+@gpu
+def test_pack_cache_follows_every_change_of_the_list():
+    """ObstacleList2D.pack caches the packed / ingested obstacle image; any change of any field -- a method call, a
+    plain attribute assignment, an in-place tensor update, an obstacle added or removed -- must be seen."""
+    rng = np.random.default_rng(3)
+    N = 64
+    s = torch.from_numpy(np.stack([rng.uniform(-5, 5, N), rng.uniform(-5, 5, N), rng.uniform(-1, 1, N), rng.uniform(3, 12, N)]))
+    ur = torch.from_numpy(np.stack([rng.uniform(-2, 2, N), rng.uniform(-0.4, 0.4, N)]))
+
+    def build(cx, cy, a, th, vel=None):
+        c = DBM_CBF_2DS(alpha=1.0)
+        c.set_model_params(1.45, 1.45)
+        for j in range(3):
+            e = Ellipse2D(a[j], 1.5, Vector2(cx[j].clone(), cy[j].clone()), theta=th[j], buffer=0.5)
+            if vel is not None:
+                e.update_velocity(vel[j])
+            c.obstacle_list2d[j] = e
+        c.update_state(s)
+        return c
+
+    cx = [torch.from_numpy(rng.uniform(5, 20, N)) for _ in range(3)]
+    cy = [torch.from_numpy(rng.uniform(-4, 4, N)) for _ in range(3)]
+    a, th = [3.0, 4.0, 2.5], [0.1, -0.7, 1.3]
+    ctl = build(cx, cy, a, th)
+    u0 = ctl.solve_cbf(ur)
+    assert torch.equal(u0, ctl.solve_cbf(ur))
+    # 1. plain attribute assignment of a scalar field
+    ctl.obstacle_list2d[1].theta = 0.4
+    th2 = [0.1, 0.4, 1.3]
+    assert torch.equal(ctl.solve_cbf(ur), build(cx, cy, a, th2).solve_cbf(ur))
+    # 2. in-place update of a tensor field
+    ctl.obstacle_list2d[0].center.x.add_(1.25)
+    cx2 = [cx[0] + 1.25, cx[1], cx[2]]
+    assert torch.equal(ctl.solve_cbf(ur), build(cx2, cy, a, th2).solve_cbf(ur))
+    # 3. a method of the reference API, and a moving obstacle (no longer STATIC)
+    ctl.obstacle_list2d[2].update_velocity(Vector2(0.5, -0.25))
+    ref = build(cx2, cy, a, th2, vel=[Vector2(0, 0), Vector2(0, 0), Vector2(0.5, -0.25)])
+    assert torch.equal(ctl.solve_cbf(ur), ref.solve_cbf(ur))
+    # 4. an obstacle leaves
+    ctl.obstacle_list2d.pop(1)
+    ref.obstacle_list2d.pop(1)
+    assert torch.equal(ctl.solve_cbf(ur), ref.solve_cbf(ur))
+    assert not torch.equal(u0, ctl.solve_cbf(ur))
