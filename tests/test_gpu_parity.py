@@ -685,3 +685,106 @@ def test_full_size_config2_rollout_properties_and_oracle_sample(prepared):
     assert same.mean() >= 0.99, same.mean()
     err = _relerr(g["state"][:, idx], r["state"]).max(axis=0)
     assert np.median(err) <= 1e-12 and (err[same] <= 1e-6).mean() >= 0.9
+
+
+def test_rollout_config3_reference_run(golden_dir):
+    """BASELINE config #3 against the reference ITSELF: tests/golden/reference_vectors_radial_loop.npz holds three
+    600-frame runs of radial_dynamic_obstacles.py (the whole module executed: spawner, single_obstacle_CBF1, animate).
+    The GPU rollout from the spawn state must follow them frame by frame -- states, controls, active sets -- for as
+    long as the seeker is outside the ego's 0.5 m neighbourhood (afterwards its heading is atan2 of a near-zero
+    offset, rdo.py:205, and the 1-ulp libm differences between CUDA and glibc decide where it goes)."""
+    from sccav_cbf_b200 import scenarios as sc
+    gold = np.load(os.path.join(golden_dir, "reference_vectors_radial_loop.npz"))
+    tags = ["m1_s0", "m1_s1", "m1_s2"]
+    state = np.stack([gold[t + "_ego"][1] for t in tags], axis=1)
+    obst = np.zeros((1, 8, 3))
+    for j, t in enumerate(tags):
+        cx, cy, vx, vy, r = gold[t + "_obs"][1, 0]
+        obst[0, :, j] = [cx, cy, r, r, 1.0, vx, vy, 0.0]
+    b = sc.ScenarioBatch("config3_reference", state, [o.SLOT_RADIAL], obst, None,
+                         dict(seeker=1, dt=1.0 / 30.0, alpha=1.0, nominal=o.NOMINAL_CONST, uref0=0.0, uref1=0.0), T=599)
+    g = _run(b, record_stride=1)
+    assert (g["steps"] == 599).all()
+    for j, t in enumerate(tags):
+        ego, u, row, obs = (gold[t + "_" + k] for k in ("ego", "u", "row", "obs"))
+        sep = np.hypot(obs[1:, 0, 0] - ego[1:, 0], obs[1:, 0, 1] - ego[1:, 1])
+        far = np.logical_and.accumulate(sep > 0.5)
+        assert far.sum() > 60
+        es = np.abs(g["traj"][:, 0:4, j] - ego[1:]).max(axis=1)
+        eu = np.abs(g["traj"][:, 4:6, j] - u[1:]).max(axis=1)
+        assert es[far].max() <= 1e-9 and eu[far].max() <= 1e-9, (t, es[far].max(), eu[far].max())
+        assert np.array_equal(g["traj_mask"][far, j] != 0, row[1:, 3][far] != 0)
+        assert (g["traj_mask"][far, j] != 0).sum() > 20
+        assert np.isfinite(g["traj"][:, :, j]).all()
+        assert es.max() <= 1e-6 and eu.max() <= 1e-6          # (observed: 5e-16 over all 599 frames, contact included)
+        print(t, "frames outside 0.5 m:", int(far.sum()), "of 599; max |state err| there %.2e; over all frames %.2e" % (es[far].max(), es.max()))
+
+
+# ------------------------------------------------------------------------------------------ teacher forcing, every mode
+def _teacher_forced_steps(batch, ts, flags, n_min_frac=0.5, u_tol=1e-9, x_tol=1e-12):
+    """Strict per-step parity of the ROLLOUT kernel itself: the oracle runs the scenario free and records every
+    step; at each sampled step t the GPU is launched for ONE step from the oracle's state (and, for seekers, the
+    oracle's obstacle state) -- controls to u_tol, active sets and way-point indices identical, next state to x_tol
+    (relative).  A one-step launch starts its monotone index clamp from the nearest way-point, so vehicles whose
+    oracle clamp is engaged at t (target index ahead of the nearest point) are left out of that step."""
+    from sccav_cbf_b200 import ops
+    prm_o = {k: v for k, v in batch.params.items() if k != "flags"}
+    kw = {k: getattr(batch, k) for k in ("alpha", "R", "target_speed") if getattr(batch, k) is not None}
+    r = co.rollout(co.default_params(**prm_o), batch.slot_desc, batch.state, batch.obst, batch.course, batch.T, record_stride=1, **kw)
+    prm = ops.make_params(**dict(batch.params, flags=flags, terminate=0))
+    course = None if batch.course is None else tuple(T_(c, torch.float64) for c in batch.course)
+    gkw = {k: T_(v, torch.float64) for k, v in kw.items()}
+    seeker = bool(batch.params.get("seeker"))
+    checked = 0
+    for t in ts:
+        alive = r["steps"] > t + 1                                   # the oracle has a step t and a state after it
+        st = r["traj"][t, 0:4]
+        if seeker:                                                   # obstacle state at step t: re-run the oracle up to t
+            obst_t = co.rollout(co.default_params(**prm_o), batch.slot_desc, batch.state, batch.obst, batch.course, t, **kw)["obst"] if t > 0 else batch.obst
+        else:
+            obst_t = batch.obst
+        if batch.course is not None:
+            cx, cy, _ = batch.course
+            L = batch.params.get("L", 2.9)
+            fx = st[0] + L * np.cos(st[2]); fy = st[1] + L * np.sin(st[2])
+            ok = np.zeros(batch.N, bool)
+            for n in np.nonzero(alive)[0]:
+                dx = fx[n] - cx; dy = fy[n] - cy
+                ok[n] = int(np.argmin(dx * dx + dy * dy)) == r["traj_idx"][t, n]
+            alive &= ok
+        assert alive.mean() >= n_min_frac, (t, alive.mean())
+        st_in = np.where(np.isfinite(st), st, 0.0)
+        g = ops.rollout(prm, batch.slot_desc, T_(st_in, torch.float64), None if obst_t is None else T_(obst_t, torch.float64), course, 1,
+                        record_stride=1, **gkw)
+        torch.cuda.synchronize()
+        gu = g["traj"][0, 4:6].cpu().numpy()[:, alive]; ru = r["traj"][t, 4:6][:, alive]
+        assert (np.abs(gu - ru) <= u_tol * (1.0 + np.abs(ru))).all(), (t, np.abs(gu - ru).max())
+        assert np.array_equal(g["traj_mask"][0].cpu().numpy().view(np.uint32)[alive], r["traj_mask"][t][alive]), t
+        if batch.course is not None:
+            assert np.array_equal(g["traj_idx"][0].cpu().numpy()[alive], r["traj_idx"][t][alive]), t
+        gx = g["state"].cpu().numpy()[:, alive]; rx = r["traj"][t + 1, 0:4][:, alive]
+        assert (np.abs(gx - rx) <= x_tol * (1.0 + np.abs(rx))).all(), (t, np.abs(gx - rx).max())
+        checked += int(alive.sum())
+    return checked
+
+
+@pytest.mark.parametrize("flags", [0, 1, 4, 5])
+def test_teacher_forced_rollout_step_config2_every_row_mode(flags):
+    """Config 2 in the library-default arithmetic (0), with prepared rows (1), with the fused steering (4) and in the
+    mode bench.py times (5 = both): every sampled step of the rollout kernel against the oracle, strictly."""
+    from sccav_cbf_b200 import scenarios as sc
+    b = sc.config2(n_total=65536, M=8, T=260, lo=8192, hi=8192 + 384)
+    n = _teacher_forced_steps(b, list(range(0, 250, 6)), flags)
+    assert n > 10000
+
+
+@pytest.mark.parametrize("flags", [0, 5])
+def test_teacher_forced_rollout_step_configs_3_4_5(flags):
+    from sccav_cbf_b200 import scenarios as sc
+    b3 = sc.config3(n_total=262144, M=16, T=420, lo=1000, hi=1000 + 192)
+    assert _teacher_forced_steps(b3, [0, 1, 2, 5, 17, 60, 150, 299, 418], flags, u_tol=1e-8) > 1500
+    b4 = sc.config4(n_total=1048576, M=8, T=260, lo=300000, hi=300000 + 256)
+    assert _teacher_forced_steps(b4, list(range(0, 250, 17)), flags, n_min_frac=0.15) > 1500
+    lo = 11 * 65536 + 5
+    b5 = sc.config5(n_total=16777216, T=280, lo=lo, hi=lo + 256)
+    assert _teacher_forced_steps(b5, list(range(0, 270, 13)), flags, n_min_frac=0.15) > 1500

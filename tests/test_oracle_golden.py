@@ -252,3 +252,68 @@ def test_polynomial_lane_fit_equals_numpy_polyfit():
             c = o.fit_polynomial(x, y, n, sg)
             ref = np.polyfit(x, y, n, w=1.0 / sg)[::-1]
             assert np.allclose(c, ref, rtol=1e-9, atol=1e-10)
+
+
+# ------------------------------------------------------------------------------------------ config 3 closed loop
+@pytest.fixture(scope="module")
+def radial_loop(golden_dir):
+    """Produced by EXECUTING the reference's radial_dynamic_obstacles.py -- the whole module: RadialObstacleSpawner,
+    single_obstacle_CBF1 and animate() for 600 frames (tests/golden/gen_reference_vectors_radial_loop.py)."""
+    return np.load(os.path.join(golden_dir, "reference_vectors_radial_loop.npz"))
+
+
+RADIAL_PRM = dict(model=o.MODEL_DBM, nominal=o.NOMINAL_CONST, uref0=0.0, uref1=0.0, seeker=1, dt=1.0 / 30.0, alpha=1.0)
+
+
+def radial_fields(obs_row):
+    """RADIAL slot fields (include/sccav_cbf.h) from a recorded (cx, cy, vx, vy, r): a = b = r, kv = 1 (rdo.py:462-463)."""
+    cx, cy, vx, vy, r = obs_row
+    return [cx, cy, r, r, 1.0, vx, vy, 0.0]
+
+
+@pytest.mark.parametrize("tag", ["m1_s0", "m1_s1", "m1_s2"])
+def test_radial_closed_loop_reproduces_reference_animate(radial_loop, tag):
+    """BASELINE config 3 pinned to the reference ITSELF: the order filter -> update_com(dt = 1/30) -> update_seekers
+    (rdo.py:456-487), the spawn state (seeker velocity = ego speed = 0, :186), the seeker law (:193-239).  The scalar
+    oracle reproduces all 599 frames after the spawn BIT FOR BIT -- states, controls, active sets -- including the
+    frames after the seeker has reached the ego and circles it."""
+    ego, u, row, obs = (radial_loop[tag + "_" + k] for k in ("ego", "u", "row", "obs"))
+    assert np.all(ego[0] == 0.0) and np.all(ego[1] == 0.0) and np.all(u[0] == 0.0)       # frame 0: nothing spawned yet
+    r = o.rollout(ego[1], [o.SLOT_RADIAL], [radial_fields(obs[1, 0])], None, 599, params=RADIAL_PRM, record=True)
+    st = np.array(r["rec"]["state"]); uu = np.array(r["rec"]["u"]); mk = np.array(r["rec"]["mask"])
+    assert np.array_equal(st, ego[1:])
+    assert np.array_equal(uu, u[1:])
+    assert np.array_equal(mk != 0, row[1:, 3] != 0) and (mk != 0).sum() > 40
+    assert np.array_equal(np.array(r["state"]), radial_loop[tag + "_final_ego"])
+    fo = radial_loop[tag + "_final_obs"][0]
+    assert r["fields"][0][0] == fo[0] and r["fields"][0][1] == fo[1] and r["fields"][0][5] == fo[2] and r["fields"][0][6] == fo[3]
+
+
+def test_radial_closed_loop_c_oracle(radial_loop):
+    """The C oracle (the checker of the GPU tests and the CPU baseline) on the same three runs, as ONE batch."""
+    from oracle import c_oracle as co
+    tags = ["m1_s0", "m1_s1", "m1_s2"]
+    state = np.stack([radial_loop[t + "_ego"][1] for t in tags], axis=1)
+    obst = np.stack([np.array(radial_fields(radial_loop[t + "_obs"][1, 0])) for t in tags], axis=1)[None]
+    res = co.rollout(co.default_params(**RADIAL_PRM), [o.SLOT_RADIAL], state, np.ascontiguousarray(obst), None, 599, record_stride=1)
+    for j, t in enumerate(tags):
+        ego, u = radial_loop[t + "_ego"], radial_loop[t + "_u"]
+        assert np.abs(res["traj"][:, 0:4, j] - ego[1:]).max() <= 1e-12
+        assert np.abs(res["traj"][:, 4:6, j] - u[1:]).max() <= 1e-12
+        assert np.array_equal(res["traj_mask"][:, j] != 0, radial_loop[t + "_row"][1:, 3] != 0)
+
+
+def test_seeker_law_for_a_crowd(radial_loop):
+    """16 seekers spawned by the reference's spawner and moved by its update_seekers for 598 frames: the oracle's
+    seeker_update, fed the ego states the reference visited, reproduces every centre and velocity bit for bit."""
+    ego, obs = radial_loop["m16_s0_ego"], radial_loop["m16_s0_obs"]
+    assert obs.shape == (600, 16, 5) and not np.isnan(obs[1:]).any()
+    d0 = np.hypot(obs[1, :, 0], obs[1, :, 1])
+    assert (d0 >= 10.0).all() and (d0 <= 20.0).all() and (obs[1, :, 4] >= 1.5).all() and (obs[1, :, 4] <= 2.0).all()   # rdo.py:55-56
+    assert np.all(obs[1, :, 2:4] == 0.0)                                   # spawned with the ego's speed (0), rdo.py:186
+    f = [radial_fields(obs[1, j]) for j in range(16)]
+    for i in range(1, 599):
+        for j in range(16):
+            o.seeker_update(f[j], ego[i + 1, 0], ego[i + 1, 1], 1.0 / 30.0)
+            assert f[j][0] == obs[i + 1, j, 0] and f[j][1] == obs[i + 1, j, 1]
+            assert f[j][5] == obs[i + 1, j, 2] and f[j][6] == obs[i + 1, j, 3]
