@@ -535,6 +535,42 @@ def main():
         nt = per_gpu(131072)
         lot, hit = sc.shard_range(nt * world, rank, world)
         flat.update(run_config_leg("target1m", sc.config2(n_total=nt * world, M=8, T=1000, seed=0, lo=lot, hi=hit), dtype, fl, dev, flush, sh))
+        # Monte-Carlo over ROADS: 64 roads x 1,024 vehicles x 8 ellipses x 1000 steps in ONE launch (sccav_rollout_roads_*)
+        # against 64 launches with one road each (what the road-per-launch interface costs); rank 0 only
+        if rank == 0:
+            n_roads, per_road = 64, max(32, int(1024 * sc_))
+            (rcx, rcy, rcyaw, rnp), rnph, rstate, robst = sc.roads(n_roads, per_road, M=8, seed=4, dtype=dtype, device=dev)
+            rprm = ops.make_params(flags=fl)
+            rsd = [0x40] * 8                                              # SLOT_ELLIPSE | SLOT_STATIC
+            d_rs = torch.from_numpy(rstate).to(device=dev, dtype=dtype); d_ro = torch.from_numpy(robst).to(device=dev, dtype=dtype)
+            rout = {}
+            ops.rollout(rprm, rsd, d_rs, d_ro, (rcx, rcy, rcyaw), 1000, course_np=rnp, out=rout)
+            torch.cuda.synchronize()
+            rms = []
+            for _ in range(2):
+                flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); rr = ops.rollout(rprm, rsd, d_rs, d_ro, (rcx, rcy, rcyaw), 1000, course_np=rnp, out=rout); e1.record()
+                torch.cuda.synchronize()
+                rms.append(e0.elapsed_time(e1))
+            rsolves = float(rr["steps"].sum().item()) * 8
+            singles = [(rcx[c, :rnph[c]].contiguous(), rcy[c, :rnph[c]].contiguous(), rcyaw[c, :rnph[c]].contiguous(),
+                        d_rs[:, c * per_road:(c + 1) * per_road].contiguous(), d_ro[:, :, c * per_road:(c + 1) * per_road].contiguous())
+                       for c in range(n_roads)]
+            souts = [{} for _ in range(n_roads)]
+            for rep in range(2):
+                flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for c, (a_, b_, c_, s_, o_) in enumerate(singles):
+                    ops.rollout(rprm, rsd, s_, o_, (a_, b_, c_), 1000, out=souts[c])
+                e1.record()
+                torch.cuda.synchronize()
+                sms = e0.elapsed_time(e1)
+            same = all(torch.equal(souts[c]["state"], rr["state"][:, c * per_road:(c + 1) * per_road]) for c in range(n_roads))
+            flat.update({"roads64_value": rsolves / (min(rms) * 1e-3), "roads64_ms": min(rms), "roads64_vehicles": n_roads * per_road,
+                         "roads64_one_launch_per_road_ms": sms, "roads64_bit_identical_to_single_road_launches": bool(same)})
+            del singles, souts, rout, d_rs, d_ro
         flat["config_legs_flags"] = fl
     # ---- per-call latency of the class API (one solve_cbf per tick, as the reference uses it)
     if rank == 0:

@@ -253,6 +253,22 @@ int sccav_rollout_f32(const sccav_params* p, const uint8_t* slot_desc, int32_t M
                       const float* course_yaw, int32_t P, const sccav_pervehicle* pv,
                       const sccav_rollout_out* out, void* stream);
 
+/* K3 over SEVERAL roads in one launch (Monte-Carlo over roads: the courses of sccav_spline_course_* go straight in).
+ * course_x / course_y / course_yaw: dev [C][P_max] (the layout sccav_spline_course_* writes), course_np: dev [C] int32 =
+ * points course c has (clamped to [1, P_max]).  The N vehicles are grouped by road: vehicles [c N/C, (c+1) N/C) drive
+ * road c (N must be a multiple of C).  Every road is staged, indexed and driven exactly as a launch of sccav_rollout_*
+ * with that road alone would: the results are bit-identical, the C launches and C course builds are not paid.
+ * Replaces a loop over calc_spline_course (cubic_spline_planner.py:178-190) + the per-road while-loop of
+ * stanley_controller_ellipse.py:630-830.  Stanley nominal control only. */
+int sccav_rollout_roads_f64(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N, int32_t T,
+                            const double* state, double* obst, const double* course_x, const double* course_y,
+                            const double* course_yaw, int32_t P_max, int32_t C, const int32_t* course_np,
+                            const sccav_pervehicle* pv, const sccav_rollout_out* out, void* stream);
+int sccav_rollout_roads_f32(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N, int32_t T,
+                            const float* state, float* obst, const float* course_x, const float* course_y,
+                            const float* course_yaw, int32_t P_max, int32_t C, const int32_t* course_np,
+                            const sccav_pervehicle* pv, const sccav_rollout_out* out, void* stream);
+
 /* Host-buffer variants (what a host-language caller of the reference binds): all array pointers
  * (including those inside pv / out) are HOST memory; the call copies inputs to the current
  * device, runs the kernel, copies results back and synchronises `stream` before returning. */
@@ -337,8 +353,8 @@ int sccav_actuator_shaping_f32(int64_t N, const float* u, double max_steer, doub
  *   wx, wy  [C][K]      way-points (K >= 2 per course, K <= 64)
  *   cx, cy, cyaw, ck [C][P_max]   samples; ck may be NULL; only the first min(np, P_max) of a course are written
  *   np_out  [C] int32   number of samples course c HAS (compare with P_max)
- * DEVICE pointers, asynchronous on `stream`.  Per-scenario roads: generate C courses, then launch one
- * rollout per group of vehicles with its course (each launch takes course pointers). */
+ * DEVICE pointers, asynchronous on `stream`.  Per-scenario roads: generate C courses, then hand all of them to ONE
+ * sccav_rollout_roads_* launch. */
 #define SCCAV_MAX_KNOTS 64
 int sccav_spline_course_f64(int32_t C, int32_t K, const double* wx, const double* wy, double ds, int32_t P_max,
                             double* cx, double* cy, double* cyaw, double* ck, int32_t* np_out, void* stream);

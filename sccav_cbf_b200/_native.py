@@ -76,7 +76,7 @@ SYMBOLS = [
     "sccav_barrier_partials_f64", "sccav_barrier_partials_f32", "sccav_stanley_control_f64", "sccav_stanley_control_f32",
     "sccav_prepare_obstacles_f64", "sccav_prepare_obstacles_f32", "sccav_ingest_boxes_f64", "sccav_ingest_boxes_f32",
     "sccav_actuator_shaping_f64", "sccav_actuator_shaping_f32", "sccav_spline_course_f64", "sccav_spline_course_f32",
-    "sccav_fit_lanes_f64", "sccav_fit_lanes_f32",
+    "sccav_fit_lanes_f64", "sccav_fit_lanes_f32", "sccav_rollout_roads_f64", "sccav_rollout_roads_f32",
 ]
 
 
@@ -119,6 +119,8 @@ def lib() -> C.CDLL:
         f.argtypes = [PP, i64, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]
         f = getattr(L, "sccav_rollout_launch_info_" + sfx)
         f.argtypes = [C.c_char_p, i32, i64, i32, vp]
+        f = getattr(L, "sccav_rollout_roads_" + sfx)
+        f.argtypes = [PP, C.c_char_p, i32, i64, i32, vp, vp, vp, vp, vp, i32, i32, vp, PV, RO, vp]
         f = getattr(L, "sccav_qp2_solve_" + sfx)
         f.argtypes = [PP, i32, i64, vp, vp, vp, PV, vp, vp, vp, i32, vp]
         for host in ("", "host_"):

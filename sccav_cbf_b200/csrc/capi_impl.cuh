@@ -335,9 +335,36 @@ int rollout_launch_shape(int M, int64_t N, int np, bool stan, int spec, int& gri
     return SCCAV_OK;
 }
 
+// Several roads in one launch: choose the block so that the CTAs of all roads fill the SMs in as few waves as possible
+// (a road's vehicles never share a CTA with another road's: the course lives in the CTA's shared memory).
+int roads_geometry(const void* kern, int M, int np, int n_roads, int64_t group, int& grid, int& block, size_t& smem, int& ctas_per_road) {
+    const RolloutSmem<real> lay(np, true);
+    const size_t cap = (size_t)max_smem_optin();
+    cudaFuncAttributes fa;
+    SCCAV_CUDA_CHECK(cudaFuncGetAttributes(&fa, kern));
+    const int max_block = std::min(fa.maxThreadsPerBlock / 32 * 32, SCCAV_ROLLOUT_MAXB);
+    double best_cost = 1e300;
+    block = 0;
+    for (int b = max_block; b >= 64; b -= 32) {
+        const size_t sm = lay.course_bytes + (size_t)3 * (M > 0 ? M : 1) * b * sizeof(real);
+        if (sm > cap) continue;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) { cudaGetLastError(); continue; }
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, b, sm) != cudaSuccess || occ < 1) { cudaGetLastError(); continue; }
+        const int64_t cpr = (group + b - 1) / b;
+        const int64_t ctas = cpr * n_roads;
+        const int64_t waves = (ctas + (int64_t)occ * sm_count() - 1) / ((int64_t)occ * sm_count());
+        // a wave of a latency-bound kernel lasts about as long as its resident warps take turns: waves x resident threads
+        const double cost = (double)waves * std::min<int64_t>((int64_t)occ * b, (ctas + sm_count() - 1) / sm_count() * b);
+        if (cost < best_cost) { best_cost = cost; block = b; smem = sm; ctas_per_road = (int)cpr; grid = (int)ctas; }
+    }
+    if (!block) { set_error("a road of %d points does not fit in shared memory", np); return SCCAV_EINVAL; }
+    return SCCAV_OK;
+}
+
 int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N, int32_t T, const real* state,
                real* obst, const real* cx, const real* cy, const real* cyaw, int32_t P, const sccav_pervehicle* pv,
-               const sccav_rollout_out* out, cudaStream_t st) {
+               const sccav_rollout_out* out, cudaStream_t st, int32_t n_roads = 0, const int32_t* road_np = nullptr) {
     int rc = check_common(p, slot_desc, M, N, true);
     if (rc) return rc;
     if (T < 0) { set_error("T < 0"); return SCCAV_EINVAL; }
@@ -349,8 +376,14 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
     if (M > 0 && !obst) { set_error("obst is NULL"); return SCCAV_EINVAL; }
     const bool stan = p->nominal == SCCAV_NOMINAL_STANLEY;
     if (stan && (P < 1 || !cx || !cy || !cyaw)) { set_error("Stanley nominal control needs a course (P >= 1)"); return SCCAV_EINVAL; }
+    if (n_roads > 0) {
+        if (!stan) { set_error("several roads need the Stanley nominal controller"); return SCCAV_EINVAL; }
+        if (!road_np) { set_error("road_np is NULL"); return SCCAV_EINVAL; }
+        if (N % n_roads != 0) { set_error("N = %lld vehicles do not split evenly over %d roads", (long long)N, n_roads); return SCCAV_EINVAL; }
+    }
     keep_pool_memory();
     RolloutArgs<real> a;
+    a.n_roads = n_roads; a.road_stride = P; a.road_np = road_np; a.group = n_roads > 0 ? N / n_roads : 0; a.ctas_per_road = 0;
     a.P = convert(p); a.sd = make_desc(slot_desc, M); a.M = M; a.N = N; a.T_steps = T; a.np = stan ? P : 0;
     a.state = state; a.obst = obst; a.cx = cx; a.cy = cy; a.cyaw = cyaw; a.pv = make_pv(pv);
     a.o_state = (real*)out->state; a.o_steps = out->steps; a.o_tidx = out->target_idx; a.o_nact = out->n_active;
@@ -389,7 +422,12 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
         if (me != cudaSuccess) { if (prep) cudaFreeAsync(prep, st); SCCAV_CUDA_CHECK(me); }
         a.pre = (real*)scratch;
     }
-    const rollout_fn kern = rollout_instance(course_smem, spec, fast, (p->flags & SCCAV_FLAG_FUSED_STEER) != 0);
+    rollout_fn kern = rollout_instance(course_smem, spec, fast, (p->flags & SCCAV_FLAG_FUSED_STEER) != 0);
+    if (n_roads > 0) {
+        kern = rollout_instance(true, spec, fast, (p->flags & SCCAV_FLAG_FUSED_STEER) != 0);
+        rc = roads_geometry((const void*)kern, M, a.np, n_roads, a.group, grid, block, smem, a.ctas_per_road);
+        if (rc) { if (a.pre) cudaFreeAsync(a.pre, st); if (prep) cudaFreeAsync(prep, st); return rc; }
+    }
     cudaError_t le = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (le == cudaSuccess) { kern<<<grid, block, smem, st>>>(a); le = cudaGetLastError(); }
     count_launch();
@@ -519,6 +557,15 @@ int SCCAV_FN(sccav_rollout_)(const sccav_params* p, const uint8_t* slot_desc, in
                              const sccav_pervehicle* pv, const sccav_rollout_out* out, void* stream) {
     return sccav::do_rollout(p, slot_desc, M, N, T, state, obst, course_x, course_y, course_yaw, P, pv, out,
                              (cudaStream_t)stream);
+}
+
+int SCCAV_FN(sccav_rollout_roads_)(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N, int32_t T,
+                                   const SCCAV_REAL* state, SCCAV_REAL* obst, const SCCAV_REAL* course_x,
+                                   const SCCAV_REAL* course_y, const SCCAV_REAL* course_yaw, int32_t P_max, int32_t C,
+                                   const int32_t* course_np, const sccav_pervehicle* pv, const sccav_rollout_out* out, void* stream) {
+    if (C < 1) { sccav::set_error("C < 1"); return SCCAV_EINVAL; }
+    return sccav::do_rollout(p, slot_desc, M, N, T, state, obst, course_x, course_y, course_yaw, P_max, pv, out,
+                             (cudaStream_t)stream, C, course_np);
 }
 
 int SCCAV_FN(sccav_rollout_launch_info_)(const uint8_t* slot_desc, int32_t M, int64_t N, int32_t P, int32_t* info) {

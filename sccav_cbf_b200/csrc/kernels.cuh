@@ -796,6 +796,11 @@ template <typename T> struct RolloutArgs {
     const T* cx;
     const T* cy;
     const T* cyaw;
+    // several roads in one launch (sccav_rollout_roads_*): road c = course arrays + c * road_stride with road_np[c]
+    // points; its vehicles are [c * group, (c + 1) * group), served by ctas_per_road consecutive CTAs.  n_roads = 0: one road.
+    int n_roads, road_stride, ctas_per_road;
+    int64_t group;
+    const int32_t* road_np;
     PerVehicle<T> pv;
     // outputs
     T* o_state;
@@ -935,8 +940,17 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
     typedef Real<T> R;
     typedef typename R::T2 T2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int np = a.np;
-    const RolloutSmem<T> lay(np, COURSE_SMEM);
+    // the road of this CTA (the shared-memory layout is sized for the longest road, a.np)
+    const int road = a.n_roads > 0 ? (int)(blockIdx.x / a.ctas_per_road) : 0;
+    int np = a.np;
+    if (a.n_roads > 0) {
+        np = a.road_np[road];
+        np = np < 1 ? 1 : (np > a.np ? a.np : np);
+    }
+    const T* __restrict__ g_cx = a.cx + (a.n_roads > 0 ? (int64_t)road * a.road_stride : 0);
+    const T* __restrict__ g_cy = a.cy + (a.n_roads > 0 ? (int64_t)road * a.road_stride : 0);
+    const T* __restrict__ g_cyaw = a.cyaw + (a.n_roads > 0 ? (int64_t)road * a.road_stride : 0);
+    const RolloutSmem<T> lay(a.np, COURSE_SMEM);
     T2* s_cxy = reinterpret_cast<T2*>(smem_raw);
     T* s_cyaw = reinterpret_cast<T*>(smem_raw + lay.off_cyaw);
     T* rows = reinterpret_cast<T*>(smem_raw + lay.off_rows) + threadIdx.x;
@@ -949,9 +963,14 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
     ci.np = np; ci.nleaf = 0; ci.nlev = 0;
     // stage the course once per CTA (leaf-padded) and build the capsules of its tree
     if (COURSE_SMEM && stan)
-        ci = course_stage<T, T2>(smem_raw, lay, np, a.cx, a.cy, a.cyaw, s_cyaw, reinterpret_cast<double*>(smem_raw + lay.off_rows));
+        ci = course_stage<T, T2>(smem_raw, lay, np, g_cx, g_cy, g_cyaw, s_cyaw, reinterpret_cast<double*>(smem_raw + lay.off_rows));
     const int64_t N = a.N;
-    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a.n_roads > 0) {
+        const int64_t in_road = (int64_t)(blockIdx.x - road * a.ctas_per_road) * blockDim.x + threadIdx.x;
+        if (in_road >= a.group) return;
+        n = (int64_t)road * a.group + in_road;
+    }
     if (n >= N) return;
 
     const Params<T>& P = a.P;
@@ -988,7 +1007,7 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
         else {
             T best = R::inf();
             for (int i = 0; i < np; ++i) {
-                T dx = fx - a.cx[i], dy = fy - a.cy[i];
+                T dx = fx - g_cx[i], dy = fy - g_cy[i];
                 T d2 = dx * dx + dy * dy;
                 if (d2 < best) { best = d2; target_idx = i; }
             }
@@ -1017,12 +1036,12 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
                 T best = R::inf();
                 int idx = 0;
                 for (int i = 0; i < np; ++i) {
-                    T dx = fx - a.cx[i], dy = fy - a.cy[i];
+                    T dx = fx - g_cx[i], dy = fy - g_cy[i];
                     T d2 = dx * dx + dy * dy;
                     if (d2 < best) { best = d2; idx = i; }
                 }
                 evals += np;
-                d_ref = stanley_law<T, T2>(P, R::make2(a.cx[idx], a.cy[idx]), a.cyaw, idx, fx, fy, yaw, v, target_idx);
+                d_ref = stanley_law<T, T2>(P, R::make2(g_cx[idx], g_cy[idx]), g_cyaw, idx, fx, fy, yaw, v, target_idx);
             }
             ur0 = (model == SCCAV_MODEL_KBM) ? tspeed : a_ref;                             // sce.py:646-648
             ur1 = d_ref;

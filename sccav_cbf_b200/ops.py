@@ -216,11 +216,13 @@ ROLLOUT_SUMMARY = ("steps", "target_idx", "n_active", "n_infeasible", "h_min", "
 
 def rollout(params: Params, slot_desc, state: torch.Tensor, obst: Optional[torch.Tensor], course, T: int,
             alpha=None, R=None, target_speed=None, count=None, record_stride: int = 0, summary: bool = True,
-            out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+            out: Optional[Dict[str, torch.Tensor]] = None, course_np: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """K3: persistent closed-loop rollout of T steps (stanley_controller_ellipse.py:630-830 /
     radial_dynamic_obstacles.py:427-507).
 
-    ``course`` = (cx, cy, cyaw) tensors [P] (ignored for NOMINAL_CONST; may be None then).
+    ``course`` = (cx, cy, cyaw) tensors [P] (ignored for NOMINAL_CONST; may be None then), or [C, P_max] tensors with
+    ``course_np`` int32 [C] for C roads in ONE launch (vehicles [c N/C, (c+1) N/C) drive road c) -- bit-identical to C
+    launches with one road each.
     ``obst`` is updated in place when ``params.seeker``.  Returns a dict: ``state`` [4,N] final,
     the summary arrays of ROLLOUT_SUMMARY, and with ``record_stride`` > 0 ``traj`` [T_rec,7,N]
     (NaN-initialised), ``traj_idx`` / ``traj_mask`` [T_rec,N] (-1 / 0 initialised).
@@ -238,11 +240,25 @@ def rollout(params: Params, slot_desc, state: torch.Tensor, obst: Optional[torch
         if not obst.is_contiguous():
             raise ValueError("obst must be contiguous (it is updated in place for moving obstacles)")
         obst = _chk(obst, (M, nv.NFIELD, N), dt, dev, "obst")
+    roads = 0
     if course is not None:
-        cx, cy, cyaw = course
-        P = cx.shape[0]
-        cx = _chk(cx, (P,), dt, dev, "course_x"); cy = _chk(cy, (P,), dt, dev, "course_y")
-        cyaw = _chk(cyaw, (P,), dt, dev, "course_yaw")
+        cx, cy, cyaw = course[:3]
+        if cx.dim() == 2:
+            # several roads [C, P_max] (the output of spline_course): ONE launch, vehicles grouped by road
+            if not state.is_cuda:
+                raise ValueError("several roads per launch take CUDA tensors")
+            roads, P = int(cx.shape[0]), int(cx.shape[1])
+            if course_np is None:
+                raise ValueError("course_np (int32 [C]: points of every road) is required with [C, P_max] courses")
+            cx = _chk(cx, (roads, P), dt, dev, "course_x"); cy = _chk(cy, (roads, P), dt, dev, "course_y")
+            cyaw = _chk(cyaw, (roads, P), dt, dev, "course_yaw")
+            course_np = _chk(course_np, (roads,), torch.int32, dev, "course_np")
+            if N % roads:
+                raise ValueError("%d vehicles do not split evenly over %d roads" % (N, roads))
+        else:
+            P = cx.shape[0]
+            cx = _chk(cx, (P,), dt, dev, "course_x"); cy = _chk(cy, (P,), dt, dev, "course_y")
+            cyaw = _chk(cyaw, (P,), dt, dev, "course_yaw")
     else:
         cx = cy = cyaw = None
         P = 0
@@ -281,7 +297,12 @@ def rollout(params: Params, slot_desc, state: torch.Tensor, obst: Optional[torch
         ro.traj_mask = buf("traj_mask", (trec, N), torch.int32, 0).data_ptr()
     args = (C.byref(prm), sd, M, N, int(T), _ptr(state), _ptr(obst), _ptr(cx), _ptr(cy), _ptr(cyaw), P,
             C.byref(pv), C.byref(ro))
-    if state.is_cuda:
+    if roads:
+        with torch.cuda.device(dev):
+            nv.check(getattr(L, "sccav_rollout_roads_" + _SFX[dt])(
+                C.byref(prm), sd, M, N, int(T), _ptr(state), _ptr(obst), _ptr(cx), _ptr(cy), _ptr(cyaw), P, roads,
+                _ptr(course_np), C.byref(pv), C.byref(ro), _stream(dev)))
+    elif state.is_cuda:
         with torch.cuda.device(dev):
             nv.check(getattr(L, "sccav_rollout_" + _SFX[dt])(*args, _stream(dev)))
     else:

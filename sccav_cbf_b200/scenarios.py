@@ -201,3 +201,37 @@ def config5(n_total: int = 16777216, T: int = 300, seed: int = 3, lo: int = 0, h
     R[3] = r11
     return ScenarioBatch("config5", np.ascontiguousarray(state), c1.slot_desc, obst, c1.course,
                          dict(terminate=1), T=T, alpha=alpha, R=R)
+
+
+def roads(n_roads: int, per_road: int, M: int = 8, seed: int = 4, dtype=None, device=None):
+    """Monte-Carlo over ROADS: every road is the config-1 course with its inner way-points moved by
+    U(-8, 8) m -- so the roads differ in shape and length -- generated on the device by the course kernel
+    (sccav_spline_course_*); per road, config-2 style vehicles and M static ellipses placed along THAT road.
+    Returns ((cx, cy, cyaw [C, P_max], np [C]) device tensors, np host array, state [4, N], obst [M, 8, N]) with
+    N = n_roads * per_road and the vehicles grouped by road -- the input of ONE sccav_rollout_roads_* launch."""
+    import torch
+    from . import ops
+    dtype = torch.float64 if dtype is None else dtype
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    rng = np.random.default_rng([seed, n_roads])
+    wx = np.tile(np.array([0.0, 100.0, 100.0, 50.0, 60.0]), (n_roads, 1))
+    wy = np.tile(np.array([0.0, 0.0, -30.0, -20.0, 0.0]), (n_roads, 1))
+    wx[:, 1:] += rng.uniform(-8, 8, (n_roads, 4)); wy[:, 1:] += rng.uniform(-8, 8, (n_roads, 4))
+    if n_roads > 1:
+        wx[1, 4] += 25.0                                             # one road clearly longer than the others
+    cx, cy, cyaw, npts = ops.spline_courses(torch.from_numpy(wx).to(device=device, dtype=dtype),
+                                            torch.from_numpy(wy).to(device=device, dtype=dtype), ds=0.1)
+    nph = npts.cpu().numpy()
+    cxh, cyh, cyawh = cx.double().cpu().numpy(), cy.double().cpu().numpy(), cyaw.double().cpu().numpy()
+    states, obsts = [], []
+    for c in range(n_roads):
+        n = int(nph[c])
+        states.append(_init_states(rng, per_road))
+        o = np.zeros((M, nv.NFIELD, per_road))
+        idx = rng.integers(150, n - 150, size=(M, per_road))
+        off = rng.uniform(-6.0, 6.0, (M, per_road))
+        o[:, 0] = cxh[c][idx] - off * np.sin(cyawh[c][idx]); o[:, 1] = cyh[c][idx] + off * np.cos(cyawh[c][idx])
+        o[:, 2] = rng.uniform(2.0, 6.0, (M, per_road)) + 0.5; o[:, 3] = rng.uniform(1.0, 3.0, (M, per_road)) + 0.5
+        o[:, 4] = rng.uniform(-np.pi, np.pi, (M, per_road))
+        obsts.append(o)
+    return (cx, cy, cyaw, npts), nph, np.ascontiguousarray(np.concatenate(states, axis=1)), np.ascontiguousarray(np.concatenate(obsts, axis=2))

@@ -788,3 +788,36 @@ def test_teacher_forced_rollout_step_configs_3_4_5(flags):
     lo = 11 * 65536 + 5
     b5 = sc.config5(n_total=16777216, T=280, lo=lo, hi=lo + 256)
     assert _teacher_forced_steps(b5, list(range(0, 270, 13)), flags, n_min_frac=0.15) > 1500
+
+
+@pytest.mark.parametrize("flags", [0, 5])
+def test_rollout_over_several_roads_equals_one_launch_per_road(flags):
+    """sccav_rollout_roads_*: C roads from the course kernel (KC) in ONE rollout launch -- vehicles grouped by road,
+    one road per CTA -- against C launches with one road each: every output bit for bit, trajectories included."""
+    from sccav_cbf_b200 import ops
+    n_roads, per_road, M, Tn = 6, 160, 4, 240
+    from sccav_cbf_b200 import scenarios as sc
+    (cx, cy, cyaw, npts), nph, state, obst = sc.roads(n_roads, per_road, M, seed=77)
+    assert len(set(nph.tolist())) > 1 and nph.max() <= cx.shape[1]
+    prm = ops.make_params(flags=flags, terminate=1)
+    sd = [o.SLOT_ELLIPSE | 0x40] * M
+    g = ops.rollout(prm, sd, T_(state, torch.float64), T_(obst, torch.float64), (cx, cy, cyaw), Tn, record_stride=8, course_np=npts)
+    torch.cuda.synchronize()
+    g = {k: v.cpu().numpy() for k, v in g.items()}
+    assert len(np.unique(g["steps"])) > 1 and (g["n_active"] > 0).any()
+    for c in range(n_roads):
+        sl = slice(c * per_road, (c + 1) * per_road)
+        one = (cx[c, :nph[c]].contiguous(), cy[c, :nph[c]].contiguous(), cyaw[c, :nph[c]].contiguous())
+        r = ops.rollout(prm, sd, T_(state[:, sl], torch.float64), T_(obst[:, :, sl], torch.float64), one, Tn, record_stride=8)
+        torch.cuda.synchronize()
+        for k, v in r.items():
+            a, b = g[k][..., sl], v.cpu().numpy()
+            assert np.array_equal(a, b, equal_nan=True), (c, k)
+    # and the oracle on one of the roads (canonical arithmetic only)
+    if flags == 0:
+        c = 1
+        sl = slice(c * per_road, (c + 1) * per_road)
+        course = tuple(t[c, :nph[c]].cpu().numpy() for t in (cx, cy, cyaw))
+        r = co.rollout(co.default_params(terminate=1), sd, state[:, sl], obst[:, :, sl], course, Tn)
+        for k in ("steps", "target_idx", "n_active", "n_infeasible"):
+            assert (g[k][sl] == r[k]).mean() >= 0.99, k
