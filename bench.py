@@ -489,8 +489,21 @@ def main():
     torch.cuda.synchronize()
     e2e_s = sh.max(time.perf_counter() - t0)
     sh.barrier()
-    e2e_value = solves_per_step * args.steps / e2e_s
+    e2e_sync_value = solves_per_step * args.steps / e2e_s
     assert int(hres["steps"].sum().item()) == int(vehicle_steps_rank)
+    # ---- the same through the PIPELINED host API (sccav_pipeline_*): every step still uploads ALL of its inputs (states
+    #      and obstacles, pinned host memory) and downloads its results; the course is resident in the handle, and with two
+    #      submissions in flight the copies of step i+1 / i-1 run beside the kernel of step i
+    pipe = cl.pipeline(depth=2)
+    cl.run_pipelined(pipe, 2)
+    sh.barrier()
+    t0 = time.perf_counter()
+    pres = cl.run_pipelined(pipe, args.steps)
+    e2e_pipe_s = sh.max(time.perf_counter() - t0)
+    sh.barrier()
+    assert int(pres["steps"].sum().item()) == int(vehicle_steps_rank)
+    pipe.close()
+    e2e_value = solves_per_step * args.steps / e2e_pipe_s
 
     # ---- the other BASELINE.json configurations at their full per-GPU sizes (flat keys: whole-job solves/s, ms,
     #      oracle-sample parity of rank 0's shard).  Every rank runs its shard; no collective on the path.
@@ -762,9 +775,13 @@ def main():
                        "l2": "flushed (256 MB write) between timed iterations; inputs 36 MB/GPU",
                        "rows": args.rows, "other_row_mode": other, "fp32_variant": fp32_variant,
                        "seed": 0, "active_step_checksum": checksum},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cl.h2d_bytes(), "d2h_bytes_per_step": cl.d2h_bytes(),
-                    "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "path": "sccav_rollout_host_%s (C-ABI, host pointers): H2D + rollout kernel + D2H inside the call" % args.dtype},
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": cl.h2d_bytes() - sum(t.numel() * t.element_size() for t in (cl.h_course or ())),
+                    "d2h_bytes_per_step": cl.d2h_bytes(), "ms_per_step": 1e3 * e2e_pipe_s / args.steps,
+                    "path": "sccav_pipeline_submit/wait_%s (C-ABI, pinned host pointers, 2 submissions in flight): H2D of the step's "
+                            "states + obstacles, rollout kernel, D2H of its results -- every step; the course is resident" % args.dtype,
+                    "synchronous_value": e2e_sync_value, "synchronous_ms_per_step": 1e3 * e2e_s / args.steps,
+                    "synchronous_path": "sccav_rollout_host_%s: one blocking call per step, H2D + kernel + D2H in sequence" % args.dtype},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
@@ -773,6 +790,8 @@ def main():
             "wall_s_timed_region": t_wall1 - t_wall0,
             "vs_reference_note": "N GPUs over ONE host's CPU threads when n_gpus > 1 (the CPU arm does not scale with --gpus)",
         }
+        flat["e2e_sync_value"] = e2e_sync_value
+        flat["e2e_over_value"] = e2e_value / value
         line.update(flat)
         line["ncu_metrics_stale"] = NCU_STALE[0]
         print(json.dumps(line), flush=True)

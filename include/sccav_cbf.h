@@ -289,6 +289,33 @@ int sccav_rollout_host_f32(const sccav_params* p, const uint8_t* slot_desc, int3
                            const float* course_yaw, int32_t P, const sccav_pervehicle* pv,
                            const sccav_rollout_out* out, void* stream);
 
+/* Pipelined host API for repeated rollouts of one shape (Monte-Carlo batches streamed from the host): a handle owns
+ * the device buffers, three streams and the events; the course -- and, optionally, static obstacles -- are uploaded
+ * ONCE at creation and stay resident; every submission copies its inputs (HOST pointers, ideally pinned) on a copy
+ * stream, runs the rollout on a compute stream and copies the per-vehicle summaries back on a third stream, so that the
+ * upload of submission i + 1 and the download of submission i - 1 overlap the kernel of submission i.
+ *   create : `depth` (1..8) submissions may be in flight; obst_resident (host, may be NULL) = obstacles shared by every
+ *            submission (not with params.seeker); record_stride must be 0 (summaries only).
+ *   submit : returns at once with a ticket; obst = NULL uses the resident obstacles; the host buffers of a submission
+ *            (inputs AND outputs) must stay untouched until its ticket has been waited for.  With params.seeker the
+ *            moved obstacles are written back into `obst`.
+ *   wait   : blocks until the outputs of `ticket` (one of the last `depth` submissions) are in host memory.
+ * Same results as sccav_rollout_host_* on the same inputs (same kernels).  Not re-entrant per handle. */
+int sccav_pipeline_create_f64(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N, int32_t T,
+                              const double* course_x, const double* course_y, const double* course_yaw, int32_t P,
+                              const double* obst_resident, int32_t depth, void** handle_out);
+int sccav_pipeline_create_f32(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N, int32_t T,
+                              const float* course_x, const float* course_y, const float* course_yaw, int32_t P,
+                              const float* obst_resident, int32_t depth, void** handle_out);
+int sccav_pipeline_submit_f64(void* handle, const double* state, const double* obst, const sccav_pervehicle* pv,
+                              const sccav_rollout_out* out, int64_t* ticket_out);
+int sccav_pipeline_submit_f32(void* handle, const float* state, const float* obst, const sccav_pervehicle* pv,
+                              const sccav_rollout_out* out, int64_t* ticket_out);
+int sccav_pipeline_wait_f64(void* handle, int64_t ticket);
+int sccav_pipeline_wait_f32(void* handle, int64_t ticket);
+int sccav_pipeline_destroy_f64(void* handle);
+int sccav_pipeline_destroy_f32(void* handle);
+
 /* Obstacle ingest for repeated solves (the batched counterpart of constructing Ellipse2D objects,
  * cbf/obstacles.py:146-165, once and then calling solve_cbf every tick): every ELLIPSE slot of
  * obst_in [M][8][N] is rewritten as an ELLIPSE_PREP slot into obst_out [M][8][N] (may alias obst_in),
@@ -386,6 +413,10 @@ int sccav_fit_lanes_f32(int32_t C, int32_t K, const float* x, const float* y, co
 int sccav_measure_fma_peak(int32_t dtype, double* tflops_out);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t sccav_launch_count(void);
+/* The library allocates its scratch and the device side of the host-buffer entry points from a stream-ordered memory
+ * pool of its own (one per device; freed blocks are kept for the next call up to 1 GiB, SCCAV_POOL_KEEP_MB overrides).
+ * The device's default pool is not touched.  This call returns everything the pool holds to the driver. */
+int sccav_trim_pool(void);
 
 /* Launch shape the rollout entry point would use for (slot_desc[M], N, P) on the current device:
  * info[8] = grid, block, dynamic smem bytes, registers/thread, max threads/block of the kernel,

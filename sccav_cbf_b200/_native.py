@@ -77,6 +77,9 @@ SYMBOLS = [
     "sccav_prepare_obstacles_f64", "sccav_prepare_obstacles_f32", "sccav_ingest_boxes_f64", "sccav_ingest_boxes_f32",
     "sccav_actuator_shaping_f64", "sccav_actuator_shaping_f32", "sccav_spline_course_f64", "sccav_spline_course_f32",
     "sccav_fit_lanes_f64", "sccav_fit_lanes_f32", "sccav_rollout_roads_f64", "sccav_rollout_roads_f32",
+    "sccav_trim_pool",
+    "sccav_pipeline_create_f64", "sccav_pipeline_create_f32", "sccav_pipeline_submit_f64", "sccav_pipeline_submit_f32",
+    "sccav_pipeline_wait_f64", "sccav_pipeline_wait_f32", "sccav_pipeline_destroy_f64", "sccav_pipeline_destroy_f32",
 ]
 
 
@@ -121,6 +124,10 @@ def lib() -> C.CDLL:
         f.argtypes = [C.c_char_p, i32, i64, i32, vp]
         f = getattr(L, "sccav_rollout_roads_" + sfx)
         f.argtypes = [PP, C.c_char_p, i32, i64, i32, vp, vp, vp, vp, vp, i32, i32, vp, PV, RO, vp]
+        getattr(L, "sccav_pipeline_create_" + sfx).argtypes = [PP, C.c_char_p, i32, i64, i32, vp, vp, vp, i32, vp, i32, C.POINTER(vp)]
+        getattr(L, "sccav_pipeline_submit_" + sfx).argtypes = [vp, vp, vp, PV, RO, C.POINTER(i64)]
+        getattr(L, "sccav_pipeline_wait_" + sfx).argtypes = [vp, i64]
+        getattr(L, "sccav_pipeline_destroy_" + sfx).argtypes = [vp]
         f = getattr(L, "sccav_qp2_solve_" + sfx)
         f.argtypes = [PP, i32, i64, vp, vp, vp, PV, vp, vp, vp, i32, vp]
         for host in ("", "host_"):

@@ -8,6 +8,7 @@
 #include <cstring>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "capi_common.h"
@@ -31,7 +32,6 @@ struct DevAttr {
     int sms = 0;
     int smem = 0;
     int smem_sm = 0;
-    bool pool = false;
 };
 static DevAttr g_attr[64];
 
@@ -53,21 +53,40 @@ static DevAttr& attr() {
     return a;
 }
 
-// The entry points take their scratch from the device's stream-ordered pool (cudaMallocAsync).  By
-// default the pool hands freed memory back to the driver at every synchronisation, so each call would
-// map tens of MB again (milliseconds); keep what was used once.
-void keep_pool_memory() {
-    DevAttr& a = attr();
-    if (a.pool) return;
-    a.pool = true;
+// The entry points take their scratch and the host-variant buffers from a stream-ordered pool OF THEIR OWN (one per
+// device, created on first use): freed blocks stay in the pool for the next call -- mapping tens of MB again at every
+// call costs milliseconds -- but only up to a bounded threshold (default 1 GiB, SCCAV_POOL_KEEP_MB), and the device's
+// default pool, which other libraries in the process use, is left alone.  sccav_trim_pool() gives everything back.
+static cudaMemPool_t g_pool[64] = {};
+static std::mutex g_pool_mu;
+
+cudaMemPool_t lib_pool() {
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t keep = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    if (dev < 0 || dev >= 64) dev = 0;
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    if (!g_pool[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) {
+            cudaGetLastError();
+            cudaDeviceGetDefaultMemPool(&pool, dev);            // (very old drivers: fall back to the default pool, untouched)
+        } else {
+            uint64_t keep = 1024ull << 20;
+            if (const char* e = getenv("SCCAV_POOL_KEEP_MB")) keep = (uint64_t)strtoull(e, nullptr, 10) << 20;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        g_pool[dev] = pool;
     }
-    cudaGetLastError();
+    return g_pool[dev];
+}
+
+cudaError_t pool_alloc(void** p, size_t bytes, cudaStream_t st) {
+    return cudaMallocFromPoolAsync(p, bytes ? bytes : 1, lib_pool(), st);
 }
 
 int sm_count() { return attr().sms; }
@@ -181,6 +200,12 @@ int sccav_measure_fma_peak(int32_t dtype, double* tflops_out) {
 }
 
 int64_t sccav_launch_count(void) { return sccav::g_launches.load(); }
+
+int sccav_trim_pool(void) {
+    cudaMemPool_t pool = sccav::lib_pool();
+    if (pool) SCCAV_CUDA_CHECK(cudaMemPoolTrimTo(pool, 0));
+    return SCCAV_OK;
+}
 
 }  // extern "C"
 

@@ -12,7 +12,7 @@ int max_smem_optin();    // max opt-in dynamic shared memory per block of the cu
 int max_smem_per_sm();   // shared memory of one SM
 bool k12_coop_enabled(int spec);   // SCCAV_K12_QP=thread|coop overrides the staged kernel's QP form
 bool k12_staged_enabled(int spec); // SCCAV_K12_PIPE=0|1 overrides the choice between the direct-load and the staged filter-step kernel
-void keep_pool_memory(); // once per device: the stream-ordered pool keeps freed scratch for the next call
+cudaError_t pool_alloc(void** p, size_t bytes, cudaStream_t st);   // stream-ordered allocation from the library's own pool
 }  // namespace sccav
 
 #define SCCAV_CUDA_CHECK(expr)                                                              \

@@ -381,7 +381,6 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
         if (!road_np) { set_error("road_np is NULL"); return SCCAV_EINVAL; }
         if (N % n_roads != 0) { set_error("N = %lld vehicles do not split evenly over %d roads", (long long)N, n_roads); return SCCAV_EINVAL; }
     }
-    keep_pool_memory();
     RolloutArgs<real> a;
     a.n_roads = n_roads; a.road_stride = P; a.road_np = road_np; a.group = n_roads > 0 ? N / n_roads : 0; a.ctas_per_road = 0;
     a.P = convert(p); a.sd = make_desc(slot_desc, M); a.M = M; a.N = N; a.T_steps = T; a.np = stan ? P : 0;
@@ -403,7 +402,7 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
     bool any_ellipse = false;
     for (int m = 0; m < M; ++m) any_ellipse |= (slot_desc[m] & SCCAV_SLOT_TYPE_MASK) == SCCAV_SLOT_ELLIPSE;
     if (filt && any_ellipse && (p->flags & SCCAV_FLAG_PREPARED_ROWS) && !p->seeker) {
-        SCCAV_CUDA_CHECK(cudaMallocAsync(&prep, (size_t)M * SCCAV_NFIELD * (size_t)N * sizeof(real), st));
+        SCCAV_CUDA_CHECK(pool_alloc(&prep, (size_t)M * SCCAV_NFIELD * (size_t)N * sizeof(real), st));
         rc = do_prepare(slot_desc, M, N, obst, (real*)prep, desc2, st);
         if (rc) { cudaFreeAsync(prep, st); return rc; }
         a.obst = (real*)prep;
@@ -418,7 +417,7 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
     a.pre = nullptr;
     if (any_ellipse && T >= 2 && filt) {
         void* scratch = nullptr;
-        cudaError_t me = cudaMallocAsync(&scratch, (size_t)M * SCCAV_NPRE * (size_t)N * sizeof(real), st);
+        cudaError_t me = pool_alloc(&scratch, (size_t)M * SCCAV_NPRE * (size_t)N * sizeof(real), st);
         if (me != cudaSuccess) { if (prep) cudaFreeAsync(prep, st); SCCAV_CUDA_CHECK(me); }
         a.pre = (real*)scratch;
     }
@@ -443,7 +442,7 @@ struct DevBuf {
     cudaStream_t st;
     explicit DevBuf(cudaStream_t s) : st(s) {}
     ~DevBuf() { if (p) cudaFreeAsync(p, st); }
-    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, st); }
+    cudaError_t alloc(size_t bytes) { return pool_alloc(&p, bytes, st); }
     cudaError_t upload(const void* src, size_t bytes) {
         cudaError_t e = alloc(bytes);
         if (e != cudaSuccess) return e;
@@ -451,10 +450,195 @@ struct DevBuf {
     }
 };
 
+// ---- pipelined host API: device buffers, streams and events owned by a handle; the upload of submission i + 1 and
+// the download of submission i - 1 run beside the kernel of submission i
+struct PipeSlot {
+    void* in[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};        // state, obst, alpha, R, target_speed, count
+    void* out[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t h2d_done = nullptr, kernel_done = nullptr, d2h_done = nullptr;
+};
+
+struct Pipeline {
+    uint32_t magic = 0x53434356u + sizeof(real);
+    sccav_params prm;
+    uint8_t desc[SCCAV_MAX_ROWS];
+    int M = 0, T = 0, P = 0, depth = 0, device = 0;
+    int64_t N = 0;
+    void *cx = nullptr, *cy = nullptr, *cyaw = nullptr, *obst_resident = nullptr;
+    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+    PipeSlot* slots = nullptr;
+    int64_t next = 0;
+};
+
+void pipeline_free(Pipeline* pl) {
+    if (!pl) return;
+    if (pl->s_in) cudaStreamSynchronize(pl->s_in);
+    if (pl->s_run) cudaStreamSynchronize(pl->s_run);
+    if (pl->s_out) cudaStreamSynchronize(pl->s_out);
+    for (int i = 0; pl->slots && i < pl->depth; ++i) {
+        PipeSlot& s = pl->slots[i];
+        for (void* p : s.in) if (p) cudaFree(p);
+        for (void* p : s.out) if (p) cudaFree(p);
+        if (s.h2d_done) cudaEventDestroy(s.h2d_done);
+        if (s.kernel_done) cudaEventDestroy(s.kernel_done);
+        if (s.d2h_done) cudaEventDestroy(s.d2h_done);
+    }
+    delete[] pl->slots;
+    for (void* p : {pl->cx, pl->cy, pl->cyaw, pl->obst_resident}) if (p) cudaFree(p);
+    if (pl->s_in) cudaStreamDestroy(pl->s_in);
+    if (pl->s_run) cudaStreamDestroy(pl->s_run);
+    if (pl->s_out) cudaStreamDestroy(pl->s_out);
+    pl->magic = 0;
+    delete pl;
+}
+
 }  // namespace
 }  // namespace sccav
 
 extern "C" {
+
+int SCCAV_FN(sccav_pipeline_create_)(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N, int32_t T,
+                                     const SCCAV_REAL* course_x, const SCCAV_REAL* course_y, const SCCAV_REAL* course_yaw, int32_t P,
+                                     const SCCAV_REAL* obst_resident, int32_t depth, void** handle_out) {
+    using namespace sccav;
+    typedef SCCAV_REAL real;
+    if (!handle_out) { set_error("handle_out is NULL"); return SCCAV_EINVAL; }
+    *handle_out = nullptr;
+    int rc = check_common(p, slot_desc, M, N, true);
+    if (rc) return rc;
+    if (N < 1 || T < 0) { set_error("N < 1 or T < 0"); return SCCAV_EINVAL; }
+    if (depth < 1 || depth > 8) { set_error("depth must be in [1, 8], got %d", depth); return SCCAV_EINVAL; }
+    if (p->record_stride != 0) { set_error("the pipelined API returns the per-vehicle summaries only (record_stride must be 0)"); return SCCAV_EINVAL; }
+    const bool stan = p->nominal == SCCAV_NOMINAL_STANLEY;
+    if (stan && (P < 1 || !course_x || !course_y || !course_yaw)) { set_error("Stanley nominal control needs a course"); return SCCAV_EINVAL; }
+    if (obst_resident && p->seeker) { set_error("moving obstacles (params.seeker) cannot be resident: pass them with every submission"); return SCCAV_EINVAL; }
+    Pipeline* pl = new (std::nothrow) Pipeline();
+    if (!pl) { set_error("out of host memory"); return SCCAV_ENOMEM; }
+    pl->prm = *p; pl->M = M; pl->N = N; pl->T = T; pl->P = stan ? P : 0; pl->depth = depth;
+    memset(pl->desc, 0, sizeof(pl->desc));
+    for (int m = 0; m < M; ++m) pl->desc[m] = slot_desc[m];
+    cudaGetDevice(&pl->device);
+    const size_t n = (size_t)N;
+    const size_t obst_b = (size_t)M * SCCAV_NFIELD * n * sizeof(real);
+#define SCCAV_PL_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("%s failed: %s", #expr, cudaGetErrorString(_e)); pipeline_free(pl); return SCCAV_ECUDA; } } while (0)
+    SCCAV_PL_CHECK(cudaStreamCreateWithFlags(&pl->s_in, cudaStreamNonBlocking));
+    SCCAV_PL_CHECK(cudaStreamCreateWithFlags(&pl->s_run, cudaStreamNonBlocking));
+    SCCAV_PL_CHECK(cudaStreamCreateWithFlags(&pl->s_out, cudaStreamNonBlocking));
+    if (pl->P > 0) {
+        const size_t cb = (size_t)P * sizeof(real);
+        SCCAV_PL_CHECK(cudaMalloc(&pl->cx, cb)); SCCAV_PL_CHECK(cudaMalloc(&pl->cy, cb)); SCCAV_PL_CHECK(cudaMalloc(&pl->cyaw, cb));
+        SCCAV_PL_CHECK(cudaMemcpyAsync(pl->cx, course_x, cb, cudaMemcpyHostToDevice, pl->s_in));
+        SCCAV_PL_CHECK(cudaMemcpyAsync(pl->cy, course_y, cb, cudaMemcpyHostToDevice, pl->s_in));
+        SCCAV_PL_CHECK(cudaMemcpyAsync(pl->cyaw, course_yaw, cb, cudaMemcpyHostToDevice, pl->s_in));
+    }
+    if (obst_resident && M > 0) {
+        SCCAV_PL_CHECK(cudaMalloc(&pl->obst_resident, obst_b));
+        SCCAV_PL_CHECK(cudaMemcpyAsync(pl->obst_resident, obst_resident, obst_b, cudaMemcpyHostToDevice, pl->s_in));
+    }
+    pl->slots = new (std::nothrow) PipeSlot[depth];
+    if (!pl->slots) { pipeline_free(pl); set_error("out of host memory"); return SCCAV_ENOMEM; }
+    const size_t in_b[6] = {4 * n * sizeof(real), pl->obst_resident ? 0 : obst_b, n * sizeof(real), 4 * n * sizeof(real), n * sizeof(real), n * 4};
+    const size_t out_b[10] = {4 * n * sizeof(real), n * 4, n * 4, n * 4, n * 4, n * sizeof(real), n * sizeof(real), n * sizeof(real), n * sizeof(real), n * 4};
+    for (int i = 0; i < depth; ++i) {
+        PipeSlot& s = pl->slots[i];
+        for (int k = 0; k < 6; ++k) if (in_b[k]) SCCAV_PL_CHECK(cudaMalloc(&s.in[k], in_b[k]));
+        for (int k = 0; k < 10; ++k) SCCAV_PL_CHECK(cudaMalloc(&s.out[k], out_b[k]));
+        SCCAV_PL_CHECK(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+        SCCAV_PL_CHECK(cudaEventCreateWithFlags(&s.kernel_done, cudaEventDisableTiming));
+        SCCAV_PL_CHECK(cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming));
+    }
+    SCCAV_PL_CHECK(cudaStreamSynchronize(pl->s_in));
+#undef SCCAV_PL_CHECK
+    *handle_out = pl;
+    return SCCAV_OK;
+}
+
+int SCCAV_FN(sccav_pipeline_submit_)(void* handle, const SCCAV_REAL* state, const SCCAV_REAL* obst, const sccav_pervehicle* pv,
+                                     const sccav_rollout_out* out, int64_t* ticket_out) {
+    using namespace sccav;
+    typedef SCCAV_REAL real;
+    Pipeline* pl = (Pipeline*)handle;
+    if (!pl || pl->magic != 0x53434356u + sizeof(real)) { set_error("not a pipeline handle of this precision"); return SCCAV_EINVAL; }
+    if (!state || !out || !out->state) { set_error("state / out->state is NULL"); return SCCAV_EINVAL; }
+    if (pl->M > 0 && !obst && !pl->obst_resident) { set_error("obst is NULL and the pipeline holds no resident obstacles"); return SCCAV_EINVAL; }
+    if (out->traj || out->traj_idx || out->traj_mask) { set_error("the pipelined API returns the per-vehicle summaries only"); return SCCAV_EINVAL; }
+    PipeSlot& s = pl->slots[pl->next % pl->depth];
+    const size_t n = (size_t)pl->N;
+    const size_t obst_b = (size_t)pl->M * SCCAV_NFIELD * n * sizeof(real);
+    // inputs of this slot were last read by the kernel of submission (next - depth)
+    SCCAV_CUDA_CHECK(cudaStreamWaitEvent(pl->s_in, s.kernel_done, 0));
+    SCCAV_CUDA_CHECK(cudaMemcpyAsync(s.in[0], state, 4 * n * sizeof(real), cudaMemcpyHostToDevice, pl->s_in));
+    real* d_obst = (real*)pl->obst_resident;
+    if (pl->M > 0 && obst && !pl->obst_resident) {
+        SCCAV_CUDA_CHECK(cudaMemcpyAsync(s.in[1], obst, obst_b, cudaMemcpyHostToDevice, pl->s_in));
+        d_obst = (real*)s.in[1];
+    }
+    sccav_pervehicle dpv = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (pv && pv->alpha) { SCCAV_CUDA_CHECK(cudaMemcpyAsync(s.in[2], pv->alpha, n * sizeof(real), cudaMemcpyHostToDevice, pl->s_in)); dpv.alpha = s.in[2]; }
+    if (pv && pv->R) { SCCAV_CUDA_CHECK(cudaMemcpyAsync(s.in[3], pv->R, 4 * n * sizeof(real), cudaMemcpyHostToDevice, pl->s_in)); dpv.R = s.in[3]; }
+    if (pv && pv->target_speed) { SCCAV_CUDA_CHECK(cudaMemcpyAsync(s.in[4], pv->target_speed, n * sizeof(real), cudaMemcpyHostToDevice, pl->s_in)); dpv.target_speed = s.in[4]; }
+    if (pv && pv->count) { SCCAV_CUDA_CHECK(cudaMemcpyAsync(s.in[5], pv->count, n * 4, cudaMemcpyHostToDevice, pl->s_in)); dpv.count = (const int32_t*)s.in[5]; }
+    SCCAV_CUDA_CHECK(cudaEventRecord(s.h2d_done, pl->s_in));
+    // kernel: after this slot's upload, and after the download that last read this slot's outputs
+    SCCAV_CUDA_CHECK(cudaStreamWaitEvent(pl->s_run, s.h2d_done, 0));
+    SCCAV_CUDA_CHECK(cudaStreamWaitEvent(pl->s_run, s.d2h_done, 0));
+    sccav_rollout_out dout;
+    memset(&dout, 0, sizeof(dout));
+    dout.state = s.out[0];
+    if (out->steps) dout.steps = (int32_t*)s.out[1];
+    if (out->target_idx) dout.target_idx = (int32_t*)s.out[2];
+    if (out->n_active) dout.n_active = (int32_t*)s.out[3];
+    if (out->n_infeasible) dout.n_infeasible = (int32_t*)s.out[4];
+    if (out->h_min) dout.h_min = s.out[5];
+    if (out->beta_min) dout.beta_min = s.out[6];
+    if (out->beta_max) dout.beta_max = s.out[7];
+    if (out->beta_int) dout.beta_int = s.out[8];
+    if (out->n_evals) dout.n_evals = (int32_t*)s.out[9];
+    int rc = do_rollout(&pl->prm, pl->desc, pl->M, pl->N, pl->T, (const real*)s.in[0], d_obst, (const real*)pl->cx, (const real*)pl->cy,
+                        (const real*)pl->cyaw, pl->P, &dpv, &dout, pl->s_run);
+    if (rc) return rc;
+    SCCAV_CUDA_CHECK(cudaEventRecord(s.kernel_done, pl->s_run));
+    // download
+    SCCAV_CUDA_CHECK(cudaStreamWaitEvent(pl->s_out, s.kernel_done, 0));
+    SCCAV_CUDA_CHECK(cudaMemcpyAsync(out->state, s.out[0], 4 * n * sizeof(real), cudaMemcpyDeviceToHost, pl->s_out));
+#define SCCAV_PL_BACK(field, k, bytes) if (out->field) SCCAV_CUDA_CHECK(cudaMemcpyAsync(out->field, s.out[k], bytes, cudaMemcpyDeviceToHost, pl->s_out));
+    SCCAV_PL_BACK(steps, 1, n * 4)
+    SCCAV_PL_BACK(target_idx, 2, n * 4)
+    SCCAV_PL_BACK(n_active, 3, n * 4)
+    SCCAV_PL_BACK(n_infeasible, 4, n * 4)
+    SCCAV_PL_BACK(h_min, 5, n * sizeof(real))
+    SCCAV_PL_BACK(beta_min, 6, n * sizeof(real))
+    SCCAV_PL_BACK(beta_max, 7, n * sizeof(real))
+    SCCAV_PL_BACK(beta_int, 8, n * sizeof(real))
+    SCCAV_PL_BACK(n_evals, 9, n * 4)
+#undef SCCAV_PL_BACK
+    if (pl->M > 0 && pl->prm.seeker && obst) SCCAV_CUDA_CHECK(cudaMemcpyAsync((void*)obst, s.in[1], obst_b, cudaMemcpyDeviceToHost, pl->s_out));
+    SCCAV_CUDA_CHECK(cudaEventRecord(s.d2h_done, pl->s_out));
+    if (ticket_out) *ticket_out = pl->next;
+    ++pl->next;
+    return SCCAV_OK;
+}
+
+int SCCAV_FN(sccav_pipeline_wait_)(void* handle, int64_t ticket) {
+    using namespace sccav;
+    Pipeline* pl = (Pipeline*)handle;
+    if (!pl || pl->magic != 0x53434356u + sizeof(SCCAV_REAL)) { set_error("not a pipeline handle of this precision"); return SCCAV_EINVAL; }
+    if (ticket < 0 || ticket >= pl->next || ticket < pl->next - pl->depth) {
+        set_error("ticket %lld is not one of the last %d submissions", (long long)ticket, pl->depth);
+        return SCCAV_EINVAL;
+    }
+    SCCAV_CUDA_CHECK(cudaEventSynchronize(pl->slots[ticket % pl->depth].d2h_done));
+    return SCCAV_OK;
+}
+
+int SCCAV_FN(sccav_pipeline_destroy_)(void* handle) {
+    using namespace sccav;
+    Pipeline* pl = (Pipeline*)handle;
+    if (!pl) return SCCAV_OK;
+    if (pl->magic != 0x53434356u + sizeof(SCCAV_REAL)) { set_error("not a pipeline handle of this precision"); return SCCAV_EINVAL; }
+    pipeline_free(pl);
+    return SCCAV_OK;
+}
 
 int SCCAV_FN(sccav_barrier_rows_)(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64_t N,
                                   const SCCAV_REAL* state, const SCCAV_REAL* obst, const sccav_pervehicle* pv,
@@ -601,7 +785,6 @@ int SCCAV_FN(sccav_filter_step_host_)(const sccav_params* p, const uint8_t* slot
     if (N == 0) return SCCAV_OK;
     if (!state || !obst || !u_ref || !u_out) { set_error("NULL array argument"); return SCCAV_EINVAL; }
     const size_t n = (size_t)N;
-    keep_pool_memory();
     DevBuf d_state(st), d_obst(st), d_uref(st), d_alpha(st), d_R(st), d_cnt(st), d_u(st), d_mask(st), d_status(st), d_hmin(st);
     SCCAV_CUDA_CHECK(d_state.upload(state, 4 * n * sizeof(real)));
     SCCAV_CUDA_CHECK(d_obst.upload(obst, (size_t)M * SCCAV_NFIELD * n * sizeof(real)));

@@ -821,3 +821,39 @@ def test_rollout_over_several_roads_equals_one_launch_per_road(flags):
         r = co.rollout(co.default_params(terminate=1), sd, state[:, sl], obst[:, :, sl], course, Tn)
         for k in ("steps", "target_idx", "n_active", "n_infeasible"):
             assert (g[k][sl] == r[k]).mean() >= 0.99, k
+
+
+@pytest.mark.parametrize("depth,resident", [(1, False), (2, False), (3, True)])
+def test_pipelined_host_api_equals_the_synchronous_host_call(depth, resident):
+    """sccav_pipeline_*: uploads, kernels and downloads of neighbouring submissions overlap on three streams.  Five
+    submissions with DIFFERENT inputs each must come back exactly as the synchronous host entry point returns them."""
+    from sccav_cbf_b200 import ops, scenarios as sc
+    from sccav_cbf_b200.rollout import RolloutPipeline
+    N, M, Tn = 700, 8, 120
+    batches = [sc.config2(n_total=65536, M=M, T=Tn, lo=k * 1000, hi=k * 1000 + N) for k in range(5)]
+    if resident:
+        for b in batches[1:]:
+            b.obst = batches[0].obst
+    prm = ops.make_params(flags=5)
+    course = tuple(torch.from_numpy(np.ascontiguousarray(c)) for c in batches[0].course)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    ob0 = pin(batches[0].obst)
+    pipe = RolloutPipeline(prm, batches[0].slot_desc, N, Tn, course, obst_resident=ob0 if resident else None, depth=depth)
+    states = [pin(b.state) for b in batches]
+    obsts = [pin(b.obst) for b in batches]
+    tickets, got = [], []
+    for k in range(5):
+        tickets.append(pipe.submit(states[k], None if resident else obsts[k]))
+        if len(tickets) >= depth:
+            t = tickets.pop(0)
+            got.append({kk: v.clone() for kk, v in pipe.wait(t).items()})
+    while tickets:
+        got.append({kk: v.clone() for kk, v in pipe.wait(tickets.pop(0)).items()})
+    with pytest.raises(Exception):
+        pipe.wait(99)
+    pipe.close()
+    for k in range(5):
+        ref = ops.rollout(prm, batches[k].slot_desc, states[k], obsts[k], course, Tn)
+        for kk in ("state", "steps", "target_idx", "n_active", "n_infeasible", "h_min", "beta_int", "n_evals"):
+            assert torch.equal(got[k][kk], ref[kk]), (k, kk)
+    assert not torch.equal(got[0]["state"], got[1]["state"])
