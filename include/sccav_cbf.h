@@ -407,6 +407,46 @@ int sccav_fit_lanes_f64(int32_t C, int32_t K, const double* x, const double* y, 
 int sccav_fit_lanes_f32(int32_t C, int32_t K, const float* x, const float* y, const float* sigma, const int32_t* count,
                         int32_t degree, float* coeffs, int32_t* status, void* stream);
 
+/* KD -- the per-tick loop of the CARLA driver for N ego vehicles, T ticks in ONE launch
+ * (carla_scripts/multi_obstacle_CBF_local_with_lanes.py:861-983), everything a tick carries over kept in registers:
+ *   delta, idx = lateral_stanley.control()      cbf/controllers.py:104-151 -- class form: front axle at params.L (= lf),
+ *                                               atan2(k e, v + ks) with params.k_stanley / ks_stanley, its own last target index
+ *   delta *= rad_to_steer                       :876-877
+ *   acc_pid.set_dt(dt_t); u_a = acc_pid.control(v, trajectory[idx][3])    cbf/controllers.py:153-180 (kp, ki, kd)
+ *   obstacle list = the n_fixed leading slots of `obst` as the caller set them (the two PolyLane boundaries, :913-916)
+ *                   + one fresh CollisionCone2D(hypot(extent), s, [x, y, yaw, |v|]) per box of the tick (:918-928)
+ *   u = solve_cbf([u_a, delta])                 DBM_CBF_2DS, cbf/cbf.py:166-220; an empty list passes u_ref through (:935-936)
+ *   throttle / brake / steer                    :955-980 (sccav_actuator_shaping_* semantics)
+ * Inputs per tick (time-major, DEVICE pointers): ego [T][4][N] -- the simulator owns the plant; ego = NULL closes the
+ * loop with a stand-in plant instead (State.update_com on the filtered (a, delta) with the tick's dt, from state0 [4][N]);
+ * box_id [T][K][N] (< 0 = none) / box [T][K][6][N] as for sccav_ingest_boxes_* (K = 0: the slots of `obst` are used as
+ * they are, pv->count gives each vehicle's number); dt [T] (NULL: params.dt every tick).  slot_desc[M]: slots
+ * [n_fixed, M) must be per-vehicle CONE slots when K > 0.  trajectory = (x, y, yaw, v)[P].
+ * Carried between calls (read and written): target_idx [N] (LateralStanley's last target index), carry [4][N] =
+ * PID e_prev, PID integral, throttle_prev, brake_prev.  Outputs: act_out [T][3][N] = throttle, brake, steer;
+ * optional u_out [T][2][N] filtered (a, delta), active_out [T][N], target_idx_out [T][N], state_out [4][N]. */
+typedef struct sccav_drive_params {
+    double kp, ki, kd;          /* PID1 gains (the driver: 1.0, 0.01, 0.01, :660)                       */
+    double rad_to_steer;        /* convert_rad_to_steer (:876)                                          */
+    double max_steer_cmd;       /* clamp of the steer command (the driver: 1, :875)                      */
+    double rate;                /* largest rise of throttle / brake per tick (the driver: 0.1, :961,967) */
+    double cone_buffer;         /* CollisionCone2D default buffer 1.5 (cbf/obstacles.py:341)             */
+    int32_t act_flags;          /* SCCAV_ACT_*                                                          */
+    int32_t reserved;
+} sccav_drive_params;
+int sccav_drive_ticks_f64(const sccav_params* p, const sccav_drive_params* dp, const uint8_t* slot_desc, int32_t M, int32_t n_fixed,
+                          int64_t N, int32_t T, const double* state0, const double* ego, int32_t K, const int32_t* box_id,
+                          const double* box, const double* dt, double* obst, const double* traj_x, const double* traj_y,
+                          const double* traj_yaw, const double* traj_v, int32_t P, const sccav_pervehicle* pv, int32_t* target_idx,
+                          double* carry, double* act_out, double* u_out, uint32_t* active_out, int32_t* target_idx_out,
+                          double* state_out, void* stream);
+int sccav_drive_ticks_f32(const sccav_params* p, const sccav_drive_params* dp, const uint8_t* slot_desc, int32_t M, int32_t n_fixed,
+                          int64_t N, int32_t T, const float* state0, const float* ego, int32_t K, const int32_t* box_id,
+                          const float* box, const float* dt, float* obst, const float* traj_x, const float* traj_y,
+                          const float* traj_yaw, const float* traj_v, int32_t P, const sccav_pervehicle* pv, int32_t* target_idx,
+                          float* carry, float* act_out, float* u_out, uint32_t* active_out, int32_t* target_idx_out,
+                          float* state_out, void* stream);
+
 /* Measurement helpers used by bench.py (not part of the reference-facing path). */
 /* Launches an unrolled FMA chain kernel and returns the achieved TFLOP/s (FMA = 2 flop) on the
  * current device; `dtype` 64 or 32.  Used as the measured FP64/FP32 CUDA-core peak. */

@@ -929,3 +929,64 @@ def rollout(s0, slot_types, fields, course, T, params=None, record=False, teache
     if record:
         out['rec'] = rec
     return out
+
+
+def drive_ticks(s0, ego, box_ids, boxes, dts, fixed_types, fixed_fields, M, traj, params=None, drive=None,
+                target_idx=0, carry=(0.0, 0.0, 0.0, 0.0)):
+    """The per-tick loop of the CARLA driver for ONE ego vehicle, tick by tick
+    (carla_scripts/multi_obstacle_CBF_local_with_lanes.py:861-983):
+
+      delta, idx = lateral_stanley.control()   cbf/controllers.py:104-151 (class form: offset lf, softening ks)
+      delta *= rad_to_steer                     :876-877
+      acc_pid.set_dt(dt); u_a = acc_pid.control(v, trajectory[idx][3])      cbf/controllers.py:153-180, :897-903
+      list = fixed obstacles (the lanes, :913-916) + one CollisionCone2D(hypot(extent), s, [x, y, yaw, |v|]) per box (:918-928)
+      u = solve_cbf([u_a, delta]) unless the list is empty (:935-953)
+      throttle / brake / steer                  :955-976
+
+    ego: list of T states (the simulator's), or None -> stand-in plant State.update_com from s0 with the tick's dt.
+    box_ids[t] / boxes[t]: K ids (< 0 = none) / K boxes (extent.x, extent.y, x, y, yaw, speed); dts[t] the tick's dt.
+    traj = (x, y, yaw, v) lists.  Returns per-tick lists act (throttle, brake, steer), u, mask, idx + final carry / state."""
+    p = dict(DEFAULT_PARAMS)
+    if params:
+        p.update(params)
+    d = dict(kp=1.0, ki=0.01, kd=0.01, rad_to_steer=1.0, max_steer_cmd=1.0, rate=0.1, cone_buffer=1.5, reset_brake=False)
+    if drive:
+        d.update(drive)
+    tx, ty, tyaw, tv = traj
+    s = [float(v) for v in (s0 if s0 is not None else ego[0])]
+    pid = PID1(kp=d['kp'], kd=d['kd'], ki=d['ki'])
+    pid.eprev, pid.ie = float(carry[0]), float(carry[1])
+    thr_prev, brk_prev = float(carry[2]), float(carry[3])
+    last_idx = int(target_idx)
+    T = len(dts)
+    out = dict(act=[], u=[], mask=[], idx=[])
+    for t in range(T):
+        if ego is not None:
+            s = [float(v) for v in ego[t]]
+        dt = float(dts[t])
+        delta, last_idx = stanley_control(s[0], s[1], s[2], s[3], tx, ty, tyaw, last_idx, p['k'], p['L'], p.get('ks', 0.0))
+        delta = delta * d['rad_to_steer']
+        pid.dt = dt
+        u_a = pid.control(s[3], float(tv[last_idx]))
+        types = list(fixed_types)
+        fields = [list(map(float, f)) for f in fixed_fields]
+        for k, bid in enumerate(box_ids[t]):
+            if bid < 0 or len(types) >= M:
+                continue
+            ex, ey, lx, ly, yaw_o, sp = (float(v) for v in boxes[t][k])
+            types.append(SLOT_CONE)
+            fields.append([lx, ly, yaw_o, sp, float(np.hypot(ex, ey)) + d['cone_buffer'], 0.0, 0.0, 0.0])
+        if len(types) < 1:
+            u0, u1, mask = u_a, delta, 0
+        else:
+            u0, u1, mask, _st, _raw, _hm = filter_step(MODEL_DBM, s, [u_a, delta], types, fields, p['alpha'], p['lr'], p['lf'],
+                                                       p['L'], p['R'], 0)
+        thr, brk, steer = actuator_shaping(u0, u1, thr_prev, brk_prev, d['max_steer_cmd'], d['rate'], d['reset_brake'])
+        thr_prev, brk_prev = thr, brk
+        out['act'].append([thr, brk, steer]); out['u'].append([u0, u1]); out['mask'].append(mask); out['idx'].append(last_idx)
+        if ego is None:
+            s, _beta = plant_update_com(s, u0, u1, dt, p['lr'], p['lf'], p['max_steer'])
+    out['carry'] = [pid.eprev, pid.ie, thr_prev, brk_prev]
+    out['target_idx'] = last_idx
+    out['state'] = s
+    return out

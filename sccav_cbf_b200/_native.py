@@ -50,6 +50,12 @@ class PerVehicle(C.Structure):
                 ("aug", C.c_void_p)]
 
 
+class DriveParams(C.Structure):
+    _fields_ = [("kp", C.c_double), ("ki", C.c_double), ("kd", C.c_double), ("rad_to_steer", C.c_double),
+                ("max_steer_cmd", C.c_double), ("rate", C.c_double), ("cone_buffer", C.c_double),
+                ("act_flags", C.c_int32), ("reserved", C.c_int32)]
+
+
 class RolloutOut(C.Structure):
     _fields_ = [
         ("state", C.c_void_p), ("steps", C.c_void_p), ("target_idx", C.c_void_p), ("n_active", C.c_void_p),
@@ -77,7 +83,7 @@ SYMBOLS = [
     "sccav_prepare_obstacles_f64", "sccav_prepare_obstacles_f32", "sccav_ingest_boxes_f64", "sccav_ingest_boxes_f32",
     "sccav_actuator_shaping_f64", "sccav_actuator_shaping_f32", "sccav_spline_course_f64", "sccav_spline_course_f32",
     "sccav_fit_lanes_f64", "sccav_fit_lanes_f32", "sccav_rollout_roads_f64", "sccav_rollout_roads_f32",
-    "sccav_trim_pool",
+    "sccav_trim_pool", "sccav_drive_ticks_f64", "sccav_drive_ticks_f32",
     "sccav_pipeline_create_f64", "sccav_pipeline_create_f32", "sccav_pipeline_submit_f64", "sccav_pipeline_submit_f32",
     "sccav_pipeline_wait_f64", "sccav_pipeline_wait_f32", "sccav_pipeline_destroy_f64", "sccav_pipeline_destroy_f32",
 ]
@@ -124,6 +130,8 @@ def lib() -> C.CDLL:
         f.argtypes = [C.c_char_p, i32, i64, i32, vp]
         f = getattr(L, "sccav_rollout_roads_" + sfx)
         f.argtypes = [PP, C.c_char_p, i32, i64, i32, vp, vp, vp, vp, vp, i32, i32, vp, PV, RO, vp]
+        getattr(L, "sccav_drive_ticks_" + sfx).argtypes = [PP, C.POINTER(DriveParams), C.c_char_p, i32, i32, i64, i32, vp, vp, i32, vp, vp, vp, vp,
+                                                            vp, vp, vp, vp, i32, PV, vp, vp, vp, vp, vp, vp, vp, vp]
         getattr(L, "sccav_pipeline_create_" + sfx).argtypes = [PP, C.c_char_p, i32, i64, i32, vp, vp, vp, i32, vp, i32, C.POINTER(vp)]
         getattr(L, "sccav_pipeline_submit_" + sfx).argtypes = [vp, vp, vp, PV, RO, C.POINTER(i64)]
         getattr(L, "sccav_pipeline_wait_" + sfx).argtypes = [vp, i64]

@@ -752,6 +752,48 @@ int SCCAV_FN(sccav_rollout_roads_)(const sccav_params* p, const uint8_t* slot_de
                              (cudaStream_t)stream, C, course_np);
 }
 
+int SCCAV_FN(sccav_drive_ticks_)(const sccav_params* p, const sccav_drive_params* dp, const uint8_t* slot_desc, int32_t M, int32_t n_fixed,
+                                 int64_t N, int32_t T, const SCCAV_REAL* state0, const SCCAV_REAL* ego, int32_t K, const int32_t* box_id,
+                                 const SCCAV_REAL* box, const SCCAV_REAL* dt, SCCAV_REAL* obst, const SCCAV_REAL* traj_x,
+                                 const SCCAV_REAL* traj_y, const SCCAV_REAL* traj_yaw, const SCCAV_REAL* traj_v, int32_t P,
+                                 const sccav_pervehicle* pv, int32_t* target_idx, SCCAV_REAL* carry, SCCAV_REAL* act_out,
+                                 SCCAV_REAL* u_out, uint32_t* active_out, int32_t* target_idx_out, SCCAV_REAL* state_out, void* stream) {
+    using namespace sccav;
+    typedef SCCAV_REAL real;
+    int rc = check_common(p, slot_desc, M, N, true);
+    if (rc) return rc;
+    if (!dp) { set_error("drive params is NULL"); return SCCAV_EINVAL; }
+    if (p->model != SCCAV_MODEL_DBM) { set_error("the driver tick uses DBM_CBF_2DS (model DBM)"); return SCCAV_EINVAL; }
+    if (T < 0 || K < 0 || n_fixed < 0 || n_fixed > M) { set_error("T < 0, K < 0 or n_fixed outside [0, M]"); return SCCAV_EINVAL; }
+    if (P < 1 || !traj_x || !traj_y || !traj_yaw || !traj_v) { set_error("a trajectory (x, y, yaw, v)[P >= 1] is required"); return SCCAV_EINVAL; }
+    if (N == 0 || T == 0) return SCCAV_OK;
+    if (!state0 && !ego) { set_error("either the ego stream or the initial state of the stand-in plant is required"); return SCCAV_EINVAL; }
+    if (K > 0 && (!box_id || !box)) { set_error("box_id / box is NULL"); return SCCAV_EINVAL; }
+    if ((M > 0 && !obst) || !target_idx || !carry || !act_out) { set_error("NULL array argument"); return SCCAV_EINVAL; }
+    for (int m = n_fixed; m < M && K > 0; ++m)
+        if ((slot_desc[m] & SCCAV_SLOT_TYPE_MASK) != SCCAV_SLOT_CONE || (slot_desc[m] & SCCAV_SLOT_SHARED)) {
+            set_error("slot %d is rebuilt from the boxes every tick: it must be a per-vehicle CONE slot", m);
+            return SCCAV_EINVAL;
+        }
+    DriveArgs<real> a;
+    a.P = convert(p); a.sd = make_desc(slot_desc, M); a.M = M; a.n_fixed = n_fixed; a.K = K; a.T_ticks = T; a.np = P; a.N = N;
+    a.kp = (real)dp->kp; a.ki = (real)dp->ki; a.kd = (real)dp->kd; a.rad_to_steer = (real)dp->rad_to_steer;
+    a.max_steer_cmd = (real)dp->max_steer_cmd; a.rate = (real)dp->rate; a.cone_buffer = (real)dp->cone_buffer; a.act_flags = dp->act_flags;
+    a.state0 = state0; a.ego = ego; a.box_id = K > 0 ? box_id : nullptr; a.box = box; a.dt = dt; a.obst = obst;
+    a.cx = traj_x; a.cy = traj_y; a.cyaw = traj_yaw; a.cv = traj_v; a.pv = make_pv(pv);
+    a.target_idx = target_idx; a.carry = carry; a.act = act_out; a.u = u_out; a.mask = active_out; a.tidx = target_idx_out; a.o_state = state_out;
+    const RolloutSmem<real> lay(P, true);
+    int block = 256;
+    size_t smem = lay.course_bytes + (size_t)3 * (M > 0 ? M : 1) * block * sizeof(real);
+    while (smem > (size_t)max_smem_optin() && block > 32) { block >>= 1; smem = lay.course_bytes + (size_t)3 * (M > 0 ? M : 1) * block * sizeof(real); }
+    if (smem > (size_t)max_smem_optin()) { set_error("trajectory of %d points does not fit in shared memory", P); return SCCAV_EINVAL; }
+    SCCAV_CUDA_CHECK(cudaFuncSetAttribute(drive_ticks_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    drive_ticks_kernel<real><<<(int)((N + block - 1) / block), block, smem, (cudaStream_t)stream>>>(a);
+    count_launch();
+    SCCAV_CUDA_CHECK(cudaGetLastError());
+    return SCCAV_OK;
+}
+
 int SCCAV_FN(sccav_rollout_launch_info_)(const uint8_t* slot_desc, int32_t M, int64_t N, int32_t P, int32_t* info) {
     using namespace sccav;
     if (!info || N < 1 || M < 0 || M > SCCAV_MAX_ROWS || (M > 0 && !slot_desc)) { set_error("bad argument"); return SCCAV_EINVAL; }

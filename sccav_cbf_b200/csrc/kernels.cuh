@@ -186,30 +186,38 @@ template <typename T> struct ActuatorArgs {
     T* steer;
 };
 
+// (a, delta) -> (throttle, brake, steer); tp / bp = the previous tick's throttle / brake (read, then replaced)
+template <typename T>
+__device__ __forceinline__ void actuator_step(T ua, T d, T max_steer, T rate, int flags, T& tp, T& bp, T& throttle, T& brake, T& steer) {
+    typedef Real<T> R;
+    brake = bp;                                                   // `brake` is the driver's variable of the last tick
+    if (ua > T(0)) {
+        throttle = R::tanh_(ua);
+        throttle = fmax(T(0), fmin(T(1), throttle));              // :959-960
+        if (throttle - tp > rate) throttle = tp + rate;           // :961-962
+        if (flags & SCCAV_ACT_RESET_BRAKE) brake = T(0);
+    } else {
+        throttle = T(0);                                          // :964
+        brake = -R::tanh_(ua);
+        brake = fmax(T(0), fmin(T(1), brake));                    // :965-966
+        if (brake - bp > rate) brake = bp + rate;                 // :967-968
+    }
+    if (d > T(0)) d = fmax(T(0), fmin(d, max_steer));             // :973-976
+    else d = fmax(-max_steer, fmin(d, T(0)));
+    tp = throttle;                                                // :970-971
+    bp = brake;
+    steer = d;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) actuator_kernel(const __grid_constant__ ActuatorArgs<T> a) {
-    typedef Real<T> R;
     const int64_t N = a.N;
     for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
-        const T ua = a.u[n];
-        T d = a.u[N + n];
-        const T tp = a.thr_prev[n], bp = a.brk_prev[n];
-        T throttle, brake = bp;                                   // `brake` is the driver's variable of the last tick
-        if (ua > T(0)) {
-            throttle = R::tanh_(ua);
-            throttle = fmax(T(0), fmin(T(1), throttle));          // :959-960
-            if (throttle - tp > a.rate) throttle = tp + a.rate;   // :961-962
-            if (a.flags & SCCAV_ACT_RESET_BRAKE) brake = T(0);
-        } else {
-            throttle = T(0);                                      // :964
-            brake = -R::tanh_(ua);
-            brake = fmax(T(0), fmin(T(1), brake));                // :965-966
-            if (brake - bp > a.rate) brake = bp + a.rate;         // :967-968
-        }
-        if (d > T(0)) d = fmax(T(0), fmin(d, a.max_steer));       // :973-976
-        else d = fmax(-a.max_steer, fmin(d, T(0)));
-        a.thr_prev[n] = throttle;                                 // :970-971
-        a.brk_prev[n] = brake;
+        T tp = a.thr_prev[n], bp = a.brk_prev[n];
+        T throttle, brake, d;
+        actuator_step<T>(a.u[n], a.u[N + n], a.max_steer, a.rate, a.flags, tp, bp, throttle, brake, d);
+        a.thr_prev[n] = tp;
+        a.brk_prev[n] = bp;
         if (a.thr) a.thr[n] = throttle;
         if (a.brk) a.brk[n] = brake;
         if (a.steer) a.steer[n] = d;
@@ -1186,6 +1194,134 @@ __global__ void __launch_bounds__(256) stanley_kernel(const __grid_constant__ St
         a.target_idx[n] = use;
         if (a.err) a.err[n] = e;
     }
+}
+
+// ------------------------------------------------------------------------------------------ KD
+// The per-tick loop of the CARLA driver (carla_scripts/multi_obstacle_CBF_local_with_lanes.py:861-983), T ticks in ONE
+// launch, thread = ego vehicle, everything a tick carries over in registers:
+//   lateral_stanley.control   cbf/controllers.py:104-151 (front axle at lf, atan2(k e, v + ks), its own last_target_idx)
+//   delta *= rad_to_steer     :876-877
+//   acc_pid.set_dt / control  cbf/controllers.py:153-180 (kp, ki, kd; the tick's own dt), reference speed = trajectory[idx][3]
+//   obstacle list             the shared lane slots + one fresh CollisionCone2D per actor box of the tick (:913-928)
+//   solve_cbf                 DBM_CBF_2DS (cbf/cbf.py:166-220); an empty list passes u_ref through (:935-936)
+//   throttle / brake / steer  :955-980
+// The ego state of every tick comes from the caller's stream (the simulator owns the plant); without a stream a
+// stand-in plant -- State.update_com with the filtered (a, delta) and the tick's dt -- closes the loop.
+template <typename T> struct DriveArgs {
+    Params<T> P;
+    SlotDesc sd;
+    int M, n_fixed, K, T_ticks, np;
+    int64_t N;
+    T kp, ki, kd, rad_to_steer, max_steer_cmd, rate, cone_buffer;
+    int act_flags;
+    const T* state0;       // [4][N] initial ego state (stand-in plant) or NULL
+    const T* ego;          // [T][4][N] ego state of every tick or NULL
+    const int32_t* box_id; // [T][K][N] or NULL (K = 0: the cone slots of `obst` are used as they are, count from pv)
+    const T* box;          // [T][K][6][N]
+    const T* dt;           // [T] or NULL (P.dt)
+    T* obst;               // [M][8][N]: slots [0, n_fixed) given by the caller, the rest rebuilt from the boxes every tick
+    const T* cx; const T* cy; const T* cyaw; const T* cv;      // trajectory (x, y, yaw, v) [np]
+    PerVehicle<T> pv;
+    int32_t* target_idx;   // [N] in / out: LateralStanley's last target index
+    T* carry;              // [4][N] in / out: PID e_prev, PID integral, throttle_prev, brake_prev
+    T* act;                // [T][3][N] throttle, brake, steer
+    T* u;                  // [T][2][N] filtered (a, delta) or NULL
+    uint32_t* mask;        // [T][N] or NULL
+    int32_t* tidx;         // [T][N] or NULL
+    T* o_state;            // [4][N] final ego state or NULL
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) drive_ticks_kernel(const __grid_constant__ DriveArgs<T> a) {
+    typedef Real<T> R;
+    typedef typename R::T2 T2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int np = a.np;
+    const RolloutSmem<T> lay(np, true);
+    T* s_cyaw = reinterpret_cast<T*>(smem_raw + lay.off_cyaw);
+    T* rows = reinterpret_cast<T*>(smem_raw + lay.off_rows) + threadIdx.x;
+    const int stride = blockDim.x;
+    const CourseIndex<T, T2> ci = course_stage<T, T2>(smem_raw, lay, np, a.cx, a.cy, a.cyaw, s_cyaw,
+                                                      reinterpret_cast<double*>(smem_raw + lay.off_rows));
+    const int64_t N = a.N;
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const Params<T>& P = a.P;
+    T alpha, R00, R01, R10, R11;
+    load_weights<T>(P, a.pv, N, n, alpha, R00, R01, R10, R11);
+    T x = T(0), y = T(0), yaw = T(0), v = T(0);
+    if (a.state0) { x = a.state0[n]; y = a.state0[N + n]; yaw = a.state0[2 * N + n]; v = a.state0[3 * N + n]; }
+    int last_idx = a.target_idx[n], near_idx = last_idx, adv = 0;
+    T eprev = a.carry[n], ie = a.carry[N + n], thr_prev = a.carry[2 * N + n], brk_prev = a.carry[3 * N + n];
+    int Mv = slot_count<T>(a.pv, a.M, n);
+    for (int t = 0; t < a.T_ticks; ++t) {
+        if (a.ego) {
+            const T* e = a.ego + (int64_t)t * 4 * N + n;
+            x = e[0]; y = e[N]; yaw = e[2 * N]; v = e[3 * N];
+        }
+        const T dt = a.dt ? a.dt[t] : P.dt;
+        // ---- LateralStanley.control (class form: front axle at L = lf)
+        T syaw, cyw;
+        R::sincos_(yaw, &syaw, &cyw);
+        const T fx = x + P.L * cyw, fy = y + P.L * syaw;
+        const int idx = course_nearest<T, T2>(ci, fx, fy, near_idx + adv, nullptr);
+        adv = idx - near_idx;
+        adv = adv < -4 * SCCAV_LEAF ? 0 : (adv > 4 * SCCAV_LEAF ? 0 : adv);
+        near_idx = idx;
+        T delta = stanley_law<T, T2>(P, ci.pt(idx), s_cyaw, idx, fx, fy, yaw, v, last_idx);
+        delta = delta * a.rad_to_steer;                                                  // :876-877
+        // ---- PID1.control(ego_v, trajectory[target_idx][3])
+        const T e = a.cv[last_idx] - v;                                                  // controllers.py:174
+        const T de = (e - eprev) / dt;                                                   // :175
+        ie = ie + dt * e;                                                                // :176
+        const T u_a = (a.kp * e + a.ki * ie) + a.kd * de;                                // :178
+        eprev = e;
+        // ---- obstacle list of the tick: fixed slots, then one fresh cone per box (from_bounding_box semantics)
+        if (a.box_id) {
+            int w = a.n_fixed;
+            for (int k = 0; k < a.K; ++k) {
+                const int32_t id = a.box_id[((int64_t)t * a.K + k) * N + n];
+                if (id < 0 || w >= a.M) continue;
+                // CollisionCone2D(a_cone = hypot(extent), s, s_obs = [x, y, yaw, |v|]) with the default buffer  (:918-928;
+                // the driver builds the cone itself, so the actor's yaw is kept -- from_bounding_box would zero it)
+                const T* bx = a.box + ((int64_t)t * a.K + k) * SCCAV_BOX_FIELDS * N + n;
+                T* dst = a.obst + (int64_t)w * SCCAV_NFIELD * N + n;
+                dst[0] = bx[2 * N]; dst[N] = bx[3 * N]; dst[2 * N] = bx[4 * N]; dst[3 * N] = bx[5 * N];
+                dst[4 * N] = R::hypot_(bx[0], bx[N]) + a.cone_buffer;
+                dst[5 * N] = T(0); dst[6 * N] = T(0); dst[7 * N] = T(0);
+                ++w;
+            }
+            Mv = w;
+        }
+        // ---- solve_cbf
+        T u0 = u_a, u1 = delta, u1raw = delta, hmin = R::inf();
+        uint32_t mask = 0u;
+        if (Mv > 0)
+            filter_vehicle<T, SCCAV_SPEC_GENERIC, -1>(P, a.sd, Mv, N, n, a.obst, x, y, yaw, v, syaw, cyw, alpha, R00, R01, R10, R11,
+                                                       a.pv.R == nullptr, u_a, delta, rows, stride, u0, u1, u1raw, mask, hmin);
+        // ---- actuators
+        T throttle, brake, steer;
+        actuator_step<T>(u0, u1, a.max_steer_cmd, a.rate, a.act_flags, thr_prev, brk_prev, throttle, brake, steer);
+        T* o = a.act + (int64_t)t * 3 * N + n;
+        o[0] = throttle; o[N] = brake; o[2 * N] = steer;
+        if (a.u) { a.u[(int64_t)t * 2 * N + n] = u0; a.u[((int64_t)t * 2 + 1) * N + n] = u1; }
+        if (a.mask) a.mask[(int64_t)t * N + n] = mask;
+        if (a.tidx) a.tidx[(int64_t)t * N + n] = last_idx;
+        // ---- stand-in plant (no ego stream): State.update_com, sce.py:122-131, with the tick's dt
+        if (!a.ego) {
+            T dl = u1;
+            if (dl < -P.max_steer) dl = -P.max_steer;
+            if (dl > P.max_steer) dl = P.max_steer;
+            const T beta = R::atan2_(P.lr * R::tan_(dl), P.lf + P.lr);
+            x = x + (v * cyw - (v * syaw) * beta) * dt;
+            y = y + (v * syaw + (v * cyw) * beta) * dt;
+            yaw = yaw + ((v * beta) / P.lr) * dt;
+            v = v + u0 * dt;
+        }
+    }
+    a.target_idx[n] = last_idx;
+    a.carry[n] = eprev; a.carry[N + n] = ie; a.carry[2 * N + n] = thr_prev; a.carry[3 * N + n] = brk_prev;
+    if (a.o_state) { a.o_state[n] = x; a.o_state[N + n] = y; a.o_state[2 * N + n] = yaw; a.o_state[3 * N + n] = v; }
 }
 
 }  // namespace sccav

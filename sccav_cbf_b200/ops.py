@@ -465,3 +465,58 @@ def rollout_launch_info(slot_desc, N: int, P: int, dtype=torch.float64) -> Dict[
     nv.check(getattr(L, "sccav_rollout_launch_info_" + _SFX[dtype])(sd, len(sd), int(N), int(P), info))
     keys = ("grid", "block", "smem_bytes", "registers", "max_threads_per_block", "ctas_per_sm", "course_in_smem", "sms")
     return dict(zip(keys, [int(v) for v in info]))
+
+
+def drive_ticks(params: Params, slot_desc, n_fixed: int, obst: torch.Tensor, traj, target_idx: torch.Tensor, carry: torch.Tensor,
+                T: int, state0: Optional[torch.Tensor] = None, ego: Optional[torch.Tensor] = None, box_id: Optional[torch.Tensor] = None,
+                box: Optional[torch.Tensor] = None, dt: Optional[torch.Tensor] = None, count: Optional[torch.Tensor] = None,
+                kp: float = 1.0, ki: float = 0.01, kd: float = 0.01, rad_to_steer: float = 1.0, max_steer_cmd: float = 1.0,
+                rate: float = 0.1, cone_buffer: float = 1.5, act_flags: int = 0, want_u: bool = True, want_state: bool = True):
+    """KD: T ticks of the CARLA driver's loop (multi_obstacle_CBF_local_with_lanes.py:861-983) for N egos in ONE launch:
+    LateralStanley.control (class form) -> PID1 with the tick's dt -> lanes + one fresh CollisionCone2D per box -> solve_cbf
+    -> throttle / brake / steer.  ``ego`` [T,4,N] = the simulator's ego states (or None: stand-in plant update_com from
+    ``state0`` [4,N]); ``box_id`` [T,K,N] int32 / ``box`` [T,K,6,N]; ``dt`` [T]; ``traj`` = (x, y, yaw, v) [P];
+    ``obst`` [M,8,N] whose first ``n_fixed`` slots are the caller's (lanes); ``target_idx`` int32 [N] and ``carry`` [4,N]
+    (PID e_prev, integral, throttle_prev, brake_prev) are updated IN PLACE.  Returns a dict: act [T,3,N], u [T,2,N],
+    active_mask [T,N], target_idx [T,N], state [4,N]."""
+    L = _need_cuda_lib()
+    sd = slot_bytes(slot_desc)
+    M = len(sd)
+    N = obst.shape[-1] if M > 0 else target_idx.shape[0]
+    dtp, dev = carry.dtype, carry.device
+    if not carry.is_cuda:
+        raise ValueError("drive_ticks takes CUDA tensors")
+    for t, name in ((obst, "obst"), (target_idx, "target_idx"), (carry, "carry")):
+        if not t.is_contiguous():
+            raise ValueError("%s must be contiguous (it is updated in place)" % name)
+    obst = _chk(obst, (M, nv.NFIELD, N), dtp, dev, "obst")
+    carry = _chk(carry, (4, N), dtp, dev, "carry")
+    target_idx = _chk(target_idx, (N,), torch.int32, dev, "target_idx")
+    tx, ty, tyaw, tv = traj
+    P = tx.shape[0]
+    tx = _chk(tx, (P,), dtp, dev, "traj_x"); ty = _chk(ty, (P,), dtp, dev, "traj_y")
+    tyaw = _chk(tyaw, (P,), dtp, dev, "traj_yaw"); tv = _chk(tv, (P,), dtp, dev, "traj_v")
+    K = 0
+    if box_id is not None:
+        K = box_id.shape[1]
+        box_id = _chk(box_id, (T, K, N), torch.int32, dev, "box_id")
+        box = _chk(box, (T, K, nv.BOX_FIELDS, N), dtp, dev, "box")
+    if ego is not None:
+        ego = _chk(ego, (T, 4, N), dtp, dev, "ego")
+    if state0 is not None:
+        state0 = _chk(state0, (4, N), dtp, dev, "state0")
+    if dt is not None:
+        dt = _chk(dt, (T,), dtp, dev, "dt")
+    pv, keep = _pv(N, dtp, dev, count=count)
+    dp = nv.DriveParams(kp, ki, kd, rad_to_steer, max_steer_cmd, rate, cone_buffer, int(act_flags), 0)
+    act = torch.empty((T, 3, N), dtype=dtp, device=dev)
+    u = torch.empty((T, 2, N), dtype=dtp, device=dev) if want_u else None
+    mask = torch.empty((T, N), dtype=torch.int32, device=dev)
+    tidx = torch.empty((T, N), dtype=torch.int32, device=dev)
+    st = torch.empty((4, N), dtype=dtp, device=dev) if want_state else None
+    with torch.cuda.device(dev):
+        nv.check(getattr(L, "sccav_drive_ticks_" + _SFX[dtp])(
+            C.byref(params), C.byref(dp), sd, M, int(n_fixed), N, int(T), _ptr(state0), _ptr(ego), K, _ptr(box_id), _ptr(box), _ptr(dt),
+            _ptr(obst), _ptr(tx), _ptr(ty), _ptr(tyaw), _ptr(tv), P, C.byref(pv), _ptr(target_idx), _ptr(carry), _ptr(act), _ptr(u),
+            _ptr(mask), _ptr(tidx), _ptr(st), _stream(dev)))
+    return {"act": act, "u": u, "active_mask": mask, "target_idx": tidx, "state": st}
