@@ -585,14 +585,6 @@ def main():
                          "roads64_one_launch_per_road_ms": sms, "roads64_bit_identical_to_single_road_launches": bool(same)})
             del singles, souts, rout, d_rs, d_ro
         flat["config_legs_flags"] = fl
-    # ---- per-call latency of the class API (one solve_cbf per tick, as the reference uses it)
-    if rank == 0:
-        try:
-            flat["solve_cbf_latency_us_n1"] = solve_cbf_latency(dev, 1)
-            flat["solve_cbf_latency_us_n1024"] = solve_cbf_latency(dev, 1024)
-        except Exception as exc:          # keep the bench line even if the class API leg fails
-            flat["solve_cbf_latency_error"] = repr(exc)[:200]
-
     # ---- roofline of the dominant kernel (rollout): fp64 FMA peak measured on this GPU, now
     peak_tf = ops.measure_fma_peak(dtype)
     flops_per_launch = rollout_flops(evals_rank, vehicle_steps_rank, M)
@@ -737,6 +729,14 @@ def main():
                                  "achieved": 16 * esize * n_op * M / (ims * 1e-3) / 1e9,
                                  "frac": 16 * esize * n_op * M / (ims * 1e-3) / 1e9 / hbm_peak, "ms": ims}
         del st, ob, ur, obp, u_p, st_p
+
+    # ---- per-call latency of the class API (one solve_cbf per tick, as the reference uses it)
+    if rank == 0:
+        try:
+            flat["solve_cbf_latency_us_n1"] = solve_cbf_latency(dev, 1)
+            flat["solve_cbf_latency_us_n1024"] = solve_cbf_latency(dev, 1024)
+        except Exception as exc:          # keep the bench line even if the class API leg fails
+            flat["solve_cbf_latency_error"] = repr(exc)[:200]
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the box's host cores, bounded sample
     cpu = None
