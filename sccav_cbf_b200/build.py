@@ -50,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(CSRC, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + ARCH + [c for c in COMMON if not c.startswith("--use_fast_math")] + extra + ["-c", s, "-o", o]
+            cmd = [nvcc] + ARCH + [c for c in COMMON if not c.startswith("--use_fast_math")] + extra + os.environ.get("SCCAV_NVCC_EXTRA", "").split() + ["-c", s, "-o", o]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), flush=True)

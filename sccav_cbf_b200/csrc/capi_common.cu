@@ -215,6 +215,7 @@ static void debug_course_index(const double* cx, const double* cy, int P, const 
                                const int32_t* hint, int64_t nq, int32_t* idx, int32_t* idx_full, int64_t* evals) {
     std::vector<T2> xy(course_nslot(P));
     for (int i = 0; i < P; ++i) { xy[course_slot(i)].x = (T)cx[i]; xy[course_slot(i)].y = (T)cy[i]; }
+    for (int i = P; i < course_nleaf(P) * SCCAV_LEAF; ++i) xy[course_slot(i)] = xy[course_slot(P - 1)];
     // same construction as course_stage (kernels.cuh): origin = the middle point of the course
     T org[2] = {xy[course_slot(P / 2)].x, xy[course_slot(P / 2)].y};
     double e = 0.0;

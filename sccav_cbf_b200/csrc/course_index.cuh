@@ -39,14 +39,16 @@ namespace sccav {
 #define SCCAV_LEAF (1 << SCCAV_LEAF_SHIFT)
 #define SCCAV_FAN_SHIFT 3
 #define SCCAV_FAN (1 << SCCAV_FAN_SHIFT)
-#define SCCAV_MAX_LEVELS 8          /* 8 levels of fan-out 8 over leaves of 8 points: far more than any course */
-#define SCCAV_TOP_MAX 8             /* the top level holds at most this many nodes (<= 32): all of them are tested.  A flat top
-                                       of 32 tight nodes instead of 4 loose ones + their children was measured: 13.1 vs 12.3 ms */
+#define SCCAV_MAX_LEVELS 7          /* 7 levels of fan-out 8 over leaves of 8 points (16 M points): far more than any course */
+#define SCCAV_TOP_MAX SCCAV_FAN     /* the top level holds at most 8 nodes, siblings under a virtual root.  (A flat top of 32 tight
+                                       nodes instead of 4 loose ones + their children was measured: 13.1 vs 12.3 ms) */
 
 // position of course point i in the padded point array (one spare slot after every leaf)
 __host__ __device__ __forceinline__ int course_slot(int i) { return i + (i >> SCCAV_LEAF_SHIFT); }
 __host__ __device__ __forceinline__ int course_nleaf(int np) { return (np + SCCAV_LEAF - 1) / SCCAV_LEAF; }
-__host__ __device__ __forceinline__ int course_nslot(int np) { return np + course_nleaf(np); }
+// (whole leaves: the tail of the last leaf is filled with copies of the last point -- equal distances, later indices:
+// they can never win the strict first-minimum comparison -- so that every leaf scan is the same 8 unrolled points)
+__host__ __device__ __forceinline__ int course_nslot(int np) { return course_nleaf(np) * (SCCAV_LEAF + 1); }
 
 // Levels of the tree over a course of np points: level 0 = the leaves, level k + 1 has ceil(n_k / 8) nodes; the
 // top level has at most SCCAV_TOP_MAX nodes, all siblings under a root that is never tested (long, curved nodes
@@ -155,12 +157,12 @@ template <typename T> __host__ __device__ __forceinline__ float index_reach32(T 
 }
 
 template <typename T, typename T2>
-__host__ __device__ __forceinline__ IndexQuery index_query(const CourseIndex<T, T2>& ci, T fx, T fy, T best) {
+__host__ __device__ __forceinline__ IndexQuery index_query(const CourseIndex<T, T2>& ci, T fx, T fy) {
     IndexQuery q;
     q.qx = (float)(fx - ci.org[0]);
     q.qy = (float)(fy - ci.org[1]);
     q.slack = 2e-6f * ((fabsf(q.qx) + fabsf(q.qy)) + ci.ext[0]);
-    q.base = (index_reach32<T>(best) + q.slack) * 1.000002f;
+    q.base = INFINITY;                                  // no incumbent yet: nothing can be skipped
     return q;
 }
 
@@ -208,29 +210,19 @@ __host__ __device__ __forceinline__ uint32_t index_test8(const CourseIndex<T, T2
 }
 
 // Scan one leaf in ascending index order (strict <: first minimum inside the leaf), then merge
-// lexicographically with the running (best, ib).
+// lexicographically with the running (best, ib).  The staged array holds whole leaves (course_nslot).
 template <typename T, typename T2>
 __host__ __device__ __forceinline__ void index_scan_leaf(const CourseIndex<T, T2>& ci, int leaf, T fx, T fy, T& best, int& ib) {
     const int lo = leaf << SCCAV_LEAF_SHIFT;
     const T2* p = ci.xy + lo + leaf;                       // course_slot(lo)
-    const int cnt = (ci.np - lo < SCCAV_LEAF) ? ci.np - lo : SCCAV_LEAF;
     T lb = (T)INFINITY;
     int li = 0;
-    if (cnt == SCCAV_LEAF) {
 #pragma unroll
-        for (int j = 0; j < SCCAV_LEAF; ++j) {
-            T2 q = p[j];
-            T dx = fx - q.x, dy = fy - q.y;
-            T d2 = dx * dx + dy * dy;
-            if (d2 < lb) { lb = d2; li = j; }
-        }
-    } else {
-        for (int j = 0; j < cnt; ++j) {
-            T2 q = p[j];
-            T dx = fx - q.x, dy = fy - q.y;
-            T d2 = dx * dx + dy * dy;
-            if (d2 < lb) { lb = d2; li = j; }
-        }
+    for (int j = 0; j < SCCAV_LEAF; ++j) {
+        T2 q = p[j];
+        T dx = fx - q.x, dy = fy - q.y;
+        T d2 = dx * dx + dy * dy;
+        if (d2 < lb) { lb = d2; li = j; }
     }
     li += lo;
     if (lb < best || (lb == best && li < ib)) { best = lb; ib = li; }
@@ -261,6 +253,13 @@ __host__ __device__ __forceinline__ int lowest_bit64(uint64_t m) {
 // Exact global nearest index (first minimum) of (fx, fy) over the whole course.
 // hint: any index (the predicted nearest index; clamped into [0, np)); evals (optional) counts
 // distance evaluations + capsule tests for the roofline accounting.
+//
+// ONE work loop: `pending` holds, per level, the nodes still to be processed in the group of the current position's
+// ancestor (8 bits a level): a level-0 entry is a leaf to scan, an entry of level k >= 1 a node to OPEN (its 8 children
+// are tested in one batch; those that cannot be excluded become entries one level down).  It starts with the two leaves
+// around the hint and their ancestors up to the virtual root -- opening an ancestor tests the siblings of the level below,
+// which is the climb -- and always takes the lowest level first, i.e. the nearest work.  Every lane of a warp runs the
+// same two pieces of code (one batch of tests, one leaf scan) whatever level or node it is working on.
 template <typename T, typename T2>
 __host__ __device__ inline int course_nearest(const CourseIndex<T, T2>& ci, T fx, T fy, int hint, int* evals) {
     if (hint < 0) hint = 0;
@@ -275,42 +274,16 @@ __host__ __device__ inline int course_nearest(const CourseIndex<T, T2>& ci, T fx
     if ((hi >> SCCAV_FAN_SHIFT) != (lo >> SCCAV_FAN_SHIFT)) hi = lo;        // (a last group of one leaf)
     T best = (T)INFINITY;
     int ib = ci.np;
-    int ne = 2 * SCCAV_LEAF;
-    index_scan_leaf<T, T2>(ci, lo, fx, fy, best, ib);
-    if (hi != lo) index_scan_leaf<T, T2>(ci, hi, fx, fy, best, ib);
-    // NaN / overflowing query (np.argmin of all-NaN is 0): no usable bound, do what the reference does
-    if (!(best < (T)INFINITY)) return course_nearest_full<T, T2>(ci.xy, ci.np, fx, fy);
-    IndexQuery q = index_query<T, T2>(ci, fx, fy, best);
-    // climb: at every level below the top, the siblings of the scanned leaves' ancestor; at the top, every other node.
-    // pending: byte k = the nodes of level k, in the group of the current position's ancestor, that still have to be
-    // opened; top_pending: the same for the (up to 32) nodes of the top level.
-    uint64_t pending = 0u;
-    uint32_t top_pending = 0u;
-    const int top = ci.nlev - 1;
-    for (int k = 0; k < top; ++k) {
-        const int own = lo >> (SCCAV_FAN_SHIFT * k);
-        const uint32_t m = index_test8<T, T2>(ci, k, own >> SCCAV_FAN_SHIFT, own, k == 0 ? hi : own, q, ne);
-        pending |= (uint64_t)m << (8 * k);
-    }
-    {
-        const int own = lo >> (SCCAV_FAN_SHIFT * top), own2 = hi >> (SCCAV_FAN_SHIFT * top);
-        const int ngrp = (ci.lev[2 * top + 1] + SCCAV_FAN - 1) >> SCCAV_FAN_SHIFT;
-        for (int g = 0; g < ngrp; ++g) top_pending |= index_test8<T, T2>(ci, top, g, own, own2, q, ne) << (8 * g);
-    }
-    // open what could not be excluded, lowest level (= nearest) first
+    int ne = 0;
+    IndexQuery q = index_query<T, T2>(ci, fx, fy);
+    uint64_t pending = (1ull << (lo & (SCCAV_FAN - 1))) | (1ull << (hi & (SCCAV_FAN - 1)));
+    for (int k = 1; k <= ci.nlev; ++k) pending |= 1ull << (8 * k + ((lo >> (SCCAV_FAN_SHIFT * k)) & (SCCAV_FAN - 1)));
     int cur = lo;
-    while (pending | top_pending) {
-        int m, node;
-        if (pending) {
-            const int bit = lowest_bit64(pending);
-            pending &= pending - 1u;
-            m = bit >> 3;
-            node = ((cur >> (SCCAV_FAN_SHIFT * (m + 1))) << SCCAV_FAN_SHIFT) + (bit & 7);
-        } else {
-            node = lowest_bit64(top_pending);
-            top_pending &= top_pending - 1u;
-            m = top;
-        }
+    while (pending) {
+        const int bit = lowest_bit64(pending);
+        pending &= pending - 1u;
+        const int m = bit >> 3;
+        const int node = ((cur >> (SCCAV_FAN_SHIFT * (m + 1))) << SCCAV_FAN_SHIFT) + (bit & 7);
         cur = node << (SCCAV_FAN_SHIFT * m);
         if (m == 0) {
             const T before = best;
@@ -318,9 +291,13 @@ __host__ __device__ inline int course_nearest(const CourseIndex<T, T2>& ci, T fx
             ne += SCCAV_LEAF;
             if (best < before) q.base = (index_reach32<T>(best) + q.slack) * 1.000002f;
         } else {
-            pending |= (uint64_t)index_test8<T, T2>(ci, m - 1, node, -1, -1, q, ne) << (8 * (m - 1));
+            // children of `node`, except the scanned leaves / their ancestor (which has its own entry)
+            const int sh = SCCAV_FAN_SHIFT * (m - 1);
+            pending |= (uint64_t)index_test8<T, T2>(ci, m - 1, node, lo >> sh, hi >> sh, q, ne) << (8 * (m - 1));
         }
     }
+    // NaN / overflowing query (np.argmin of all-NaN is 0): nothing could be compared, do what the reference does
+    if (!(best < (T)INFINITY)) return course_nearest_full<T, T2>(ci.xy, ci.np, fx, fy);
     if (evals) *evals += ne;
     return ib;
 }

@@ -896,6 +896,8 @@ __device__ __forceinline__ CourseIndex<T, T2> course_stage(unsigned char* smem, 
         if (s_cyaw) s_cyaw[i] = cyaw[i];
         ext = fmax(ext, fmax(fabs((double)px - (double)ox), fabs((double)py - (double)oy)));
     }
+    // the tail of the last leaf: copies of the last point (course_nslot)
+    for (int i = np + threadIdx.x; i < ci.nleaf * SCCAV_LEAF; i += blockDim.x) s_cxy[course_slot(i)] = R::make2(cx[np - 1], cy[np - 1]);
     // extent of the course around the origin: CTA-wide max
     ext = warp_max<double>(ext);
     if (lane == 0) scratch[warp] = ext;

@@ -27,7 +27,7 @@ template <> struct Real<double> {
     static __device__ __forceinline__ double par_eps() { return 1e-12; }
     static __device__ __forceinline__ double tie_eps() { return 1e-9; }
     static __device__ __forceinline__ double qp_tie_margin() { return 1e-6; }
-    static __device__ __forceinline__ double qp_res_margin() { return 1e-4; }
+    static __device__ __forceinline__ double qp_res_margin() { return 1.25e-7; }
     static __device__ __forceinline__ double lane_xtol() { return 1e-12; }
     static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
     static __device__ __forceinline__ void sincos_(double x, double* s, double* c) { ::sincos(x, s, c); }
@@ -52,7 +52,7 @@ template <> struct Real<float> {
     static __device__ __forceinline__ float par_eps() { return 1e-5f; }
     static __device__ __forceinline__ float tie_eps() { return 1e-4f; }
     static __device__ __forceinline__ float qp_tie_margin() { return 1e-2f; }
-    static __device__ __forceinline__ float qp_res_margin() { return 1e-2f; }
+    static __device__ __forceinline__ float qp_res_margin() { return 1.25e-3f; }
     static __device__ __forceinline__ float lane_xtol() { return 1e-6f; }
     static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
     static __device__ __forceinline__ void sincos_(float x, float* s, float* c) { ::sincosf(x, s, c); }
@@ -470,6 +470,7 @@ __device__ __forceinline__ bool qp_check(const RowView<T>& rv, int m, T u0, T u1
 // for an all-ellipse problem the whole pair phase vanishes.
 struct RowNz {
     uint32_t nz0, nz1;
+    uint32_t viol = 0xffffffffu;   // rows the reference point violates strictly (rk < 0); all ones = not recorded
     __device__ __forceinline__ bool any_pair() const { return nz0 != 0u && nz1 != 0u; }
     __device__ __forceinline__ bool pair(int j, int k) const {
         return (((nz0 >> j) | (nz0 >> k)) & ((nz1 >> j) | (nz1 >> k)) & 1u) != 0u;
@@ -495,7 +496,17 @@ __device__ __forceinline__ int qp2_solve_active_full(const RowView<T>& rv, int m
     T worst;
     T fbw = worst0, fb0 = r0, fb1 = r1;
     uint32_t fbm = 0u;
-    for (int k = 0; k < m; ++k) {
+    // singles, in index order.  The rows r violates (rk < 0, the same operations as here) were recorded while the rows
+    // were written: each lane walks ITS OWN violated rows, so a warp runs as many iterations as its busiest lane has
+    // candidates (one or two) instead of one per distinct row index among its lanes.
+#ifdef SCCAV_NO_VIOL
+    uint32_t todo = (m >= 32 ? 0xffffffffu : ((1u << m) - 1u));
+#else
+    uint32_t todo = nz.viol & (m >= 32 ? 0xffffffffu : ((1u << m) - 1u));
+#endif
+    while (todo) {
+        const int k = __ffs((int)todo) - 1;
+        todo &= todo - 1u;
         T a0 = rv.A0(k), a1 = rv.A1(k), bk = rv.b(k);
         T rk = (a0 * r0 + a1 * r1) - bk;
         if (!(rk < T(0))) continue;
@@ -546,14 +557,17 @@ __device__ __forceinline__ int qp2_solve_active_full(const RowView<T>& rv, int m
 // rk^2 / den.  One scan finds it (ratios compared by cross-multiplication, no division), its candidate
 // is formed with the operations of the enumeration and checked against every row.  The enumeration --
 // which returns the FIRST accepted single in index order -- is still run whenever its answer could
-// differ: the candidate fails (optimum on a pair, or infeasible rows), another violated row is within
-// 1e-6 of the largest ratio (a tie: the earlier row may be accepted within the feasibility tolerance),
-// or the winning residual is within 1e-4 of its own rounding scale.  Otherwise a row j != k has
-// d_j < d_k (1 - 5e-7): its candidate misses row k by more than 5e-7 |rk|, 5 orders above the
-// acceptance tolerance, so the enumeration rejects it and accepts k -- same point, same bits.
+// differ: the candidate fails (optimum on a pair, or infeasible rows); another violated row is within
+// 1e-6 of the largest ratio (qp_tie_margin: a tie, the earlier row may be accepted within the feasibility
+// tolerance); or the winning residual is small against its own rounding scale (qp_res_margin).
+// Otherwise a row j != k has d_j < d_k (1 - 5e-7): by Cauchy-Schwarz in the metric of the cost its candidate
+// misses row k by at least 5e-7 |rk|, and the guard  |rk| qp_res_margin > feas_eps scale_k  (qp_res_margin =
+// 5e-7 / 4) puts that miss a factor 4 above the acceptance tolerance feas_eps scale_k of row k -- so the
+// enumeration rejects j and accepts k: same point, same bits.
 // tests/test_gpu_parity.py::test_qp_shortcut_equals_enumeration compares the two bit for bit.
-// The scan runs inside the row loop (QpScan::row, all lanes converged, predicated); finish() forms and
-// checks the winner's candidate and returns true (and the solution) if the shortcut answers the problem.
+// The scan runs inside the row loop (QpScan::row, all lanes converged, predicated) or, in the rollout, over the
+// stored rows of the lanes whose reference point is infeasible; finish() forms and checks the winner's candidate
+// and returns true (and the solution) if the shortcut answers the problem.
 template <typename T> struct QpScan {
     T bn, bd;      // largest ratio  rk^2 / den  as a fraction
     T sn, sd;      // runner-up
@@ -760,6 +774,7 @@ __device__ __forceinline__ void put_row(const Params<T>& P, const Partials<T>& p
     if (-rk > worst) worst = -rk;
     T tol = R::feas_eps() * ((R::abs_(t0) + R::abs_(t1)) + R::abs_(b));
     if (!(rk >= -tol)) feas = false;
+    if (rk < T(0)) nz.viol |= 1u << m;
     if (SCAN) scan->row(m, A0, A1, rk, *Ri);
 }
 
@@ -802,7 +817,7 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
     // rows -> shared memory; an inactive step never re-reads them
     bool feas = true;
     T worst = -R::inf();
-    RowNz nz{0u, 0u};
+    RowNz nz{0u, 0u, 0u};                                      // (violated rows are recorded by put_row)
     QpScan<T> scan;
     scan.reset();
     if (SPEC == SCCAV_SPEC_ELLIPSE) {
@@ -900,6 +915,8 @@ __device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc
         RInv<T> Ri;
         if (uniform_R) { Ri.i00 = P.Ri[0]; Ri.i01 = P.Ri[1]; Ri.i10 = P.Ri[2]; Ri.i11 = P.Ri[3]; }
         else Ri = RInv<T>(R00, R01, R10, R11);
+        // (plain enumeration: the one-scan shortcut of the filter-step kernels was measured here -- the larger loop body
+        // costs more in instruction fetch than the scan saves: 14.1 vs 12.9 ms on config 2)
         status = qp2_solve_active<T>(rv, M, ph.nz, ph.r0, ph.r1, R00, R01, R10, R11, Ri, ph.worst, q0, q1, mask);
     }
     u0 = q0;

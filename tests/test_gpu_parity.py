@@ -857,3 +857,62 @@ def test_pipelined_host_api_equals_the_synchronous_host_call(depth, resident):
         for kk in ("state", "steps", "target_idx", "n_active", "n_infeasible", "h_min", "beta_int", "n_evals"):
             assert torch.equal(got[k][kk], ref[kk]), (k, kk)
     assert not torch.equal(got[0]["state"], got[1]["state"])
+
+
+def test_qp_kernels_against_an_independent_solver():
+    """K2 (thread and warp forms) and K12's cooperative QP on random feasible problems with single-row and PAIR optima,
+    against scipy's SLSQP (shares no code with this repo)."""
+    from sccav_cbf_b200 import ops
+    from tests.test_oracle_c_and_qp import _scipy_qp, random_qps
+    rng = np.random.default_rng(77)
+    m = 6
+    probs = random_qps(rng, 256, m)
+    for Rw in ((1.0, 0.0, 0.0, 1.0), (2.0, 0.3, 0.3, 0.7)):
+        sel = [p for p in probs if p[4] == Rw]
+        N = len(sel)
+        A = np.zeros((2, m, N)); b = np.zeros((m, N)); r = np.zeros((2, N))
+        for n, (A0, A1, bb, rr, _) in enumerate(sel):
+            A[0, :, n] = A0; A[1, :, n] = A1; b[:, n] = bb; r[:, n] = rr
+        prm = ops.make_params(R=list(Rw))
+        outs = [ops.qp2_solve(prm, T(A), T(b), T(r), warp_per_problem=w) for w in (False, True)]
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+        u = outs[0][0].cpu().numpy(); mask = outs[0][1].cpu().numpy().view(np.uint32)
+        n_ok = n_pair = 0
+        for n, (A0, A1, bb, rr, _) in enumerate(sel):
+            xs, ok = _scipy_qp(A0, A1, bb, rr, Rw)
+            if not ok:
+                continue
+            n_ok += 1
+            assert np.abs(u[:, n] - xs).max() <= 1e-6 * (1 + np.abs(xs).max()), (n, u[:, n], xs)
+            n_pair += bin(int(mask[n])).count("1") == 2
+        assert n_ok > 60 and n_pair > 10, (n_ok, n_pair)
+
+
+def test_rollout_does_not_depend_on_what_ran_before():
+    """The rollout stages its course and index in shared memory and takes scratch from a memory pool: neither may be read
+    before it is written.  Same launch before and after unrelated kernels have left other contents in shared memory and
+    in the pool: bit-identical outputs, and every way-point index inside the course (a padded leaf tail is never hit)."""
+    from sccav_cbf_b200 import ops, scenarios as sc
+    b = sc.config2(n_total=65536, M=8, T=1000, lo=0, hi=2048)
+    course = tuple(T_(c, torch.float64) for c in b.course)
+    outs = []
+    for flags in (0, 5):
+        prm = ops.make_params(flags=flags)
+        for rep in range(2):
+            if rep == 1:
+                rng = np.random.default_rng(5)
+                N2 = 131072
+                for slots in ([0] * 8, [0, 1, 2, 3, 4, 0, 1, 2], [3] * 16):
+                    s2 = H.random_states(rng, N2); ob2 = H.random_slots(rng, N2, slots, s2); ur2 = H.random_uref(rng, N2)
+                    p2 = ops.make_params(R=[1.0, 0.3, 0.3, 2.5], alpha=1.3)
+                    ops.filter_step(p2, slots, T(s2), T(ob2), T(ur2))
+                    A, bb, _ = ops.barrier_rows(p2, slots, T(s2), T(ob2))
+                    ops.qp2_solve(p2, A, bb, T(ur2))
+                junk = torch.full((64 * 1024 * 1024,), float("nan"), dtype=torch.float64, device=dev()); del junk
+            g = ops.rollout(prm, b.slot_desc, T_(b.state, torch.float64), T_(b.obst, torch.float64), course, b.T)
+            torch.cuda.synchronize()
+            outs.append({k: v.cpu().numpy() for k, v in g.items()})
+        a, c = outs[-2], outs[-1]
+        for k in a:
+            assert np.array_equal(a[k], c[k], equal_nan=True), (flags, k)
+        assert (a["target_idx"] >= 0).all() and (a["target_idx"] < len(b.course[0])).all()

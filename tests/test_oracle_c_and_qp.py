@@ -214,3 +214,48 @@ def test_qp_shortcut_theory_most_violated_row_in_the_metric_of_R():
             assert status == o.STATUS_ACTIVE and mask == 1 << kb, (it, mask, kb)
             assert abs(c[0] - u0) <= 1e-12 * (1 + abs(u0)) and abs(c[1] - u1) <= 1e-12 * (1 + abs(u1))
     assert n_single > 500 and n_accept > 500
+
+
+def _scipy_qp(A0, A1, b, r, R):
+    """An INDEPENDENT solver for min (u - r)^T R (u - r) s.t. A u >= b: scipy's SLSQP (nothing of this repo inside)."""
+    from scipy.optimize import minimize
+    R = np.asarray(R, dtype=np.float64).reshape(2, 2)
+    A = np.stack([A0, A1], axis=1)
+    res = minimize(lambda u: (u - r) @ R @ (u - r), x0=np.array(r, dtype=np.float64), jac=lambda u: 2.0 * R @ (u - r), method="SLSQP",
+                   constraints=[{"type": "ineq", "fun": lambda u: A @ u - b, "jac": lambda u: A}], options={"ftol": 1e-15, "maxiter": 200})
+    return res.x, res.success
+
+
+def random_qps(rng, n, m):
+    """Feasible random problems around a reference point that violates one to three rows (single and pair optima)."""
+    out = []
+    while len(out) < n:
+        A0 = rng.normal(0, 1, m); A1 = rng.normal(0, 1, m)
+        inner = rng.normal(0, 1, 2)                                    # a point every row admits: the problem is feasible
+        b = A0 * inner[0] + A1 * inner[1] - rng.uniform(0.05, 2.0, m)
+        r = inner + rng.normal(0, 2.5, 2)
+        R = (1.0, 0.0, 0.0, 1.0) if len(out) % 2 else (2.0, 0.3, 0.3, 0.7)
+        out.append((A0, A1, b, r, R))
+    return out
+
+
+def test_exact_qp_against_an_independent_solver():
+    """the golden vectors take their QP solutions from this repo's own exact solver, so the solver needs a check
+    that shares no code with it.  300 random feasible problems (m = 2..8 rows, optima on no row, one row and a PAIR of rows,
+    diagonal and full weights) against scipy's SLSQP: same optimum to 1e-6, and the active set qp2_exact reports is tight."""
+    rng = np.random.default_rng(20261017)
+    n_pair = n_single = n_ok = 0
+    for i, (A0, A1, b, r, R) in enumerate(random_qps(rng, 300, 2 + rng.integers(0, 7))):
+        u0, u1, mask, status = o.qp2_exact(list(A0), list(A1), list(b), float(r[0]), float(r[1]), R)[:4]
+        xs, ok = _scipy_qp(A0, A1, b, r, R)
+        assert status != o.STATUS_INFEASIBLE
+        if not ok:                       # (SLSQP sometimes stops on its line search at this ftol; it is the checker, not the subject)
+            continue
+        n_ok += 1
+        assert abs(u0 - xs[0]) <= 1e-6 * (1 + abs(xs[0])) and abs(u1 - xs[1]) <= 1e-6 * (1 + abs(xs[1])), (i, u0, u1, xs)
+        act = [k for k in range(len(b)) if (mask >> k) & 1]
+        for k in act:
+            assert abs(A0[k] * u0 + A1[k] * u1 - b[k]) <= 1e-9 * (1 + abs(b[k]))
+        n_pair += len(act) == 2
+        n_single += len(act) == 1
+    assert n_ok > 150 and n_pair > 30 and n_single > 60, (n_ok, n_pair, n_single)
