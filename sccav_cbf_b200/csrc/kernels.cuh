@@ -1064,7 +1064,7 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
         uint32_t mask = 0u;
         int status = SCCAV_STATUS_INACTIVE;
         if (filt)
-            status = filter_vehicle<T, SPEC, MODEL>(P, a.sd, Mv, N, n, a.obst, x, y, yaw, v, syaw, cyw, alpha, R00, R01, R10, R11, a.pv.R == nullptr,
+            status = filter_vehicle<T, SPEC, MODEL, FAST>(P, a.sd, Mv, N, n, a.obst, x, y, yaw, v, syaw, cyw, alpha, R00, R01, R10, R11, a.pv.R == nullptr,
                                              ur0, ur1, rows, stride, u0, u1, u1raw, mask, hmin, a.pre, moving, !fused);
         // ---- plant
         T px = x, py = y, pyaw = yaw, pv_ = v;

@@ -489,7 +489,7 @@ template <typename T> struct RInv {
 
 // Enumeration with the least-violation bookkeeping of oracle.qp2_exact (every candidate checked against
 // every row), minus the pairs that RowNz proves degenerate.
-template <typename T>
+template <typename T, bool VIOL = true>
 __device__ __forceinline__ int qp2_solve_active_full(const RowView<T>& rv, int m, RowNz nz, T r0, T r1, T R00, T R01, T R10, T R11,
                                                   const RInv<T>& Ri, T worst0, T& u0o, T& u1o, uint32_t& masko) {
     typedef Real<T> R;
@@ -499,11 +499,10 @@ __device__ __forceinline__ int qp2_solve_active_full(const RowView<T>& rv, int m
     // singles, in index order.  The rows r violates (rk < 0, the same operations as here) were recorded while the rows
     // were written: each lane walks ITS OWN violated rows, so a warp runs as many iterations as its busiest lane has
     // candidates (one or two) instead of one per distinct row index among its lanes.
-#ifdef SCCAV_NO_VIOL
-    uint32_t todo = (m >= 32 ? 0xffffffffu : ((1u << m) - 1u));
-#else
-    uint32_t todo = nz.viol & (m >= 32 ? 0xffffffffu : ((1u << m) - 1u));
-#endif
+    // (VIOL = false walks every row index: where most lanes of a warp are active at once and violate many rows -- the
+    // seeker crowds of config 3 -- the plain loop, whose row loads run ahead of the candidates, is the faster one:
+    // 119 vs 136 ms)
+    uint32_t todo = (VIOL ? nz.viol : 0xffffffffu) & (m >= 32 ? 0xffffffffu : ((1u << m) - 1u));
     while (todo) {
         const int k = __ffs((int)todo) - 1;
         todo &= todo - 1u;
@@ -606,11 +605,11 @@ template <typename T> struct QpScan {
 
 // The reference point r violates at least one row (worst0 = its largest violation): one thread, one problem.
 // (The persistent rollout uses this form: plain enumeration, no shortcut -- its warps are not converged.)
-template <typename T>
+template <typename T, bool VIOL = true>
 __device__ __forceinline__ int qp2_solve_active(const RowView<T>& rv, int m, RowNz nz, T r0, T r1,
                                                 T R00, T R01, T R10, T R11, const RInv<T>& Ri, T worst0,
                                                 T& u0o, T& u1o, uint32_t& masko) {
-    return qp2_solve_active_full<T>(rv, m, nz, r0, r1, R00, R01, R10, R11, Ri, worst0, u0o, u1o, masko);
+    return qp2_solve_active_full<T, VIOL>(rv, m, nz, r0, r1, R00, R01, R10, R11, Ri, worst0, u0o, u1o, masko);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -896,7 +895,7 @@ __device__ __forceinline__ T filter_convert(const Params<T>& P, T q0, T q1, T r0
 }
 
 // all three phases by one thread (the persistent rollout kernel; K12 compacts phase 2 across the CTA)
-template <typename T, int SPEC, int MODEL = -1>
+template <typename T, int SPEC, int MODEL = -1, bool VIOL = true>
 __device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc& sd, int M, int64_t N, int64_t n,
                                               const T* __restrict__ obst, T x, T y, T th, T v, T sth, T cth,
                                               T alpha, T R00, T R01, T R10, T R11, bool uniform_R, T uref0, T uref1,
@@ -917,7 +916,7 @@ __device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc
         else Ri = RInv<T>(R00, R01, R10, R11);
         // (plain enumeration: the one-scan shortcut of the filter-step kernels was measured here -- the larger loop body
         // costs more in instruction fetch than the scan saves: 14.1 vs 12.9 ms on config 2)
-        status = qp2_solve_active<T>(rv, M, ph.nz, ph.r0, ph.r1, R00, R01, R10, R11, Ri, ph.worst, q0, q1, mask);
+        status = qp2_solve_active<T, VIOL>(rv, M, ph.nz, ph.r0, ph.r1, R00, R01, R10, R11, Ri, ph.worst, q0, q1, mask);
     }
     u0 = q0;
     u1raw = q1;
