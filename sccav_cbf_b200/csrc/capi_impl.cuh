@@ -114,7 +114,11 @@ int do_prepare(const uint8_t* slot_desc, int32_t M, int64_t N, const real* in, r
     PrepareArgs<real> a;
     a.sd = make_desc(slot_desc, M); a.M = M; a.N = N; a.in = in; a.out = out;
     const int block = 256;
-    prepare_obstacles_kernel<real><<<stream_grid((int64_t)M * N, block), block, 0, st>>>(a);
+    const size_t vec = 2 * sizeof(real);
+    if ((N & 1) == 0 && ((uintptr_t)in % vec) == 0 && ((uintptr_t)out % vec) == 0)
+        prepare_obstacles_vec2_kernel<real><<<stream_grid((int64_t)M * (N / 2), block), block, 0, st>>>(a);
+    else
+        prepare_obstacles_kernel<real><<<stream_grid((int64_t)M * N, block), block, 0, st>>>(a);
     count_launch();
     SCCAV_CUDA_CHECK(cudaGetLastError());
     return SCCAV_OK;

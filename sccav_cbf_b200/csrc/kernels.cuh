@@ -64,6 +64,33 @@ template <typename T> struct PrepareArgs {
     T* out;
 };
 
+// Two adjacent vehicles per thread: every field is one 16-byte (fp64) / 8-byte (fp32) load and store -- LDG.E.128 /
+// STG.E.128 on the SoA rows, twice the bytes in flight per thread.  Used when N is even and the buffers are aligned.
+template <typename T>
+__global__ void __launch_bounds__(256) prepare_obstacles_vec2_kernel(const __grid_constant__ PrepareArgs<T> a) {
+    typedef typename Real<T>::T2 T2;
+    const int64_t N = a.N, H = N >> 1;
+    const int64_t total = (int64_t)a.M * H;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int m = (int)(i / H);
+        const int64_t n2 = i - (int64_t)m * H;
+        const T2* f = reinterpret_cast<const T2*>(a.in + (int64_t)m * SCCAV_NFIELD * N) + n2;
+        T2* o = reinterpret_cast<T2*>(a.out + (int64_t)m * SCCAV_NFIELD * N) + n2;
+        T2 v[SCCAV_NFIELD];
+#pragma unroll
+        for (int k = 0; k < SCCAV_NFIELD; ++k) v[k] = f[k * H];
+        if ((a.sd.d[m] & SCCAV_SLOT_TYPE_MASK) == SCCAV_SLOT_ELLIPSE) {
+            T m00, m01, m10, m11, wx, wy;
+            ellipse_prepare<T>(v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, m00, m01, m10, m11, wx, wy);
+            v[2].x = m00; v[3].x = m01; v[4].x = m10; v[5].x = m11; v[6].x = wx; v[7].x = wy;
+            ellipse_prepare<T>(v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, m00, m01, m10, m11, wx, wy);
+            v[2].y = m00; v[3].y = m01; v[4].y = m10; v[5].y = m11; v[6].y = wx; v[7].y = wy;
+        }
+#pragma unroll
+        for (int k = 0; k < SCCAV_NFIELD; ++k) o[k * H] = v[k];
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) prepare_obstacles_kernel(const __grid_constant__ PrepareArgs<T> a) {
     const int64_t N = a.N;

@@ -916,3 +916,26 @@ def test_rollout_does_not_depend_on_what_ran_before():
         for k in a:
             assert np.array_equal(a[k], c[k], equal_nan=True), (flags, k)
         assert (a["target_idx"] >= 0).all() and (a["target_idx"] < len(b.course[0])).all()
+
+
+@pytest.mark.parametrize("N", [4096, 4097, 2, 1])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_prepare_kernel_vector_and_scalar_forms_agree(N, dtype):
+    """KP has a two-vehicles-per-thread form (16-byte loads / stores on the SoA rows) for even N and aligned buffers and a
+    scalar form otherwise (odd N; a view that starts one element in): same bits, mixed slot types, in place too."""
+    from sccav_cbf_b200 import ops
+    rng = np.random.default_rng(N)
+    slots = [o.SLOT_ELLIPSE, o.SLOT_CONE, o.SLOT_ELLIPSE | o.SLOT_STATIC, o.SLOT_RADIAL, o.SLOT_ELLIPSE]
+    s = H.random_states(rng, N + 1)
+    ob = H.random_slots(rng, N + 1, slots, s)
+    sd_np, ob_np = _prepare_np(slots, ob)
+    full = T(ob, dtype)                                       # N + 1 columns: an odd / even pair of the same data
+    sd1, out_all = ops.prepare_obstacles(slots, full)
+    sd2, out_n = ops.prepare_obstacles(slots, full[:, :, :N].contiguous())
+    assert sd1 == sd2 == sd_np
+    assert torch.equal(out_all[:, :, :N], out_n)              # the two forms of the kernel, bit for bit
+    tol = 1e-13 if dtype == torch.float64 else 2e-6
+    assert close(out_n, ob_np[:, :, :N], rtol=tol) < 1.0
+    buf = full[:, :, :N].contiguous()
+    ops.prepare_obstacles(slots, buf, out=buf)
+    assert torch.equal(buf, out_n)
