@@ -6,8 +6,8 @@
 // This header returns THE SAME index -- the lexicographic minimum of (d2_i, i), d2_i computed with
 // the same operations as the full scan -- while evaluating 16 points:
 //
-//   * the course is cut into leaves of 8 consecutive points; leaves are the bottom level of a tree of
-//     fan-out 8 (node j of level k = nodes 8j .. 8j+7 of level k-1); every node carries a CAPSULE: a
+//   * the course is cut into leaves of 8 consecutive points; leaves are the bottom level of a BINARY tree
+//     (node j of level h = leaves [j 2^h, (j + 1) 2^h)); every node carries a CAPSULE: a
 //     chord from (about) its first to its last point and a radius rho >= max_i dist(p_i, chord);
 //   * for every point p_i of a node  |f - p_i| >= dist(f, chord) - rho  (triangle inequality through the
 //     chord point closest to p_i), so a node is skipped only when  dist(f, chord) > sqrt(best) + rho + slack.
@@ -19,11 +19,13 @@
 //     magnitude above their sum (<= 5e-7 of the same quantity) -- and sqrt(best) is rounded up.  Neither a
 //     smaller distance nor an equal one with a smaller index can therefore hide in a skipped node;
 //   * the search scans the two leaves around a hint (the index predicted from the previous ticks), which
-//     makes the bound tight immediately, then CLIMBS: at every level the siblings of the scanned leaves'
-//     ancestor are tested in ONE unrolled batch of 8 independent tests (the same code, the same trip count
-//     and eight-fold instruction-level parallelism for every lane of a warp).  A sibling that cannot be
-//     excluded is opened: its 8 children are tested in another batch, a surviving leaf is scanned.  Any
-//     hint gives the same result, only the cost differs.
+//     makes the bound tight immediately, then tests the CANONICAL COVER of everything else: the leaves left
+//     of the window are the disjoint union of at most one node per level (the set bits of the window's
+//     leaf index), the leaves right of it likewise -- nodes that grow geometrically with their distance
+//     from the window, so a node is never large where it is close.  At most two tests per level, the same
+//     loop for every lane of a warp, about 8 tests per query.  A cover node that cannot be excluded is
+//     OPENED: its two children are tested, the surviving ones opened in turn (depth first, a bit per level
+//     as the stack), a surviving leaf is scanned.  Any hint gives the same result, only the cost differs.
 //
 // In shared memory every leaf is padded by one point so that lanes scanning different leaves hit
 // different banks.  Functions are __host__ __device__: tests/test_course_index.py runs them on the CPU
@@ -37,11 +39,7 @@ namespace sccav {
 
 #define SCCAV_LEAF_SHIFT 3
 #define SCCAV_LEAF (1 << SCCAV_LEAF_SHIFT)
-#define SCCAV_FAN_SHIFT 3
-#define SCCAV_FAN (1 << SCCAV_FAN_SHIFT)
-#define SCCAV_MAX_LEVELS 7          /* 7 levels of fan-out 8 over leaves of 8 points (16 M points): far more than any course */
-#define SCCAV_TOP_MAX SCCAV_FAN     /* the top level holds at most 8 nodes, siblings under a virtual root.  (A flat top of 32 tight
-                                       nodes instead of 4 loose ones + their children was measured: 13.1 vs 12.3 ms) */
+#define SCCAV_MAX_LEVELS 16         /* binary levels over leaves of 8 points: 2^16 leaves = 524,288 points, far more than any course */
 
 // position of course point i in the padded point array (one spare slot after every leaf)
 __host__ __device__ __forceinline__ int course_slot(int i) { return i + (i >> SCCAV_LEAF_SHIFT); }
@@ -50,26 +48,24 @@ __host__ __device__ __forceinline__ int course_nleaf(int np) { return (np + SCCA
 // they can never win the strict first-minimum comparison -- so that every leaf scan is the same 8 unrolled points)
 __host__ __device__ __forceinline__ int course_nslot(int np) { return course_nleaf(np) * (SCCAV_LEAF + 1); }
 
-// Levels of the tree over a course of np points: level 0 = the leaves, level k + 1 has ceil(n_k / 8) nodes; the
-// top level has at most SCCAV_TOP_MAX nodes, all siblings under a root that is never tested (long, curved nodes
-// have loose capsules: a flat top of tight ones is tested in full instead -- the same loads for every lane).  A node is 32 bytes (chord float4,
-// (1/len^2, radius) float2, 8 spare); a group of 8 siblings is followed by 16 spare bytes, so that lanes of a warp
-// reading the same member of DIFFERENT groups hit different banks (the stride between groups is 272 B = 17 x 16 B).
-// lev[2k] = first 16-byte unit of level k in the node storage, lev[2k + 1] = number of nodes of level k.
+// Levels of the tree over a course of np points: level 0 = the leaves, level h has ceil(nleaf / 2^h) nodes, node j of
+// level h = leaves [j 2^h, (j + 1) 2^h) (the last node of a level may be short); the top level is the first with at
+// most two nodes -- the root is never tested, a window is never empty.  A node is 32 bytes: chord float4, then
+// (1 / len^2, radius) float2 and 8 spare bytes.
+// lev[2h] = first 16-byte unit of level h in the node storage, lev[2h + 1] = number of nodes of level h.
 // Returns the number of levels (>= 1); *units (optional) = 16-byte units of node storage.  lev may be NULL.
 #define SCCAV_NODE_UNITS 2          /* 16-byte units per node */
-#define SCCAV_GROUP_UNITS 17        /* 16-byte units per group of 8 nodes (8 x 2 + 1 spare) */
 __host__ __device__ inline int course_levels(int np, int* lev, int* units) {
-    int cnt = course_nleaf(np), o = 0, k = 0;
+    int cnt = course_nleaf(np), o = 0, h = 0;
     for (;;) {
-        if (lev) { lev[2 * k] = o; lev[2 * k + 1] = cnt; }
-        o += ((cnt + SCCAV_FAN - 1) >> SCCAV_FAN_SHIFT) * SCCAV_GROUP_UNITS;
-        ++k;
-        if (cnt <= SCCAV_TOP_MAX || k >= SCCAV_MAX_LEVELS) break;
-        cnt = (cnt + SCCAV_FAN - 1) >> SCCAV_FAN_SHIFT;
+        if (lev) { lev[2 * h] = o; lev[2 * h + 1] = cnt; }
+        o += cnt * SCCAV_NODE_UNITS;
+        ++h;
+        if (cnt <= 2 || h >= SCCAV_MAX_LEVELS) break;
+        cnt = (cnt + 1) >> 1;
     }
     if (units) *units = o;
-    return k;
+    return h;
 }
 __host__ __device__ inline int course_node_units(int np) {
     int u;
@@ -87,17 +83,15 @@ template <typename T, typename T2> struct CourseIndex {
     int np, nleaf, nlev;
     __host__ __device__ __forceinline__ T2 pt(int i) const { return xy[course_slot(i)]; }
     // first unit of node n of the level that starts at unit `base`
-    static __host__ __device__ __forceinline__ int unit(int base, int n) {
-        return base + (n >> SCCAV_FAN_SHIFT) * SCCAV_GROUP_UNITS + (n & (SCCAV_FAN - 1)) * SCCAV_NODE_UNITS;
-    }
+    static __host__ __device__ __forceinline__ int unit(int base, int n) { return base + n * SCCAV_NODE_UNITS; }
 };
 
-// point range [lo, hi) of node j of level k
-__host__ __device__ __forceinline__ void node_range(int np, int k, int j, int& lo, int& hi) {
-    const int sh = SCCAV_FAN_SHIFT * k + SCCAV_LEAF_SHIFT;
-    const int64_t l = (int64_t)j << sh, h = (int64_t)(j + 1) << sh;
+// point range [lo, hi) of node j of level h
+__host__ __device__ __forceinline__ void node_range(int np, int h, int j, int& lo, int& hi) {
+    const int sh = h + SCCAV_LEAF_SHIFT;
+    const int64_t l = (int64_t)j << sh, u = (int64_t)(j + 1) << sh;
     lo = (int)(l < np ? l : np);
-    hi = (int)(h < np ? h : np);
+    hi = (int)(u < np ? u : np);
 }
 
 // fp32 chord of a node from its first and last point (double precision, relative to the origin)
@@ -174,39 +168,17 @@ __host__ __device__ __forceinline__ float sat01(float t) {
 #endif
 }
 
-// One batch: the (up to) 8 nodes of group `group` of level `level`, except ex0 / ex1.  Returns the bit mask of the
-// nodes that can NOT be excluded (a NaN anywhere keeps the node: conservative).
-template <typename T, typename T2>
-__host__ __device__ __forceinline__ uint32_t index_test8(const CourseIndex<T, T2>& ci, int level, int group, int ex0, int ex1,
-                                                         const IndexQuery& q, int& ne) {
-    const int first = group << SCCAV_FAN_SHIFT;
-    const int left = ci.lev[2 * level + 1] - first;                         // nodes of the level from `first` on
-    // which of the 8 members exist and are wanted (one register -> 8 predicates)
-    uint32_t want = left >= SCCAV_FAN ? 0xffu : ((1u << (left > 0 ? left : 0)) - 1u);
-    const uint32_t e0 = (uint32_t)(ex0 - first), e1 = (uint32_t)(ex1 - first);
-    if (e0 < (uint32_t)SCCAV_FAN) want &= ~(1u << e0);
-    if (e1 < (uint32_t)SCCAV_FAN) want &= ~(1u << e1);
-    const float4* __restrict__ g = ci.node + ci.lev[2 * level] + group * SCCAV_GROUP_UNITS;
-    uint32_t mask = 0u;
-#pragma unroll
-    for (int j = 0; j < SCCAV_FAN; ++j) {
-        if (want & (1u << j)) {
-            const float4 c = g[SCCAV_NODE_UNITS * j];
-            const float2 r = *reinterpret_cast<const float2*>(g + SCCAV_NODE_UNITS * j + 1);
-            const float vx = q.qx - c.x, vy = q.qy - c.y;
-            const float t = sat01(fmaf(vx, c.z, vy * c.w) * r.x);
-            const float ex = fmaf(-t, c.z, vx), ey = fmaf(-t, c.w, vy);
-            const float d2 = fmaf(ex, ex, ey * ey);
-            const float thr = q.base + r.y;
-            if (!(d2 > thr * thr)) mask |= 1u << j;
-        }
-    }
-#ifdef __CUDA_ARCH__
-    ne += __popc(want);
-#else
-    ne += __builtin_popcount(want);
-#endif
-    return mask;
+// One capsule test: true = node j of the level whose storage starts at g can NOT be excluded (a NaN anywhere keeps
+// the node: conservative).
+__host__ __device__ __forceinline__ bool index_test(const float4* __restrict__ g, int j, const IndexQuery& q) {
+    const float4 c = g[SCCAV_NODE_UNITS * j];
+    const float2 r = *reinterpret_cast<const float2*>(g + SCCAV_NODE_UNITS * j + 1);
+    const float vx = q.qx - c.x, vy = q.qy - c.y;
+    const float t = sat01(fmaf(vx, c.z, vy * c.w) * r.x);
+    const float ex = fmaf(-t, c.z, vx), ey = fmaf(-t, c.w, vy);
+    const float d2 = fmaf(ex, ex, ey * ey);
+    const float thr = q.base + r.y;
+    return !(d2 > thr * thr);
 }
 
 // Scan one leaf in ascending index order (strict <: first minimum inside the leaf), then merge
@@ -242,6 +214,14 @@ __host__ __device__ inline int course_nearest_full(const T2* xy, int np, T fx, T
     return ib;
 }
 
+__host__ __device__ __forceinline__ int lowest_bit32(uint32_t m) {
+#ifdef __CUDA_ARCH__
+    return __ffs((int)m) - 1;
+#else
+    return __builtin_ctz(m);
+#endif
+}
+
 __host__ __device__ __forceinline__ int lowest_bit64(uint64_t m) {
 #ifdef __CUDA_ARCH__
     return __ffsll((long long)m) - 1;
@@ -250,50 +230,108 @@ __host__ __device__ __forceinline__ int lowest_bit64(uint64_t m) {
 #endif
 }
 
+// The cover of everything outside the window [w, w + 2), in leaf units: at level h (nodes of 2^h leaves)
+//   left of the window   a = ((w + 1) >> h) - 1:  node a - 1 if a > 0, and node a - 2 if a is even as well;
+//   right of the window  b = (w >> h) + 2:        node b if it exists, and node b + 1 if b is even (and it exists).
+// (The boundary of what is covered so far is a multiple of 2^h at level h; one node is taken where that leaves a
+// multiple of 2^(h+1), two otherwise -- never none.  So a node of 2^h leaves lies at least 2^h - 1 leaves from the
+// window: a node is never large where it is close, which is what makes its capsule test succeed -- canonical
+// segment-tree covers put a node of any size right next to the window and were measured to fail 2 - 3 times per query.)
+// slot 0, 1 = left, 2, 3 = right.  Returns the node index, or -1 if the slot is empty at this level.
+__host__ __device__ __forceinline__ int cover_node(int w, int h, int slot, int cnt) {
+    if (slot < 2) {
+        const int a = ((w + 1) >> h) - 1;
+        if (a <= 0) return -1;
+        if (slot == 0) return a - 1;
+        return (a & 1) ? -1 : a - 2;
+    }
+    const int b = (w >> h) + 2;
+    if (slot == 2) return b < cnt ? b : -1;
+    return (!(b & 1) && b + 1 < cnt) ? b + 1 : -1;
+}
+
 // Exact global nearest index (first minimum) of (fx, fy) over the whole course.
 // hint: any index (the predicted nearest index; clamped into [0, np)); evals (optional) counts
 // distance evaluations + capsule tests for the roofline accounting.
 //
-// ONE work loop: `pending` holds, per level, the nodes still to be processed in the group of the current position's
-// ancestor (8 bits a level): a level-0 entry is a leaf to scan, an entry of level k >= 1 a node to OPEN (its 8 children
-// are tested in one batch; those that cannot be excluded become entries one level down).  It starts with the two leaves
-// around the hint and their ancestors up to the virtual root -- opening an ancestor tests the siblings of the level below,
-// which is the climb -- and always takes the lowest level first, i.e. the nearest work.  Every lane of a warp runs the
-// same two pieces of code (one batch of tests, one leaf scan) whatever level or node it is working on.
+// 1. WINDOW: the two leaves [w, w + 2) around the hint are scanned (16 exact distances): the incumbent.
+// 2. COVER (cover_node): one or two nodes per level on either side of the window, growing geometrically with their
+//    distance from it.  Every lane of a warp runs the same loop over the levels with four independent tests in each;
+//    about 18 of them are live per query and (measured on config 2's queries) 0.04 - 0.2 per query fail.
+// 3. A cover node that cannot be excluded is OPENED, nearest (lowest level) first: both children are tested; a
+//    surviving child is opened in turn (the left one first, one bit per level remembers a surviving right one), a
+//    surviving leaf is scanned, which tightens the bound for everything after it.
 template <typename T, typename T2>
 __host__ __device__ inline int course_nearest(const CourseIndex<T, T2>& ci, T fx, T fy, int hint, int* evals) {
     if (hint < 0) hint = 0;
     if (hint >= ci.np) hint = ci.np - 1;
-    // the two leaves around the hint, inside the hint's group of 8 leaves
-    const int leaf0 = hint >> SCCAV_LEAF_SHIFT;
-    int lo = ((hint & (SCCAV_LEAF - 1)) >= SCCAV_LEAF / 2) ? leaf0 : leaf0 - 1;
-    if ((lo & (SCCAV_FAN - 1)) == SCCAV_FAN - 1) lo = (lo == leaf0) ? lo - 1 : lo + 1;
-    if (lo > ci.nleaf - 2) lo = ci.nleaf - 2;
-    if (lo < 0) lo = 0;
-    int hi = (lo + 1 < ci.nleaf) ? lo + 1 : lo;
-    if ((hi >> SCCAV_FAN_SHIFT) != (lo >> SCCAV_FAN_SHIFT)) hi = lo;        // (a last group of one leaf)
+    const int L = ci.nleaf;
+    int w = ((hint + SCCAV_LEAF / 2) >> SCCAV_LEAF_SHIFT) - 1;
+    if (w > L - 2) w = L - 2;
+    if (w < 0) w = 0;
     T best = (T)INFINITY;
     int ib = ci.np;
-    int ne = 0;
+    int ne = 2 * SCCAV_LEAF;
     IndexQuery q = index_query<T, T2>(ci, fx, fy);
-    uint64_t pending = (1ull << (lo & (SCCAV_FAN - 1))) | (1ull << (hi & (SCCAV_FAN - 1)));
-    for (int k = 1; k <= ci.nlev; ++k) pending |= 1ull << (8 * k + ((lo >> (SCCAV_FAN_SHIFT * k)) & (SCCAV_FAN - 1)));
-    int cur = lo;
-    while (pending) {
-        const int bit = lowest_bit64(pending);
-        pending &= pending - 1u;
-        const int m = bit >> 3;
-        const int node = ((cur >> (SCCAV_FAN_SHIFT * (m + 1))) << SCCAV_FAN_SHIFT) + (bit & 7);
-        cur = node << (SCCAV_FAN_SHIFT * m);
-        if (m == 0) {
+    index_scan_leaf<T, T2>(ci, w, fx, fy, best, ib);
+    if (L > 1) index_scan_leaf<T, T2>(ci, w + 1, fx, fy, best, ib);
+    q.base = (index_reach32<T>(best) + q.slack) * 1.000002f;
+    // ---- cover
+    uint64_t fail = 0ull;                   // bit 4h + slot: that cover node survives
+    for (int h = 0; h < ci.nlev - 1; ++h) {        // (the top level -- at most two nodes -- is never part of a cover)
+        const float4* __restrict__ g = ci.node + ci.lev[2 * h];
+        const int cnt = ci.lev[2 * h + 1];
+        const int a = ((w + 1) >> h) - 1, b = (w >> h) + 2;
+        const bool l0 = a > 0, l1 = l0 && !(a & 1), r0 = b < cnt, r1 = !(b & 1) && b + 1 < cnt;
+        uint32_t f = 0u;
+        if (l0 && index_test(g, a - 1, q)) f |= 1u;
+        if (l1 && index_test(g, a - 2, q)) f |= 2u;
+        if (r0 && index_test(g, b, q)) f |= 4u;
+        if (r1 && index_test(g, b + 1, q)) f |= 8u;
+        ne += (int)l0 + (int)l1 + (int)r0 + (int)r1;
+        fail |= (uint64_t)f << (4 * h);
+    }
+    // ---- survivors
+    while (fail) {
+        const int bit = lowest_bit64(fail);
+        fail &= fail - 1ull;
+        int h = bit >> 2;
+        int j = cover_node(w, h, bit & 3, ci.lev[2 * h + 1]);
+        if (h == 0) {
             const T before = best;
-            index_scan_leaf<T, T2>(ci, node, fx, fy, best, ib);
+            index_scan_leaf<T, T2>(ci, j, fx, fy, best, ib);
             ne += SCCAV_LEAF;
             if (best < before) q.base = (index_reach32<T>(best) + q.slack) * 1.000002f;
-        } else {
-            // children of `node`, except the scanned leaves / their ancestor (which has its own entry)
-            const int sh = SCCAV_FAN_SHIFT * (m - 1);
-            pending |= (uint64_t)index_test8<T, T2>(ci, m - 1, node, lo >> sh, hi >> sh, q, ne) << (8 * (m - 1));
+            continue;
+        }
+        uint32_t pend = 0u;                 // bit k: the right child at level k of the path's ancestor at level k + 1 survives
+        for (;;) {
+            // open node (h, j), h >= 1
+            const int hc = h - 1, c = 2 * j;
+            const float4* __restrict__ g = ci.node + ci.lev[2 * hc];
+            const bool has1 = c + 1 < ci.lev[2 * hc + 1];
+            bool f0 = index_test(g, c, q);
+            bool f1 = has1 && index_test(g, c + 1, q);
+            ne += 1 + (int)has1;
+            if (hc == 0) {
+                const T before = best;
+                if (f0) { index_scan_leaf<T, T2>(ci, c, fx, fy, best, ib); ne += SCCAV_LEAF; }
+                if (f1) { index_scan_leaf<T, T2>(ci, c + 1, fx, fy, best, ib); ne += SCCAV_LEAF; }
+                if (best < before) q.base = (index_reach32<T>(best) + q.slack) * 1.000002f;
+                f0 = f1 = false;
+            }
+            if (f0) {
+                if (f1) pend |= 1u << hc;
+                h = hc; j = c;
+            } else if (f1) {
+                h = hc; j = c + 1;
+            } else {
+                if (!pend) break;
+                const int k = lowest_bit32(pend);
+                pend &= pend - 1u;
+                j = ((c >> (k - hc)) | 1);  // the path's ancestor at level k was a left child: its right sibling
+                h = k;
+            }
         }
     }
     // NaN / overflowing query (np.argmin of all-NaN is 0): nothing could be compared, do what the reference does

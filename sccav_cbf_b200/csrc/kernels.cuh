@@ -876,7 +876,7 @@ __device__ __forceinline__ void seeker_update(T* f, int64_t fs, T ex, T ey, T dt
 #define SCCAV_ROLLOUT_MAXB 448
 
 // Shared-memory layout of the rollout kernel (bytes), shared by the launcher and the kernel:
-//   [ course xy : T2 x nslot (leaf-padded) ][ tree nodes : 16 B x units ][ header : level table int x 16, origin T x 2, extent float ]
+//   [ course xy : T2 x nslot (leaf-padded) ][ tree nodes : 16 B x units ][ header : level table int x 32, origin T x 2, extent float ]
 //   [ cyaw : T x np_pad ][ rows : T x 3 M block ]
 template <typename T> struct RolloutSmem {
     int nslot, units, np_pad;
@@ -888,7 +888,7 @@ template <typename T> struct RolloutSmem {
         size_t o = (size_t)nslot * 2 * sizeof(T);
         o = (o + 15) & ~(size_t)15;
         off_node = o; o += (size_t)units * 16;
-        off_hdr = o; o += course_smem ? 96 : 0;        // 16 ints | 2 T (at +64) | float (at +80)
+        off_hdr = o; o += course_smem ? 160 : 0;       // 2 x SCCAV_MAX_LEVELS ints | 2 T (at +128) | float (at +144)
         off_cyaw = o; o += (size_t)np_pad * sizeof(T);
         off_rows = o;
         course_bytes = o;
@@ -906,8 +906,8 @@ __device__ __forceinline__ CourseIndex<T, T2> course_stage(unsigned char* smem, 
     typedef Real<T> R;
     T2* s_cxy = reinterpret_cast<T2*>(smem);
     int* s_lev = reinterpret_cast<int*>(smem + lay.off_hdr);
-    T* s_org = reinterpret_cast<T*>(smem + lay.off_hdr + 64);
-    float* s_ext = reinterpret_cast<float*>(smem + lay.off_hdr + 80);
+    T* s_org = reinterpret_cast<T*>(smem + lay.off_hdr + 128);
+    float* s_ext = reinterpret_cast<float*>(smem + lay.off_hdr + 144);
     CourseIndex<T, T2> ci;
     ci.xy = s_cxy;
     ci.node = reinterpret_cast<float4*>(smem + lay.off_node);
@@ -958,10 +958,10 @@ __device__ __forceinline__ CourseIndex<T, T2> course_stage(unsigned char* smem, 
                 ci.node[u + 1] = make_float4(r.x, r.y, 0.f, 0.f);
             }
         }
-        base += ((cnt + SCCAV_FAN - 1) >> SCCAV_FAN_SHIFT) * SCCAV_GROUP_UNITS;
+        base += cnt * SCCAV_NODE_UNITS;
         ++k;
-        if (cnt <= SCCAV_TOP_MAX || k >= SCCAV_MAX_LEVELS) break;
-        cnt = (cnt + SCCAV_FAN - 1) >> SCCAV_FAN_SHIFT;
+        if (cnt <= 2 || k >= SCCAV_MAX_LEVELS) break;
+        cnt = (cnt + 1) >> 1;
     }
     ci.nlev = k;
     __syncthreads();
