@@ -227,7 +227,7 @@ static void debug_course_index(const double* cx, const double* cy, int P, const 
     std::vector<float4> nodes(units);
     CourseIndex<T, T2> ci;
     ci.xy = xy.data();
-    ci.node = nodes.data(); ci.lev = lev; ci.org = org; ci.ext = &ext;
+    ci.node = nodes.data(); ci.lev = lev; ci.org = org; ci.ext = &ext; ci.ncover = nullptr;
     ci.np = P; ci.nleaf = course_nleaf(P); ci.nlev = nlev;
     for (int k = 0; k < nlev; ++k)
         for (int j = 0; j < lev[2 * k + 1]; ++j) {

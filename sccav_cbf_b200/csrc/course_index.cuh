@@ -80,6 +80,7 @@ template <typename T, typename T2> struct CourseIndex {
     const int* lev;    // [2 nlev] first unit and node count of every level
     const T* org;      // origin (x, y) of the fp32 frame: a point of the course
     const float* ext;  // [1] inflated max-norm extent of the course around the origin
+    const uint8_t* ncover;  // [nleaf] cover_count per window leaf, or NULL (computed on the fly)
     int np, nleaf, nlev;
     __host__ __device__ __forceinline__ T2 pt(int i) const { return xy[course_slot(i)]; }
     // first unit of node n of the level that starts at unit `base`
@@ -250,6 +251,15 @@ __host__ __device__ __forceinline__ int cover_node(int w, int h, int slot, int c
     return (!(b & 1) && b + 1 < cnt) ? b + 1 : -1;
 }
 
+// number of cover nodes of the window at leaf w (what the search tests before anything fails): a function of w alone,
+// tabulated per course where the search runs in a kernel (CourseIndex::ncover)
+__host__ __device__ inline int cover_count(int w, int nlev, const int* lev) {
+    int c = 0;
+    for (int h = 0; h < nlev - 1; ++h)
+        for (int s = 0; s < 4; ++s) c += cover_node(w, h, s, lev[2 * h + 1]) >= 0;
+    return c;
+}
+
 // Exact global nearest index (first minimum) of (fx, fy) over the whole course.
 // hint: any index (the predicted nearest index; clamped into [0, np)); evals (optional) counts
 // distance evaluations + capsule tests for the roofline accounting.
@@ -276,21 +286,20 @@ __host__ __device__ inline int course_nearest(const CourseIndex<T, T2>& ci, T fx
     index_scan_leaf<T, T2>(ci, w, fx, fy, best, ib);
     if (L > 1) index_scan_leaf<T, T2>(ci, w + 1, fx, fy, best, ib);
     q.base = (index_reach32<T>(best) + q.slack) * 1.000002f;
-    // ---- cover
+    // ---- cover: four tests per level, evaluated unconditionally (an empty slot tests node 0 and drops the answer:
+    // the warp would run the slot for its other lanes anyway, and straight-line code lets the four interleave)
     uint64_t fail = 0ull;                   // bit 4h + slot: that cover node survives
     for (int h = 0; h < ci.nlev - 1; ++h) {        // (the top level -- at most two nodes -- is never part of a cover)
         const float4* __restrict__ g = ci.node + ci.lev[2 * h];
         const int cnt = ci.lev[2 * h + 1];
         const int a = ((w + 1) >> h) - 1, b = (w >> h) + 2;
         const bool l0 = a > 0, l1 = l0 && !(a & 1), r0 = b < cnt, r1 = !(b & 1) && b + 1 < cnt;
-        uint32_t f = 0u;
-        if (l0 && index_test(g, a - 1, q)) f |= 1u;
-        if (l1 && index_test(g, a - 2, q)) f |= 2u;
-        if (r0 && index_test(g, b, q)) f |= 4u;
-        if (r1 && index_test(g, b + 1, q)) f |= 8u;
-        ne += (int)l0 + (int)l1 + (int)r0 + (int)r1;
+        const bool f0 = index_test(g, l0 ? a - 1 : 0, q), f1 = index_test(g, l1 ? a - 2 : 0, q);
+        const bool f2 = index_test(g, r0 ? b : 0, q), f3 = index_test(g, r1 ? b + 1 : 0, q);
+        const uint32_t f = (l0 && f0 ? 1u : 0u) | (l1 && f1 ? 2u : 0u) | (r0 && f2 ? 4u : 0u) | (r1 && f3 ? 8u : 0u);
         fail |= (uint64_t)f << (4 * h);
     }
+    ne += ci.ncover ? (int)ci.ncover[w] : cover_count(w, ci.nlev, ci.lev);
     // ---- survivors
     while (fail) {
         const int bit = lowest_bit64(fail);

@@ -877,10 +877,10 @@ __device__ __forceinline__ void seeker_update(T* f, int64_t fs, T ex, T ey, T dt
 
 // Shared-memory layout of the rollout kernel (bytes), shared by the launcher and the kernel:
 //   [ course xy : T2 x nslot (leaf-padded) ][ tree nodes : 16 B x units ][ header : level table int x 32, origin T x 2, extent float ]
-//   [ cyaw : T x np_pad ][ rows : T x 3 M block ]
+//   [ cover counts : 1 B x nleaf, padded to 16 ][ cyaw : T x np_pad ][ rows : T x 3 M block ]
 template <typename T> struct RolloutSmem {
     int nslot, units, np_pad;
-    size_t off_node, off_hdr, off_cyaw, off_rows, course_bytes;
+    size_t off_node, off_hdr, off_ncov, off_cyaw, off_rows, course_bytes;
     __host__ __device__ RolloutSmem(int np, bool course_smem) {
         nslot = course_smem ? course_nslot(np) : 0;
         units = course_smem ? course_node_units(np) : 0;
@@ -889,6 +889,7 @@ template <typename T> struct RolloutSmem {
         o = (o + 15) & ~(size_t)15;
         off_node = o; o += (size_t)units * 16;
         off_hdr = o; o += course_smem ? 160 : 0;       // 2 x SCCAV_MAX_LEVELS ints | 2 T (at +128) | float (at +144)
+        off_ncov = o; o += course_smem ? (((size_t)course_nleaf(np) + 15) & ~(size_t)15) : 0;
         off_cyaw = o; o += (size_t)np_pad * sizeof(T);
         off_rows = o;
         course_bytes = o;
@@ -965,6 +966,10 @@ __device__ __forceinline__ CourseIndex<T, T2> course_stage(unsigned char* smem, 
     }
     ci.nlev = k;
     __syncthreads();
+    uint8_t* s_ncov = reinterpret_cast<uint8_t*>(smem + lay.off_ncov);
+    for (int w = threadIdx.x; w < ci.nleaf; w += blockDim.x) s_ncov[w] = (uint8_t)cover_count(w, k, s_lev);
+    ci.ncover = s_ncov;
+    __syncthreads();
     return ci;
 }
 
@@ -996,7 +1001,7 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
     const int model = FAST ? SCCAV_MODEL_DBM : a.P.model;
     constexpr int MODEL = FAST ? SCCAV_MODEL_DBM : -1;
     CourseIndex<T, T2> ci;
-    ci.xy = s_cxy; ci.node = nullptr; ci.lev = nullptr; ci.org = nullptr; ci.ext = nullptr;
+    ci.xy = s_cxy; ci.node = nullptr; ci.lev = nullptr; ci.org = nullptr; ci.ext = nullptr; ci.ncover = nullptr;
     ci.np = np; ci.nleaf = 0; ci.nlev = 0;
     // stage the course once per CTA (leaf-padded) and build the capsules of its tree
     if (COURSE_SMEM && stan)
