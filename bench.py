@@ -671,6 +671,30 @@ def main():
             "fp64_pipe_active_pct_ncu": ncu_st.get("fp64_pipe_active_pct"), "issue_active_pct_ncu": ncu_st.get("issue_active_pct"),
             "active_frac": float((st_p == 1).double().mean().item()), "infeasible_frac": float((st_p == 2).double().mean().item()),
         }
+        # the same prepared solve with beta in / beta out (SCCAV_FLAG_BETA_IO): callers that integrate their plant in beta
+        # (State.update_com) skip the delta <-> beta conversions of cbf.py:175,216 -- two tan + two atan2 per solve
+        from sccav_cbf_b200 import _native as _nv
+        prm_b = ops.make_params(flags=_nv.FLAG_BETA_IO)
+        ur_b = ur.clone()
+        ur_b[1] = torch.atan2(prm.lr * torch.tan(ur[1]), torch.full_like(ur[1], prm.lf + prm.lr))
+        for _ in range(3):
+            u_b, _, st_b, _ = ops.filter_step(prm_b, sdp, st, obp, ur_b)
+        bevs = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); ops.filter_step(prm_b, sdp, st, obp, ur_b); e1.record()
+            bevs.append((e0, e1))
+        torch.cuda.synchronize()
+        bms = statistics.mean(e0.elapsed_time(e1) for e0, e1 in bevs)
+        beta_of_u = torch.atan2(prm.lr * torch.tan(u_p[1]), torch.full_like(u_p[1], prm.lf + prm.lr))
+        roofline_op["prepared_beta_io"] = {
+            "kernel": roofline_op["prepared"]["kernel"] + ", SCCAV_FLAG_BETA_IO", "algorithmic_bytes_per_solve": pbps,
+            "achieved": pbps * n_op * M / (bms * 1e-3) / 1e9, "frac": pbps * n_op * M / (bms * 1e-3) / 1e9 / hbm_peak,
+            "solves_per_s": n_op * M / (bms * 1e-3), "ms": bms,
+            "statuses_equal_delta_io": bool(torch.equal(st_b, st_p)),
+            "max_abs_beta_diff_vs_delta_io": float((u_b[1] - beta_of_u).abs().max().item()),
+        }
+        del ur_b, u_b, st_b, beta_of_u
         # the same batch with the colliding pairs removed: an obstacle whose ellipse already contains its vehicle
         # (h < 0.05 -- a crash, not a tick the filter is meant for) is moved 1 km away.  The random batch above
         # keeps them (5.7 % of its problems have contradictory rows), which makes it QP-heavy on purpose.
@@ -766,6 +790,8 @@ def main():
         flat["operator_canonical_hbm_frac"] = roofline_op["frac"]
         flat["operator_prepared_hbm_frac"] = roofline_op["prepared"]["frac"]
         flat["operator_prepared_ms"] = roofline_op["prepared"]["ms"]
+        flat["operator_prepared_beta_io_hbm_frac"] = roofline_op["prepared_beta_io"]["frac"]
+        flat["operator_prepared_beta_io_ms"] = roofline_op["prepared_beta_io"]["ms"]
         if "frac" in roofline_op.get("class_api", {}):
             flat["class_api_hbm_frac"] = roofline_op["class_api"]["frac"]
             flat["class_api_ms"] = roofline_op["class_api"]["ms"]

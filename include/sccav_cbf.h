@@ -108,6 +108,12 @@ extern "C" {
  * steering clips, a few ulp apart otherwise (two tan + two atan2 per step are not evaluated); |beta*| >= 1.5 takes the
  * literal sequence.  delta is still produced for the steps that are recorded.  The reference order stays the default. */
 #define SCCAV_FLAG_FUSED_STEER 4
+/* filter entry points (sccav_filter_step_*), model DBM: the steering component of u_ref and of u is the slip angle
+ * beta -- the QP's own coordinate -- instead of the steering angle delta: neither beta_ref = atan2(lr tan delta_ref, L)
+ * (cbf.py:175) nor delta = atan2(L tan beta*, lr) (cbf.py:216) is evaluated.  For callers that already hold beta (a plant
+ * integrated in beta, like State.update_com, sce.py:122-131): the same QP on the same rows, two tan + two atan2 per
+ * solve cheaper.  Rejected (SCCAV_EINVAL) by every other model and by the rollout / drive-tick entry points.          */
+#define SCCAV_FLAG_BETA_IO 8
 
 #define SCCAV_STATUS_INACTIVE 0    /* u == u_ref                                               */
 #define SCCAV_STATUS_ACTIVE 1      /* KKT optimum with 1 or 2 active rows                      */

@@ -23,6 +23,7 @@ SLOT_SHARED = 0x80
 FLAG_PREPARED_ROWS = 1
 FLAG_QP_ENUMERATE = 2
 FLAG_FUSED_STEER = 4
+FLAG_BETA_IO = 8
 BOX_FIELDS = 6
 INGEST_UPDATE, INGEST_REBUILD = 0, 1
 ACT_RESET_BRAKE = 1

@@ -225,19 +225,26 @@ static void debug_course_index(const double* cx, const double* cy, int P, const 
     int lev[2 * SCCAV_MAX_LEVELS], units;
     const int nlev = course_levels(P, lev, &units);
     std::vector<float4> nodes(units);
+    std::vector<float2> irs(units);
     CourseIndex<T, T2> ci;
     ci.xy = xy.data();
-    ci.node = nodes.data(); ci.lev = lev; ci.org = org; ci.ext = &ext; ci.ncover = nullptr;
+    ci.chord = nodes.data(); ci.ir = irs.data(); ci.lev = lev; ci.org = org; ci.ext = &ext;
     ci.np = P; ci.nleaf = course_nleaf(P); ci.nlev = nlev;
     for (int k = 0; k < nlev; ++k)
         for (int j = 0; j < lev[2 * k + 1]; ++j) {
             float4 c;
             float2 r;
             capsule_build<T, T2>(xy.data(), P, k, j, (double)org[0], (double)org[1], ext, c, r);
-            const int u = CourseIndex<T, T2>::unit(lev[2 * k], j);
-            nodes[u] = c;
-            nodes[u + 1] = make_float4(r.x, r.y, 0.f, 0.f);
+            nodes[lev[2 * k] + j] = c;
+            irs[lev[2 * k] + j] = r;
         }
+    // the cover table and the dummy node, as course_stage builds them
+    const int kc = cover_kc(nlev), dummy = units - 1;
+    std::vector<uint16_t> cov((size_t)ci.nleaf * kc);
+    std::vector<uint8_t> ncov(ci.nleaf);
+    dummy_node(nodes.data(), irs.data(), dummy);
+    for (int w = 0; w < ci.nleaf; ++w) ncov[w] = (uint8_t)cover_row(w, nlev, lev, kc, dummy, cov.data() + (size_t)w * kc);
+    ci.ncover = ncov.data(); ci.cov = cov.data(); ci.kc = kc; ci.dummy = dummy;
     for (int64_t k = 0; k < nq; ++k) {
         int ne = 0;
         idx[k] = course_nearest<T, T2>(ci, (T)fx[k], (T)fy[k], hint ? hint[k] : 0, &ne);

@@ -36,6 +36,10 @@ int check_common(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int
         if (t > SCCAV_SLOT_LANE_SQRT) { set_error("slot %d: unknown type %d", m, t); return SCCAV_EINVAL; }
     }
     if (p->model < 0 || p->model > SCCAV_MODEL_SADBM) { set_error("unknown model %d", p->model); return SCCAV_EINVAL; }
+    if ((p->flags & SCCAV_FLAG_BETA_IO) && p->model != SCCAV_MODEL_DBM) {
+        set_error("SCCAV_FLAG_BETA_IO: model DBM only (got model %d)", p->model);
+        return SCCAV_EINVAL;
+    }
     double det = p->R[0] * p->R[3] - p->R[1] * p->R[2];
     if (!(p->R[0] > 0.0) || !(det > 0.0)) {
         // set_qp_cost_weight (cbf.py:154-157) expects a symmetric positive definite 2x2
@@ -375,6 +379,7 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
     if (p->record_stride < 0) { set_error("record_stride < 0"); return SCCAV_EINVAL; }
     if (p->model == SCCAV_MODEL_DUM) { set_error("model DUM has no closed loop (the reference has no unicycle plant on this path)"); return SCCAV_EINVAL; }
     if (p->model == SCCAV_MODEL_SADBM) { set_error("model SADBM has no closed loop here (filter entry points only)"); return SCCAV_EINVAL; }
+    if (p->flags & SCCAV_FLAG_BETA_IO) { set_error("SCCAV_FLAG_BETA_IO: filter entry points only (the rollout's nominal controller produces delta)"); return SCCAV_EINVAL; }
     if (N == 0) return SCCAV_OK;
     if (!state || !out || !out->state) { set_error("state / out->state is NULL"); return SCCAV_EINVAL; }
     if (M > 0 && !obst) { set_error("obst is NULL"); return SCCAV_EINVAL; }
@@ -414,7 +419,10 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
         any_ellipse = false;
     }
     const int spec = filt ? choose_spec(desc2, M) : SCCAV_SPEC_GENERIC;
-    const bool fast = p->model == SCCAV_MODEL_DBM && stan && !p->seeker;
+    // (the compile-time ELLIPSE instances read the weights and the target speed from the launch parameters: per-vehicle ones
+    // take the general instances)
+    const bool uniform_w = !pv || (!pv->alpha && !pv->R && !pv->target_speed);
+    const bool fast = p->model == SCCAV_MODEL_DBM && stan && !p->seeker && (spec == SCCAV_SPEC_GENERIC || uniform_w);
     rc = rollout_launch_shape(M, N, a.np, stan, spec, grid, block, smem, course_smem);
     if (rc) { if (prep) cudaFreeAsync(prep, st); return rc; }
     // scratch for the loop-invariant terms of canonical ellipses: stream-ordered, lives for this launch
@@ -768,6 +776,7 @@ int SCCAV_FN(sccav_drive_ticks_)(const sccav_params* p, const sccav_drive_params
     if (rc) return rc;
     if (!dp) { set_error("drive params is NULL"); return SCCAV_EINVAL; }
     if (p->model != SCCAV_MODEL_DBM) { set_error("the driver tick uses DBM_CBF_2DS (model DBM)"); return SCCAV_EINVAL; }
+    if (p->flags & SCCAV_FLAG_BETA_IO) { set_error("SCCAV_FLAG_BETA_IO: filter entry points only"); return SCCAV_EINVAL; }
     if (T < 0 || K < 0 || n_fixed < 0 || n_fixed > M) { set_error("T < 0, K < 0 or n_fixed outside [0, M]"); return SCCAV_EINVAL; }
     if (P < 1 || !traj_x || !traj_y || !traj_yaw || !traj_v) { set_error("a trajectory (x, y, yaw, v)[P >= 1] is required"); return SCCAV_EINVAL; }
     if (N == 0 || T == 0) return SCCAV_OK;

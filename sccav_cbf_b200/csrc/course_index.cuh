@@ -50,23 +50,26 @@ __host__ __device__ __forceinline__ int course_nslot(int np) { return course_nle
 
 // Levels of the tree over a course of np points: level 0 = the leaves, level h has ceil(nleaf / 2^h) nodes, node j of
 // level h = leaves [j 2^h, (j + 1) 2^h) (the last node of a level may be short); the top level is the first with at
-// most two nodes -- the root is never tested, a window is never empty.  A node is 32 bytes: chord float4, then
-// (1 / len^2, radius) float2 and 8 spare bytes.
-// lev[2h] = first 16-byte unit of level h in the node storage, lev[2h + 1] = number of nodes of level h.
-// Returns the number of levels (>= 1); *units (optional) = 16-byte units of node storage.  lev may be NULL.
-#define SCCAV_NODE_UNITS 2          /* 16-byte units per node */
+// most two nodes -- the root is never tested, a window is never empty.  A node is 24 bytes in two arrays: its chord
+// (float4) and (1 / len^2, radius) (float2).
+// lev[2h] = id of the first node of level h (ids run through the levels), lev[2h + 1] = number of nodes of level h.
+// Returns the number of levels (>= 1); *units (optional) = number of node ids, the dummy node included.  lev may be NULL.
 __host__ __device__ inline int course_levels(int np, int* lev, int* units) {
     int cnt = course_nleaf(np), o = 0, h = 0;
     for (;;) {
         if (lev) { lev[2 * h] = o; lev[2 * h + 1] = cnt; }
-        o += cnt * SCCAV_NODE_UNITS;
+        o += cnt;
         ++h;
         if (cnt <= 2 || h >= SCCAV_MAX_LEVELS) break;
         cnt = (cnt + 1) >> 1;
     }
-    if (units) *units = o;
+    if (units) *units = o + 1;                     // + the dummy node (cover_row)
     return h;
 }
+// row length of the cover table: a window has at most three cover nodes per level and four at one (cover_node), and the top
+// level is never part of a cover; rounded up to the 8 entries one 16-byte load brings
+__host__ __device__ __forceinline__ int cover_kc(int nlev) { return ((3 * (nlev - 1) + 1) + 7) & ~7; }
+
 __host__ __device__ inline int course_node_units(int np) {
     int u;
     course_levels(np, nullptr, &u);
@@ -76,15 +79,17 @@ __host__ __device__ inline int course_node_units(int np) {
 // View of a staged course: padded points + the fp32 capsules of the tree nodes
 template <typename T, typename T2> struct CourseIndex {
     const T2* xy;      // [course_nslot(np)] padded points, point i at course_slot(i)
-    float4* node;      // node storage (16-byte units): chord (start x, y, vector z, w) at +0, (1 / |chord|^2 or 0, radius) at +1
+    float4* chord;     // [node id] chord (start x, y, vector z, w)
+    float2* ir;        // [node id] (1 / |chord|^2 or 0, radius)
     const int* lev;    // [2 nlev] first unit and node count of every level
     const T* org;      // origin (x, y) of the fp32 frame: a point of the course
     const float* ext;  // [1] inflated max-norm extent of the course around the origin
-    const uint8_t* ncover;  // [nleaf] cover_count per window leaf, or NULL (computed on the fly)
+    const uint8_t* ncover;  // [nleaf] cover_count per window leaf
+    const uint16_t* cov;    // [nleaf][kc] the cover of every window leaf: node ids, nearest first,
+                            // padded with the id of the DUMMY node (a capsule at infinity: its test never fails)
+    int kc, dummy;          // row length of cov (a multiple of 8), id of the dummy node
     int np, nleaf, nlev;
     __host__ __device__ __forceinline__ T2 pt(int i) const { return xy[course_slot(i)]; }
-    // first unit of node n of the level that starts at unit `base`
-    static __host__ __device__ __forceinline__ int unit(int base, int n) { return base + n * SCCAV_NODE_UNITS; }
 };
 
 // point range [lo, hi) of node j of level h
@@ -169,11 +174,10 @@ __host__ __device__ __forceinline__ float sat01(float t) {
 #endif
 }
 
-// One capsule test: true = node j of the level whose storage starts at g can NOT be excluded (a NaN anywhere keeps
-// the node: conservative).
-__host__ __device__ __forceinline__ bool index_test(const float4* __restrict__ g, int j, const IndexQuery& q) {
-    const float4 c = g[SCCAV_NODE_UNITS * j];
-    const float2 r = *reinterpret_cast<const float2*>(g + SCCAV_NODE_UNITS * j + 1);
+// One capsule test: true = node `id` can NOT be excluded (a NaN anywhere keeps the node: conservative).
+__host__ __device__ __forceinline__ bool index_test(const float4* __restrict__ chord, const float2* __restrict__ ir, int id, const IndexQuery& q) {
+    const float4 c = chord[id];
+    const float2 r = ir[id];
     const float vx = q.qx - c.x, vy = q.qy - c.y;
     const float t = sat01(fmaf(vx, c.z, vy * c.w) * r.x);
     const float ex = fmaf(-t, c.z, vx), ey = fmaf(-t, c.w, vy);
@@ -251,13 +255,28 @@ __host__ __device__ __forceinline__ int cover_node(int w, int h, int slot, int c
     return (!(b & 1) && b + 1 < cnt) ? b + 1 : -1;
 }
 
-// number of cover nodes of the window at leaf w (what the search tests before anything fails): a function of w alone,
-// tabulated per course where the search runs in a kernel (CourseIndex::ncover)
-__host__ __device__ inline int cover_count(int w, int nlev, const int* lev) {
+// The cover of window leaf w as a row of node ids, nearest (lowest level) first, padded with the dummy id;
+// returns the number of cover nodes.  Built once per course (course_stage in kernels.cuh, the host test hook).
+__host__ __device__ inline int cover_row(int w, int nlev, const int* lev, int kc, int dummy, uint16_t* row) {
     int c = 0;
     for (int h = 0; h < nlev - 1; ++h)
-        for (int s = 0; s < 4; ++s) c += cover_node(w, h, s, lev[2 * h + 1]) >= 0;
+        for (int s = 0; s < 4; ++s) {
+            const int j = cover_node(w, h, s, lev[2 * h + 1]);
+            if (j >= 0 && c < kc) row[c++] = (uint16_t)(lev[2 * h] + j);
+        }
+    for (int k = c; k < kc; ++k) row[k] = (uint16_t)dummy;
     return c;
+}
+// the dummy node: a capsule so far away that d2 overflows to +inf, which no finite threshold reaches
+__host__ __device__ __forceinline__ void dummy_node(float4* chord, float2* ir, int dummy) {
+    chord[dummy] = make_float4(3.0e38f, 3.0e38f, 0.f, 0.f);
+    ir[dummy] = make_float2(0.f, 0.f);
+}
+// (level, index) of node `id`
+__host__ __device__ inline void unit_node(const int* lev, int nlev, int id, int& h, int& j) {
+    h = 0;
+    while (h + 1 < nlev && id >= lev[2 * (h + 1)]) ++h;
+    j = id - lev[2 * h];
 }
 
 // Exact global nearest index (first minimum) of (fx, fy) over the whole course.
@@ -286,26 +305,36 @@ __host__ __device__ inline int course_nearest(const CourseIndex<T, T2>& ci, T fx
     index_scan_leaf<T, T2>(ci, w, fx, fy, best, ib);
     if (L > 1) index_scan_leaf<T, T2>(ci, w + 1, fx, fy, best, ib);
     q.base = (index_reach32<T>(best) + q.slack) * 1.000002f;
-    // ---- cover: four tests per level, evaluated unconditionally (an empty slot tests node 0 and drops the answer:
-    // the warp would run the slot for its other lanes anyway, and straight-line code lets the four interleave)
-    uint64_t fail = 0ull;                   // bit 4h + slot: that cover node survives
-    for (int h = 0; h < ci.nlev - 1; ++h) {        // (the top level -- at most two nodes -- is never part of a cover)
-        const float4* __restrict__ g = ci.node + ci.lev[2 * h];
-        const int cnt = ci.lev[2 * h + 1];
-        const int a = ((w + 1) >> h) - 1, b = (w >> h) + 2;
-        const bool l0 = a > 0, l1 = l0 && !(a & 1), r0 = b < cnt, r1 = !(b & 1) && b + 1 < cnt;
-        const bool f0 = index_test(g, l0 ? a - 1 : 0, q), f1 = index_test(g, l1 ? a - 2 : 0, q);
-        const bool f2 = index_test(g, r0 ? b : 0, q), f3 = index_test(g, r1 ? b + 1 : 0, q);
-        const uint32_t f = (l0 && f0 ? 1u : 0u) | (l1 && f1 ? 2u : 0u) | (r0 && f2 ? 4u : 0u) | (r1 && f3 ? 8u : 0u);
-        fail |= (uint64_t)f << (4 * h);
+    // NaN / overflowing query (np.argmin of all-NaN is 0): nothing can be compared, do what the reference does
+    if (!(best < (T)INFINITY)) return course_nearest_full<T, T2>(ci.xy, ci.np, fx, fy);
+    // ---- cover: the window's row of the cover table, four independent tests per 8-byte load (a padding entry
+    // tests the dummy node, which never fails: the warp would run the slot for its other lanes anyway)
+    uint64_t fail = 0ull;                   // bit k: cover node k of the row survives
+    {
+        // (four tests per batch; eight per 16-byte load measured the same, and computing the cover from w at every level
+        // instead of reading the table costs 40 more instructions per level for the same time at 128 registers)
+        const uint2* __restrict__ row = reinterpret_cast<const uint2*>(ci.cov + (size_t)w * ci.kc);
+        const float4* __restrict__ g = ci.chord;
+        const float2* __restrict__ gi = ci.ir;
+        for (int c = 0; c < (ci.kc >> 2); ++c) {
+            const uint2 e = row[c];
+            uint32_t f = 0u;
+            f |= index_test(g, gi, (int)(e.x & 0xffffu), q) ? 1u : 0u;
+            f |= index_test(g, gi, (int)(e.x >> 16), q) ? 2u : 0u;
+            f |= index_test(g, gi, (int)(e.y & 0xffffu), q) ? 4u : 0u;
+            f |= index_test(g, gi, (int)(e.y >> 16), q) ? 8u : 0u;
+            fail |= (uint64_t)f << (4 * c);
+        }
     }
-    ne += ci.ncover ? (int)ci.ncover[w] : cover_count(w, ci.nlev, ci.lev);
+    ne += (int)ci.ncover[w];
     // ---- survivors
     while (fail) {
         const int bit = lowest_bit64(fail);
         fail &= fail - 1ull;
-        int h = bit >> 2;
-        int j = cover_node(w, h, bit & 3, ci.lev[2 * h + 1]);
+        const int unit = ci.cov[(size_t)w * ci.kc + bit];
+        if (unit == ci.dummy) continue;     // (only an overflowing threshold gets here)
+        int h, j;
+        unit_node(ci.lev, ci.nlev, unit, h, j);
         if (h == 0) {
             const T before = best;
             index_scan_leaf<T, T2>(ci, j, fx, fy, best, ib);
@@ -317,10 +346,10 @@ __host__ __device__ inline int course_nearest(const CourseIndex<T, T2>& ci, T fx
         for (;;) {
             // open node (h, j), h >= 1
             const int hc = h - 1, c = 2 * j;
-            const float4* __restrict__ g = ci.node + ci.lev[2 * hc];
+            const int id0 = ci.lev[2 * hc] + c;
             const bool has1 = c + 1 < ci.lev[2 * hc + 1];
-            bool f0 = index_test(g, c, q);
-            bool f1 = has1 && index_test(g, c + 1, q);
+            bool f0 = index_test(ci.chord, ci.ir, id0, q);
+            bool f1 = has1 && index_test(ci.chord, ci.ir, id0 + 1, q);
             ne += 1 + (int)has1;
             if (hc == 0) {
                 const T before = best;
@@ -343,8 +372,6 @@ __host__ __device__ inline int course_nearest(const CourseIndex<T, T2>& ci, T fx
             }
         }
     }
-    // NaN / overflowing query (np.argmin of all-NaN is 0): nothing could be compared, do what the reference does
-    if (!(best < (T)INFINITY)) return course_nearest_full<T, T2>(ci.xy, ci.np, fx, fy);
     if (evals) *evals += ne;
     return ib;
 }

@@ -673,7 +673,7 @@ __global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_kernel(const 
                 T sth, cth;
                 R::sincos_(th, &sth, &cth);
                 if (a.P.model == SCCAV_MODEL_SADBM) { augv[0] = a.pv.aug[n]; augv[1] = a.pv.aug[N + n]; }
-                ph = filter_rows<T, SPEC, COOP>(a.P, a.sd, Mv, N, n, a.obst, x, y, th, v, sth, cth, alpha, ur0, ur1, rows, stride,
+                ph = filter_rows<T, SPEC, COOP, -1, true>(a.P, a.sd, Mv, N, n, a.obst, x, y, th, v, sth, cth, alpha, ur0, ur1, rows, stride,
                                                 hmin, nullptr, 0xffffffffu, &Ri, augv);
             }
         }
@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_kernel(const 
                 a.pv.aug[n] = beta_new;
                 a.pv.aug[N + n] = R::atan2_(a.P.lr * R::tan_(ur1), a.P.lf + a.P.lr);
             } else
-            if (Mv > 0) { u0 = q0; u1 = filter_convert<T>(a.P, q0, q1, ph.r0); }
+            if (Mv > 0) { u0 = q0; u1 = filter_convert<T, -1, true>(a.P, q0, q1, ph.r0); }
             a.u[n] = u0;
             a.u[N + n] = u1;
             if (a.mask) a.mask[n] = mask;
@@ -770,6 +770,7 @@ __global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_staged_kernel
         T r0 = ur0, r1;
         if (model == SCCAV_MODEL_KBM) r1 = (ur0 * R::tan_(ur1)) / P.L;                      // cbf.py:75
         else if (model == SCCAV_MODEL_DUM) r1 = ur1;                                         // cbf.py:253
+        else if (P.flags & SCCAV_FLAG_BETA_IO) r1 = ur1;                                     // the caller holds beta
         else r1 = R::atan2_(P.lr * R::tan_(ur1), P.lf + P.lr);                               // cbf.py:175
         T hmin = R::inf(), worst = -R::inf();
         bool feas = true;
@@ -807,7 +808,7 @@ __global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_staged_kernel
         }
         if (valid) {
             T u0 = ur0, u1 = ur1;                                           // empty obstacle list: u = u_ref
-            if (Mv > 0) { u0 = q0; u1 = filter_convert<T>(P, q0, q1, r0); }
+            if (Mv > 0) { u0 = q0; u1 = filter_convert<T, -1, true>(P, q0, q1, r0); }
             a.u[n] = u0;
             a.u[N + n] = u1;
             if (a.mask) a.mask[n] = mask;
@@ -876,11 +877,12 @@ __device__ __forceinline__ void seeker_update(T* f, int64_t fs, T ex, T ey, T dt
 #define SCCAV_ROLLOUT_MAXB 448
 
 // Shared-memory layout of the rollout kernel (bytes), shared by the launcher and the kernel:
-//   [ course xy : T2 x nslot (leaf-padded) ][ tree nodes : 16 B x units ][ header : level table int x 32, origin T x 2, extent float ]
-//   [ cover counts : 1 B x nleaf, padded to 16 ][ cyaw : T x np_pad ][ rows : T x 3 M block ]
+//   [ course xy : T2 x nslot (leaf-padded) ][ node chords : 16 B x nodes ][ node (1 / len^2, radius) : 8 B x nodes ][ header : level table int x 32, origin T x 2, extent float ]
+//   [ cover table : 2 B x nleaf x kc ][ cover counts : 1 B x nleaf, padded to 16 ][ cyaw : T x np_pad ][ rows : T x 3 M block ]
 template <typename T> struct RolloutSmem {
     int nslot, units, np_pad;
-    size_t off_node, off_hdr, off_ncov, off_cyaw, off_rows, course_bytes;
+    int kc;
+    size_t off_node, off_ir, off_hdr, off_cov, off_ncov, off_cyaw, off_rows, course_bytes;
     __host__ __device__ RolloutSmem(int np, bool course_smem) {
         nslot = course_smem ? course_nslot(np) : 0;
         units = course_smem ? course_node_units(np) : 0;
@@ -888,7 +890,10 @@ template <typename T> struct RolloutSmem {
         size_t o = (size_t)nslot * 2 * sizeof(T);
         o = (o + 15) & ~(size_t)15;
         off_node = o; o += (size_t)units * 16;
+        off_ir = o; o += ((size_t)units * 8 + 15) & ~(size_t)15;
         off_hdr = o; o += course_smem ? 160 : 0;       // 2 x SCCAV_MAX_LEVELS ints | 2 T (at +128) | float (at +144)
+        kc = course_smem ? cover_kc(course_levels(np, nullptr, nullptr)) : 0;
+        off_cov = o; o += ((size_t)course_nleaf(np) * kc * sizeof(uint16_t) + 15) & ~(size_t)15;
         off_ncov = o; o += course_smem ? (((size_t)course_nleaf(np) + 15) & ~(size_t)15) : 0;
         off_cyaw = o; o += (size_t)np_pad * sizeof(T);
         off_rows = o;
@@ -911,7 +916,8 @@ __device__ __forceinline__ CourseIndex<T, T2> course_stage(unsigned char* smem, 
     float* s_ext = reinterpret_cast<float*>(smem + lay.off_hdr + 144);
     CourseIndex<T, T2> ci;
     ci.xy = s_cxy;
-    ci.node = reinterpret_cast<float4*>(smem + lay.off_node);
+    ci.chord = reinterpret_cast<float4*>(smem + lay.off_node);
+    ci.ir = reinterpret_cast<float2*>(smem + lay.off_ir);
     ci.lev = s_lev; ci.org = s_org; ci.ext = s_ext;
     ci.np = np; ci.nleaf = course_nleaf(np);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
@@ -954,21 +960,24 @@ __device__ __forceinline__ CourseIndex<T, T2> course_stage(unsigned char* smem, 
             m = warp_max<double>(m);
             if (lane == 0) {
                 const float2 r = capsule_ir(inv, m, extf);
-                const int u = CourseIndex<T, T2>::unit(base, j);
-                ci.node[u] = c;
-                ci.node[u + 1] = make_float4(r.x, r.y, 0.f, 0.f);
+                ci.chord[base + j] = c;
+                ci.ir[base + j] = r;
             }
         }
-        base += cnt * SCCAV_NODE_UNITS;
+        base += cnt;
         ++k;
         if (cnt <= 2 || k >= SCCAV_MAX_LEVELS) break;
         cnt = (cnt + 1) >> 1;
     }
     ci.nlev = k;
     __syncthreads();
+    // the cover of every window leaf (course_index.cuh), and the dummy node its padding points at
     uint8_t* s_ncov = reinterpret_cast<uint8_t*>(smem + lay.off_ncov);
-    for (int w = threadIdx.x; w < ci.nleaf; w += blockDim.x) s_ncov[w] = (uint8_t)cover_count(w, k, s_lev);
-    ci.ncover = s_ncov;
+    uint16_t* s_cov = reinterpret_cast<uint16_t*>(smem + lay.off_cov);
+    const int dummy = base;                  // the first id after the last level
+    if (threadIdx.x == 0) dummy_node(ci.chord, ci.ir, dummy);
+    for (int w = threadIdx.x; w < ci.nleaf; w += blockDim.x) s_ncov[w] = (uint8_t)cover_row(w, k, s_lev, lay.kc, dummy, s_cov + (size_t)w * lay.kc);
+    ci.ncover = s_ncov; ci.cov = s_cov; ci.kc = lay.kc; ci.dummy = dummy;
     __syncthreads();
     return ci;
 }
@@ -1001,7 +1010,7 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
     const int model = FAST ? SCCAV_MODEL_DBM : a.P.model;
     constexpr int MODEL = FAST ? SCCAV_MODEL_DBM : -1;
     CourseIndex<T, T2> ci;
-    ci.xy = s_cxy; ci.node = nullptr; ci.lev = nullptr; ci.org = nullptr; ci.ext = nullptr; ci.ncover = nullptr;
+    ci.xy = s_cxy; ci.chord = nullptr; ci.ir = nullptr; ci.lev = nullptr; ci.org = nullptr; ci.ext = nullptr; ci.ncover = nullptr; ci.cov = nullptr; ci.kc = 0; ci.dummy = 0;
     ci.np = np; ci.nleaf = 0; ci.nlev = 0;
     // stage the course once per CTA (leaf-padded) and build the capsules of its tree
     if (COURSE_SMEM && stan)
@@ -1017,9 +1026,13 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
 
     const Params<T>& P = a.P;
     T x = a.state[n], y = a.state[N + n], yaw = a.state[2 * N + n], v = a.state[3 * N + n];
+    // the compile-time ellipse instances are launched with launch-wide weights and target speed only (the launcher
+    // sends per-vehicle ones to the general instances): constant-bank operands instead of 12 registers held across the loop
+    constexpr bool UW = FAST && SPEC != SCCAV_SPEC_GENERIC;
     T alpha, R00, R01, R10, R11;
-    load_weights<T>(P, a.pv, N, n, alpha, R00, R01, R10, R11);
-    const T tspeed = a.pv.target_speed ? a.pv.target_speed[n] : P.target_speed;
+    if (UW) { alpha = P.alpha; R00 = P.R[0]; R01 = P.R[1]; R10 = P.R[2]; R11 = P.R[3]; }
+    else load_weights<T>(P, a.pv, N, n, alpha, R00, R01, R10, R11);
+    const T tspeed = UW ? P.target_speed : (a.pv.target_speed ? a.pv.target_speed[n] : P.target_speed);
     const int last_idx = np - 1;
     const int Mv = slot_count<T>(a.pv, a.M, n);
     const bool filt = Mv > 0 && model != SCCAV_MODEL_NONE;
@@ -1096,7 +1109,7 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
         uint32_t mask = 0u;
         int status = SCCAV_STATUS_INACTIVE;
         if (filt)
-            status = filter_vehicle<T, SPEC, MODEL, FAST>(P, a.sd, Mv, N, n, a.obst, x, y, yaw, v, syaw, cyw, alpha, R00, R01, R10, R11, a.pv.R == nullptr,
+            status = filter_vehicle<T, SPEC, MODEL, FAST>(P, a.sd, Mv, N, n, a.obst, x, y, yaw, v, syaw, cyw, alpha, R00, R01, R10, R11, UW || a.pv.R == nullptr,
                                              ur0, ur1, rows, stride, u0, u1, u1raw, mask, hmin, a.pre, moving, !fused);
         // ---- plant
         T px = x, py = y, pyaw = yaw, pv_ = v;

@@ -787,7 +787,9 @@ template <typename T> struct RowPhase {
 };
 
 // phase 1: u_ref -> QP coordinates, rows of all slots -> shared memory, feasibility of the reference point
-template <typename T, int SPEC, bool SCAN = false, int MODEL = -1>
+// BIO: honour SCCAV_FLAG_BETA_IO (the filter-step kernels; the closed-loop kernels reject the flag on the host and do
+// not even test it -- one more live value in their time loop was measured at 2.7 % of the rollout)
+template <typename T, int SPEC, bool SCAN = false, int MODEL = -1, bool BIO = false>
 __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const SlotDesc& sd, int M, int64_t N, int64_t n,
                                                    const T* __restrict__ obst, T x, T y, T th, T v, T sth, T cth,
                                                    T alpha, T uref0, T uref1, T* rows, int stride, T& hmin,
@@ -812,6 +814,7 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
     } else
     if (model == SCCAV_MODEL_KBM) r1 = (uref0 * R::tan_(uref1)) / P.L;                  // cbf.py:75
     else if (model == SCCAV_MODEL_DUM) r1 = uref1;                                       // cbf.py:253: u_ref as given
+    else if (BIO && (P.flags & SCCAV_FLAG_BETA_IO)) r1 = uref1;                          // the caller holds beta
     else r1 = R::atan2_(P.lr * R::tan_(uref1), P.lf + P.lr);                             // cbf.py:175
     // rows -> shared memory; an inactive step never re-reads them
     bool feas = true;
@@ -882,7 +885,7 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
 }
 
 // phase 3: QP coordinates -> (a | v, delta)
-template <typename T, int MODEL = -1>
+template <typename T, int MODEL = -1, bool BIO = false>
 __device__ __forceinline__ T filter_convert(const Params<T>& P, T q0, T q1, T r0) {
     typedef Real<T> R;
     const int model = MODEL >= 0 ? MODEL : P.model;
@@ -891,6 +894,7 @@ __device__ __forceinline__ T filter_convert(const Params<T>& P, T q0, T q1, T r0
         return R::atan2_(q1 * P.L, r0);                                                  // cbf.py:109
     }
     if (model == SCCAV_MODEL_DUM) return q1;                                             // cbf.py:293: u as solved
+    if (BIO && (P.flags & SCCAV_FLAG_BETA_IO)) return q1;                                // beta out, as it came in
     return R::atan2_((P.lf + P.lr) * R::tan_(q1), P.lr);                                 // cbf.py:216
 }
 

@@ -939,3 +939,48 @@ def test_prepare_kernel_vector_and_scalar_forms_agree(N, dtype):
     buf = full[:, :, :N].contiguous()
     ops.prepare_obstacles(slots, buf, out=buf)
     assert torch.equal(buf, out_n)
+
+
+@pytest.mark.parametrize("name", ["ellipse8", "mixed", "prepared_static"])
+def test_filter_step_beta_io_flag(name):
+    """SCCAV_FLAG_BETA_IO (model DBM): beta in, beta out -- the same QP on the same rows as the delta interface
+    (cbf.py:175,216 are the only lines it skips).  Checked against the delta-interface solve of the same problems
+    (GPU and oracle) through beta = atan2(lr tan delta, L): controls 1e-9, identical active sets and statuses; an
+    inactive problem returns its u_ref bit for bit.  Direct-load, generic and staged kernels."""
+    from sccav_cbf_b200 import ops, _native as nv
+    N = 4096
+    static = name == "prepared_static"
+    slots = [o.SLOT_ELLIPSE | o.SLOT_STATIC] * 8 if static else SLOTSETS[name]
+    rng = np.random.default_rng(zlib.crc32(name.encode()) + 9)
+    s = H.random_states(rng, N)
+    ob = H.random_slots(rng, N, slots, s)
+    ur = H.random_uref(rng, N)
+    prm_d = ops.make_params(alpha=1.1)
+    prm_b = ops.make_params(alpha=1.1, flags=nv.FLAG_BETA_IO)
+    lr, L = prm_d.lr, prm_d.lf + prm_d.lr
+    sd, obt = slots, T(ob)
+    if static:
+        sd, obt = ops.prepare_obstacles(slots, obt)
+    ur_b = ur.copy()
+    ur_b[1] = np.arctan2(lr * np.tan(ur[1]), L)
+    u_d, mask_d, st_d, hmin_d = ops.filter_step(prm_d, sd, T(s), obt, T(ur))
+    u_b, mask_b, st_b, hmin_b = ops.filter_step(prm_b, sd, T(s), obt, T(ur_b))
+    assert torch.equal(mask_d, mask_b) and torch.equal(st_d, st_b) and torch.equal(hmin_d, hmin_b)
+    # (the QP's beta* is not confined to (-pi/2, pi/2); delta = atan2(L tan beta*, lr) folds it, so the two interfaces are
+    # compared through delta, modulo pi)
+    ud, ub = u_d.cpu().numpy(), u_b.cpu().numpy()
+
+    def mod_pi(a):
+        return np.abs((a + np.pi / 2) % np.pi - np.pi / 2)
+    assert close(ub[0], ud[0]) < 1.0
+    assert mod_pi(np.arctan2(L * np.tan(ub[1]), lr) - ud[1]).max() < 1e-9
+    inactive = (st_b == 0).cpu().numpy()
+    assert inactive.any() and (~inactive).mean() > 0.02
+    assert np.array_equal(ub[:, inactive], ur_b[:, inactive])
+    # the oracle's delta-interface answer, converted
+    ref = co.filter_step(co.default_params(alpha=1.1), slots, s, ob, ur)
+    assert (mask_b.cpu().numpy().view(np.uint32) == ref["mask"]).all()
+    assert mod_pi(np.arctan2(L * np.tan(ub[1]), lr) - ref["u"][1]).max() < 1e-9
+    # every other model and the closed-loop entry points refuse the flag
+    with pytest.raises(Exception):
+        ops.filter_step(ops.make_params(model=o.MODEL_KBM, flags=nv.FLAG_BETA_IO), sd, T(s), obt, T(ur))
