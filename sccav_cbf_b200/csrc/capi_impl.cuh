@@ -322,14 +322,14 @@ rollout_fn rollout_instance(bool course_smem, int spec, bool fast = false, bool 
 
 // grid / block / dynamic shared memory of a rollout launch; the block is capped by what the
 // kernel's register count allows (cudaFuncGetAttributes), the course goes to shared memory if it fits
-int rollout_launch_shape(int M, int64_t N, int np, bool stan, int spec, int& grid, int& block, size_t& smem, bool& course_smem) {
+int rollout_launch_shape(int M, int64_t N, int np, bool stan, int spec, int& grid, int& block, size_t& smem, bool& course_smem, bool trig = false) {
     rollout_geometry(N, grid, block);
     cudaFuncAttributes fa;
     SCCAV_CUDA_CHECK(cudaFuncGetAttributes(&fa, (const void*)rollout_instance(true, spec)));
     const int max_block = fa.maxThreadsPerBlock / 32 * 32;
     if (block > max_block) { block = max_block; grid = (int)((N + block - 1) / block); }
     const size_t cap = (size_t)max_smem_optin();
-    const RolloutSmem<real> lay(np, true);
+    const RolloutSmem<real> lay(np, true, trig);
     size_t rows_b = (size_t)3 * (M > 0 ? M : 1) * block * sizeof(real);
     course_smem = stan && (lay.course_bytes + rows_b <= cap);
     smem = rows_b + (course_smem ? lay.course_bytes : 0);
@@ -345,8 +345,8 @@ int rollout_launch_shape(int M, int64_t N, int np, bool stan, int spec, int& gri
 
 // Several roads in one launch: choose the block so that the CTAs of all roads fill the SMs in as few waves as possible
 // (a road's vehicles never share a CTA with another road's: the course lives in the CTA's shared memory).
-int roads_geometry(const void* kern, int M, int np, int n_roads, int64_t group, int& grid, int& block, size_t& smem, int& ctas_per_road) {
-    const RolloutSmem<real> lay(np, true);
+int roads_geometry(const void* kern, int M, int np, int n_roads, int64_t group, int& grid, int& block, size_t& smem, int& ctas_per_road, bool trig = false) {
+    const RolloutSmem<real> lay(np, true, trig);
     const size_t cap = (size_t)max_smem_optin();
     cudaFuncAttributes fa;
     SCCAV_CUDA_CHECK(cudaFuncGetAttributes(&fa, kern));
@@ -423,7 +423,11 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
     // take the general instances)
     const bool uniform_w = !pv || (!pv->alpha && !pv->R && !pv->target_speed);
     const bool fast = p->model == SCCAV_MODEL_DBM && stan && !p->seeker && (spec == SCCAV_SPEC_GENERIC || uniform_w);
-    rc = rollout_launch_shape(M, N, a.np, stan, spec, grid, block, smem, course_smem);
+    // (the fused-steer compile-time instances stage (sin, cos) of the course yaws: twice the bytes of that table)
+    const bool trig = fast && (p->flags & SCCAV_FLAG_FUSED_STEER) != 0;
+    rc = rollout_launch_shape(M, N, a.np, stan, spec, grid, block, smem, course_smem, trig);
+    // (a course that fits only without that table runs the general instance, which reads the flag at run time)
+    if (!rc && trig && !course_smem && n_roads == 0) rc = rollout_launch_shape(M, N, a.np, stan, spec, grid, block, smem, course_smem, false);
     if (rc) { if (prep) cudaFreeAsync(prep, st); return rc; }
     // scratch for the loop-invariant terms of canonical ellipses: stream-ordered, lives for this launch
     a.pre = nullptr;
@@ -436,7 +440,7 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
     rollout_fn kern = rollout_instance(course_smem, spec, fast, (p->flags & SCCAV_FLAG_FUSED_STEER) != 0);
     if (n_roads > 0) {
         kern = rollout_instance(true, spec, fast, (p->flags & SCCAV_FLAG_FUSED_STEER) != 0);
-        rc = roads_geometry((const void*)kern, M, a.np, n_roads, a.group, grid, block, smem, a.ctas_per_road);
+        rc = roads_geometry((const void*)kern, M, a.np, n_roads, a.group, grid, block, smem, a.ctas_per_road, trig);
         if (rc) { if (a.pre) cudaFreeAsync(a.pre, st); if (prep) cudaFreeAsync(prep, st); return rc; }
     }
     cudaError_t le = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -883,7 +883,8 @@ template <typename T> struct RolloutSmem {
     int nslot, units, np_pad;
     int kc;
     size_t off_node, off_ir, off_hdr, off_cov, off_ncov, off_cyaw, off_rows, course_bytes;
-    __host__ __device__ RolloutSmem(int np, bool course_smem) {
+    // trig: the cyaw region holds (sin, cos) of every course yaw instead of the yaw (the fused-steer instances)
+    __host__ __device__ RolloutSmem(int np, bool course_smem, bool trig = false) {
         nslot = course_smem ? course_nslot(np) : 0;
         units = course_smem ? course_node_units(np) : 0;
         np_pad = course_smem ? ((np + 1) & ~1) : 0;
@@ -895,7 +896,7 @@ template <typename T> struct RolloutSmem {
         kc = course_smem ? cover_kc(course_levels(np, nullptr, nullptr)) : 0;
         off_cov = o; o += ((size_t)course_nleaf(np) * kc * sizeof(uint16_t) + 15) & ~(size_t)15;
         off_ncov = o; o += course_smem ? (((size_t)course_nleaf(np) + 15) & ~(size_t)15) : 0;
-        off_cyaw = o; o += (size_t)np_pad * sizeof(T);
+        off_cyaw = o; o += (size_t)np_pad * sizeof(T) * (trig ? 2 : 1);
         off_rows = o;
         course_bytes = o;
     }
@@ -905,7 +906,7 @@ template <typename T> struct RolloutSmem {
 // (course_index.cuh).  Called by every thread of the CTA; `scratch` = at least 32 doubles of shared memory that are
 // free during the build.  Nodes are built warp-cooperatively: the lanes of a warp share the points of one node and
 // reduce the largest chord distance (a maximum: the same radius as the serial capsule_build).
-template <typename T, typename T2>
+template <typename T, typename T2, bool TRIG = false>
 __device__ __forceinline__ CourseIndex<T, T2> course_stage(unsigned char* smem, const RolloutSmem<T>& lay, int np,
                                                            const T* __restrict__ cx, const T* __restrict__ cy,
                                                            const T* __restrict__ cyaw, T* s_cyaw, double* scratch) {
@@ -927,7 +928,10 @@ __device__ __forceinline__ CourseIndex<T, T2> course_stage(unsigned char* smem, 
     for (int i = threadIdx.x; i < np; i += blockDim.x) {
         T px = cx[i], py = cy[i];
         s_cxy[course_slot(i)] = R::make2(px, py);
-        if (s_cyaw) s_cyaw[i] = cyaw[i];
+        if (s_cyaw) {
+            if (TRIG) { T sc, cc; R::sincos_(cyaw[i], &sc, &cc); s_cyaw[2 * i] = sc; s_cyaw[2 * i + 1] = cc; }
+            else s_cyaw[i] = cyaw[i];
+        }
         ext = fmax(ext, fmax(fabs((double)px - (double)ox), fabs((double)py - (double)oy)));
     }
     // the tail of the last leaf: copies of the last point (course_nslot)
@@ -1001,7 +1005,8 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
     const T* __restrict__ g_cx = a.cx + (a.n_roads > 0 ? (int64_t)road * a.road_stride : 0);
     const T* __restrict__ g_cy = a.cy + (a.n_roads > 0 ? (int64_t)road * a.road_stride : 0);
     const T* __restrict__ g_cyaw = a.cyaw + (a.n_roads > 0 ? (int64_t)road * a.road_stride : 0);
-    const RolloutSmem<T> lay(a.np, COURSE_SMEM);
+    constexpr bool TRIG = FAST && FUSED == 1;       // (sin, cos) of the course yaws in place of the yaws (stanley_law_beta)
+    const RolloutSmem<T> lay(a.np, COURSE_SMEM, TRIG);
     T2* s_cxy = reinterpret_cast<T2*>(smem_raw);
     T* s_cyaw = reinterpret_cast<T*>(smem_raw + lay.off_cyaw);
     T* rows = reinterpret_cast<T*>(smem_raw + lay.off_rows) + threadIdx.x;
@@ -1014,7 +1019,7 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
     ci.np = np; ci.nleaf = 0; ci.nlev = 0;
     // stage the course once per CTA (leaf-padded) and build the capsules of its tree
     if (COURSE_SMEM && stan)
-        ci = course_stage<T, T2>(smem_raw, lay, np, g_cx, g_cy, g_cyaw, s_cyaw, reinterpret_cast<double*>(smem_raw + lay.off_rows));
+        ci = course_stage<T, T2, TRIG>(smem_raw, lay, np, g_cx, g_cy, g_cyaw, s_cyaw, reinterpret_cast<double*>(smem_raw + lay.off_rows));
     const int64_t N = a.N;
     int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (a.n_roads > 0) {
@@ -1081,9 +1086,18 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
         if (P.terminate && !(P.t_max >= time && last_idx > target_idx)) break;          // sce.py:630
         // ---- nominal control
         T ur0, ur1;
+        T beta_ref = T(0);                   // (fused-steer instances: the reference point's beta, formed by the Stanley law itself)
         if (stan) {
             T a_ref = P.Kp * (tspeed - v);                                                 // sce.py:135-143
             T d_ref;
+            if (COURSE_SMEM && TRIG) {
+                // fused steering: beta_ref straight from the Stanley law (path.cuh, stanley_law_beta); delta_ref itself is only
+                // needed by a vehicle without obstacles, which takes the literal law on the yaws in global memory
+                T fx, fy;
+                const int idx = stanley_search<T, T2>(P, ci, x, y, syaw, cyw, near_idx, adv, &evals, fx, fy);
+                if (filt) { beta_ref = stanley_law_beta<T, T2>(P, ci.pt(idx), reinterpret_cast<const T2*>(s_cyaw), idx, fx, fy, v, target_idx, syaw, cyw); d_ref = T(0); }
+                else d_ref = stanley_law<T, T2, true>(P, ci.pt(idx), g_cyaw, idx, fx, fy, yaw, v, target_idx, syaw, cyw);
+            } else
             if (COURSE_SMEM) d_ref = stanley<T, T2, (FUSED == 1)>(P, ci, s_cyaw, x, y, yaw, v, syaw, cyw, target_idx, near_idx, adv, &evals);
             else {
                 // global-memory course fallback (P too large for shared memory): exhaustive scan
@@ -1110,7 +1124,7 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
         int status = SCCAV_STATUS_INACTIVE;
         if (filt)
             status = filter_vehicle<T, SPEC, MODEL, FAST>(P, a.sd, Mv, N, n, a.obst, x, y, yaw, v, syaw, cyw, alpha, R00, R01, R10, R11, UW || a.pv.R == nullptr,
-                                             ur0, ur1, rows, stride, u0, u1, u1raw, mask, hmin, a.pre, moving, !fused);
+                                             ur0, ur1, rows, stride, u0, u1, u1raw, mask, hmin, a.pre, moving, !fused, TRIG ? &beta_ref : nullptr);
         // ---- plant
         T px = x, py = y, pyaw = yaw, pv_ = v;
         T beta = T(0);

@@ -794,7 +794,7 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
                                                    const T* __restrict__ obst, T x, T y, T th, T v, T sth, T cth,
                                                    T alpha, T uref0, T uref1, T* rows, int stride, T& hmin,
                                                    const T* __restrict__ pre = nullptr, uint32_t moving = 0xffffffffu,
-                                                   const RInv<T>* Ri = nullptr, const T* aug = nullptr) {
+                                                   const RInv<T>* Ri = nullptr, const T* aug = nullptr, const T* r1_pre = nullptr) {
     typedef Real<T> R;
     hmin = R::inf();
     T vlr = v / P.lr;                                                                   // cbf.py:160 (g_c[2][1])
@@ -815,6 +815,7 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
     if (model == SCCAV_MODEL_KBM) r1 = (uref0 * R::tan_(uref1)) / P.L;                  // cbf.py:75
     else if (model == SCCAV_MODEL_DUM) r1 = uref1;                                       // cbf.py:253: u_ref as given
     else if (BIO && (P.flags & SCCAV_FLAG_BETA_IO)) r1 = uref1;                          // the caller holds beta
+    else if (r1_pre) r1 = *r1_pre;                                                       // (the rollout's fused-steer instances)
     else r1 = R::atan2_(P.lr * R::tan_(uref1), P.lf + P.lr);                             // cbf.py:175
     // rows -> shared memory; an inactive step never re-reads them
     bool feas = true;
@@ -905,9 +906,9 @@ __device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc
                                               T alpha, T R00, T R01, T R10, T R11, bool uniform_R, T uref0, T uref1,
                                               T* rows, int stride, T& u0, T& u1, T& u1raw, uint32_t& mask, T& hmin,
                                               const T* __restrict__ pre = nullptr, uint32_t moving = 0xffffffffu,
-                                              bool convert = true) {
+                                              bool convert = true, const T* r1_pre = nullptr) {
     const RowPhase<T> ph = filter_rows<T, SPEC, false, MODEL>(P, sd, M, N, n, obst, x, y, th, v, sth, cth, alpha, uref0, uref1,
-                                                rows, stride, hmin, pre, moving);
+                                                rows, stride, hmin, pre, moving, nullptr, nullptr, r1_pre);
     T q0 = ph.r0, q1 = ph.r1;
     int status = SCCAV_STATUS_INACTIVE;
     mask = 0u;
@@ -973,6 +974,46 @@ __device__ __forceinline__ T stanley_law(const Params<T>& P, CXY c, const T* __r
     T theta_d = R::atan2_(P.k_stanley * e, v + P.ks_stanley);
     target_idx = idx;
     return theta_e + theta_d;
+}
+
+// SCCAV_FLAG_FUSED_STEER, the Stanley law in the QP's own coordinate.  The reference forms delta_ref = theta_e +
+// atan2(k e, v + ks) (sce.py:159-167) and the filter turns it into beta_ref = atan2(lr tan(delta_ref), L) (cbf.py:175).
+// tan has period pi and tan(atan2(y, x)) = y / x, so with (se, ce) = sin / cos(cyaw - yaw) -- from the sin / cos of the
+// course yaws staged once per CTA and the sin / cos of the vehicle's yaw the plant already holds --
+//   tan(delta_ref) = (se (v + ks) + ce k e) / (ce (v + ks) - se k e)
+// and beta_ref is ONE atan2 of (lr num, L den) folded into the right half plane: the same function of the same state, a
+// few ulp from the literal sequence (normalize_angle, atan2, tan, atan2), which is what the flag allows.
+template <typename T, typename CXY>
+__device__ __forceinline__ T stanley_law_beta(const Params<T>& P, CXY c, const CXY* __restrict__ trig, int idx, T fx, T fy, T v,
+                                              int& target_idx, T syaw, T cyw) {
+    typedef Real<T> R;
+    const T e = (fx - c.x) * syaw + (fy - c.y) * (-cyw);
+    if (target_idx >= idx) idx = target_idx;                                             // sce.py:159-160
+    target_idx = idx;
+    const CXY t = trig[idx];                                                             // (sin, cos) of cyaw[idx]
+    const T se = t.x * cyw - t.y * syaw, ce = t.y * cyw + t.x * syaw;
+    const T ye = P.k_stanley * e, xe = v + P.ks_stanley;
+    T num = se, den = ce;
+    if (ye != T(0) || xe != T(0)) {                                                      // atan2(0, 0) = 0
+        num = se * xe + ce * ye;
+        den = ce * xe - se * ye;
+    }
+    T yy = P.lr * num, xx = (P.lf + P.lr) * den;
+    if (xx < T(0)) { yy = -yy; xx = -xx; }
+    return R::atan2_(yy, xx);
+}
+
+// the search half of stanley(): front axle, nearest index, hint bookkeeping
+template <typename T, typename T2>
+__device__ __forceinline__ int stanley_search(const Params<T>& P, const CourseIndex<T, T2>& ci, T x, T y, T syaw, T cyw,
+                                              int& near_idx, int& adv, int* evals, T& fx, T& fy) {
+    fx = x + P.L * cyw;
+    fy = y + P.L * syaw;
+    const int idx = course_nearest<T, T2>(ci, fx, fy, near_idx + adv, evals);
+    adv = idx - near_idx;
+    adv = adv < -4 * SCCAV_LEAF ? 0 : (adv > 4 * SCCAV_LEAF ? 0 : adv);      // a jump is not a trend
+    near_idx = idx;
+    return idx;
 }
 
 // course staged in shared memory with its capsule tree: exact pruned nearest search.  The hint is the previous
