@@ -316,7 +316,8 @@ __host__ __device__ inline int course_nearest(const CourseIndex<T, T2>& ci, T fx
         const uint2* __restrict__ row = reinterpret_cast<const uint2*>(ci.cov + (size_t)w * ci.kc);
         const float4* __restrict__ g = ci.chord;
         const float2* __restrict__ gi = ci.ir;
-        for (int c = 0; c < (ci.kc >> 2); ++c) {
+        const int nc = ((int)ci.ncover[w] + 3) >> 2;        // (batches that hold a real node; a warp runs its largest count)
+        for (int c = 0; c < nc; ++c) {
             const uint2 e = row[c];
             uint32_t f = 0u;
             f |= index_test(g, gi, (int)(e.x & 0xffffu), q) ? 1u : 0u;

@@ -755,12 +755,21 @@ __device__ __forceinline__ int qp2_solve_active_warp(bool need, const T* warp_ro
 
 // row of one slot into shared memory + running feasibility test of the reference point
 // (qp_check(r) of qp2_solve, evaluated on the fly with the same operations)
-template <typename T, bool SCAN = false, int PITCH = 3, int MODEL = -1>
+// ELL: the slot is an ellipse and the model is DBM at compile time (the rollout's compile-time instances): h_theta = h_v = 0,
+// so the terms 0 * (v / lr) of A1 and A0 * r0 = 0 of the test are not evaluated (sums with an exact zero: the same values,
+// up to the sign of a zero that nothing reads), and v / lr itself is never formed.
+template <typename T, bool SCAN = false, int PITCH = 3, int MODEL = -1, bool ELL = false>
 __device__ __forceinline__ void put_row(const Params<T>& P, const Partials<T>& p, T sth, T cth, T v, T alpha, T vlr, T r0, T r1,
                                         T* rows, int stride, int m, T& hmin, T& worst, bool& feas, RowNz& nz,
                                         QpScan<T>* scan = nullptr, const RInv<T>* Ri = nullptr) {
     typedef Real<T> R;
     T A0, A1, b;
+    if (ELL) {
+        A0 = T(0);
+        A1 = p.hx * ((-v) * sth) + p.hy * (v * cth);                                     // dbm_row with h_theta = 0
+        const T Lf = p.hx * (v * cth) + p.hy * (v * sth);
+        b = -((Lf + alpha * p.h) + p.ht);
+    } else
     model_row<T, MODEL>(P, p, sth, cth, v, alpha, vlr, A0, A1, b);
     rows[(PITCH * m + 0) * stride] = A0;
     rows[(PITCH * m + 1) * stride] = A1;
@@ -768,10 +777,10 @@ __device__ __forceinline__ void put_row(const Params<T>& P, const Partials<T>& p
     if (p.h < hmin) hmin = p.h;
     if (A0 != T(0)) nz.nz0 |= 1u << m;
     if (A1 != T(0)) nz.nz1 |= 1u << m;
-    T t0 = A0 * r0, t1 = A1 * r1;
-    T rk = (t0 + t1) - b;
+    T t0 = ELL ? T(0) : A0 * r0, t1 = A1 * r1;
+    T rk = ELL ? t1 - b : (t0 + t1) - b;
     if (-rk > worst) worst = -rk;
-    T tol = R::feas_eps() * ((R::abs_(t0) + R::abs_(t1)) + R::abs_(b));
+    T tol = R::feas_eps() * ((ELL ? R::abs_(t1) : R::abs_(t0) + R::abs_(t1)) + R::abs_(b));
     if (!(rk >= -tol)) feas = false;
     if (rk < T(0)) nz.viol |= 1u << m;
     if (SCAN) scan->row(m, A0, A1, rk, *Ri);
@@ -836,7 +845,7 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
                 T vx = T(0), vy = T(0);
                 if ((moving >> m) & 1u) { vx = f[5 * N]; vy = f[6 * N]; }
                 Partials<T> p = ellipse_partials_pre<T>(x, y, cx, cy, a, b, vx, vy, q, N);
-                put_row<T, SCAN, 3, MODEL>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
+                put_row<T, SCAN, 3, MODEL, MODEL == SCCAV_MODEL_DBM>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
             }
         } else {
             const bool st_ = (sd.d[0] & SCCAV_SLOT_STATIC) != 0;      // static: the velocity fields are not read
@@ -866,7 +875,7 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
             T wx = T(0), wy = T(0);
             if (!is_static) { wx = f[6 * N]; wy = f[7 * N]; }
             Partials<T> p = ellipse_prep_partials<T>(x, y, f[0], f[N], f[2 * N], f[3 * N], f[4 * N], f[5 * N], wx, wy, is_static);
-            put_row<T, SCAN, 3, MODEL>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
+            put_row<T, SCAN, 3, MODEL, MODEL == SCCAV_MODEL_DBM>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
         }
     } else {
         T rsth = sth, rcth = cth;                              // trig of the row assembly (theta + beta under SADBM)
