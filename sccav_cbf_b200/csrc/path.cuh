@@ -840,12 +840,21 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
             // needs neither its velocity nor a^2, b^2 (h_t = -2 (. * 0 + . * 0) = 0)
             const int64_t ps = (int64_t)SCCAV_NPRE * N;
             const T* q = pre + n;
-            for (int m = 0; m < M; ++m, f += ss, q += ps) {
-                T cx = f[0], cy = f[N], a = f[2 * N], b = f[3 * N];
-                T vx = T(0), vy = T(0);
-                if ((moving >> m) & 1u) { vx = f[5 * N]; vy = f[6 * N]; }
-                Partials<T> p = ellipse_partials_pre<T>(x, y, cx, cy, a, b, vx, vy, q, N);
-                put_row<T, SCAN, 3, MODEL, MODEL == SCCAV_MODEL_DBM>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
+            // (two loops: the per-row test of the moving bit costs predicated instructions in every row)
+            if (moving == 0u) {
+                for (int m = 0; m < M; ++m, f += ss, q += ps) {
+                    T cx = f[0], cy = f[N], a = f[2 * N], b = f[3 * N];
+                    Partials<T> p = ellipse_partials_pre<T>(x, y, cx, cy, a, b, T(0), T(0), q, N);
+                    put_row<T, SCAN, 3, MODEL, MODEL == SCCAV_MODEL_DBM>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
+                }
+            } else {
+                for (int m = 0; m < M; ++m, f += ss, q += ps) {
+                    T cx = f[0], cy = f[N], a = f[2 * N], b = f[3 * N];
+                    T vx = T(0), vy = T(0);
+                    if ((moving >> m) & 1u) { vx = f[5 * N]; vy = f[6 * N]; }
+                    Partials<T> p = ellipse_partials_pre<T>(x, y, cx, cy, a, b, vx, vy, q, N);
+                    put_row<T, SCAN, 3, MODEL, MODEL == SCCAV_MODEL_DBM>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
+                }
             }
         } else {
             const bool st_ = (sd.d[0] & SCCAV_SLOT_STATIC) != 0;      // static: the velocity fields are not read
@@ -870,12 +879,19 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
 #define SCCAV_PREP_UNROLL 2
 #endif
         constexpr int kPrepUnroll = SCCAV_PREP_UNROLL;
+        // (two loops: a run-time is_static inside one loop costs ten predicated instructions per row)
+        if (is_static) {
 #pragma unroll kPrepUnroll
-        for (int m = 0; m < M; ++m, f += ss) {
-            T wx = T(0), wy = T(0);
-            if (!is_static) { wx = f[6 * N]; wy = f[7 * N]; }
-            Partials<T> p = ellipse_prep_partials<T>(x, y, f[0], f[N], f[2 * N], f[3 * N], f[4 * N], f[5 * N], wx, wy, is_static);
-            put_row<T, SCAN, 3, MODEL, MODEL == SCCAV_MODEL_DBM>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
+            for (int m = 0; m < M; ++m, f += ss) {
+                Partials<T> p = ellipse_prep_partials<T>(x, y, f[0], f[N], f[2 * N], f[3 * N], f[4 * N], f[5 * N], T(0), T(0), true);
+                put_row<T, SCAN, 3, MODEL, MODEL == SCCAV_MODEL_DBM>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
+            }
+        } else {
+#pragma unroll kPrepUnroll
+            for (int m = 0; m < M; ++m, f += ss) {
+                Partials<T> p = ellipse_prep_partials<T>(x, y, f[0], f[N], f[2 * N], f[3 * N], f[4 * N], f[5 * N], f[6 * N], f[7 * N], false);
+                put_row<T, SCAN, 3, MODEL, MODEL == SCCAV_MODEL_DBM>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
+            }
         }
     } else {
         T rsth = sth, rcth = cth;                              // trig of the row assembly (theta + beta under SADBM)
