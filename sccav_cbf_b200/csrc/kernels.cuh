@@ -791,7 +791,7 @@ __global__ void __launch_bounds__(256, SCCAV_K12_MINB) filter_step_staged_kernel
                 }
                 else if (NF >= 8) p = ellipse_prep_partials<T>(x, y, g[0], g[1], g[2], g[3], g[4], g[5], g[NF - 2], g[NF - 1]);
                 else p = ellipse_prep_partials<T>(x, y, g[0], g[1], g[2], g[3], g[4], g[5], T(0), T(0), true);
-                put_row<T, COOP, NF, MODEL>(P, p, sth, cth, v, alpha, vlr, r0, r1, stage, B, m, hmin, worst, feas, nz, &scan, &Ri);
+                put_row<T, COOP, NF, MODEL, MODEL == SCCAV_MODEL_DBM>(P, p, sth, cth, v, alpha, vlr, r0, r1, stage, B, m, hmin, worst, feas, nz, &scan, &Ri);
             }
         }
         T q0 = r0, q1 = r1;
