@@ -2,6 +2,8 @@
 // (SCCAV_REAL = double, compiled with -fmad=false) and capi_f32.cu (SCCAV_REAL = float).
 #pragma once
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -289,17 +291,18 @@ int do_filter_step(const sccav_params* p, const uint8_t* slot_desc, int32_t M, i
 }
 
 // Launch geometry of the persistent rollout: one vehicle per thread, ONE CTA per SM per wave.
-// For N <= 148*448 the block is sized so that a single balanced wave covers the batch
-// (e.g. N = 65,536 -> 147 CTAs of 448 threads); larger batches run 448-thread CTAs in many waves.
+// For N <= 148*512 the block is sized so that a single balanced wave covers the batch
+// (e.g. N = 65,536 -> 147 CTAs of 448 threads); larger batches run 512-thread CTAs in many waves.
 void rollout_geometry(int64_t N, int& grid, int& block) {
     const int sms = sm_count();
-    int64_t per_sm = (N + sms - 1) / sms;
-    if (per_sm <= SCCAV_ROLLOUT_MAXB) {
-        block = (int)((per_sm + 31) / 32 * 32);
-        if (block < 32) block = 32;
-    } else {
-        block = SCCAV_ROLLOUT_MAXB;               // many waves of full CTAs (144 registers/thread: one CTA per SM)
-    }
+    // balanced waves: as few waves of one CTA per SM as SCCAV_ROLLOUT_MAXB allows, every SM the same share of each
+    // (131,072 vehicles: 2 waves of 443 per SM -> 448-thread CTAs, not a full wave of 512 and a ragged one)
+    const int64_t waves = (N + (int64_t)sms * SCCAV_ROLLOUT_MAXB - 1) / ((int64_t)sms * SCCAV_ROLLOUT_MAXB);
+    const int64_t w1 = waves < 1 ? 1 : waves;
+    const int64_t per_cta = (N + w1 * sms - 1) / (w1 * sms);
+    block = (int)((per_cta + 31) / 32 * 32);
+    if (block < 32) block = 32;
+    if (block > SCCAV_ROLLOUT_MAXB) block = SCCAV_ROLLOUT_MAXB;
     grid = (int)((N + block - 1) / block);
 }
 
@@ -362,8 +365,11 @@ int roads_geometry(const void* kern, int M, int np, int n_roads, int64_t group, 
         const int64_t cpr = (group + b - 1) / b;
         const int64_t ctas = cpr * n_roads;
         const int64_t waves = (ctas + (int64_t)occ * sm_count() - 1) / ((int64_t)occ * sm_count());
-        // a wave of a latency-bound kernel lasts about as long as its resident warps take turns: waves x resident threads
-        const double cost = (double)waves * std::min<int64_t>((int64_t)occ * b, (ctas + sm_count() - 1) / sm_count() * b);
+        // a wave of a latency-bound kernel lasts about as long as its resident warps take turns: waves x resident threads --
+        // but never less than what ~10 warps take (below that an SM idles between the dependent instructions of its few
+        // warps: 1,024 CTAs of 64 threads in 7 waves were measured at 27 ms against 11 ms for 128 CTAs of 512 in one)
+        const int64_t resident = std::min<int64_t>((int64_t)occ * b, (ctas + sm_count() - 1) / sm_count() * b);
+        const double cost = (double)waves * (double)std::max<int64_t>(resident, 320);
         if (cost < best_cost) { best_cost = cost; block = b; smem = sm; ctas_per_road = (int)cpr; grid = (int)ctas; }
     }
     if (!block) { set_error("a road of %d points does not fit in shared memory", np); return SCCAV_EINVAL; }
@@ -443,6 +449,7 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
         rc = roads_geometry((const void*)kern, M, a.np, n_roads, a.group, grid, block, smem, a.ctas_per_road, trig);
         if (rc) { if (a.pre) cudaFreeAsync(a.pre, st); if (prep) cudaFreeAsync(prep, st); return rc; }
     }
+    if (getenv("SCCAV_DEBUG_LAUNCH")) fprintf(stderr, "[sccav] rollout launch: grid %d block %d smem %zu roads %d ctas_per_road %d spec %d fast %d\n", grid, block, smem, n_roads, a.ctas_per_road, spec, (int)fast);
     cudaError_t le = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (le == cudaSuccess) { kern<<<grid, block, smem, st>>>(a); le = cudaGetLastError(); }
     count_launch();

@@ -871,10 +871,11 @@ __device__ __forceinline__ void seeker_update(T* f, int64_t fs, T ex, T ey, T dt
     f[fs] = cy + vy * dt;
 }
 
-// 448 threads = 14 warps: the register file is per SM sub-partition (16,384 registers each, warps
-// dealt round-robin), so a CTA of more than 12 warps caps the kernel at 128 registers per thread;
-// 65,536 vehicles / 148 SMs = 443 vehicles per SM is why the CTA is this large.
-#define SCCAV_ROLLOUT_MAXB 448
+// Up to 512 threads = 16 warps per CTA, one CTA per SM: the register file is per SM sub-partition (16,384 registers
+// each, warps dealt round-robin), so a CTA of more than 12 warps caps the kernel at 128 registers per thread -- the same
+// cap for 14 warps (65,536 vehicles / 148 SMs = 443 vehicles per SM: config 2 runs 448-thread CTAs in one wave) and for
+// 16 (batches of many waves, and 1,024-vehicle roads as two CTAs).
+#define SCCAV_ROLLOUT_MAXB 512
 
 // Shared-memory layout of the rollout kernel (bytes), shared by the launcher and the kernel:
 //   [ course xy : T2 x nslot (leaf-padded) ][ node chords : 16 B x nodes ][ node (1 / len^2, radius) : 8 B x nodes ][ header : level table int x 32, origin T x 2, extent float ]
