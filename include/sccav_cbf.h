@@ -479,6 +479,13 @@ int sccav_debug_course_index_host(const double* cx, const double* cy, int32_t P,
                                   const int32_t* hint, int64_t nq, int32_t dtype, int32_t* idx_out,
                                   int32_t* idx_full_out, int64_t* evals_out);
 
+/* TEST HOOK, host-only, launches nothing: the cover table of the search for a course of P points (csrc/course_index.cuh,
+ * cover_row).  For every window leaf w in [0, nleaf): up to kc cover nodes as (level, index) pairs -- node (h, j) = leaves
+ * [j 2^h, (j + 1) 2^h) -- nearest first; count_out[w] = how many.  *nleaf_out, *nlev_out, *kc_out describe the tree; a first
+ * call with level_out = NULL returns only those.  level_out / index_out hold nleaf * kc entries each. */
+int sccav_debug_cover_host(int32_t P, int32_t* nleaf_out, int32_t* nlev_out, int32_t* kc_out, int32_t* count_out,
+                           int32_t* level_out, int32_t* index_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,7 +78,7 @@ SYMBOLS = [
     "sccav_barrier_rows_f64", "sccav_barrier_rows_f32", "sccav_qp2_solve_f64", "sccav_qp2_solve_f32",
     "sccav_filter_step_f64", "sccav_filter_step_f32", "sccav_rollout_f64", "sccav_rollout_f32",
     "sccav_filter_step_host_f64", "sccav_filter_step_host_f32", "sccav_rollout_host_f64", "sccav_rollout_host_f32",
-    "sccav_measure_fma_peak", "sccav_launch_count", "sccav_debug_course_index_host",
+    "sccav_measure_fma_peak", "sccav_launch_count", "sccav_debug_course_index_host", "sccav_debug_cover_host",
     "sccav_rollout_launch_info_f64", "sccav_rollout_launch_info_f32",
     "sccav_barrier_partials_f64", "sccav_barrier_partials_f32", "sccav_stanley_control_f64", "sccav_stanley_control_f32",
     "sccav_prepare_obstacles_f64", "sccav_prepare_obstacles_f32", "sccav_ingest_boxes_f64", "sccav_ingest_boxes_f32",
@@ -110,6 +110,7 @@ def lib() -> C.CDLL:
     L.sccav_measure_fma_peak.argtypes = [i32, C.POINTER(C.c_double)]
     L.sccav_launch_count.restype = i64
     L.sccav_debug_course_index_host.argtypes = [vp, vp, i32, vp, vp, vp, i64, i32, vp, vp, vp]
+    L.sccav_debug_cover_host.argtypes = [i32, vp, vp, vp, vp, vp, vp]
     for sfx in ("f64", "f32"):
         f = getattr(L, "sccav_barrier_rows_" + sfx)
         f.argtypes = [PP, C.c_char_p, i32, i64, vp, vp, PV, vp, vp, vp, vp]

@@ -256,6 +256,29 @@ static void debug_course_index(const double* cx, const double* cy, int P, const 
 
 extern "C" {
 
+int sccav_debug_cover_host(int32_t P, int32_t* nleaf_out, int32_t* nlev_out, int32_t* kc_out, int32_t* count_out,
+                           int32_t* level_out, int32_t* index_out) {
+    using namespace sccav;
+    if (P < 1 || !nleaf_out || !nlev_out || !kc_out) { set_error("bad argument"); return SCCAV_EINVAL; }
+    int lev[2 * SCCAV_MAX_LEVELS], units;
+    const int nlev = course_levels(P, lev, &units);
+    const int nleaf = course_nleaf(P), kc = cover_kc(nlev), dummy = units - 1;
+    *nleaf_out = nleaf; *nlev_out = nlev; *kc_out = kc;
+    if (!level_out || !index_out || !count_out) return SCCAV_OK;
+    if (units > 65535) { set_error("course too long for 16-bit node ids"); return SCCAV_EINVAL; }
+    std::vector<uint16_t> row(kc);
+    for (int w = 0; w < nleaf; ++w) {
+        count_out[w] = cover_row(w, nlev, lev, kc, dummy, row.data());
+        for (int k = 0; k < kc; ++k) {
+            int h = -1, j = -1;
+            if (row[k] != dummy) unit_node(lev, nlev, row[k], h, j);
+            level_out[(size_t)w * kc + k] = h;
+            index_out[(size_t)w * kc + k] = j;
+        }
+    }
+    return SCCAV_OK;
+}
+
 int sccav_debug_course_index_host(const double* cx, const double* cy, int32_t P, const double* fx, const double* fy,
                                   const int32_t* hint, int64_t nq, int32_t dtype, int32_t* idx_out,
                                   int32_t* idx_full_out, int64_t* evals_out) {

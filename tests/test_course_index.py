@@ -145,3 +145,42 @@ def test_closed_loop_queries_cost_a_few_dozen_evaluations():
     idx, full, ev = run(cx, cy, fx, fy, hint)
     assert np.array_equal(idx, full)
     assert ev.mean() < 60, ev.mean()
+
+
+def _cover(P):
+    L = nv.lib()
+    nleaf = C.c_int32(); nlev = C.c_int32(); kc = C.c_int32()
+    assert L.sccav_debug_cover_host(P, C.addressof(nleaf), C.addressof(nlev), C.addressof(kc), None, None, None) == 0
+    cnt = np.empty(nleaf.value, np.int32)
+    lev = np.empty((nleaf.value, kc.value), np.int32); idx = np.empty((nleaf.value, kc.value), np.int32)
+    assert L.sccav_debug_cover_host(P, C.addressof(nleaf), C.addressof(nlev), C.addressof(kc), cnt.ctypes.data,
+                                    lev.ctypes.data, idx.ctypes.data) == 0
+    return nleaf.value, nlev.value, kc.value, cnt, lev, idx
+
+
+@pytest.mark.parametrize("P", [1, 8, 9, 16, 17, 24, 25, 63, 64, 65, 255, 1000, 2034, 2360, 4999, 8191])
+def test_cover_is_a_partition_that_grows_with_distance(P):
+    """The search proves its answer by excluding a COVER of everything outside the two-leaf window
+    (course_index.cuh, cover_node / cover_row).  For every window leaf w of a course of P points:
+    the cover nodes and the window tile the leaves [0, nleaf) exactly -- no leaf missing, none twice --,
+    the row fits the table (count <= kc, kc = 3 (nlev - 1) + 1 rounded up to 8), the top level is never used,
+    and a node of 2^h leaves lies at least 2^h - 1 leaves from the window (never large where it is close)."""
+    nleaf, nlev, kc, cnt, lev, idx = _cover(P)
+    assert nleaf == (P + 7) // 8 and kc % 8 == 0 and kc >= 3 * (nlev - 1) + 1
+    for w in range(max(nleaf - 1, 1)):
+        win = (w, min(w + 2, nleaf))
+        seen = np.zeros(nleaf, np.int32)
+        seen[win[0]:win[1]] += 1
+        assert 0 <= cnt[w] <= kc
+        assert (lev[w, cnt[w]:] == -1).all()
+        last_level = -1
+        for h, j in zip(lev[w, :cnt[w]], idx[w, :cnt[w]]):
+            assert 0 <= h < max(nlev - 1, 1)
+            assert h >= last_level                      # nearest (smallest) first
+            last_level = h
+            lo, hi = j << h, min((j + 1) << h, nleaf)
+            assert lo < hi
+            seen[lo:hi] += 1
+            gap = win[0] - hi if hi <= win[0] else lo - win[1]
+            assert gap >= (1 << h) - 1, (w, h, j, gap)
+        assert (seen == 1).all(), (P, w, np.flatnonzero(seen != 1)[:8])
