@@ -368,6 +368,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-operator", action="store_true", help="skip the regime-(i) operator roofline leg")
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs 3 / 4 / 5 / 1M-vehicle-target legs")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the CPUs of its GPU's NUMA node")
     ap.add_argument("--config-scale", type=float, default=1.0, help="shrink the vehicle counts of the extra config legs (smoke runs)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -378,7 +379,7 @@ def main():
     import torch
 
     from sccav_cbf_b200 import ops, scenarios as sc
-    from sccav_cbf_b200.dist import Shards
+    from sccav_cbf_b200.dist import Shards, bind_to_gpu_numa_node
     from sccav_cbf_b200.rollout import ClosedLoopRollout
 
     if not torch.cuda.is_available():
@@ -386,6 +387,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    all_cpus = os.sched_getaffinity(0)
+    numa_cpus = None if args.no_numa_bind else bind_to_gpu_numa_node(local)   # before any pinned buffer is allocated
     sh = Shards(backend="nccl", device=dev)
     rank, world = sh.rank, sh.world
 
@@ -770,6 +773,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import c_oracle as co
+        os.sched_setaffinity(0, all_cpus)          # the CPU arm gets every host core back
         threads = co.num_threads()
         rate, _, _ = cpu_rollout_rate(max(threads, 8), M, T, threads)
         n = int(max(threads, min(NV, rate * args.cpu_seconds / (M * T))))
@@ -818,6 +822,7 @@ def main():
             "roofline_operator": roofline_op,
             "cpu_baseline": cpu,
             "wall_s_timed_region": t_wall1 - t_wall0,
+            "host_cpu_affinity": ("%d CPUs of the GPU's NUMA node (NVML ideal affinity)" % len(numa_cpus)) if numa_cpus else "unchanged",
             "vs_reference_note": "N GPUs over ONE host's CPU threads when n_gpus > 1 (the CPU arm does not scale with --gpus)",
         }
         flat["e2e_sync_value"] = e2e_sync_value
