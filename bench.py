@@ -530,7 +530,9 @@ def main():
         # config 3: 262,144 vehicles x 16 moving circles (radial-dynamic TV-CBF, seekers), 600 frames
         n3 = per_gpu(262144)
         lo3, hi3 = sc.shard_range(n3 * world, rank, world)
-        flat.update(run_config_leg("config3", sc.config3(n_total=n3 * world, M=16, T=600, lo=lo3, hi=hi3), dtype, fl, dev, flush, sh))
+        # (config 3's fast mode adds SCCAV_FLAG_SEEKER_DIRECT = 16: seeker headings as normalised offsets)
+        flat.update(run_config_leg("config3", sc.config3(n_total=n3 * world, M=16, T=600, lo=lo3, hi=hi3), dtype, (fl | 16) if fl else 0, dev, flush, sh))
+        flat["config3_flags"] = (fl | 16) if fl else 0
         # config 4: 1,048,576 vehicles x (8 ellipses + 2 lanes), fp64 and fp32
         n4 = per_gpu(1048576)
         lo4, hi4 = sc.shard_range(n4 * world, rank, world)

@@ -114,6 +114,12 @@ extern "C" {
  * integrated in beta, like State.update_com, sce.py:122-131): the same QP on the same rows, two tan + two atan2 per
  * solve cheaper.  Rejected (SCCAV_EINVAL) by every other model and by the rollout / drive-tick entry points.          */
 #define SCCAV_FLAG_BETA_IO 8
+/* rollout with seekers (sccav_params.seeker): the seeker's velocity direction is the normalised offset (dx, dy) / hypot(dx, dy)
+ * instead of sincos(atan2(dy, dx)) (radial_dynamic_obstacles.py:193-239): the same unit vector to a few ulp, one atan2 and
+ * one sincos per seeker and step cheaper.  With SCCAV_FLAG_PREPARED_ROWS the rollout also evaluates RADIAL rows with the
+ * reciprocals 1 / a, 1 / b formed once per launch and v / (1 + v), 1 / (1 + v)^2 once per step (eight divisions per row in
+ * the reference's order, rdo.py:391-405).  Opt-in like the other fast forms; the reference order stays the default.       */
+#define SCCAV_FLAG_SEEKER_DIRECT 16
 
 #define SCCAV_STATUS_INACTIVE 0    /* u == u_ref                                               */
 #define SCCAV_STATUS_ACTIVE 1      /* KKT optimum with 1 or 2 active rows                      */

@@ -64,6 +64,7 @@ FLAG_PREPARED_ROWS = 1  # sccav_params.flags (GPU rollout only; the oracle's ari
 FLAG_QP_ENUMERATE = 2   # GPU only: no QP shortcut (the oracle always enumerates)
 FLAG_FUSED_STEER = 4    # GPU rollout only: beta = clamp(beta*) (the oracle always runs beta* -> delta -> clip -> beta)
 FLAG_BETA_IO = 8        # GPU filter step only: beta in / beta out (the oracle keeps the reference's delta interface; tests convert)
+FLAG_SEEKER_DIRECT = 16  # GPU rollout only: seeker direction as the normalised offset (the oracle keeps sincos(atan2))
 NFIELD = 8
 
 MODEL_DBM = 0      # DBM_CBF_2DS  (cbf/cbf.py:112-220)

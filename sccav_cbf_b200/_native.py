@@ -24,6 +24,7 @@ FLAG_PREPARED_ROWS = 1
 FLAG_QP_ENUMERATE = 2
 FLAG_FUSED_STEER = 4
 FLAG_BETA_IO = 8
+FLAG_SEEKER_DIRECT = 16
 BOX_FIELDS = 6
 INGEST_UPDATE, INGEST_REBUILD = 0, 1
 ACT_RESET_BRAKE = 1

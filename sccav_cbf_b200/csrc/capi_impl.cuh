@@ -437,7 +437,11 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
     if (rc) { if (prep) cudaFreeAsync(prep, st); return rc; }
     // scratch for the loop-invariant terms of canonical ellipses: stream-ordered, lives for this launch
     a.pre = nullptr;
-    if (any_ellipse && T >= 2 && filt) {
+    // (+ the reciprocal half axes of RADIAL slots when the rows are prepared; those launches get it for one step as well)
+    bool radial_prep = false;
+    if (p->flags & SCCAV_FLAG_PREPARED_ROWS)
+        for (int m = 0; m < M; ++m) radial_prep |= (desc2[m] & SCCAV_SLOT_TYPE_MASK) == SCCAV_SLOT_RADIAL;
+    if (((any_ellipse && T >= 2) || (radial_prep && T >= 1)) && filt) {
         void* scratch = nullptr;
         cudaError_t me = pool_alloc(&scratch, (size_t)M * SCCAV_NPRE * (size_t)N * sizeof(real), st);
         if (me != cudaSuccess) { if (prep) cudaFreeAsync(prep, st); SCCAV_CUDA_CHECK(me); }

@@ -855,15 +855,23 @@ template <typename T> struct RolloutArgs {
 };
 
 // RadialObstacleSpawner.update_seekers -- radial_dynamic_obstacles.py:193-239
+// direct (SCCAV_FLAG_SEEKER_DIRECT): (cos, sin) of the heading as the normalised offset -- the same unit vector, a few ulp from
+// sincos(atan2(dy, dx)); a seeker exactly on the ego heads along +x like atan2(0, 0) = 0
 template <typename T>
-__device__ __forceinline__ void seeker_update(T* f, int64_t fs, T ex, T ey, T dt, T k, T vmin) {
+__device__ __forceinline__ void seeker_update(T* f, int64_t fs, T ex, T ey, T dt, T k, T vmin, bool direct = false) {
     typedef Real<T> R;
     T cx = f[0], cy = f[fs];
-    T yaw = R::atan2_(ey - cy, ex - cx);
-    T vmag = k * R::hypot_(ex - cx, ey - cy);
+    const T hyp = R::hypot_(ex - cx, ey - cy);
+    T vmag = k * hyp;
     if (vmag < vmin) vmag = vmin;
     T s, c;
-    R::sincos_(yaw, &s, &c);
+    if (direct) {
+        if (hyp > T(0)) { c = (ex - cx) / hyp; s = (ey - cy) / hyp; }
+        else { c = T(1); s = T(0); }
+    } else {
+        T yaw = R::atan2_(ey - cy, ex - cx);
+        R::sincos_(yaw, &s, &c);
+    }
     T vx = vmag * c, vy = vmag * s;
     f[5 * fs] = vx;
     f[6 * fs] = vy;
@@ -1049,6 +1057,15 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
     if (a.pre && filt) {
         for (int m = 0; m < Mv; ++m) {
             const int desc = a.sd.d[m];
+            if ((desc & SCCAV_SLOT_TYPE_MASK) == SCCAV_SLOT_RADIAL && (P.flags & SCCAV_FLAG_PREPARED_ROWS)) {
+                // prepared RADIAL rows: the reciprocals of the (constant) half axes, once per launch
+                const int64_t nr = (desc & SCCAV_SLOT_SHARED) ? 0 : n;
+                const T* fr = a.obst + (int64_t)m * SCCAV_NFIELD * N + nr;
+                T* pr = a.pre + (int64_t)m * SCCAV_NPRE * N + n;
+                pr[0] = T(1) / fr[2 * N];
+                pr[N] = T(1) / fr[3 * N];
+                continue;
+            }
             if ((desc & SCCAV_SLOT_TYPE_MASK) != SCCAV_SLOT_ELLIPSE) continue;
             const int64_t nn = (desc & SCCAV_SLOT_SHARED) ? 0 : n;
             const T* f = a.obst + (int64_t)m * SCCAV_NFIELD * N + nn;
@@ -1166,7 +1183,8 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
             for (int m = 0; m < Mv; ++m) {
                 const int desc = a.sd.d[m];
                 if ((desc & SCCAV_SLOT_TYPE_MASK) == SCCAV_SLOT_RADIAL && !(desc & SCCAV_SLOT_SHARED))
-                    seeker_update<T>(a.obst + (int64_t)m * SCCAV_NFIELD * N + n, N, x, y, P.dt, P.seeker_k, P.seeker_vmin);
+                    seeker_update<T>(a.obst + (int64_t)m * SCCAV_NFIELD * N + n, N, x, y, P.dt, P.seeker_k, P.seeker_vmin,
+                                     (P.flags & SCCAV_FLAG_SEEKER_DIRECT) != 0);
             }
         }
         // ---- bookkeeping

@@ -210,6 +210,26 @@ __device__ __forceinline__ Partials<T> radial_partials(T x, T y, T v, T cx, T cy
     return o;
 }
 
+// SCCAV_FLAG_PREPARED_ROWS in the rollout: the same functions with the reciprocals 1 / a, 1 / b from the launch's scratch and
+// vo = v / (1 + v), iopv2 = 1 / (1 + v)^2 formed once per step -- no division per row (eight in the reference's order)
+template <typename T> struct RadialStep {
+    T vo, iopv2;
+};
+template <typename T>
+__device__ __forceinline__ Partials<T> radial_partials_fast(T x, T y, T cx, T cy, T ia, T ib, T kv, T vx, T vy, const RadialStep<T>& rs) {
+    Partials<T> o;
+    T dx = x - cx, dy = y - cy;
+    T da = dx * ia, db = dy * ib;
+    o.h = ((da * da + db * db) - T(1)) - kv * rs.vo;
+    T iaa = ia * ia, ibb = ib * ib;
+    o.hx = (T(2) * dx) * iaa;
+    o.hy = (T(2) * dy) * ibb;
+    o.hth = T(0);
+    o.hv = (-kv) * rs.iopv2;
+    o.ht = T(-2) * ((dx * iaa) * vx + (dy * ibb) * vy);
+    return o;
+}
+
 // D_CBF -- test_scripts/stanley_controller_ellipse.py:251-255
 template <typename T>
 __device__ __forceinline__ Partials<T> distance_partials(T x, T y, T cx, T cy, T Ds) {
@@ -336,7 +356,7 @@ template <typename T>
 __device__ __forceinline__ Partials<T> slot_partials(int desc, const T* __restrict__ f, int64_t fs,
                                                      T x, T y, T th, T v, T sth, T cth,
                                                      const T* pre = nullptr, int64_t ps = 0,
-                                                     const T* ego_beta = nullptr) {
+                                                     const T* ego_beta = nullptr, const RadialStep<T>* rs = nullptr) {
     const int type = desc & SCCAV_SLOT_TYPE_MASK;
     const bool is_static = (desc & SCCAV_SLOT_STATIC) != 0;
     // f points at field 0 of this slot for this vehicle; fs = stride between fields (N)
@@ -365,6 +385,7 @@ __device__ __forceinline__ Partials<T> slot_partials(int desc, const T* __restri
             return lane_partials<T>(x, y, c, buf, type == SCCAV_SLOT_LANE_SQRT);
         }
         case SCCAV_SLOT_RADIAL: {
+            if (rs && pre) return radial_partials_fast<T>(x, y, f[0], f[fs], pre[0], pre[ps], f[4 * fs], f[5 * fs], f[6 * fs], *rs);
             T cx = f[0], cy = f[fs], a = f[2 * fs], b = f[3 * fs], kv = f[4 * fs], vx = f[5 * fs], vy = f[6 * fs];
             return radial_partials<T>(x, y, v, cx, cy, a, b, kv, vx, vy);
         }
@@ -896,12 +917,16 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
     } else {
         T rsth = sth, rcth = cth;                              // trig of the row assembly (theta + beta under SADBM)
         if (sadbm) R::sincos_(th + ego_beta, &rsth, &rcth);
+        // prepared RADIAL rows (the rollout with SCCAV_FLAG_PREPARED_ROWS: `pre` then holds 1 / a, 1 / b of those slots)
+        RadialStep<T> rstep;
+        const bool rfast = pre != nullptr && (P.flags & SCCAV_FLAG_PREPARED_ROWS) != 0;
+        if (rfast) { const T opv = T(1) + v; rstep.vo = v / opv; rstep.iopv2 = T(1) / (opv * opv); }
         for (int m = 0; m < M; ++m) {
             const int desc = sd.d[m];
             const int64_t nn = (desc & SCCAV_SLOT_SHARED) ? 0 : n;
             const T* f = obst + (int64_t)m * SCCAV_NFIELD * N + nn;
             const T* pr = pre ? pre + (int64_t)m * SCCAV_NPRE * N + n : nullptr;
-            Partials<T> p = slot_partials<T>(desc, f, N, x, y, th, v, sth, cth, pr, N, sadbm ? &ego_beta : nullptr);
+            Partials<T> p = slot_partials<T>(desc, f, N, x, y, th, v, sth, cth, pr, N, sadbm ? &ego_beta : nullptr, rfast ? &rstep : nullptr);
             put_row<T, SCAN, 3, MODEL>(P, p, rsth, rcth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
         }
     }

@@ -101,7 +101,7 @@ def test_header_constants_match_their_python_mirrors():
         "SCCAV_SLOT_LANE_SQRT": "SLOT_LANE_SQRT", "SCCAV_SLOT_STATIC": "SLOT_STATIC",
         "SCCAV_MODEL_DBM": "MODEL_DBM", "SCCAV_MODEL_KBM": "MODEL_KBM", "SCCAV_MODEL_NONE": "MODEL_NONE", "SCCAV_MODEL_DUM": "MODEL_DUM",
         "SCCAV_MODEL_SADBM": "MODEL_SADBM", "SCCAV_FLAG_PREPARED_ROWS": "FLAG_PREPARED_ROWS", "SCCAV_FLAG_QP_ENUMERATE": "FLAG_QP_ENUMERATE",
-        "SCCAV_FLAG_FUSED_STEER": "FLAG_FUSED_STEER", "SCCAV_FLAG_BETA_IO": "FLAG_BETA_IO",
+        "SCCAV_FLAG_FUSED_STEER": "FLAG_FUSED_STEER", "SCCAV_FLAG_BETA_IO": "FLAG_BETA_IO", "SCCAV_FLAG_SEEKER_DIRECT": "FLAG_SEEKER_DIRECT",
     }
     for c_name, py_name in pairs.items():
         assert c_name in defs, c_name

@@ -754,8 +754,8 @@ def _teacher_forced_steps(batch, ts, flags, n_min_frac=0.5, u_tol=1e-9, x_tol=1e
             alive &= ok
         assert alive.mean() >= n_min_frac, (t, alive.mean())
         st_in = np.where(np.isfinite(st), st, 0.0)
-        g = ops.rollout(prm, batch.slot_desc, T_(st_in, torch.float64), None if obst_t is None else T_(obst_t, torch.float64), course, 1,
-                        record_stride=1, **gkw)
+        d_obst = None if obst_t is None else T_(obst_t, torch.float64)
+        g = ops.rollout(prm, batch.slot_desc, T_(st_in, torch.float64), d_obst, course, 1, record_stride=1, **gkw)
         torch.cuda.synchronize()
         gu = g["traj"][0, 4:6].cpu().numpy()[:, alive]; ru = r["traj"][t, 4:6][:, alive]
         assert (np.abs(gu - ru) <= u_tol * (1.0 + np.abs(ru))).all(), (t, np.abs(gu - ru).max())
@@ -764,6 +764,10 @@ def _teacher_forced_steps(batch, ts, flags, n_min_frac=0.5, u_tol=1e-9, x_tol=1e
             assert np.array_equal(g["traj_idx"][0].cpu().numpy()[alive], r["traj_idx"][t][alive]), t
         gx = g["state"].cpu().numpy()[:, alive]; rx = r["traj"][t + 1, 0:4][:, alive]
         assert (np.abs(gx - rx) <= x_tol * (1.0 + np.abs(rx))).all(), (t, np.abs(gx - rx).max())
+        if seeker:                                                   # the seekers after the step, against the oracle's
+            obst_n = co.rollout(co.default_params(**prm_o), batch.slot_desc, batch.state, batch.obst, batch.course, t + 1, **kw)["obst"]
+            go = d_obst.cpu().numpy()[:, :, alive]; ro = obst_n[:, :, alive]
+            assert (np.abs(go - ro) <= 1e-11 * (1.0 + np.abs(ro))).all(), (t, np.abs(go - ro).max())
         checked += int(alive.sum())
     return checked
 
@@ -780,9 +784,11 @@ def test_teacher_forced_rollout_step_config2_every_row_mode(flags):
 
 @pytest.mark.parametrize("flags", [0, 5])
 def test_teacher_forced_rollout_step_configs_3_4_5(flags):
+    """(config 3 in its fast mode also takes SCCAV_FLAG_SEEKER_DIRECT = 16 and, with the prepared rows, the division-free
+    RADIAL rows; the seekers after the step are compared with the oracle's as well)"""
     from sccav_cbf_b200 import scenarios as sc
     b3 = sc.config3(n_total=262144, M=16, T=420, lo=1000, hi=1000 + 192)
-    assert _teacher_forced_steps(b3, [0, 1, 2, 5, 17, 60, 150, 299, 418], flags, u_tol=1e-8) > 1500
+    assert _teacher_forced_steps(b3, [0, 1, 2, 5, 17, 60, 150, 299, 418], (flags | 16) if flags else 0, u_tol=1e-8) > 1500
     b4 = sc.config4(n_total=1048576, M=8, T=260, lo=300000, hi=300000 + 256)
     assert _teacher_forced_steps(b4, list(range(0, 250, 17)), flags, n_min_frac=0.15) > 1500
     lo = 11 * 65536 + 5
