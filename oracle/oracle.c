@@ -35,6 +35,7 @@
 #define LANE_MAX_IT 50
 #define LANE_LS_MAX 30
 #define LANE_XTOL 1e-12
+#define LANE_DTOL (8 * 0x1p-52)   /* a step may raise D by its rounding noise (oracle.py, lane_closest_x) */
 
 typedef struct { double h, hx, hy, hth, hv, ht; } part_t;
 
@@ -132,6 +133,7 @@ static double lane_closest_x(const double* c, double px, double py) {
         double hess = (1 + dg * dg) + ey * ddg;
         double step = (hess > 0) ? -grad / hess : -grad;
         double D0 = ex * ex + ey * ey;
+        double Dacc = D0 + LANE_DTOL * D0;
         double t = 1.0, xn = x;
         int ok = 0;
         for (int ls = 0; ls < LANE_LS_MAX; ++ls) {
@@ -139,7 +141,7 @@ static double lane_closest_x(const double* c, double px, double py) {
             xn = x + t * step;
             poly3(c, xn, &gn, &u1, &u2);
             double Dn = (xn - px) * (xn - px) + (gn - py) * (gn - py);
-            if (Dn <= D0) { ok = 1; break; }
+            if (Dn <= Dacc) { ok = 1; break; }
             t = t * 0.5;
         }
         if (!ok) break;

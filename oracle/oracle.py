@@ -83,6 +83,7 @@ QP_TIE_EPS = 1e-9      # infeasible fallback: a later candidate must beat the in
 LANE_MAX_IT = 50
 LANE_LS_MAX = 30
 LANE_XTOL = 1e-12
+LANE_DTOL = 8 * 2.0 ** -52   # a step is accepted if it does not increase D beyond its rounding noise (8 ulp)
 
 
 def normalize_angle(angle):
@@ -210,7 +211,9 @@ def lane_closest_x(c, px, py):
     Hessian carrying a typo (obstacles.py:673).  The typo only changes the path,
     not the fixed point, so this oracle runs a safeguarded Newton on the half-gradient
     ``(x-px) + (g-py) g'`` with the correct half-Hessian ``1 + g'^2 + (g-py) g''`` and a
-    backtracking line search on D; stops when the accepted step is <= 1e-12 (1+|x|).
+    backtracking line search on D (a step may raise D by its rounding noise, 8 ulp: near the minimum
+    the full Newton step changes D by less than that, and rejecting it there turns the quadratic
+    convergence into a bisection of ~20 iterations); stops when the accepted step is <= 1e-12 (1+|x|).
     """
     x = px
     for _ in range(LANE_MAX_IT):
@@ -224,6 +227,7 @@ def lane_closest_x(c, px, py):
         else:
             step = -grad
         D0 = ex * ex + ey * ey
+        Dacc = D0 + LANE_DTOL * D0
         t = 1.0
         ok = False
         xn = x
@@ -231,7 +235,7 @@ def lane_closest_x(c, px, py):
             xn = x + t * step
             gn, _, _ = _poly3(c, xn)
             Dn = (xn - px) * (xn - px) + (gn - py) * (gn - py)
-            if Dn <= D0:
+            if Dn <= Dacc:
                 ok = True
                 break
             t = t * 0.5
