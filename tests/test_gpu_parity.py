@@ -990,3 +990,24 @@ def test_filter_step_beta_io_flag(name):
     # every other model and the closed-loop entry points refuse the flag
     with pytest.raises(Exception):
         ops.filter_step(ops.make_params(model=o.MODEL_KBM, flags=nv.FLAG_BETA_IO), sd, T(s), obt, T(ur))
+
+
+@pytest.mark.parametrize("P", [1, 2, 8, 9, 17, 65, 200])
+@pytest.mark.parametrize("flags", [0, 5])
+def test_rollout_short_courses_way_point_indices(P, flags):
+    """Courses of one leaf, two leaves, a ragged last leaf, one tree level, ...: the shared-memory tree, the cover table and
+    the search in the kernel against the oracle's exhaustive scan -- way-point index of every recorded step identical, the
+    states to 1e-9 (canonical; 60 steps: short enough that the 1-ulp libm differences have not been amplified)."""
+    from sccav_cbf_b200 import scenarios as sc
+    b = sc.config2(n_total=65536, M=8, T=60, lo=4096, hi=4096 + 256)
+    cx, cy, cyaw = b.course
+    sel = np.linspace(0, 400, P).round().astype(int) if P > 1 else np.array([40])
+    b.course = (np.ascontiguousarray(cx[sel]), np.ascontiguousarray(cy[sel]), np.ascontiguousarray(cyaw[sel]))
+    b.params = dict(b.params, flags=flags)
+    g = _run(b, record_stride=1)
+    bo = sc.ScenarioBatch(b.name, b.state, b.slot_desc, b.obst, b.course, {k: v for k, v in b.params.items() if k != "flags"}, T=b.T)
+    r = _oracle(bo, record_stride=1)
+    assert np.array_equal(g["traj_idx"], r["traj_idx"])
+    assert np.array_equal(g["steps"], r["steps"]) and np.array_equal(g["target_idx"], r["target_idx"])
+    err = np.abs(g["state"] - r["state"]) / (1.0 + np.abs(r["state"]))
+    assert err.max() < (1e-9 if flags == 0 else 1e-7), err.max()       # (the fast modes are a few ulp per step away by design)
