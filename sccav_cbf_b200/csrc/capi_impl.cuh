@@ -448,10 +448,28 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
         a.pre = (real*)scratch;
     }
     rollout_fn kern = rollout_instance(course_smem, spec, fast, (p->flags & SCCAV_FLAG_FUSED_STEER) != 0);
+    // compile-time prepared instance on static ellipses: the loop reads the packed symmetric form (pack_sym_kernel)
+    a.sym = nullptr;
+    void* symbuf = nullptr;
+    if (prep && fast && (course_smem || n_roads > 0) && spec == SCCAV_SPEC_ELLIPSE_PREP && (desc2[0] & SCCAV_SLOT_STATIC) && !getenv("SCCAV_NO_SYM")) {
+        cudaError_t me = pool_alloc(&symbuf, (size_t)M * 6 * (size_t)N * sizeof(real), st);
+        if (me != cudaSuccess) { if (a.pre) cudaFreeAsync(a.pre, st); cudaFreeAsync(prep, st); SCCAV_CUDA_CHECK(me); }
+        SymArgs<real> sa;
+        sa.M = M; sa.N = N; sa.prep = (const real*)prep; sa.sym = (Real<real>::T2*)symbuf;
+        pack_sym_kernel<real><<<stream_grid((int64_t)M * N, 256), 256, 0, st>>>(sa);
+        count_launch();
+        a.sym = symbuf;
+    }
+    // compile-time canonical-ellipse instance: room for the paired copy of the fields and hoisted terms (filled by the kernel)
+    if (!symbuf && a.pre && fast && (course_smem || n_roads > 0) && spec == SCCAV_SPEC_ELLIPSE && !getenv("SCCAV_NO_SYM")) {
+        cudaError_t me = pool_alloc(&symbuf, (size_t)M * 10 * (size_t)N * sizeof(real), st);
+        if (me != cudaSuccess) { cudaFreeAsync(a.pre, st); if (prep) cudaFreeAsync(prep, st); SCCAV_CUDA_CHECK(me); }
+        a.sym = symbuf;
+    }
     if (n_roads > 0) {
         kern = rollout_instance(true, spec, fast, (p->flags & SCCAV_FLAG_FUSED_STEER) != 0);
         rc = roads_geometry((const void*)kern, M, a.np, n_roads, a.group, grid, block, smem, a.ctas_per_road, trig);
-        if (rc) { if (a.pre) cudaFreeAsync(a.pre, st); if (prep) cudaFreeAsync(prep, st); return rc; }
+        if (rc) { if (a.pre) cudaFreeAsync(a.pre, st); if (prep) cudaFreeAsync(prep, st); if (symbuf) cudaFreeAsync(symbuf, st); return rc; }
     }
     if (getenv("SCCAV_DEBUG_LAUNCH")) fprintf(stderr, "[sccav] rollout launch: grid %d block %d smem %zu roads %d ctas_per_road %d spec %d fast %d\n", grid, block, smem, n_roads, a.ctas_per_road, spec, (int)fast);
     cudaError_t le = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -459,6 +477,7 @@ int do_rollout(const sccav_params* p, const uint8_t* slot_desc, int32_t M, int64
     count_launch();
     if (a.pre) cudaFreeAsync(a.pre, st);
     if (prep) cudaFreeAsync(prep, st);
+    if (symbuf) cudaFreeAsync(symbuf, st);
     SCCAV_CUDA_CHECK(le);
     return SCCAV_OK;
 }

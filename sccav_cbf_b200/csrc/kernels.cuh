@@ -113,6 +113,31 @@ __global__ void __launch_bounds__(256) prepare_obstacles_kernel(const __grid_con
     }
 }
 
+// Rollout-private form of static prepared ellipses: the symmetric matrix S = M^T M instead of M, in 16-byte pairs --
+//   sym[m][0][n] = (cx, cy),  sym[m][1][n] = (s00, s01),  sym[m][2][n] = (s11, 0)
+// so that  h = d^T S d - 1,  grad h = 2 S d:  three 16-byte loads and eight flops per row where the public ELLIPSE_PREP
+// slot takes six 8-byte loads and twelve.  Same functions, a few ulp from the M form (SCCAV_FLAG_PREPARED_ROWS).
+template <typename T> struct SymArgs {
+    int M;
+    int64_t N;
+    const T* prep;       // [M][8][N] ELLIPSE_PREP slots (cx, cy, m00, m01, m10, m11, ., .)
+    typename Real<T>::T2* sym;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) pack_sym_kernel(const __grid_constant__ SymArgs<T> a) {
+    typedef Real<T> R;
+    const int64_t N = a.N, total = (int64_t)a.M * N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / N, n = i - m * N;
+        const T* f = a.prep + m * SCCAV_NFIELD * N + n;
+        const T m00 = f[2 * N], m01 = f[3 * N], m10 = f[4 * N], m11 = f[5 * N];
+        typename R::T2* o = a.sym + m * 3 * N + n;
+        o[0] = R::make2(f[0], f[N]);
+        o[N] = R::make2(fma(m00, m00, m10 * m10), fma(m00, m01, m10 * m11));
+        o[2 * N] = R::make2(fma(m01, m01, m11 * m11), T(0));
+    }
+}
+
 // ------------------------------------------------------------------------------------------ KB
 // Batched ObstacleList2D.update_by_bounding_box (include/sccav_cbf.h): one thread = one vehicle's list.
 // Integer bookkeeping (which id sits in which slot) is exact; the only arithmetic is a + buffer and
@@ -829,6 +854,8 @@ template <typename T> struct RolloutArgs {
     const T* state;
     T* obst;
     T* pre;              // scratch [M][SCCAV_NPRE][N] for loop-invariant obstacle terms (may be NULL)
+    const void* sym;     // rollout-private 16-byte-paired rows: static prepared ellipses in symmetric form [M][3][N] pairs (pack_sym_kernel),
+                         // or canonical ellipses with their hoisted terms [M][5][N] pairs (written by the rollout kernel itself); or NULL
     const T* cx;
     const T* cy;
     const T* cyaw;
@@ -1070,6 +1097,16 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
             const int64_t nn = (desc & SCCAV_SLOT_SHARED) ? 0 : n;
             const T* f = a.obst + (int64_t)m * SCCAV_NFIELD * N + nn;
             ellipse_precompute<T>(f[2 * N], f[3 * N], f[4 * N], a.pre + (int64_t)m * SCCAV_NPRE * N + n, N);
+            if (FAST && SPEC == SCCAV_SPEC_ELLIPSE && a.sym && !(desc & SCCAV_SLOT_SHARED)) {
+                // + the paired copy the all-static row loop reads (path.cuh): (cx, cy), (a, b), (ct, st), (k0, k1), (k2, k3)
+                const T* q = a.pre + (int64_t)m * SCCAV_NPRE * N + n;
+                T2* g = reinterpret_cast<T2*>(const_cast<void*>(a.sym)) + (int64_t)m * 5 * N + n;
+                g[0] = R::make2(f[0], f[N]);
+                g[N] = R::make2(f[2 * N], f[3 * N]);
+                g[2 * N] = R::make2(q[0], q[N]);
+                g[3 * N] = R::make2(q[2 * N], q[3 * N]);
+                g[4 * N] = R::make2(q[4 * N], q[5 * N]);
+            }
             if (!(desc & SCCAV_SLOT_STATIC) && (f[5 * N] != T(0) || f[6 * N] != T(0))) moving |= 1u << m;
         }
     }
@@ -1142,7 +1179,8 @@ __global__ void __launch_bounds__(SCCAV_ROLLOUT_MAXB, 1) rollout_kernel(const __
         int status = SCCAV_STATUS_INACTIVE;
         if (filt)
             status = filter_vehicle<T, SPEC, MODEL, FAST>(P, a.sd, Mv, N, n, a.obst, x, y, yaw, v, syaw, cyw, alpha, R00, R01, R10, R11, UW || a.pv.R == nullptr,
-                                             ur0, ur1, rows, stride, u0, u1, u1raw, mask, hmin, a.pre, moving, !fused, TRIG ? &beta_ref : nullptr);
+                                             ur0, ur1, rows, stride, u0, u1, u1raw, mask, hmin, a.pre, moving, !fused, TRIG ? &beta_ref : nullptr,
+                                             (FAST && SPEC != SCCAV_SPEC_GENERIC) ? a.sym : nullptr);
         // ---- plant
         T px = x, py = y, pyaw = yaw, pv_ = v;
         T beta = T(0);

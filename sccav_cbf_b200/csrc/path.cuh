@@ -830,7 +830,8 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
                                                    const T* __restrict__ obst, T x, T y, T th, T v, T sth, T cth,
                                                    T alpha, T uref0, T uref1, T* rows, int stride, T& hmin,
                                                    const T* __restrict__ pre = nullptr, uint32_t moving = 0xffffffffu,
-                                                   const RInv<T>* Ri = nullptr, const T* aug = nullptr, const T* r1_pre = nullptr) {
+                                                   const RInv<T>* Ri = nullptr, const T* aug = nullptr, const T* r1_pre = nullptr,
+                                                   const void* sym = nullptr) {
     typedef Real<T> R;
     hmin = R::inf();
     T vlr = v / P.lr;                                                                   // cbf.py:160 (g_c[2][1])
@@ -868,6 +869,18 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
             const int64_t ps = (int64_t)SCCAV_NPRE * N;
             const T* q = pre + n;
             // (two loops: the per-row test of the moving bit costs predicated instructions in every row)
+            if (sym && moving == 0u) {
+                // the rollout's paired copy of (cx, cy), (a, b) and the six hoisted terms: five 16-byte loads per row instead
+                // of ten 8-byte ones, the same values into the same operations
+                typedef typename R::T2 T2;
+                const T2* g = reinterpret_cast<const T2*>(sym) + n;
+                for (int m = 0; m < M; ++m, g += 5 * N) {
+                    const T2 c = g[0], ab = g[N], t = g[2 * N], k0 = g[3 * N], k1 = g[4 * N];
+                    const T loc[6] = {t.x, t.y, k0.x, k0.y, k1.x, k1.y};
+                    Partials<T> p = ellipse_partials_pre<T>(x, y, c.x, c.y, ab.x, ab.y, T(0), T(0), loc, 1);
+                    put_row<T, SCAN, 3, MODEL, MODEL == SCCAV_MODEL_DBM>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
+                }
+            } else
             if (moving == 0u) {
                 for (int m = 0; m < M; ++m, f += ss, q += ps) {
                     T cx = f[0], cy = f[N], a = f[2 * N], b = f[3 * N];
@@ -907,6 +920,22 @@ __device__ __forceinline__ RowPhase<T> filter_rows(const Params<T>& P, const Slo
 #endif
         constexpr int kPrepUnroll = SCCAV_PREP_UNROLL;
         // (two loops: a run-time is_static inside one loop costs ten predicated instructions per row)
+        if (sym) {
+            // the rollout's packed symmetric form (kernels.cuh, pack_sym_kernel): three 16-byte loads per row
+            typedef typename R::T2 T2;
+            const T2* g = reinterpret_cast<const T2*>(sym) + n;
+#pragma unroll kPrepUnroll
+            for (int m = 0; m < M; ++m, g += 3 * N) {
+                const T2 c = g[0], s0 = g[N], s1 = g[2 * N];
+                Partials<T> p;
+                const T dx = x - c.x, dy = y - c.y;
+                const T gx = fma(s0.x, dx, s0.y * dy), gy = fma(s0.y, dx, s1.x * dy);
+                p.h = fma(gx, dx, fma(gy, dy, T(-1)));
+                p.hx = T(2) * gx; p.hy = T(2) * gy;
+                p.hth = T(0); p.hv = T(0); p.ht = T(0);
+                put_row<T, SCAN, 3, MODEL, MODEL == SCCAV_MODEL_DBM>(P, p, sth, cth, v, alpha, vlr, r0, r1, rows, stride, m, hmin, worst, feas, nz, &scan, Ri);
+            }
+        } else
         if (is_static) {
 #pragma unroll kPrepUnroll
             for (int m = 0; m < M; ++m, f += ss) {
@@ -962,9 +991,9 @@ __device__ __forceinline__ int filter_vehicle(const Params<T>& P, const SlotDesc
                                               T alpha, T R00, T R01, T R10, T R11, bool uniform_R, T uref0, T uref1,
                                               T* rows, int stride, T& u0, T& u1, T& u1raw, uint32_t& mask, T& hmin,
                                               const T* __restrict__ pre = nullptr, uint32_t moving = 0xffffffffu,
-                                              bool convert = true, const T* r1_pre = nullptr) {
+                                              bool convert = true, const T* r1_pre = nullptr, const void* sym = nullptr) {
     const RowPhase<T> ph = filter_rows<T, SPEC, false, MODEL>(P, sd, M, N, n, obst, x, y, th, v, sth, cth, alpha, uref0, uref1,
-                                                rows, stride, hmin, pre, moving, nullptr, nullptr, r1_pre);
+                                                rows, stride, hmin, pre, moving, nullptr, nullptr, r1_pre, sym);
     T q0 = ph.r0, q1 = ph.r1;
     int status = SCCAV_STATUS_INACTIVE;
     mask = 0u;
