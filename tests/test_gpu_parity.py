@@ -1011,3 +1011,27 @@ def test_rollout_short_courses_way_point_indices(P, flags):
     assert np.array_equal(g["steps"], r["steps"]) and np.array_equal(g["target_idx"], r["target_idx"])
     err = np.abs(g["state"] - r["state"]) / (1.0 + np.abs(r["state"]))
     assert err.max() < (1e-9 if flags == 0 else 1e-7), err.max()       # (the fast modes are a few ulp per step away by design)
+
+
+def test_rollout_paired_rows_equal_the_unpaired_ones(monkeypatch):
+    """The compile-time ellipse instances read their rows from 16-byte pairs (capi_impl.cuh: a rollout-private copy).  For
+    canonical ellipses it is the same values into the same operations: every output bit for bit (SCCAV_NO_SYM switches the
+    copy off).  For prepared rows the pairs hold the symmetric form d^T S d - 1 instead of |M d|^2 - 1: the same quadratic
+    form a few ulp apart -- bookkeeping identical on this batch, states to 1e-9 over 120 steps."""
+    from sccav_cbf_b200 import scenarios as sc
+    b = sc.config2(n_total=65536, M=8, T=120, lo=20000, hi=20000 + 1500)
+    for flags in (0, 4, 1, 5):
+        b.params = dict(b.params, flags=flags)
+        monkeypatch.delenv("SCCAV_NO_SYM", raising=False)
+        g = _run(b, record_stride=10)
+        monkeypatch.setenv("SCCAV_NO_SYM", "1")
+        h = _run(b, record_stride=10)
+        monkeypatch.delenv("SCCAV_NO_SYM", raising=False)
+        for k in ("steps", "target_idx", "n_active", "n_infeasible", "traj_idx", "traj_mask"):
+            assert np.array_equal(g[k], h[k]), (flags, k)
+        if flags in (0, 4):
+            for k in ("state", "h_min", "beta_int", "traj"):
+                assert np.array_equal(g[k], h[k], equal_nan=True), (flags, k)
+        else:
+            err = np.abs(g["state"] - h["state"]) / (1.0 + np.abs(h["state"]))
+            assert err.max() < 1e-9, (flags, err.max())
